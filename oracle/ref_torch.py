@@ -1,0 +1,458 @@
+"""CPU oracle for the SparseBEV decoder hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+legs may import this module.  Nothing under `sparsebev_b200/` may.
+
+It restates, in plain fp32 PyTorch that runs on the CPU, the algorithm of the reference's
+*native-PyTorch* path (the one the reference itself runs when its CUDA extension is absent):
+
+    function here                       follows (file:line under /root/reference)
+    ----------------------------------  -------------------------------------------------
+    decode_bbox                         models/bbox/utils.py:63-77
+    rotate_about_z                      models/utils.py:49-84   (VERSION 'v1.0.0' branch)
+    inverse_sigmoid                     models/utils.py:87-102
+    make_sample_points                  models/sparsebev_sampling.py:8-24
+    project_and_select_view             models/sparsebev_sampling.py:44-109
+    msmv_sampling_gridsample            models/csrc/wrapper.py:14-38
+    msmv_sampling_kernel_semantics      models/csrc/msmv_sampling/msmv_sampling_forward.cu:27-164
+    sampling_4d                         models/sparsebev_sampling.py:27-130
+    adaptive_mixing                     models/sparsebev_transformer.py:351-381
+    scale_adaptive_self_attention       models/sparsebev_transformer.py:210-248  (+ mmcv 1.6.0
+                                        MultiheadAttention = nn.MultiheadAttention + identity)
+    sampling_module                     models/sparsebev_transformer.py:270-311
+    decoder_layer                       models/sparsebev_transformer.py:162-193 (+155-160)
+    decoder / transformer               models/sparsebev_transformer.py:32-38, 56-101
+    head_forward                        models/sparsebev_head.py:69-117, 216-220 (eval path)
+
+Pinning status (see tests/golden/ and oracle/gen_golden.py): the functions whose reference
+files import in this container (`bbox/utils.py`, `utils.py`, `csrc/wrapper.py`,
+`sparsebev_sampling.py`, and the `AdaptiveMixing` class body) are pinned against the REAL
+reference through committed golden vectors.  The decoder-layer glue that needs mmcv 1.6.0
+(`MultiheadAttention`, `FFN`) cannot be imported here (mmcv is not installed, no network):
+for those the restatement follows mmcv-full 1.6.0's documented semantics and is
+"parity unpinned" beyond the `torch.nn.MultiheadAttention` it wraps.
+
+Weights are passed as a flat dict keyed exactly like the reference checkpoint, relative to
+`...transformer.decoder.decoder_layer.` (checkpoint row).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+NUM_VIEWS = 6      # hard-coded in the reference: sparsebev_sampling.py:45, sparsebev_transformer.py:61,75
+NUM_GROUPS = 4     # sparsebev_transformer.py:123
+NUM_HEADS = 8      # sparsebev_transformer.py:122
+OUT_POINTS = 128   # sparsebev_transformer.py:124
+FFN_DIM = 512      # sparsebev_transformer.py:125
+
+
+# ----------------------------------------------------------------------------- geometry
+def decode_bbox(b, pc_range):
+    """[..., 10] normalised (cx,cy,cz,logw,logl,logh,sin,cos,vx,vy) -> [..., 9] metres."""
+    lo = b.new_tensor(pc_range[:3])
+    hi = b.new_tensor(pc_range[3:])
+    xyz = b[..., 0:3] * (hi - lo) + lo
+    wlh = torch.exp(b[..., 3:6])
+    yaw = torch.atan2(b[..., 6:7], b[..., 7:8])
+    out = [xyz, wlh, yaw]
+    if b.shape[-1] > 8:
+        out.append(b[..., 8:10])
+    return torch.cat(out, dim=-1)
+
+
+def rotate_about_z(p, yaw):
+    """p [..., n, 3], yaw [..., 1] -> counter-clockwise rotation by yaw about +z."""
+    s = torch.sin(yaw)[..., None, :]   # [..., 1, 1]
+    c = torch.cos(yaw)[..., None, :]
+    x, y, z = p[..., 0:1], p[..., 1:2], p[..., 2:3]
+    return torch.cat([x * c + y * (-s), x * s + y * c, z], dim=-1)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(0, 1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def make_sample_points(query_bbox, offset, pc_range):
+    """query_bbox [B,Q,10], offset [B,Q,GP,3] -> lidar-frame points [B,Q,GP,3]."""
+    box = decode_bbox(query_bbox, pc_range)
+    centre, size, yaw = box[..., 0:3], box[..., 3:6], box[..., 6:7]
+    local = size[:, :, None, :] * offset
+    return centre[:, :, None, :] + rotate_about_z(local, yaw)
+
+
+# --------------------------------------------------------------- projection + view pick
+def project_and_select_view(points, lidar2img, image_h, image_w, eps=1e-5, return_all=False):
+    """points [B,Q,T,GP,3]; lidar2img [B,T*N,4,4] -> (uv [B,T,Q,GP,2], view [B,T,Q,GP] int64).
+
+    Homogeneous projection to every one of the N views, eps-clamped perspective divide,
+    normalisation by the (padded) image size, validity = in front of camera and strictly
+    inside (0,1)^2, then the FIRST valid view wins (view 0 when none is valid).  The validity
+    flag itself is never applied to the sampled value (reference: sparsebev_sampling.py:102-106).
+    The mat-vec is written as a fixed-order x*m0 + y*m1 + z*m2 + m3 so the CUDA kernel can
+    reproduce it bit-for-bit.
+    """
+    B, Q, T, GP, _ = points.shape
+    N = NUM_VIEWS
+    m = lidar2img.reshape(B, T, N, 1, 1, 4, 4)
+    p = points.permute(0, 2, 1, 3, 4)[:, :, None]          # [B,T,1,Q,GP,3]
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+
+    def row(i):
+        return ((x * m[..., i, 0] + y * m[..., i, 1]) + z * m[..., i, 2]) + m[..., i, 3]
+
+    cx, cy, depth = row(0), row(1), row(2)                 # [B,T,N,Q,GP]
+    safe = torch.clamp(depth, min=eps)
+    u = (cx / safe) / image_w
+    v = (cy / safe) / image_h
+    valid = (depth > eps) & (v > 0.0) & (v < 1.0) & (u > 0.0) & (u < 1.0)
+    view = torch.argmax(valid.to(torch.float32).permute(0, 1, 3, 4, 2), dim=-1)   # [B,T,Q,GP]
+    idx = view[:, :, None]                                                         # [B,T,1,Q,GP]
+    uv = torch.stack([torch.gather(u, 2, idx)[:, :, 0], torch.gather(v, 2, idx)[:, :, 0]], dim=-1)
+    if return_all:
+        return uv, view, torch.stack([u, v, safe], dim=-1), valid
+    return uv, view
+
+
+# ------------------------------------------------------------------------------ the op
+def msmv_sampling_gridsample(mlvl_feats, loc, w):
+    """Reference native-PyTorch op.  feats L x [B',C,N,H,W]; loc [B',Q,P,3]; w [B',Q,P,L]
+    -> [B',Q,C,P].  Trilinear grid_sample over the depth-N view volume, align_corners=True,
+    zero padding, scale-weighted sum over levels."""
+    assert w.shape[-1] == len(mlvl_feats)
+    Bp, C = mlvl_feats[0].shape[:2]
+    _, Q, P, _ = loc.shape
+    grid = (loc * 2 - 1)[:, :, :, None, :]
+    acc = torch.zeros(Bp, C, Q, P, dtype=mlvl_feats[0].dtype)
+    for l, f in enumerate(mlvl_feats):
+        s = F.grid_sample(f, grid, mode='bilinear', padding_mode='zeros', align_corners=True)[..., 0]
+        acc = acc + s * w[..., l].reshape(Bp, 1, Q, P)
+    return acc.permute(0, 2, 1, 3)
+
+
+def kernel_indices(loc, level_hw, num_views):
+    """Integer indices the reference CUDA kernel derives from `loc` (forward.cu:107-126,33-36):
+    view = round(z*(N-1)); per level y0 = floor(v*(H-1)), x0 = floor(u*(W-1)) and the
+    whole-tap guard.  Returns view [B',Q,P] int32, y0/x0 [B',Q,P,L] int32, inside [B',Q,P,L] bool."""
+    u, v, z = loc[..., 0], loc[..., 1], loc[..., 2]
+    zz = z * float(num_views - 1)
+    # the kernel's round() is half-away-from-zero (torch.round would be half-to-even)
+    view = (torch.sign(zz) * torch.floor(torch.abs(zz) + 0.5)).to(torch.int32)
+    ys, xs, ins = [], [], []
+    for (H, W) in level_hw:
+        y = v * float(H - 1)
+        x = u * float(W - 1)
+        ins.append((y > -1) & (x > -1) & (y < H) & (x < W))
+        ys.append(torch.floor(y).to(torch.int32))
+        xs.append(torch.floor(x).to(torch.int32))
+    return view, torch.stack(ys, -1), torch.stack(xs, -1), torch.stack(ins, -1)
+
+
+def msmv_sampling_kernel_semantics(mlvl_feats_cl, loc, w):
+    """Restatement of the reference CUDA kernel (NOT of grid_sample): channel-last feats
+    L x [B',N,H,W,C]; nearest (rounded) view, 2-D bilinear with align_corners=True, zero
+    outside, value = (w1*v1 + w2*v2 + w3*v3 + w4*v4) * scale_weight summed over levels."""
+    L = len(mlvl_feats_cl)
+    Bp, N, _, _, C = mlvl_feats_cl[0].shape
+    _, Q, P, _ = loc.shape
+    hw = [tuple(f.shape[2:4]) for f in mlvl_feats_cl]
+    view, y0, x0, inside = kernel_indices(loc, hw, N)
+    view = view.clamp(0, N - 1).long()
+    out = torch.zeros(Bp, Q, P, C, dtype=loc.dtype)
+    b_idx = torch.arange(Bp)[:, None, None].expand(Bp, Q, P)
+    for l, f in enumerate(mlvl_feats_cl):
+        H, W = hw[l]
+        y = loc[..., 1] * float(H - 1)
+        x = loc[..., 0] * float(W - 1)
+        yl, xl = y0[..., l].long(), x0[..., l].long()
+        ly, lx = y - yl, x - xl
+        hy, hx = 1 - ly, 1 - lx
+
+        def tap(yy, xx):
+            ok = inside[..., l] & (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+            val = f[b_idx, view, yy.clamp(0, H - 1), xx.clamp(0, W - 1)]      # [B',Q,P,C]
+            return val * ok[..., None]
+
+        val = ((hy * hx)[..., None] * tap(yl, xl) + (hy * lx)[..., None] * tap(yl, xl + 1)
+               + (ly * hx)[..., None] * tap(yl + 1, xl) + (ly * lx)[..., None] * tap(yl + 1, xl + 1))
+        out = out + val * w[..., l][..., None]
+    return out.permute(0, 1, 3, 2).contiguous()    # [B',Q,C,P]
+
+
+def sampling_4d(sample_points, mlvl_feats, scale_weights, lidar2img, image_h, image_w,
+                eps=1e-5, op=None, return_loc=False):
+    """sample_points [B,Q,T,G,P,3]; mlvl_feats in the layout `op` wants with leading dim
+    B*T*G; scale_weights [B,Q,G,T,P,L]; lidar2img [B,T*N,4,4] -> [B,Q,G,T*P,C].
+
+    Keeps the reference's two flattening orders: locations are flattened (b,t,g) while the
+    weights are flattened (b,g,t) (sparsebev_sampling.py:112-119), so the weight row used by
+    op-batch index i=(t*G+g) is that of (g', t') = divmod(i, T)."""
+    op = op or msmv_sampling_gridsample
+    B, Q, T, G, P, _ = sample_points.shape
+    uv, view = project_and_select_view(sample_points.reshape(B, Q, T, G * P, 3), lidar2img,
+                                       image_h, image_w, eps)
+    loc = torch.cat([uv, (view.to(uv.dtype) / (NUM_VIEWS - 1))[..., None]], dim=-1)   # [B,T,Q,GP,3]
+    loc = loc.reshape(B, T, Q, G, P, 3).permute(0, 1, 3, 2, 4, 5).reshape(B * T * G, Q, P, 3)
+    L = scale_weights.shape[-1]
+    w = scale_weights.reshape(B, Q, G, T, P, L).permute(0, 2, 3, 1, 4, 5).reshape(B * G * T, Q, P, L)
+    if return_loc:
+        return loc.contiguous(), w.contiguous()
+    sampled = op(mlvl_feats, loc.contiguous(), w.contiguous())                       # [BTG,Q,C,P]
+    C = sampled.shape[2]
+    sampled = sampled.reshape(B, T, G, Q, C, P).permute(0, 3, 2, 1, 5, 4)             # [B,Q,G,T,P,C]
+    return sampled.reshape(B, Q, G, T * P, C)
+
+
+def regroup_feats(mlvl_feats, channel_last, num_groups=NUM_GROUPS):
+    """L x [B,T*N,G*C,H,W] -> L x [B*T*G,N,H,W,C] (channel_last) or [B*T*G,C,N,H,W]
+    (sparsebev_transformer.py:73-85)."""
+    out = []
+    for f in mlvl_feats:
+        B, TN, GC, H, W = f.shape
+        N, T, G, C = NUM_VIEWS, TN // NUM_VIEWS, num_groups, GC // num_groups
+        f = f.reshape(B, T, N, G, C, H, W)
+        if channel_last:
+            f = f.permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, C)
+        else:
+            f = f.permute(0, 1, 3, 4, 2, 5, 6).reshape(B * T * G, C, N, H, W)
+        out.append(f.contiguous())
+    return out
+
+
+# ----------------------------------------------------------------------- decoder blocks
+def _ln(x, w, b):
+    return F.layer_norm(x, (x.shape[-1],), w, b)
+
+
+def adaptive_mixing(x, query, sd, prefix='mixing.', out_points=OUT_POINTS):
+    """x [B,Q,G,Pin,C], query [B,Q,D] -> [B,Q,D] (includes the +query residual)."""
+    B, Q, G, Pin, C = x.shape
+    params = F.linear(query, sd[prefix + 'parameter_generator.weight'],
+                      sd[prefix + 'parameter_generator.bias']).reshape(B * Q, G, -1)
+    m = params[..., :C * C].reshape(B * Q, G, C, C)
+    s = params[..., C * C:].reshape(B * Q, G, out_points, Pin)
+    h = torch.matmul(x.reshape(B * Q, G, Pin, C), m)
+    h = torch.relu(F.layer_norm(h, h.shape[-2:]))
+    h = torch.matmul(s, h)
+    h = torch.relu(F.layer_norm(h, h.shape[-2:]))
+    h = F.linear(h.reshape(B, Q, -1), sd[prefix + 'out_proj.weight'], sd[prefix + 'out_proj.bias'])
+    return query + h
+
+
+def pairwise_centre_dist(query_bbox, pc_range):
+    c = decode_bbox(query_bbox, pc_range)[..., :2]
+    return torch.linalg.norm(c[:, :, None, :] - c[:, None, :, :], dim=-1)     # [B,Q,Q]
+
+
+def scale_adaptive_self_attention(query_bbox, query_feat, sd, pc_range, pre_attn_mask=None,
+                                  prefix='self_attn.'):
+    """logits[b,h,i,j] = q_i.k_j/sqrt(32) - tau[b,i,h]*dist[b,i,j]; softmax; @v; out_proj;
+    + identity (mmcv MultiheadAttention, eval => dropout off)."""
+    B, Q, D = query_feat.shape
+    H, hd = NUM_HEADS, D // NUM_HEADS
+    tau = F.linear(query_feat, sd[prefix + 'gen_tau.weight'], sd[prefix + 'gen_tau.bias'])   # [B,Q,H]
+    bias = -pairwise_centre_dist(query_bbox, pc_range)[:, None] * tau.permute(0, 2, 1)[..., None]
+    if pre_attn_mask is not None:
+        bias = bias.clone()
+        bias[:, :, pre_attn_mask] = float('-inf')
+    qkv = F.linear(query_feat, sd[prefix + 'attention.attn.in_proj_weight'],
+                   sd[prefix + 'attention.attn.in_proj_bias'])
+    q, k, v = [t.reshape(B, Q, H, hd).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+    logits = torch.matmul(q * (1.0 / math.sqrt(hd)), k.transpose(-1, -2)) + bias
+    o = torch.matmul(torch.softmax(logits, dim=-1), v).transpose(1, 2).reshape(B, Q, D)
+    o = F.linear(o, sd[prefix + 'attention.attn.out_proj.weight'],
+                 sd[prefix + 'attention.attn.out_proj.bias'])
+    return query_feat + o
+
+
+def sampling_points_and_weights(query_bbox, query_feat, sd, cfg, time_diff, prefix='sampling.'):
+    """-> points [B,Q,T,G,P,3] (metres, motion-warped), weights [B,Q,G,T,P,L] (softmax over L)."""
+    B, Q = query_bbox.shape[:2]
+    T, G, P, L = cfg['num_frames'], NUM_GROUPS, cfg['num_points'], cfg['num_levels']
+    off = F.linear(query_feat, sd[prefix + 'sampling_offset.weight'],
+                   sd[prefix + 'sampling_offset.bias']).reshape(B, Q, G * P, 3)
+    pts = make_sample_points(query_bbox, off, cfg['pc_range']).reshape(B, Q, 1, G, P, 3)
+    pts = pts.expand(B, Q, T, G, P, 3)
+    shift = query_bbox[..., 8:10][:, :, None, :] * time_diff[:, None, :, None]     # [B,Q,T,2]
+    pts = torch.cat([pts[..., 0:2] - shift[:, :, :, None, None, :], pts[..., 2:3]], dim=-1)
+    sw = F.linear(query_feat, sd[prefix + 'scale_weights.weight'],
+                  sd[prefix + 'scale_weights.bias']).reshape(B, Q, G, 1, P, L)
+    sw = torch.softmax(sw, dim=-1).expand(B, Q, G, T, P, L)
+    return pts, sw
+
+
+def position_encoder(xyz, sd, prefix='position_encoder.'):
+    h = torch.relu(_ln(F.linear(xyz, sd[prefix + '0.weight'], sd[prefix + '0.bias']),
+                       sd[prefix + '1.weight'], sd[prefix + '1.bias']))
+    return torch.relu(_ln(F.linear(h, sd[prefix + '3.weight'], sd[prefix + '3.bias']),
+                          sd[prefix + '4.weight'], sd[prefix + '4.bias']))
+
+
+def ffn(x, sd, prefix='ffn.'):
+    h = torch.relu(F.linear(x, sd[prefix + 'layers.0.0.weight'], sd[prefix + 'layers.0.0.bias']))
+    return x + F.linear(h, sd[prefix + 'layers.1.weight'], sd[prefix + 'layers.1.bias'])
+
+
+def cls_branch(x, sd, prefix='cls_branch.'):
+    for i in (0, 3):
+        x = torch.relu(_ln(F.linear(x, sd[prefix + '%d.weight' % i], sd[prefix + '%d.bias' % i]),
+                           sd[prefix + '%d.weight' % (i + 1)], sd[prefix + '%d.bias' % (i + 1)]))
+    return F.linear(x, sd[prefix + '6.weight'], sd[prefix + '6.bias'])
+
+
+def reg_branch(x, sd, prefix='reg_branch.'):
+    for i in (0, 2):
+        x = torch.relu(F.linear(x, sd[prefix + '%d.weight' % i], sd[prefix + '%d.bias' % i]))
+    return F.linear(x, sd[prefix + '4.weight'], sd[prefix + '4.bias'])
+
+
+def refine_bbox(proposal, delta):
+    xyz = torch.sigmoid(delta[..., 0:3] + inverse_sigmoid(proposal[..., 0:3]))
+    return torch.cat([xyz, delta[..., 3:]], dim=-1)
+
+
+def decoder_layer(query_bbox, query_feat, mlvl_feats, sd, cfg, time_diff, lidar2img,
+                  pre_attn_mask=None, op=None, taps=None):
+    """One pass of SparseBEVTransformerDecoderLayer.forward.  mlvl_feats already regrouped for
+    `op`.  `taps` (dict) optionally receives intermediates for stage-wise parity tests."""
+    pc = cfg['pc_range']
+    q = query_feat + position_encoder(query_bbox[..., :3], sd)
+    q = _ln(scale_adaptive_self_attention(query_bbox, q, sd, pc, pre_attn_mask),
+            sd['norm1.weight'], sd['norm1.bias'])
+    pts, sw = sampling_points_and_weights(query_bbox, q, sd, cfg, time_diff)
+    sampled = sampling_4d(pts, mlvl_feats, sw, lidar2img, cfg['image_h'], cfg['image_w'], op=op)
+    mixed = _ln(adaptive_mixing(sampled, q, sd), sd['norm2.weight'], sd['norm2.bias'])
+    out = _ln(ffn(mixed, sd), sd['norm3.weight'], sd['norm3.bias'])
+    cls = cls_branch(out, sd)
+    box = refine_bbox(query_bbox, reg_branch(out, sd))
+    if time_diff.shape[1] > 1:
+        td = time_diff.clone()
+        td[td < 1e-5] = 1.0
+        box = torch.cat([box[..., :8], box[..., 8:] / td[:, 1:2, None]], dim=-1)
+    if taps is not None:
+        taps.update(after_sasa=q, points=pts, scale_weights=sw, sampled=sampled, mixed=mixed)
+    return out, cls, box
+
+
+def time_diff_from_timestamps(img_timestamp):
+    """[B][T*6] seconds -> [B,T] fp32: mean over the 6 views of (t_frame0 - t_frame)
+    (sparsebev_transformer.py:60-64; done in float64 then cast)."""
+    import numpy as np
+    ts = np.asarray(img_timestamp, dtype=np.float64).reshape(len(img_timestamp), -1, NUM_VIEWS)
+    return torch.from_numpy(np.mean(ts[:, :1, :] - ts, axis=-1).astype(np.float32))
+
+
+def decoder(query_bbox, query_feat, mlvl_feats_raw, sd, cfg, time_diff, lidar2img,
+            pre_attn_mask=None, channel_last=False, op=None):
+    """6 shared-weight layers; returns stacked (cls [Ld,B,Q,ncls], box [Ld,B,Q,10]) after nan_to_num."""
+    feats = regroup_feats(mlvl_feats_raw, channel_last)
+    cls_all, box_all = [], []
+    for _ in range(cfg['num_layers']):
+        query_feat, cls, box = decoder_layer(query_bbox, query_feat, feats, sd, cfg, time_diff,
+                                             lidar2img, pre_attn_mask, op)
+        query_bbox = box.clone()
+        cls_all.append(cls)
+        box_all.append(box)
+    return torch.nan_to_num(torch.stack(cls_all)), torch.nan_to_num(torch.stack(box_all))
+
+
+def head_forward(init_query_bbox, label_enc, mlvl_feats_raw, sd, cfg, time_diff, lidar2img, **kw):
+    """Eval path of SparseBEVHead.forward: query init, decoder, de-normalise + reorder."""
+    B = mlvl_feats_raw[0].shape[0]
+    Q = init_query_bbox.shape[0]
+    feat = torch.cat([label_enc[cfg['num_classes']].expand(Q, -1), torch.zeros(Q, 1)], dim=1)
+    cls, box = decoder(init_query_bbox[None].repeat(B, 1, 1), feat[None].repeat(B, 1, 1),
+                       mlvl_feats_raw, sd, cfg, time_diff, lidar2img, **kw)
+    pc = cfg['pc_range']
+    lo, hi = box.new_tensor(pc[:3]), box.new_tensor(pc[3:])
+    xyz = box[..., 0:3] * (hi - lo) + lo
+    box = torch.cat([xyz[..., 0:2], box[..., 3:5], xyz[..., 2:3], box[..., 5:10]], dim=-1)
+    return dict(all_cls_scores=cls, all_bbox_preds=box)
+
+
+# --------------------------------------------------------------------- synthetic inputs
+def make_state_dict(cfg, seed=0, std=0.02, embed=256):
+    """Random 'trained-like' weights (N(0,std), LayerNorm ~1/0) under the reference key names."""
+    g = torch.Generator().manual_seed(seed)
+    T, P, L = cfg['num_frames'], cfg['num_points'], cfg['num_levels']
+    G, C = NUM_GROUPS, embed // NUM_GROUPS
+    pin = T * P
+
+    def lin(name, o, i, sd, s=std, bias_s=0.02):
+        sd[name + '.weight'] = torch.randn(o, i, generator=g) * s
+        sd[name + '.bias'] = torch.randn(o, generator=g) * bias_s
+
+    def ln(name, sd):
+        sd[name + '.weight'] = 1.0 + 0.1 * torch.randn(embed, generator=g)
+        sd[name + '.bias'] = 0.1 * torch.randn(embed, generator=g)
+
+    sd = {}
+    lin('position_encoder.0', embed, 3, sd, s=0.5)
+    ln('position_encoder.1', sd)
+    lin('position_encoder.3', embed, embed, sd, s=0.06)
+    ln('position_encoder.4', sd)
+    sd['self_attn.attention.attn.in_proj_weight'] = torch.randn(3 * embed, embed, generator=g) * 0.06
+    sd['self_attn.attention.attn.in_proj_bias'] = torch.randn(3 * embed, generator=g) * 0.02
+    lin('self_attn.attention.attn.out_proj', embed, embed, sd, s=0.06)
+    lin('self_attn.gen_tau', NUM_HEADS, embed, sd, s=0.02)
+    sd['self_attn.gen_tau.bias'] = torch.rand(NUM_HEADS, generator=g) * 2.0
+    lin('sampling.sampling_offset', G * P * 3, embed, sd, s=0.02)
+    sd['sampling.sampling_offset.bias'] = torch.rand(G * P * 3, generator=g) - 0.5
+    lin('sampling.scale_weights', G * P * L, embed, sd, s=0.06)
+    lin('mixing.parameter_generator', G * (C * C + pin * OUT_POINTS), embed, sd, s=0.02, bias_s=0.05)
+    lin('mixing.out_proj', embed, G * OUT_POINTS * C, sd, s=0.01)
+    lin('ffn.layers.0.0', FFN_DIM, embed, sd, s=0.06)
+    lin('ffn.layers.1', embed, FFN_DIM, sd, s=0.05)
+    for n in ('norm1', 'norm2', 'norm3'):
+        ln(n, sd)
+    for i in (0, 3):
+        lin('cls_branch.%d' % i, embed, embed, sd, s=0.06)
+        ln('cls_branch.%d' % (i + 1), sd)
+    lin('cls_branch.6', cfg['num_classes'], embed, sd, s=0.06)
+    for i in (0, 2):
+        lin('reg_branch.%d' % i, embed, embed, sd, s=0.06)
+    lin('reg_branch.4', cfg.get('code_size', 10), embed, sd, s=0.02)
+    return sd
+
+
+def init_query_bbox(num_query, seed=0):
+    """SparseBEVHead._init_layers (sparsebev_head.py:49-64): xy on a sqrt(Q) grid, z=0, h=1.5,
+    v=0, everything else N(0,1) (nn.Embedding default)."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(num_query, 10, generator=g)
+    n = int(math.isqrt(num_query))
+    assert n * n == num_query
+    ii, jj = torch.meshgrid(torch.arange(n), torch.arange(n), indexing='ij')
+    w[:, 0] = ((ii + 0.5) / n).reshape(-1)
+    w[:, 1] = ((jj + 0.5) / n).reshape(-1)
+    w[:, 2] = 0.0
+    w[:, 5] = 1.5
+    w[:, 8:10] = 0.0
+    return w
+
+
+def camera_rig(num_frames, image_h, image_w, ego_speed=5.0, dt=0.5):
+    """Synthetic nuScenes-like 6-camera pinhole rig -> lidar2img [T*6,4,4] fp32, timestamps [T*6].
+    Order FRONT, FRONT_RIGHT, FRONT_LEFT, BACK, BACK_LEFT, BACK_RIGHT (loaders/pipelines/loading.py:54-57);
+    yaw 0,-55,+55,180,+110,-110 deg; fx=fy=1266*image_w/1600; camera 1.5 m above the lidar origin;
+    frame t is `dt*t` seconds in the past with the ego translated `ego_speed*dt*t` m backwards."""
+    import numpy as np
+    yaws = np.deg2rad([0.0, -55.0, 55.0, 180.0, 110.0, -110.0])
+    f = 1266.0 * image_w / 1600.0
+    K = np.array([[f, 0, image_w / 2.0, 0], [0, f, image_h / 2.0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    mats, stamps = [], []
+    for t in range(num_frames):
+        for n, yaw in enumerate(yaws):
+            # camera axes in lidar frame: z_cam = forward (cos yaw, sin yaw, 0), x_cam = right, y_cam = down
+            fwd = np.array([np.cos(yaw), np.sin(yaw), 0.0])
+            right = np.array([np.sin(yaw), -np.cos(yaw), 0.0])
+            down = np.array([0.0, 0.0, -1.0])
+            R = np.stack([right, down, fwd])                     # lidar -> cam rotation
+            cam_pos = np.array([-ego_speed * dt * t, 0.0, 1.5]) + 0.5 * fwd
+            E = np.eye(4)
+            E[:3, :3] = R
+            E[:3, 3] = -R @ cam_pos
+            mats.append(K @ E)
+            stamps.append(1000.0 - dt * t - 0.004 * n)
+    return torch.from_numpy(np.stack(mats).astype(np.float32)), stamps

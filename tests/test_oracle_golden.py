@@ -1,0 +1,114 @@
+"""Pin the CPU oracle (oracle/ref_torch.py) against golden vectors produced by the REAL
+reference (oracle/gen_golden.py, run in the build container where /root/reference exists)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_torch as R
+from oracle.synth import hashrand
+
+
+def _load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _feats(g, channel_first=True):
+    Bp, C, N = [int(v) for v in g['shape'][:3]] if 'shape' in g else (None, None, None)
+    return Bp, C, N
+
+
+def test_geometry_matches_reference(golden_dir):
+    g = _load(golden_dir, 'geometry.npz')
+    boxes = torch.from_numpy(g['boxes'])
+    dec = R.decode_bbox(boxes, g['pc_range'].tolist())
+    np.testing.assert_allclose(dec.numpy(), g['decoded'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(R.inverse_sigmoid(boxes[..., 0:3]).numpy(), g['inv_sig'], rtol=1e-6, atol=1e-6)
+
+
+def _op_case(golden_dir, name):
+    g = _load(golden_dir, name)
+    Bp, C, N, Q, P = [int(v) for v in g['shape']]
+    feats_cf = [hashrand((Bp, C, N, int(h), int(w)), int(s), -1.0, 1.0)
+                for (h, w), s in zip(g['hw'], g['feat_seeds'])]
+    return g, feats_cf, torch.from_numpy(g['loc']), torch.from_numpy(g['w'])
+
+
+def test_op_gridsample_restatement_is_reference(golden_dir):
+    for name in ('op_small.npz', 'op_cfg1.npz'):
+        g, feats, loc, w = _op_case(golden_dir, name)
+        out = R.msmv_sampling_gridsample(feats, loc, w)
+        np.testing.assert_allclose(out.numpy(), g['out'], rtol=0, atol=1e-6)
+
+
+def test_op_kernel_semantics_close_to_reference_gridsample(golden_dir):
+    """The CUDA-kernel semantics (rounded view, 2-D bilinear) and the grid_sample path agree
+    whenever the view coordinate is an exact integer/(N-1): SURVEY.md section 0, gotcha 3."""
+    for name in ('op_small.npz', 'op_cfg1.npz'):
+        g, feats, loc, w = _op_case(golden_dir, name)
+        feats_cl = [f.permute(0, 2, 3, 4, 1).contiguous() for f in feats]
+        out = R.msmv_sampling_kernel_semantics(feats_cl, loc, w)
+        np.testing.assert_allclose(out.numpy(), g['out'], rtol=1e-4, atol=2e-5)
+
+
+def test_sampling_4d_matches_reference(golden_dir):
+    g = _load(golden_dir, 'sampling4d.npz')
+    B, Q, T, G, P, L, C, ih, iw = [int(v) for v in g['dims']]
+    pc = g['pc_range'].tolist()
+    qb = torch.from_numpy(g['query_bbox'])
+    pts = R.make_sample_points(qb, torch.from_numpy(g['offset']), pc)
+    np.testing.assert_allclose(pts.numpy(), g['points'], rtol=1e-5, atol=1e-5)
+    pts6 = torch.from_numpy(g['points6'])
+    sw = torch.from_numpy(g['scale_weights'])
+    l2i = torch.from_numpy(g['lidar2img'])
+    loc, w = R.sampling_4d(pts6, None, sw, l2i, ih, iw, return_loc=True)
+    np.testing.assert_array_equal(w.numpy(), g['w'])
+    # view choice must be identical; uv to fp32 round-off of the 4x4 mat-vec
+    np.testing.assert_array_equal(loc[..., 2].numpy(), g['loc'][..., 2])
+    np.testing.assert_allclose(loc[..., :2].numpy(), g['loc'][..., :2], rtol=1e-5, atol=1e-5)
+    feats = [hashrand((B * T * G, C, 6, int(h), int(w_)), int(s), -1.0, 1.0)
+             for (h, w_), s in zip(g['hw'], g['feat_seeds'])]
+    out = R.sampling_4d(pts6, feats, sw, l2i, ih, iw)
+    np.testing.assert_allclose(out.numpy(), g['out'], rtol=1e-4, atol=1e-4)
+    # the (t,g) vs (g,t) flattening quirk is really there (gotcha 2)
+    assert not np.array_equal(g['w'].reshape(B, T, G, Q, P, L), g['w'].reshape(B, G, T, Q, P, L).transpose(0, 2, 1, 3, 4, 5)) or T == 1
+
+
+def test_adaptive_mixing_matches_reference(golden_dir):
+    g = _load(golden_dir, 'mixing.npz')
+    Bm, Qm, G, Pin, C = [int(v) for v in g['dims']]
+    s = [int(v) for v in g['seeds']]
+    sd = {
+        'mixing.parameter_generator.weight': hashrand((G * (C * C + Pin * 128), 256), s[0], -0.04, 0.04),
+        'mixing.parameter_generator.bias': hashrand((G * (C * C + Pin * 128),), s[1], -0.1, 0.1),
+        'mixing.out_proj.weight': hashrand((256, G * 128 * C), s[2], -0.02, 0.02),
+        'mixing.out_proj.bias': hashrand((256,), s[3], -0.05, 0.05),
+    }
+    x = hashrand((Bm, Qm, G, Pin, C), s[4], -2, 2)
+    q = hashrand((Bm, Qm, 256), s[5], -1.5, 1.5)
+    out = R.adaptive_mixing(x, q, sd)
+    np.testing.assert_allclose(out.numpy(), g['out'], rtol=1e-5, atol=1e-5)
+
+
+def test_self_attention_matches_torch_mha():
+    """mmcv 1.6.0 MultiheadAttention wraps nn.MultiheadAttention and adds the identity; pin our
+    restatement against torch's own module (the part that is available here)."""
+    torch.manual_seed(0)
+    B, Q, D = 2, 17, 256
+    mha = torch.nn.MultiheadAttention(D, 8, dropout=0.1).eval()
+    qf = torch.randn(B, Q, D)
+    qb = R.init_query_bbox(25, 1)[:Q][None].repeat(B, 1, 1)
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    sd = {'self_attn.attention.attn.in_proj_weight': mha.in_proj_weight.detach(),
+          'self_attn.attention.attn.in_proj_bias': mha.in_proj_bias.detach(),
+          'self_attn.attention.attn.out_proj.weight': mha.out_proj.weight.detach(),
+          'self_attn.attention.attn.out_proj.bias': mha.out_proj.bias.detach(),
+          'self_attn.gen_tau.weight': torch.randn(8, D) * 0.05,
+          'self_attn.gen_tau.bias': torch.rand(8) * 2}
+    ours = R.scale_adaptive_self_attention(qb, qf, sd, pc)
+    tau = torch.nn.functional.linear(qf, sd['self_attn.gen_tau.weight'], sd['self_attn.gen_tau.bias'])
+    dist = -R.pairwise_centre_dist(qb, pc)
+    mask = (dist[:, None] * tau.permute(0, 2, 1)[..., None]).flatten(0, 1)
+    with torch.no_grad():
+        ref = qf + mha(qf.transpose(0, 1), qf.transpose(0, 1), qf.transpose(0, 1), attn_mask=mask)[0].transpose(0, 1)
+    np.testing.assert_allclose(ours.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
