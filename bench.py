@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- decoder-layer samples/s of the SparseBEV hot path on B200 (BASELINE.json metric).
+
+One STEP = one scene (B=1: 900 queries x 6 cameras x T=8 frames, r50 704x256 FPN, 4 levels) pushed through ONE
+decoder layer (position encoding -> scale-adaptive self-attention -> adaptive spatio-temporal sampling ->
+adaptive mixing -> FFN -> cls/reg heads -> box refinement), i.e. SparseBEVTransformerDecoderLayer.forward.
+
+  python bench.py --gpus N --steps K --warmup W           our arm  (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                    reference arm: the reference's native-PyTorch CPU path
+                                                          (oracle port; /root/reference does not exist on the GPU box)
+Prints ONE JSON line (rank 0).  Keys: see the task contract; extra keys are documented in DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = 'decoder-layer samples/sec (900q x 6cam x 8f)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='r50_704x256')
+    ap.add_argument('--frames', type=int, default=8)
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
+    ap.add_argument('--layout', default='grouped', choices=['grouped', 'nhwc'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--breakdown', action='store_true', help='also write per-stage timings to gpurun_out/breakdown.json')
+    ap.add_argument('--cpu-steps', type=int, default=3, help='bounded CPU sample: decoder-layer passes of the oracle')
+    ap.add_argument('--skip-cpu', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def gather_algorithmic_bytes(cfg, B=1, G=4, C=64):
+    """per sampled point read L*4 corners*C*4 B of features + (3+L)*4 B of coords/weights, write C*4 B."""
+    L, T, P, Q = cfg['num_levels'], cfg['num_frames'], cfg['num_points'], cfg['num_query']
+    points = B * T * G * Q * P
+    return points * (L * 4 * C * 4 + (3 + L) * 4 + C * 4), points
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_layer_timer(cfg, steps, threads):
+    """The reference's native-PyTorch decoder-layer path restated in oracle/ref_torch.py (F.grid_sample sampling,
+    eager mixing / attention), fp32, on `threads` host threads.  Returns seconds per step (best of `steps`)."""
+    from oracle import ref_torch as R
+    from sparsebev_b200 import synthetic as S
+    torch.set_num_threads(threads)
+    T = cfg['num_frames']
+    sd = S.make_state_dict(cfg, seed=0)
+    feats = R.regroup_feats(S.make_feats(cfg['name'], T, batch=1, seed=1), channel_last=False)
+    metas = S.make_metas(cfg['name'], T, batch=1)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    qb = S.init_query_bbox(cfg['num_query'], seed=2)[None].contiguous()
+    qf = torch.randn(1, cfg['num_query'], 256, generator=torch.Generator().manual_seed(3))
+    times = []
+    with torch.no_grad():
+        for i in range(steps + 1):
+            t0 = time.perf_counter()
+            R.decoder_layer(qb, qf, feats, sd, cfg, td, l2i)
+            if i:
+                times.append(time.perf_counter() - t0)
+    return min(times), float(np.mean(times))
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 10))
+    best, mean = cpu_layer_timer(cfg, steps, threads)
+    val = 1.0 / mean
+    print(json.dumps({
+        'metric': METRIC, 'value': val, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+        'ms_per_step': mean * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'impl': 'reference',
+        'config': {'workload': '%s T=%d Q=%d L=%d, one decoder layer, B=1' % (args.config, cfg['num_frames'], cfg['num_query'], cfg['num_levels'])},
+        'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d decoder-layer passes (mean; best %.1f ms) of the reference native-PyTorch path '
+                                   'restated in oracle/ref_torch.py' % (steps, best * 1e3)},
+        'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ------------------------------------------------------------------------------------------------- ours
+def main():
+    args = parse()
+    from sparsebev_b200 import synthetic as S
+    cfg = S.layer_cfg(args.config, args.frames, num_layers=1)
+    cfg['name'] = args.config
+    if args.impl == 'reference':
+        return run_reference_arm(args, cfg)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a GPU; there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import _lib, ops
+
+    T, Q = cfg['num_frames'], cfg['num_query']
+    model = sb.SparseBEVTransformer(256, num_frames=T, num_points=cfg['num_points'], num_layers=1,
+                                    num_levels=cfg['num_levels'], pc_range=cfg['pc_range'])
+    model.load_state_dict({'decoder.decoder_layer.' + k: v for k, v in S.make_state_dict(cfg, seed=0).items()})
+    model = model.to(dev).eval()
+    layer = model.decoder.decoder_layer
+    layer.mixing.precision = args.precision
+
+    # weak scaling: every rank owns its own scene (different seed) -- the reference's only strategy is DP
+    feats_host = S.make_feats(args.config, T, batch=1, seed=100 + rank, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')
+    metas = S.make_metas(args.config, T, batch=1)
+    model.decoder.prepare_metas(metas, 1, dev)
+    feats = model.decoder.prepare_feats([f.to(dev) for f in feats_host])
+    qb_host = S.init_query_bbox(Q, seed=2)[None].contiguous().pin_memory()
+    qf_host = torch.randn(1, Q, 256, generator=torch.Generator().manual_seed(3)).pin_memory()
+    qb, qf = qb_host.to(dev), qf_host.to(dev)
+    feat_bytes = sum(f.numel() * 4 for f in feats)
+
+    def step():
+        return layer(qb, qf, feats, None, metas)
+
+    # ---- warm-up (also builds weight caches / sets function attributes), count launches of one step
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count
+    step()
+    launches_per_step = _lib.launch_count - n0
+    for _ in range(max(args.warmup - 1, 2)):
+        step()
+    torch.cuda.synchronize()
+
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(graph):
+            outs = step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        run_step()
+    ev1.record()
+    torch.cuda.synchronize(); barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * 1.0 / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API call with HOST buffers; every step copies that step's inputs (query tensors, camera
+    # metadata AND the feature pyramid) from pinned host memory and reads the results back.  Feature upload of step
+    # i+1 is double-buffered on a copy stream so it overlaps the compute of step i.
+    pinned_feats = [f.contiguous().cpu().pin_memory() for f in feats]
+    dbuf = [[torch.empty_like(f) for f in feats] for _ in range(2)]
+    l2i_host = metas[0]['lidar2img'].cpu().pin_memory()
+    td_host = metas[0]['time_diff'].cpu().pin_memory()
+    out_host = [torch.empty(1, Q, 256).pin_memory(), torch.empty(1, Q, 10).pin_memory(), torch.empty(1, Q, 10).pin_memory()]
+    copy_stream = torch.cuda.Stream()
+    h2d = feat_bytes + qb_host.numel() * 4 + qf_host.numel() * 4 + l2i_host.numel() * 4 + td_host.numel() * 4
+    d2h = sum(o.numel() * 4 for o in out_host)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, s in zip(dbuf[slot], pinned_feats):
+                d.copy_(s, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_loop(n):
+        ready = upload(0)
+        for i in range(n):
+            slot = i & 1
+            torch.cuda.current_stream().wait_event(ready)
+            if i + 1 < n:
+                ready = upload(slot ^ 1)
+            m = [dict(metas[0])]
+            m[0]['lidar2img'] = l2i_host.to(dev, non_blocking=True)
+            m[0]['time_diff'] = td_host.to(dev, non_blocking=True)
+            o = layer(qb_host.to(dev, non_blocking=True), qf_host.to(dev, non_blocking=True), dbuf[slot], None, m)
+            for h, d in zip(out_host, o):
+                h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(2)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    del pinned_feats, dbuf
+
+    # ---- roofline of the dominant kernel (fused gather), timed alone with CUDA events on the launch stream
+    x = qf.reshape(Q, 256)
+    off, lg = layer.sampling._off(x), layer.sampling._sw(x)
+    pts, sw = ops.sample_points(qb, off.reshape(1, Q, -1), lg.reshape(1, Q, -1), cfg['pc_range'], cfg['num_levels'])
+    vel = qb[..., 8:10].contiguous()
+    sw5 = sw.reshape(1, Q, 4, cfg['num_points'], cfg['num_levels'])
+    out_buf = torch.empty(1, Q, 4, T * cfg['num_points'], 64, device=dev)
+
+    def gather():
+        ops.sampling4d_fused(feats, pts, vel, metas[0]['time_diff'], metas[0]['lidar2img'], sw5, cfg['image_h'], cfg['image_w'],
+                             num_frames=T, layout=layer.sampling.feat_layout, out=out_buf)
+    for _ in range(3):
+        gather()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_g = 20
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(n_g):
+        gather()
+    g1.record()
+    torch.cuda.synchronize()
+    gather_ms = g0.elapsed_time(g1) / n_g
+    algo_bytes, n_points = gather_algorithmic_bytes(cfg)
+    peak, peak_src = measured_peaks()
+    achieved = algo_bytes / (gather_ms * 1e-3) / 1e9
+
+    clk = clocks.stop() if rank == 0 else None
+
+    breakdown = None
+    if args.breakdown and rank == 0:
+        breakdown = stage_breakdown(layer, qb, qf, feats, metas, cfg)
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'breakdown.json'), 'w') as f:
+            json.dump(breakdown, f, indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        best, mean = cpu_layer_timer(cfg, args.cpu_steps, threads)
+        cpu = {'value': 1.0 / mean, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+               'sample': '%d decoder-layer passes (mean %.0f ms, best %.0f ms) of the reference native-PyTorch path '
+                         '(oracle/ref_torch.py), same workload' % (args.cpu_steps, mean * 1e3, best * 1e3)}
+
+    if rank == 0:
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (mixing GEMMs: %s on tcgen05, fp32 accumulate)' % args.precision, 'data': 'synthetic',
+            'config': {'workload': '%s T=%d Q=%d L=%d, one decoder layer, B=1 per GPU' % (args.config, T, Q, cfg['num_levels']),
+                       'l2': 'inputs larger than L2 (feature pyramid %.0f MB per step)' % (feat_bytes / 1e6),
+                       'feat_layout': layer.sampling.feat_layout, 'cuda_graph': graph is not None, 'parallelism': 'dp%d (one scene per GPU)' % world},
+            'clocks': clk,
+            'e2e': {'value': world * 1e3 / e2e_ms, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms, 'steps': e2e_steps,
+                    'note': 'all layer inputs incl. the %.0f MB feature pyramid uploaded from pinned host memory every step '
+                            '(double-buffered on a copy stream), results read back' % (feat_bytes / 1e6)},
+            'gpu_launches': launches_per_step * args.steps,
+            'launches_per_step': launches_per_step,
+            'roofline': {'bound': 'hbm', 'kernel': 'sampling4d_c64_kernel (fused projection + multi-scale gather)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'algorithmic_bytes': algo_bytes, 'points': n_points, 'kernel_ms': gather_ms, 'peak_source': peak_src},
+            'cpu_baseline': cpu,
+            'breakdown_ms': breakdown}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def stage_breakdown(layer, qb, qf, feats, metas, cfg, iters=20):
+    """Per-stage device time (CUDA events, eager launches) -- explains ms_per_step; not part of the metric."""
+    from sparsebev_b200 import ops
+    B, Q, D = qf.shape
+    M = B * Q
+    res = {}
+
+    def timeit(name, fn):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        res[name] = a.elapsed_time(b) / iters
+        return r
+
+    x0 = qf.reshape(M, D).contiguous()
+    h = timeit('pos_enc', lambda: layer._pe1(layer._pe0(qb.reshape(M, -1), relu=True, k=3), relu=True, residual=x0))
+    q1 = timeit('sasa_block', lambda: layer.self_attn.forward_fused(qb, h.reshape(B, Q, D), None, layer.norm1))
+    sampled = timeit('sampling_block', lambda: layer.sampling(qb, q1, feats, metas))
+    q2 = timeit('mixing_block', lambda: layer.mixing.forward_fused(sampled, q1, layer.norm2))
+    x2 = q2.reshape(M, D)
+    q3 = timeit('ffn', lambda: layer._ffn1(layer._ffn0(x2, relu=True), residual=x2, res_pre_ln=True))
+
+    def heads():
+        c = q3
+        for l in layer._cls[:-1]:
+            c = l(c, relu=True)
+        c = layer._cls[-1](c)
+        r = q3
+        for l in layer._reg[:-1]:
+            r = l(r, relu=True)
+        return c, ops.refine_bbox(qb, layer._reg[-1](r).reshape(B, Q, -1), metas[0]['time_diff'])
+    timeit('heads', heads)
+    # finer split of the mixing block
+    mix = layer.mixing
+    qh, ql = ops.split_bf16(q1.reshape(M, D))
+    wh, wl = mix._pg.get(mix.parameter_generator.weight)
+    npar = mix.n_groups * mix.total_parameters
+    seg_a, seg_b = ([qh, qh, ql], [wh, wl, wh]) if mix.precision == 'bf16x3' else ([qh], [wh])
+    params = timeit('mix.param_gemm', lambda: ops.gemm_bf16_tn(seg_a, seg_b, M, npar, D, bias=mix.parameter_generator.bias))
+    yh, yl, _ = timeit('mix.mix_kernel', lambda: ops.mix(params, sampled.reshape(M, 4, -1, 64)))
+    oh, ol = mix._op.get(mix.out_proj.weight)
+    sa, sb_ = ([yh, yh, yl], [oh, ol, oh]) if mix.precision == 'bf16x3' else ([yh], [oh])
+    part = timeit('mix.out_gemm', lambda: ops.gemm_bf16_tn(sa, sb_, M, D, mix.out_proj.in_features, split_k=mix.split_k))
+    timeit('mix.reduce_ln', lambda: ops.reduce_ln(part, mix.out_proj.bias, q1.reshape(M, D), layer.norm2.weight, layer.norm2.bias))
+    # SASA split
+    attn = layer.self_attn.attention.attn
+    wt, ldw = layer.self_attn._in.get(attn.in_proj_weight)
+    qkv = timeit('sasa.in_proj', lambda: ops.dense(h, wt, ldw, 3 * D, bias=attn.in_proj_bias))
+    tau = layer.self_attn._tau(h)
+    timeit('sasa.core', lambda: ops.sasa(qkv.reshape(B, Q, 3 * D), qb, tau.reshape(B, Q, 8), cfg['pc_range'], 8))
+    return res
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,181 @@
+/* sparsebev_b200 -- C ABI of the B200-native SparseBEV decoder hot path.
+ *
+ * Plain C: raw DEVICE pointers (fp32 unless stated), sizes, and the CUDA stream to enqueue on.
+ * No torch / ATen types.  Every function
+ *   - only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy stream 0),
+ *     never synchronises the host, never allocates or frees device memory;
+ *   - is re-entrant and thread-safe (no global mutable state except the last-error string,
+ *     which is thread-local);
+ *   - returns SBEV_OK or a negative SBEV_ERR_* code; sbev_last_error() describes the failure.
+ * The caller owns and allocates every buffer (as in the reference, where the C++ host
+ * functions allocate the outputs with at::zeros and hand raw pointers to the launchers:
+ * /root/reference/models/csrc/msmv_sampling/msmv_sampling.cpp:136-148).
+ *
+ * Each entry point cites the reference interface it replaces (paths under /root/reference).
+ */
+#ifndef SPARSEBEV_B200_H_
+#define SPARSEBEV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBEV_OK               0
+#define SBEV_ERR_INVALID     -1   /* bad argument (null pointer, non-positive size, P > 32, ...) */
+#define SBEV_ERR_UNSUPPORTED -2   /* shape outside what the kernels implement */
+#define SBEV_ERR_CUDA        -3   /* CUDA runtime reported an error at launch */
+
+#define SBEV_MAX_LEVELS 5          /* c2..c6, reference: MSMVSamplingC23456 */
+#define SBEV_MAX_POINTS 32         /* reference: MAX_POINT, msmv_sampling.cpp:3 / :125 */
+
+/* version / diagnostics */
+int         sbev_abi_version(void);
+const char* sbev_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * msmv_sampling forward.
+ * Replaces: ms_deform_attn_cuda_c2345_forward / _c23456_forward (msmv_sampling.cpp:98-210) and the
+ * launchers ms_deformable_im2col_cuda_c2345/_c23456 (msmv_sampling_forward.cu:269-333), generalised
+ * to any 1 <= L <= 5.
+ *   feats  HOST array of L DEVICE pointers; feats[l] = [Bp, N, H_l, W_l, C] channel-last, contiguous
+ *   hw     HOST array of 2*L ints: H_0, W_0, H_1, W_1, ...
+ *   loc    [Bp, Q, P, 3]  (u, v in normalised image coords, view index / (N-1))
+ *   w      [Bp, Q, P, L]  scale weights
+ *   out    [Bp, Q, C, P]  every element is written (no pre-zeroing needed)
+ * Semantics are the reference CUDA kernel's: view = round(z*(N-1)); per level bilinear with
+ * align_corners=True and zero padding; sum over levels of tap*weight.  A view index outside
+ * [0, N) (undefined behaviour in the reference) contributes zero here.
+ */
+int sbev_msmv_fwd(const float* const* feats, const int* hw, int L,
+                  const float* loc, const float* w,
+                  int Bp, int N, int C, int Q, int P,
+                  float* out, void* stream);
+
+/* msmv_sampling backward.
+ * Replaces: ms_deform_attn_cuda_c2345_backward / _c23456_backward (msmv_sampling.cpp:212-360) and
+ * ms_deformable_col2im_cuda_* (msmv_sampling_backward.cu:363-448).
+ *   grad_out    [Bp, Q, C, P]
+ *   grad_feats  HOST array of L DEVICE pointers, same shapes as feats   (zero-filled here, then accumulated)
+ *   grad_loc    [Bp, Q, P, 3]   (component 2, the view coordinate, gets exactly 0 as in the reference)
+ *   grad_w      [Bp, Q, P, L]
+ */
+int sbev_msmv_bwd(const float* grad_out, const float* const* feats, const int* hw, int L,
+                  const float* loc, const float* w,
+                  int Bp, int N, int C, int Q, int P,
+                  float* const* grad_feats, float* grad_loc, float* grad_w, void* stream);
+
+/* The integer sample indices the forward kernel derives from `loc` -- for bit-exact index parity
+ * tests (same device code path as sbev_msmv_fwd: msmv_sampling_forward.cu:110,123-126,33-36).
+ *   view [Bp,Q,P] int32;  y0, x0, inside [Bp,Q,P,L] int32
+ */
+int sbev_msmv_indices(const int* hw, int L, const float* loc, int Bp, int N, int Q, int P,
+                      int32_t* view, int32_t* y0, int32_t* x0, int32_t* inside, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused adaptive spatio-temporal sampling: motion warp -> projection to T x N views -> first-valid
+ * view pick -> multi-scale gather, written straight in the layout AdaptiveMixing consumes.
+ * Replaces: sampling_4d (models/sparsebev_sampling.py:27-130) + the warp in
+ * SparseBEVSampling.inner_forward (models/sparsebev_transformer.py:286-295) + msmv_sampling.
+ *   feats         HOST array of L DEVICE pointers.  Element (b,t,g,view,y,x,c) of level l lives at
+ *                 feats[l] + (b*T+t)*stride_bt[l] + g*stride_g[l] + view*stride_v[l] + (y*W+x)*stride_px[l] + c
+ *                 (strides in floats, HOST arrays of L int64).  This covers both the reference's
+ *                 regrouped [B*T*G,N,H,W,C] layout and an un-regrouped NHWC [B,T*N,H,W,G*C] map.
+ *   points        [B, Q, G*P, 3]   lidar-frame sample points BEFORE the motion warp (metres)
+ *   velocity      [B, Q, 2]        query_bbox[..., 8:10]
+ *   time_diff     [B, T]
+ *   lidar2img     [B, T*N, 4, 4]   row-major
+ *   scale_w       [B, Q, G, P, L]  softmaxed scale weights (not expanded over T)
+ *   out           [B, Q, G, T*P, C]   point index = t*P + p
+ *   loc_out       optional (may be NULL) [B*T*G, Q, P, 3]  the (u, v, view/(N-1)) handed to the op
+ * The weight row used for (t,g) is that of group ((t*G+g)/T)%G -- the reference's (b,t,g)/(b,g,t)
+ * flattening mismatch (sparsebev_sampling.py:112-119) is reproduced on purpose.
+ */
+int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
+                        const int64_t* stride_bt, const int64_t* stride_g,
+                        const int64_t* stride_v, const int64_t* stride_px,
+                        const float* points, const float* velocity, const float* time_diff,
+                        const float* lidar2img, const float* scale_w,
+                        int B, int T, int G, int N, int C, int Q, int P,
+                        float image_h, float image_w, float eps,
+                        float* out, float* loc_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small dense building block: y = epilogue(x @ W^T), row-major fp32, with the weight given
+ * PRE-TRANSPOSED as Wt[K][ldw] (= W^T, zero-padded to ldw >= N, ldw % 4 == 0; the host mirror caches
+ * this copy per parameter).  epilogue: + bias -> (+ residual if SBEV_DENSE_RES_PRE_LN) -> LayerNorm over
+ * N (eps 1e-5, if ln_w/ln_b given) -> ReLU (if SBEV_DENSE_RELU) -> (+ residual otherwise).
+ * Replaces the nn.Linear / nn.LayerNorm / ReLU chains of position_encoder, attention in/out
+ * projections, FFN, cls/reg branches, gen_tau, sampling_offset, scale_weights
+ * (models/sparsebev_transformer.py:113-144,166-176,203,262-263) and norm1/norm3.
+ *   x [M,K] with row stride ldx >= K floats, bias [N] or NULL, ln_w/ln_b [N] or both NULL,
+ *   residual [M,N] or NULL, y [M,N]
+ */
+#define SBEV_DENSE_RELU        1
+#define SBEV_DENSE_RES_PRE_LN  2
+int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const float* bias,
+                   const float* ln_w, const float* ln_b, const float* residual,
+                   int M, int K, int N, int flags, float* y, void* stream);
+
+/* Sampling head epilogue: box decode + offset scaling + yaw rotation + softmax over levels.
+ * Replaces make_sample_points (models/sparsebev_sampling.py:8-24), decode_bbox (models/bbox/utils.py:63-77),
+ * rotation_3d_in_axis (models/utils.py:49-84) and the softmax at sparsebev_transformer.py:298-299.
+ *   query_bbox [BQ,10]; offset [BQ, GP*3] (Linear output); scale_logits [BQ, GP*L]; pc_range HOST[6]
+ *   points [BQ, GP, 3]; scale_w [BQ, GP, L]
+ */
+int sbev_sample_points_fwd(const float* query_bbox, const float* offset, const float* scale_logits,
+                           const float* pc_range, int BQ, int GP, int L,
+                           float* points, float* scale_w, void* stream);
+
+/* Box refinement closing a decoder layer (models/sparsebev_transformer.py:155-160 refine_bbox, :179-183
+ * velocity rescale): out[...,0:3] = sigmoid(delta[...,0:3] + inverse_sigmoid(proposal[...,0:3])),
+ * out[...,3:] = delta[...,3:], and if T > 1 out[...,8:] /= (time_diff[b,1] < 1e-5 ? 1 : time_diff[b,1]).
+ *   proposal, delta, out [B,Q,code_size]; time_diff [B,T]
+ */
+int sbev_refine_bbox_fwd(const float* proposal, const float* delta, const float* time_diff,
+                         int B, int Q, int T, int code_size, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Scale-adaptive self-attention core: softmax(q k^T / sqrt(hd) - tau_h * dist(c_i, c_j)) v.
+ * Replaces SparseBEVSelfAttention.inner_forward's mask build + nn.MultiheadAttention core
+ * (models/sparsebev_transformer.py:210-248); the [B*8,Q,Q] mask is never materialised.
+ *   qkv [B,Q,3*D] (in_proj output, q|k|v), query_bbox [B,Q,10] (centres are decoded in-kernel with
+ *   pc_range, HOST float[6]), tau [B,Q,H], dn_mask optional [Q,Q] uint8 (1 = blocked, query
+ *   denoising), out [B,Q,D] (heads concatenated, before out_proj)
+ */
+int sbev_sasa_fwd(const float* qkv, const float* query_bbox, const float* tau, const uint8_t* dn_mask,
+                  const float* pc_range, int B, int Q, int H, int D, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AdaptiveMixing (models/sparsebev_transformer.py:351-381).
+ * (1) dynamic-parameter generation and (3) output projection are GEMMs on the tcgen05 tensor cores
+ *     (sbev_gemm_bf16_tn below); (2) is the per-(query,group) mix:
+ *       h = relu(LN_{Pin x C}(x @ M));  y = relu(LN_{Pout x C}(S @ h))
+ *   params [BQ, G*(C*C + Pout*Pin)] fp32 (bias already added), x [BQ,G,Pin,C],
+ *   y_hi/y_lo [BQ, G*Pout*C] bf16 split of y (y ~= hi + lo) ready for the out_proj GEMM; y_f32 optional.
+ */
+int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, int Pin, int Pout, int C,
+                 uint16_t* y_hi, uint16_t* y_lo, float* y_f32, void* stream);
+
+/* fp32 -> (hi, lo) bf16 split, elementwise: hi = bf16(x), lo = bf16(x - hi). lo may be NULL. */
+int sbev_split_bf16(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void* stream);
+
+/* C[M,N] (fp32) = sum_s A_s[M,K] . B_s[N,K]^T over `nseg` operand pairs (bf16, K-major), + bias.
+ * tcgen05.mma kind::f16 with fp32 accumulators in TMEM, TMA-staged 128B-swizzled operand tiles.
+ * nseg = 1: plain bf16 GEMM; nseg = 3 with (A_hi,B_hi),(A_hi,B_lo),(A_lo,B_hi): fp32-grade "bf16x3".
+ *   split_k > 1: partial sums go to `C + z*M*N` for z in [0, split_k) (caller reduces); bias only in z=0.
+ * Requires K % 64 == 0, N % 128 == 0; rows of A beyond M are treated as zero.
+ */
+int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const* B, int nseg,
+                      const float* bias, int M, int N, int K, int split_k, float* C, void* stream);
+
+/* out[M,N] = LN(sum_z partial[z] + bias + residual) : split-K reduction fused with the residual
+ * and LayerNorm that follow mixing.out_proj (sparsebev_transformer.py:377-379 + norm2 at :171). */
+int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
+                       const float* ln_w, const float* ln_b, int M, int N, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SPARSEBEV_B200_H_ */

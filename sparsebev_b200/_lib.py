@@ -1,0 +1,89 @@
+"""ctypes binding of libsparsebev_b200.so (the C ABI declared in include/sparsebev_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'csrc', 'libsparsebev_b200.so')
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_vp = ctypes.c_void_p
+c_int = ctypes.c_int
+c_vpp = ctypes.POINTER(c_vp)
+
+# name -> argtypes; every function returns int (SBEV_OK = 0)
+SIGNATURES = {
+    'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                      c_vpp, c_vp, c_vp, c_vp],
+    'sbev_msmv_indices': [c_i32p, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'sbev_sampling4d_fwd': [c_vpp, c_i32p, c_int, c_i64p, c_i64p, c_i64p, c_i64p,
+                            c_vp, c_vp, c_vp, c_vp, c_vp,
+                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp],
+    'sbev_dense_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_refine_bbox_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_sample_points_fwd': [c_vp, c_vp, c_vp, c_f32p, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'sbev_sasa_fwd': [c_vp, c_vp, c_vp, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_mix_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    'sbev_split_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp],
+    'sbev_gemm_bf16_tn': [c_vpp, c_vpp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_reduce_ln_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error'])
+
+
+def load():
+    """Load the library once.  Raises RuntimeError (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            'sparsebev_b200: %s not found. Build it with `python -m sparsebev_b200.build` '
+            '(or `python -c "import __graft_entry__ as g; g.build()"`). There is no CPU / eager fallback.' % SO_PATH)
+    lib = ctypes.CDLL(SO_PATH)
+    lib.sbev_abi_version.restype = c_int
+    lib.sbev_last_error.restype = ctypes.c_char_p
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+launch_count = 0      # number of successful C-ABI launches (each enqueues exactly one of OUR kernels)
+
+
+def check(rc, what):
+    global launch_count
+    launch_count += 1
+    if rc != 0:
+        msg = load().sbev_last_error()
+        raise RuntimeError('%s failed (code %d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def ptr_array(ptrs):
+    return (c_vp * len(ptrs))(*ptrs)
+
+
+def i32_array(vals):
+    return (ctypes.c_int32 * len(vals))(*vals)
+
+
+def i64_array(vals):
+    return (ctypes.c_int64 * len(vals))(*vals)
+
+
+def f32_array(vals):
+    return (ctypes.c_float * len(vals))(*vals)

@@ -1,0 +1,291 @@
+// bf16 "TN" GEMM on the 5th-generation tensor cores (tcgen05 / UMMA, sm_100a only):
+//     C[M,N] (fp32) = sum_s A_s[M,K] . B_s[N,K]^T  (+ bias)
+// Used for the two dense contractions of AdaptiveMixing
+// (/root/reference/models/sparsebev_transformer.py:358 parameter_generator, :378 out_proj), which the
+// reference runs as fp32 cuBLAS SGEMMs.  fp32-grade accuracy is kept with the bf16x3 split
+//     a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi        (|error| <= ~3 * 2^-18 |a.b|)
+// expressed as three operand-pair "segments" that accumulate into the SAME TMEM accumulator, so the
+// split costs tensor-core time only -- no extra passes over C.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D loads of 128x64 (A) and BNx64 (B) bf16 boxes,
+//            128-byte swizzled, into a STAGES-deep shared-memory ring, completion on mbarriers.
+//   warp 1   allocates TMEM (BN fp32 columns x 128 lanes), then ONE thread issues
+//            tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage and
+//            tcgen05.commit's the stage's "empty" barrier; a final commit signals the epilogue.
+//   warps 2-5  epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quarter) -> registers ->
+//            padded shared staging (re-using the operand ring) -> +bias -> 512 B-per-row coalesced
+//            fp32 stores (split-K partials go to C + z*M*N).
+// Two CTAs fit per SM (96 KB smem, 128 TMEM columns each) so one CTA's epilogue overlaps the other's
+// main loop.  All mbarrier waits are bounded: a protocol bug traps instead of hanging the GPU.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace sbev {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_MAX_SEG = 3;
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && spins > (1u << 26)) __trap();      // ~seconds: protocol bug, fail loudly instead of hanging
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, densely packed 128 B rows:
+// canonical layout ((8,n),2):((8,SBO),1) in 16 B units -> LBO = 1 (unused), SBO = 1024 B (8 rows),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  Tile base is 1024 B aligned.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // version = 1
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmMaps {
+    CUtensorMap a[GEMM_MAX_SEG];
+    CUtensorMap b[GEMM_MAX_SEG];
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int nseg, int kb_per_split,
+                    const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
+    constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;     // 16 KB
+    constexpr int B_BYTES = BN * GEMM_BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int STG_LD = BN + 4;                     // staging row stride (floats)
+    static_assert(GEMM_BM * STG_LD * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GEMM_BM, z = blockIdx.z;
+    const int iters = nseg * kb_per_split;
+    const int kb0 = z * kb_per_split;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = 0; s < nseg; ++s) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[s]) : "memory");
+            }
+            for (int it = 0; it < iters; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int seg = it / kb_per_split;
+                const int kb = kb0 + (it - seg * kb_per_split);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                tma_load_2d(sa, &maps.a[seg], &full_bar[stage], kb * GEMM_BK, m0);
+                tma_load_2d(sa + A_BYTES, &maps.b[seg], &full_bar[stage], kb * GEMM_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
+            for (int it = 0; it < iters; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint64_t adesc = umma_desc_k_sw128(sa);
+                const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k)     // advance 16 bf16 = 32 B = 2 descriptor units along K
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);            // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);                   // accumulator complete
+        }
+    } else {
+        // ---- epilogue warps 2..5; TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        float* stg = reinterpret_cast<float*>(smem);
+        const int row_local = quarter * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+            float* dst = stg + row_local * STG_LD + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        __syncwarp();
+        float* Cz = C + (long long)z * M * N;
+        const bool add_bias = (bias != nullptr) && (z == 0);
+        for (int col = lane * 4; col < BN; col += 128) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias) bv = ldg4(bias + n0 + col);
+            for (int r = 0; r < 32; ++r) {
+                const int row = m0 + quarter * 32 + r;
+                if (row < M) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (quarter * 32 + r) * STG_LD + col);
+                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                    *reinterpret_cast<float4*>(Cz + (long long)row * N + n0 + col) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128 B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] box %d", (int)r, rows, cols, box_rows);
+    return SBEV_OK;
+}
+
+}  // namespace sbev
+
+using namespace sbev;
+
+extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const* B, int nseg,
+                                 const float* bias, int M, int N, int K, int split_k, float* C, void* stream) {
+    SBEV_REQUIRE(A && B && C, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: null pointer");
+    SBEV_REQUIRE(nseg >= 1 && nseg <= GEMM_MAX_SEG, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: nseg must be 1..3");
+    SBEV_REQUIRE(M > 0 && N > 0 && K > 0 && split_k >= 1, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: bad sizes");
+    SBEV_REQUIRE(K % GEMM_BK == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: K must be a multiple of 64 (got %d)", K);
+    SBEV_REQUIRE(N % 128 == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: N must be a multiple of 128 (got %d)", N);
+    SBEV_REQUIRE((K / GEMM_BK) % split_k == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: K/64 must be divisible by split_k");
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                 SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: C / bias must be 16-byte aligned");
+    constexpr int BN = 128, STAGES = 3;
+    GemmMaps maps;
+    for (int s = 0; s < nseg; ++s) {
+        SBEV_REQUIRE(A[s] && B[s], SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: null operand in segment %d", s);
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(A[s]) & 15) == 0 && (reinterpret_cast<uintptr_t>(B[s]) & 15) == 0,
+                     SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: operands must be 16-byte aligned");
+        int rc = make_map(&maps.a[s], A[s], M, K, GEMM_BM);
+        if (rc) return rc;
+        rc = make_map(&maps.b[s], B[s], N, K, BN);
+        if (rc) return rc;
+    }
+    for (int s = nseg; s < GEMM_MAX_SEG; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
+    const size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [&] {
+        cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+    dim3 grid(N / BN, (M + GEMM_BM - 1) / GEMM_BM, split_k);
+    gemm_bf16_tn_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
+        maps, nseg, (K / GEMM_BK) / split_k, bias, C, M, N);
+    return check_launch("sbev_gemm_bf16_tn");
+}

@@ -1,0 +1,561 @@
+// Multi-scale multi-view bilinear gather ("msmv_sampling") for sm_100a, and the fused
+// adaptive spatio-temporal sampling front-end.
+//
+// Behavioural reference (paths under /root/reference, nothing copied):
+//   forward kernel semantics   models/csrc/msmv_sampling/msmv_sampling_forward.cu:27-267
+//   backward kernel semantics  models/csrc/msmv_sampling/msmv_sampling_backward.cu:29-361
+//   sampling_4d                models/sparsebev_sampling.py:27-130
+//
+// Design (B200): the gather is HBM/L2-bandwidth bound -- 4 corners x L levels x 256 B rows
+// per sample point, 0.25 flop/byte.  One HALF-WARP owns one sample point: 16 lanes x float4
+// = one 256 B channel row per LDG.128, so every load instruction of a warp moves two full
+// rows, and each lane keeps 4*L independent 16 B loads in flight (16 for L=4) before the
+// first use.  Coordinates / weights are fetched once per point and broadcast by shuffle
+// instead of being re-read by all 64 channel threads as in the reference.  Work is ordered
+// slice-major ((b,t,g) outermost) so the CTAs resident at any moment share one ~23 MB slice
+// of the feature pyramid in L2.  Outputs are written as whole 256 B (fused layout) or
+// 64*P*4 B (op layout, transposed through shared memory) contiguous segments.
+#include "common.cuh"
+
+namespace sbev {
+
+struct LevelSet {
+    const float* ptr[SBEV_MAX_LEVELS];
+    int H[SBEV_MAX_LEVELS];
+    int W[SBEV_MAX_LEVELS];
+    // fused-path addressing (floats): see sbev_sampling4d_fwd in the public header
+    long long s_bt[SBEV_MAX_LEVELS], s_g[SBEV_MAX_LEVELS], s_v[SBEV_MAX_LEVELS], s_px[SBEV_MAX_LEVELS];
+};
+
+struct Tap {
+    int y0, x0;
+    float w1, w2, w3, w4;
+    bool inside, ok1, ok2, ok3, ok4;
+};
+
+// Same fp32 operation order as the reference device code (forward.cu:33-46,123-126):
+// single multiply loc*(size-1), floor, differences, products of the two 1-D weights.
+__device__ __forceinline__ Tap make_tap(float u, float v, int H, int W) {
+    Tap t;
+    const float y = v * (float)(H - 1);
+    const float x = u * (float)(W - 1);
+    t.inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+    const float yf = floorf(y), xf = floorf(x);
+    t.y0 = t.inside ? (int)yf : 0;
+    t.x0 = t.inside ? (int)xf : 0;
+    const float ly = y - yf, lx = x - xf;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    t.w1 = hy * hx; t.w2 = hy * lx; t.w3 = ly * hx; t.w4 = ly * lx;
+    const bool yl = t.y0 >= 0, yh = t.y0 + 1 <= H - 1, xl = t.x0 >= 0, xh = t.x0 + 1 <= W - 1;
+    t.ok1 = t.inside && yl && xl;
+    t.ok2 = t.inside && yl && xh;
+    t.ok3 = t.inside && yh && xl;
+    t.ok4 = t.inside && yh && xh;
+    return t;
+}
+
+__device__ __forceinline__ int view_from_coord(float z, int N) {
+    return (int)roundf(z * (float)(N - 1));     // forward.cu:110 (round-half-away-from-zero)
+}
+
+// Gather all L levels for 4 consecutive channels.  base[l] already points at
+// (slice, view, channel lane); pxs[l] = floats between neighbouring pixels.
+template <int L>
+__device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], const int (&H)[L],
+                                                const int (&W)[L], const long long (&pxs)[L],
+                                                float u, float v, const float (&wt)[L], bool live) {
+    Tap tp[L];
+    float4 c1[L], c2[L], c3[L], c4[L];
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        tp[l] = make_tap(u, v, H[l], W[l]);
+        const float* p = base[l] + ((long long)tp[l].y0 * W[l] + tp[l].x0) * pxs[l];
+        const long long row = (long long)W[l] * pxs[l];
+        c1[l] = (live && tp[l].ok1) ? ldg4(p) : zero;
+        c2[l] = (live && tp[l].ok2) ? ldg4(p + pxs[l]) : zero;
+        c3[l] = (live && tp[l].ok3) ? ldg4(p + row) : zero;
+        c4[l] = (live && tp[l].ok4) ? ldg4(p + row + pxs[l]) : zero;
+    }
+    float4 acc = zero;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        if (tp[l].inside) {
+            const Tap& t = tp[l];
+            acc.x += (t.w1 * c1[l].x + t.w2 * c2[l].x + t.w3 * c3[l].x + t.w4 * c4[l].x) * wt[l];
+            acc.y += (t.w1 * c1[l].y + t.w2 * c2[l].y + t.w3 * c3[l].y + t.w4 * c4[l].y) * wt[l];
+            acc.z += (t.w1 * c1[l].z + t.w2 * c2[l].z + t.w3 * c3[l].z + t.w4 * c4[l].z) * wt[l];
+            acc.w += (t.w1 * c1[l].w + t.w2 * c2[l].w + t.w3 * c3[l].w + t.w4 * c4[l].w) * wt[l];
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Op-boundary forward, C == 64.  One warp per (b', q): lanes < P prefetch that query's
+// coordinates and weights, the two half-warps then walk the P points two at a time, results go
+// to a per-warp shared tile [P][64] and leave as one contiguous 64*P float segment in the
+// reference's [B',Q,C,P] order.
+template <int L>
+__global__ void __launch_bounds__(256)
+msmv_fwd_c64_kernel(LevelSet lv, const float* __restrict__ loc, const float* __restrict__ wgt,
+                    int Bp, int N, int Q, int P, float* __restrict__ out) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, j = lane & 15;
+    float* tile = smem + warp * (64 * P);
+    const long long items = (long long)Bp * Q;
+    for (long long item = (long long)blockIdx.x * 8 + warp; item < items; item += (long long)gridDim.x * 8) {
+        const int b = (int)(item / Q);
+        float lu = 0.f, lvv = 0.f, lz = 0.f, lw[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) lw[l] = 0.f;
+        if (lane < P) {
+            const float* lp = loc + (item * P + lane) * 3;
+            lu = __ldg(lp); lvv = __ldg(lp + 1); lz = __ldg(lp + 2);
+            const float* wp = wgt + (item * P + lane) * L;
+#pragma unroll
+            for (int l = 0; l < L; ++l) lw[l] = __ldg(wp + l);
+        }
+        for (int p0 = 0; p0 < P; p0 += 2) {
+            const int p = p0 + half;
+            const bool live = p < P;
+            const int src = live ? p : P - 1;
+            const float u = __shfl_sync(0xffffffffu, lu, src);
+            const float v = __shfl_sync(0xffffffffu, lvv, src);
+            const float z = __shfl_sync(0xffffffffu, lz, src);
+            float wt[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) wt[l] = __shfl_sync(0xffffffffu, lw[l], src);
+            const int view = view_from_coord(z, N);
+            const bool view_ok = (view >= 0) && (view < N);
+            const float* base[L]; int H[L], W[L]; long long pxs[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = 64;
+                base[l] = lv.ptr[l] + ((long long)b * N + (view_ok ? view : 0)) * H[l] * W[l] * 64 + 4 * j;
+            }
+            const float4 acc = gather_levels<L>(base, H, W, pxs, u, v, wt, live && view_ok);
+            if (live) *reinterpret_cast<float4*>(tile + p * 64 + 4 * j) = acc;
+        }
+        __syncwarp();
+        float* dst = out + item * 64 * P;
+        for (int i = lane * 4; i < 64 * P; i += 128) {
+            float4 o;
+            o.x = tile[((i + 0) % P) * 64 + (i + 0) / P];
+            o.y = tile[((i + 1) % P) * 64 + (i + 1) / P];
+            o.z = tile[((i + 2) % P) * 64 + (i + 2) / P];
+            o.w = tile[((i + 3) % P) * 64 + (i + 3) / P];
+            *reinterpret_cast<float4*>(dst + i) = o;
+        }
+        __syncwarp();
+    }
+}
+
+// Generic-C fallback (any C, reference thread mapping but coordinates hoisted): thread per (b',q,c).
+__global__ void __launch_bounds__(256)
+msmv_fwd_generic_kernel(LevelSet lv, int L, const float* __restrict__ loc, const float* __restrict__ wgt,
+                        int Bp, int N, int C, int Q, int P, float* __restrict__ out) {
+    const long long total = (long long)Bp * Q * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long long item = idx / C;
+        const int b = (int)(item / Q);
+        for (int p = 0; p < P; ++p) {
+            const float* lp = loc + (item * P + p) * 3;
+            const float u = __ldg(lp), v = __ldg(lp + 1);
+            const int view = view_from_coord(__ldg(lp + 2), N);
+            float acc = 0.f;
+            if (view >= 0 && view < N) {
+                for (int l = 0; l < L; ++l) {
+                    const int H = lv.H[l], W = lv.W[l];
+                    const Tap t = make_tap(u, v, H, W);
+                    if (!t.inside) continue;
+                    const float* p0 = lv.ptr[l] + (((long long)b * N + view) * H * W + (long long)t.y0 * W + t.x0) * C + c;
+                    const float v1 = t.ok1 ? __ldg(p0) : 0.f;
+                    const float v2 = t.ok2 ? __ldg(p0 + C) : 0.f;
+                    const float v3 = t.ok3 ? __ldg(p0 + (long long)W * C) : 0.f;
+                    const float v4 = t.ok4 ? __ldg(p0 + (long long)W * C + C) : 0.f;
+                    acc += (t.w1 * v1 + t.w2 * v2 + t.w3 * v3 + t.w4 * v4) * __ldg(wgt + (item * P + p) * L + l);
+                }
+            }
+            out[idx * P + p] = acc;
+        }
+    }
+}
+
+__global__ void msmv_indices_kernel(LevelSet lv, int L, const float* __restrict__ loc, long long npts, int N,
+                                    int32_t* view, int32_t* y0, int32_t* x0, int32_t* inside) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npts;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float u = loc[i * 3], v = loc[i * 3 + 1];
+        view[i] = view_from_coord(loc[i * 3 + 2], N);
+        for (int l = 0; l < L; ++l) {
+            const float y = v * (float)(lv.H[l] - 1), x = u * (float)(lv.W[l] - 1);
+            y0[i * L + l] = (int)floorf(y);
+            x0[i * L + l] = (int)floorf(x);
+            inside[i * L + l] = (y > -1.f) && (x > -1.f) && (y < (float)lv.H[l]) && (x < (float)lv.W[l]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward, C == 64: half-warp per (b',q,p).  grad wrt weights and locations are owned by exactly
+// one half-warp -> shuffle reduction + plain store (deterministic, no atomics, unlike the
+// reference); only the scatter into grad_feats uses (128-bit vector) atomics.
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+#if __CUDA_ARCH__ >= 900
+    atomicAdd(reinterpret_cast<float4*>(addr), v);
+#else
+    atomicAdd(addr, v.x); atomicAdd(addr + 1, v.y); atomicAdd(addr + 2, v.z); atomicAdd(addr + 3, v.w);
+#endif
+}
+
+struct GradLevelSet { float* ptr[SBEV_MAX_LEVELS]; };
+
+template <int L>
+__global__ void __launch_bounds__(256)
+msmv_bwd_c64_kernel(LevelSet lv, GradLevelSet glv, const float* __restrict__ grad_out,
+                    const float* __restrict__ loc, const float* __restrict__ wgt,
+                    int Bp, int N, int Q, int P,
+                    float* __restrict__ grad_loc, float* __restrict__ grad_w) {
+    const int lane = threadIdx.x & 31, j = lane & 15;
+    const long long npts = (long long)Bp * Q * P;
+    const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long hw_stride = ((long long)gridDim.x * blockDim.x) >> 4;
+    const long long iters = (npts + hw_stride - 1) / hw_stride;        // uniform trip count (shuffles inside)
+    for (long long it = 0; it < iters; ++it) {
+        const long long pi_raw = hw_id + it * hw_stride;
+        const bool live = pi_raw < npts;
+        const long long pi = live ? pi_raw : npts - 1;
+        const int p = (int)(pi % P);
+        const long long item = pi / P;
+        const int b = (int)(item / Q);
+        const float u = __ldg(loc + pi * 3), v = __ldg(loc + pi * 3 + 1);
+        const int view = view_from_coord(__ldg(loc + pi * 3 + 2), N);
+        const bool view_ok = view >= 0 && view < N;
+        float4 g;
+        {
+            const float* gp = grad_out + (item * 64 + 4 * j) * P + p;
+            g.x = __ldg(gp); g.y = __ldg(gp + P); g.z = __ldg(gp + 2 * P); g.w = __ldg(gp + 3 * P);
+        }
+        float gx_acc = 0.f, gy_acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.H[l], W = lv.W[l];
+            const Tap t = make_tap(u, v, H, W);
+            const float aw = __ldg(wgt + pi * L + l);
+            float gw_part = 0.f, gx_part = 0.f, gy_part = 0.f;
+            if (t.inside && view_ok) {
+                const long long off = (((long long)b * N + view) * H * W + (long long)t.y0 * W + t.x0) * 64 + 4 * j;
+                const float* p0 = lv.ptr[l] + off;
+                float* q0 = glv.ptr[l] + off;
+                const long long row = (long long)W * 64;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v1 = t.ok1 ? ldg4(p0) : zero;
+                const float4 v2 = t.ok2 ? ldg4(p0 + 64) : zero;
+                const float4 v3 = t.ok3 ? ldg4(p0 + row) : zero;
+                const float4 v4 = t.ok4 ? ldg4(p0 + row + 64) : zero;
+                const float hy = t.w1 + t.w2, ly = t.w3 + t.w4;      // hy*(hx+lx) = hy up to 1 ulp; recompute exactly below
+                (void)hy; (void)ly;
+                const float y = v * (float)(H - 1), x = u * (float)(W - 1);
+                const float fly = y - floorf(y), flx = x - floorf(x);
+                const float fhy = 1.f - fly, fhx = 1.f - flx;
+                const float4 gv = make_float4(g.x * aw, g.y * aw, g.z * aw, g.w * aw);   // top_grad * attn_weight
+                if (live) {
+                    if (t.ok1) red_add4(q0, make_float4(t.w1 * gv.x, t.w1 * gv.y, t.w1 * gv.z, t.w1 * gv.w));
+                    if (t.ok2) red_add4(q0 + 64, make_float4(t.w2 * gv.x, t.w2 * gv.y, t.w2 * gv.z, t.w2 * gv.w));
+                    if (t.ok3) red_add4(q0 + row, make_float4(t.w3 * gv.x, t.w3 * gv.y, t.w3 * gv.z, t.w3 * gv.w));
+                    if (t.ok4) red_add4(q0 + row + 64, make_float4(t.w4 * gv.x, t.w4 * gv.y, t.w4 * gv.z, t.w4 * gv.w));
+                }
+#define SBEV_BWD_CH(comp)                                                                              \
+                {                                                                                      \
+                    const float a1 = v1.comp, a2 = v2.comp, a3 = v3.comp, a4 = v4.comp;                \
+                    const float val = t.w1 * a1 + t.w2 * a2 + t.w3 * a3 + t.w4 * a4;                   \
+                    const float gyw = -fhx * a1 - flx * a2 + fhx * a3 + flx * a4;                      \
+                    const float gxw = -fhy * a1 + fhy * a2 - fly * a3 + fly * a4;                      \
+                    gw_part += g.comp * val;                                                           \
+                    gx_part += gxw * gv.comp;                                                          \
+                    gy_part += gyw * gv.comp;                                                          \
+                }
+                SBEV_BWD_CH(x) SBEV_BWD_CH(y) SBEV_BWD_CH(z) SBEV_BWD_CH(w)
+#undef SBEV_BWD_CH
+            }
+            gw_part = half_warp_sum(gw_part);
+            gx_acc += (float)(W - 1) * half_warp_sum(gx_part);
+            gy_acc += (float)(H - 1) * half_warp_sum(gy_part);
+            if (live && j == 0) grad_w[pi * L + l] = gw_part;
+        }
+        if (live && j == 0) {
+            grad_loc[pi * 3 + 0] = gx_acc;
+            grad_loc[pi * 3 + 1] = gy_acc;
+            grad_loc[pi * 3 + 2] = 0.f;       // reference never writes the view-coordinate gradient
+        }
+    }
+}
+
+// Generic-C backward: thread per (b',q,c,p), scalar atomics everywhere (reference mapping).
+__global__ void __launch_bounds__(256)
+msmv_bwd_generic_kernel(LevelSet lv, GradLevelSet glv, int L, const float* __restrict__ grad_out,
+                        const float* __restrict__ loc, const float* __restrict__ wgt,
+                        int Bp, int N, int C, int Q, int P, float* grad_loc, float* grad_w) {
+    const long long total = (long long)Bp * Q * C * P;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(idx % P);
+        const int c = (int)((idx / P) % C);
+        const long long item = idx / ((long long)P * C);
+        const int b = (int)(item / Q);
+        const long long pi = item * P + p;
+        const float g = grad_out[idx];
+        const float u = loc[pi * 3], v = loc[pi * 3 + 1];
+        const int view = view_from_coord(loc[pi * 3 + 2], N);
+        if (view < 0 || view >= N) continue;
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.H[l], W = lv.W[l];
+            const Tap t = make_tap(u, v, H, W);
+            if (!t.inside) continue;
+            const float aw = wgt[pi * L + l], gv = g * aw;
+            const long long off = (((long long)b * N + view) * H * W + (long long)t.y0 * W + t.x0) * C + c;
+            const float* p0 = lv.ptr[l] + off;
+            float* q0 = glv.ptr[l] + off;
+            const long long row = (long long)W * C;
+            const float y = v * (float)(H - 1), x = u * (float)(W - 1);
+            const float ly = y - floorf(y), lx = x - floorf(x), hy = 1.f - ly, hx = 1.f - lx;
+            float v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+            if (t.ok1) { v1 = p0[0]; atomicAdd(q0, t.w1 * gv); }
+            if (t.ok2) { v2 = p0[C]; atomicAdd(q0 + C, t.w2 * gv); }
+            if (t.ok3) { v3 = p0[row]; atomicAdd(q0 + row, t.w3 * gv); }
+            if (t.ok4) { v4 = p0[row + C]; atomicAdd(q0 + row + C, t.w4 * gv); }
+            const float val = t.w1 * v1 + t.w2 * v2 + t.w3 * v3 + t.w4 * v4;
+            atomicAdd(grad_w + pi * L + l, g * val);
+            atomicAdd(grad_loc + pi * 3, (float)(W - 1) * (-hy * v1 + hy * v2 - ly * v3 + ly * v4) * gv);
+            atomicAdd(grad_loc + pi * 3 + 1, (float)(H - 1) * (-hx * v1 - lx * v2 + hx * v3 + lx * v4) * gv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused adaptive spatio-temporal sampling (see sbev_sampling4d_fwd in the header).
+// Half-warp per sample (b,t,g,q,p), slice-major order.  Lanes 0..N-1 of the half-warp each
+// project the point into one camera; a ballot picks the first valid view.
+struct FusedParams {
+    const float* points;     // [B,Q,G*P,3]
+    const float* velocity;   // [B,Q,2]
+    const float* time_diff;  // [B,T]
+    const float* lidar2img;  // [B,T*N,16]
+    const float* scale_w;    // [B,Q,G,P,L]
+    float* out;              // [B,Q,G,T*P,64]
+    float* loc_out;          // optional [B*T*G,Q,P,3]
+    int B, T, G, N, Q, P;
+    float image_h, image_w, eps;
+};
+
+template <int L>
+__global__ void __launch_bounds__(256)
+sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
+    const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+    const int T = prm.T, G = prm.G, N = prm.N, Q = prm.Q, P = prm.P;
+    const long long total = (long long)prm.B * T * G * Q * P;
+    const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long hw_stride = ((long long)gridDim.x * blockDim.x) >> 4;
+    const long long iters = (total + hw_stride - 1) / hw_stride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long i_raw = hw_id + it * hw_stride;
+        const bool live = i_raw < total;
+        const long long i = live ? i_raw : total - 1;
+        const int p = (int)(i % P);
+        const int q = (int)((i / P) % Q);
+        const int s = (int)(i / ((long long)P * Q));       // (b*T + t)*G + g
+        const int g = s % G;
+        const int bt = s / G;
+        const int t = bt % T;
+        const int b = bt / T;
+        const long long bq = (long long)b * Q + q;
+
+        // motion warp (sparsebev_transformer.py:286-295): xy -= vel * time_diff[t]; no FMA contraction
+        const float* pp = prm.points + (bq * G * P + g * P + p) * 3;
+        const float td = __ldg(prm.time_diff + b * T + t);
+        const float px = __fsub_rn(__ldg(pp), __fmul_rn(__ldg(prm.velocity + bq * 2), td));
+        const float py = __fsub_rn(__ldg(pp + 1), __fmul_rn(__ldg(prm.velocity + bq * 2 + 1), td));
+        const float pz = __ldg(pp + 2);
+
+        // projection to view j (sparsebev_sampling.py:50-79), fixed order ((x*m0 + y*m1) + z*m2) + m3
+        float un = 0.f, vn = 0.f;
+        bool valid = false;
+        if (j < N) {
+            const float4* m = reinterpret_cast<const float4*>(prm.lidar2img + ((long long)bt * N + j) * 16);
+            const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+            const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r0.x), __fmul_rn(py, r0.y)), __fmul_rn(pz, r0.z)), r0.w);
+            const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r1.x), __fmul_rn(py, r1.y)), __fmul_rn(pz, r1.z)), r1.w);
+            const float dz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r2.x), __fmul_rn(py, r2.y)), __fmul_rn(pz, r2.z)), r2.w);
+            const float safe = fmaxf(dz, prm.eps);
+            un = __fdiv_rn(__fdiv_rn(cx, safe), prm.image_w);
+            vn = __fdiv_rn(__fdiv_rn(cy, safe), prm.image_h);
+            valid = (dz > prm.eps) && (vn > 0.f) && (vn < 1.f) && (un > 0.f) && (un < 1.f);
+        }
+        const unsigned ball = (__ballot_sync(0xffffffffu, valid) >> (16 * half)) & 0xffffu;
+        const int view = ball ? (__ffs(ball) - 1) : 0;          // argmax of 0/1 flags: first valid, else 0
+        const float u = __shfl_sync(0xffffffffu, un, 16 * half + view);
+        const float v = __shfl_sync(0xffffffffu, vn, 16 * half + view);
+
+        // scale weights: the reference pairs loc slice (b,t,g) with weight slice (b,g',t'),
+        // (g',t') = divmod(t*G+g, T)  (sparsebev_sampling.py:112-119); weights do not depend on t'.
+        const int gw = (t * G + g) / T;
+        const float* wp = prm.scale_w + ((bq * G + gw) * P + p) * L;
+        float wt[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) wt[l] = __ldg(wp + l);
+
+        const float* base[L]; int H[L], W[L]; long long pxs[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = lv.s_px[l];
+            base[l] = lv.ptr[l] + (long long)bt * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j;
+        }
+        const float4 acc = gather_levels<L>(base, H, W, pxs, u, v, wt, live);
+        if (live) {
+            float* dst = prm.out + ((bq * G + g) * ((long long)T * P) + (long long)t * P + p) * 64 + 4 * j;
+            *reinterpret_cast<float4*>(dst) = acc;
+            if (prm.loc_out != nullptr && j == 0) {
+                float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
+                lo[0] = u; lo[1] = v; lo[2] = __fdiv_rn((float)view, (float)(N - 1));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int fill_levels(LevelSet& lv, const float* const* feats, const int* hw, int L) {
+    SBEV_REQUIRE(L >= 1 && L <= SBEV_MAX_LEVELS, SBEV_ERR_UNSUPPORTED, "num levels %d outside [1,%d]", L, SBEV_MAX_LEVELS);
+    SBEV_REQUIRE(hw != nullptr, SBEV_ERR_INVALID, "hw is null");
+    for (int l = 0; l < SBEV_MAX_LEVELS; ++l) {
+        lv.ptr[l] = nullptr; lv.H[l] = 1; lv.W[l] = 1;
+        lv.s_bt[l] = lv.s_g[l] = lv.s_v[l] = lv.s_px[l] = 0;
+    }
+    for (int l = 0; l < L; ++l) {
+        if (feats) {
+            SBEV_REQUIRE(feats[l] != nullptr, SBEV_ERR_INVALID, "feats[%d] is null", l);
+            SBEV_REQUIRE((reinterpret_cast<uintptr_t>(feats[l]) & 15) == 0, SBEV_ERR_INVALID, "feats[%d] not 16-byte aligned", l);
+            lv.ptr[l] = feats[l];
+        }
+        lv.H[l] = hw[2 * l]; lv.W[l] = hw[2 * l + 1];
+        SBEV_REQUIRE(lv.H[l] > 0 && lv.W[l] > 0, SBEV_ERR_INVALID, "level %d has non-positive size", l);
+    }
+    return SBEV_OK;
+}
+
+static int grid_for(long long work_items, int per_block, int max_blocks = 148 * 32) {
+    long long g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+}  // namespace sbev
+
+using namespace sbev;
+
+extern "C" int sbev_msmv_fwd(const float* const* feats, const int* hw, int L, const float* loc, const float* w,
+                             int Bp, int N, int C, int Q, int P, float* out, void* stream) {
+    SBEV_REQUIRE(feats && loc && w && out, SBEV_ERR_INVALID, "sbev_msmv_fwd: null pointer");
+    SBEV_REQUIRE(Bp >= 0 && Q >= 0 && N > 0 && C > 0 && P > 0, SBEV_ERR_INVALID, "sbev_msmv_fwd: bad sizes");
+    SBEV_REQUIRE(P <= SBEV_MAX_POINTS, SBEV_ERR_INVALID, "num_point exceed limits (%d > %d)", P, SBEV_MAX_POINTS);
+    LevelSet lv;
+    int rc = fill_levels(lv, feats, hw, L);
+    if (rc) return rc;
+    if ((long long)Bp * Q == 0) return SBEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 64) {
+        const size_t smem = (size_t)8 * 64 * P * sizeof(float);
+        const int grid = grid_for((long long)Bp * Q, 8);
+#define SBEV_LAUNCH_FWD(LL)                                                                                  \
+        case LL: {                                                                                           \
+            if (smem > 48 * 1024)                                                                            \
+                cudaFuncSetAttribute(msmv_fwd_c64_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            msmv_fwd_c64_kernel<LL><<<grid, 256, smem, st>>>(lv, loc, w, Bp, N, Q, P, out);                  \
+        } break;
+        switch (L) { SBEV_LAUNCH_FWD(1) SBEV_LAUNCH_FWD(2) SBEV_LAUNCH_FWD(3) SBEV_LAUNCH_FWD(4) SBEV_LAUNCH_FWD(5) }
+#undef SBEV_LAUNCH_FWD
+    } else {
+        msmv_fwd_generic_kernel<<<grid_for((long long)Bp * Q * C, 256), 256, 0, st>>>(lv, L, loc, w, Bp, N, C, Q, P, out);
+    }
+    return check_launch("sbev_msmv_fwd");
+}
+
+extern "C" int sbev_msmv_indices(const int* hw, int L, const float* loc, int Bp, int N, int Q, int P,
+                                 int32_t* view, int32_t* y0, int32_t* x0, int32_t* inside, void* stream) {
+    SBEV_REQUIRE(loc && view && y0 && x0 && inside, SBEV_ERR_INVALID, "sbev_msmv_indices: null pointer");
+    LevelSet lv;
+    int rc = fill_levels(lv, nullptr, hw, L);
+    if (rc) return rc;
+    const long long npts = (long long)Bp * Q * P;
+    if (npts == 0) return SBEV_OK;
+    msmv_indices_kernel<<<grid_for(npts, 256), 256, 0, (cudaStream_t)stream>>>(lv, L, loc, npts, N, view, y0, x0, inside);
+    return check_launch("sbev_msmv_indices");
+}
+
+extern "C" int sbev_msmv_bwd(const float* grad_out, const float* const* feats, const int* hw, int L,
+                             const float* loc, const float* w, int Bp, int N, int C, int Q, int P,
+                             float* const* grad_feats, float* grad_loc, float* grad_w, void* stream) {
+    SBEV_REQUIRE(grad_out && feats && loc && w && grad_feats && grad_loc && grad_w, SBEV_ERR_INVALID, "sbev_msmv_bwd: null pointer");
+    SBEV_REQUIRE(Bp >= 0 && Q >= 0 && N > 0 && C > 0 && P > 0, SBEV_ERR_INVALID, "sbev_msmv_bwd: bad sizes");
+    SBEV_REQUIRE(P <= SBEV_MAX_POINTS, SBEV_ERR_INVALID, "num_point exceed limits (%d > %d)", P, SBEV_MAX_POINTS);
+    LevelSet lv;
+    int rc = fill_levels(lv, feats, hw, L);
+    if (rc) return rc;
+    GradLevelSet glv;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < SBEV_MAX_LEVELS; ++l) glv.ptr[l] = nullptr;
+    for (int l = 0; l < L; ++l) {
+        SBEV_REQUIRE(grad_feats[l] != nullptr, SBEV_ERR_INVALID, "grad_feats[%d] is null", l);
+        glv.ptr[l] = grad_feats[l];
+        cudaMemsetAsync(grad_feats[l], 0, sizeof(float) * (size_t)Bp * N * lv.H[l] * lv.W[l] * C, st);
+    }
+    const long long npts = (long long)Bp * Q * P;
+    if (npts == 0) return check_launch("sbev_msmv_bwd(memset)");
+    if (C == 64) {
+        const int grid = grid_for(npts, 16);
+#define SBEV_LAUNCH_BWD(LL) case LL: msmv_bwd_c64_kernel<LL><<<grid, 256, 0, st>>>(lv, glv, grad_out, loc, w, Bp, N, Q, P, grad_loc, grad_w); break;
+        switch (L) { SBEV_LAUNCH_BWD(1) SBEV_LAUNCH_BWD(2) SBEV_LAUNCH_BWD(3) SBEV_LAUNCH_BWD(4) SBEV_LAUNCH_BWD(5) }
+#undef SBEV_LAUNCH_BWD
+    } else {
+        cudaMemsetAsync(grad_loc, 0, sizeof(float) * (size_t)npts * 3, st);
+        cudaMemsetAsync(grad_w, 0, sizeof(float) * (size_t)npts * L, st);
+        msmv_bwd_generic_kernel<<<grid_for(npts * C, 256), 256, 0, st>>>(lv, glv, L, grad_out, loc, w, Bp, N, C, Q, P, grad_loc, grad_w);
+    }
+    return check_launch("sbev_msmv_bwd");
+}
+
+extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
+                                   const int64_t* stride_bt, const int64_t* stride_g,
+                                   const int64_t* stride_v, const int64_t* stride_px,
+                                   const float* points, const float* velocity, const float* time_diff,
+                                   const float* lidar2img, const float* scale_w,
+                                   int B, int T, int G, int N, int C, int Q, int P,
+                                   float image_h, float image_w, float eps,
+                                   float* out, float* loc_out, void* stream) {
+    SBEV_REQUIRE(feats && stride_bt && stride_g && stride_v && stride_px && points && velocity && time_diff &&
+                 lidar2img && scale_w && out, SBEV_ERR_INVALID, "sbev_sampling4d_fwd: null pointer");
+    SBEV_REQUIRE(B >= 0 && T > 0 && G > 0 && N > 0 && Q >= 0 && P > 0, SBEV_ERR_INVALID, "sbev_sampling4d_fwd: bad sizes");
+    SBEV_REQUIRE(C == 64, SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: channels per group must be 64 (got %d)", C);
+    SBEV_REQUIRE(N <= 16, SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: at most 16 views (got %d)", N);
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(lidar2img) & 15) == 0, SBEV_ERR_INVALID, "lidar2img not 16-byte aligned");
+    LevelSet lv;
+    int rc = fill_levels(lv, feats, hw, L);
+    if (rc) return rc;
+    for (int l = 0; l < L; ++l) {
+        lv.s_bt[l] = stride_bt[l]; lv.s_g[l] = stride_g[l]; lv.s_v[l] = stride_v[l]; lv.s_px[l] = stride_px[l];
+        SBEV_REQUIRE(((stride_bt[l] | stride_g[l] | stride_v[l] | stride_px[l]) & 3) == 0, SBEV_ERR_INVALID,
+                     "level %d strides must be multiples of 4 floats", l);
+    }
+    const long long total = (long long)B * T * G * Q * P;
+    if (total == 0) return SBEV_OK;
+    FusedParams prm{points, velocity, time_diff, lidar2img, scale_w, out, loc_out, B, T, G, N, Q, P, image_h, image_w, eps};
+    const int grid = grid_for(total, 16, 1 << 30);
+#define SBEV_LAUNCH_FUSED(LL) case LL: sampling4d_c64_kernel<LL><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm); break;
+    switch (L) { SBEV_LAUNCH_FUSED(1) SBEV_LAUNCH_FUSED(2) SBEV_LAUNCH_FUSED(3) SBEV_LAUNCH_FUSED(4) SBEV_LAUNCH_FUSED(5) }
+#undef SBEV_LAUNCH_FUSED
+    return check_launch("sbev_sampling4d_fwd");
+}

@@ -1,0 +1,299 @@
+"""Thin torch-tensor front-ends of the C ABI (device pointers + the current CUDA stream).
+
+PyTorch here is plumbing only: allocation, stream handle, dtype/contiguity checks.  Every function
+launches hand-written sm_100a kernels through libsparsebev_b200.so; nothing falls back to eager torch.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+GROUPS = 4          # reference: num_groups hard-coded, sparsebev_transformer.py:123
+OUT_POINTS = 128    # reference: out_points hard-coded, sparsebev_transformer.py:124
+DENSE_RELU = 1
+DENSE_RES_PRE_LN = 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('%s must be a tensor' % name)
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor' % name)          # reference: AT_ASSERTM(is_cuda), msmv_sampling.cpp:113-118
+    if not t.is_contiguous():
+        raise RuntimeError('%s tensor has to be contiguous' % name)    # reference: msmv_sampling.cpp:106-111
+    if t.dtype != dtype:
+        raise RuntimeError('%s must be %s (got %s)' % (name, dtype, t.dtype))
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _levels(mlvl_feats):
+    L = len(mlvl_feats)
+    hw = []
+    for i, f in enumerate(mlvl_feats):
+        _chk(f, 'value[%d]' % i)
+        if f.dim() != 5:
+            raise RuntimeError('value[%d] must be [B, N, H, W, C]' % i)
+        hw += [f.shape[2], f.shape[3]]
+    return L, _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw)
+
+
+def msmv_forward(mlvl_feats, sampling_locations, scale_weights):
+    """feats L x [B',N,H,W,C] channel-last, loc [B',Q,P,3], w [B',Q,P,L] -> [B',Q,C,P]."""
+    lib = _lib.load()
+    L, fptr, hw = _levels(mlvl_feats)
+    loc = _chk(sampling_locations, 'sampling_loc')
+    w = _chk(scale_weights, 'attn_weight')
+    Bp, N, _, _, C = mlvl_feats[0].shape
+    _, Q, P, _ = loc.shape
+    if w.shape[-1] != L or tuple(w.shape[:3]) != (Bp, Q, P) or loc.shape[0] != Bp or loc.shape[3] != 3:
+        raise RuntimeError('shape mismatch between value, sampling_loc and attn_weight')
+    out = torch.empty(Bp, Q, C, P, device=loc.device, dtype=torch.float32)
+    with torch.cuda.device(loc.device):
+        _lib.check(lib.sbev_msmv_fwd(fptr, hw, L, loc.data_ptr(), w.data_ptr(), Bp, N, C, Q, P, out.data_ptr(), _stream()),
+                   'sbev_msmv_fwd')
+    return out
+
+
+def msmv_backward(grad_output, mlvl_feats, sampling_locations, scale_weights):
+    lib = _lib.load()
+    L, fptr, hw = _levels(mlvl_feats)
+    loc = _chk(sampling_locations, 'sampling_loc')
+    w = _chk(scale_weights, 'attn_weight')
+    go = _chk(grad_output, 'grad_output')
+    Bp, N, _, _, C = mlvl_feats[0].shape
+    _, Q, P, _ = loc.shape
+    grad_feats = [torch.empty_like(f) for f in mlvl_feats]
+    grad_loc = torch.empty_like(loc)
+    grad_w = torch.empty_like(w)
+    with torch.cuda.device(loc.device):
+        _lib.check(lib.sbev_msmv_bwd(go.data_ptr(), fptr, hw, L, loc.data_ptr(), w.data_ptr(), Bp, N, C, Q, P,
+                                     _lib.ptr_array([g.data_ptr() for g in grad_feats]), grad_loc.data_ptr(),
+                                     grad_w.data_ptr(), _stream()), 'sbev_msmv_bwd')
+    return grad_feats, grad_loc, grad_w
+
+
+def msmv_indices(level_hw, sampling_locations, num_views):
+    lib = _lib.load()
+    loc = _chk(sampling_locations, 'sampling_loc')
+    Bp, Q, P, _ = loc.shape
+    L = len(level_hw)
+    hw = _lib.i32_array([int(v) for pair in level_hw for v in pair])
+    view = torch.empty(Bp, Q, P, dtype=torch.int32, device=loc.device)
+    y0 = torch.empty(Bp, Q, P, L, dtype=torch.int32, device=loc.device)
+    x0 = torch.empty_like(y0)
+    inside = torch.empty_like(y0)
+    with torch.cuda.device(loc.device):
+        _lib.check(lib.sbev_msmv_indices(hw, L, loc.data_ptr(), Bp, num_views, Q, P, view.data_ptr(), y0.data_ptr(),
+                                         x0.data_ptr(), inside.data_ptr(), _stream()), 'sbev_msmv_indices')
+    return view, y0, x0, inside
+
+
+def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w, image_h, image_w,
+                     num_frames, num_views=6, eps=1e-5, layout='grouped', return_loc=False, out=None):
+    """Fused motion-warp + projection + view pick + gather.
+
+    layout 'grouped': feats L x [B*T*G, N, H, W, C] (the reference's regrouped op layout);
+    layout 'nhwc'   : feats L x [B, T*N, H, W, G*C] (un-regrouped, channels-last FPN output).
+    points [B,Q,G*P,3], velocity [B,Q,2], time_diff [B,T], lidar2img [B,T*N,4,4], scale_w [B,Q,G,P,L]
+    -> [B,Q,G,T*P,C] (+ loc [B*T*G,Q,P,3] when return_loc)."""
+    lib = _lib.load()
+    L = len(mlvl_feats)
+    pts = _chk(points, 'points')
+    vel = _chk(velocity, 'velocity')
+    td = _chk(time_diff, 'time_diff')
+    l2i = _chk(lidar2img, 'lidar2img')
+    sw = _chk(scale_w, 'scale_w')
+    B, Q, GP, _ = pts.shape
+    T, N, G = num_frames, num_views, GROUPS
+    P = GP // G
+    hw, s_bt, s_g, s_v, s_px = [], [], [], [], []
+    C = 0
+    for i, f in enumerate(mlvl_feats):
+        _chk(f, 'value[%d]' % i)
+        if layout == 'grouped':
+            BTG, Nf, H, W, C = f.shape
+            if BTG != B * T * G or Nf != N:
+                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,C]' % (i, tuple(f.shape), B * T * G, N))
+            s_px.append(C); s_v.append(H * W * C); s_g.append(N * H * W * C); s_bt.append(G * N * H * W * C)
+        elif layout == 'nhwc':
+            Bf, TN, H, W, GC = f.shape
+            C = GC // G
+            if Bf != B or TN != T * N:
+                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,G*C]' % (i, tuple(f.shape), B, T * N))
+            s_px.append(GC); s_v.append(H * W * GC); s_g.append(C); s_bt.append(N * H * W * GC)
+        else:
+            raise ValueError('unknown layout %r' % layout)
+        hw += [H, W]
+    if tuple(sw.shape) != (B, Q, G, P, L):
+        raise RuntimeError('scale_w must be [B,Q,G,P,L]=%s, got %s' % ((B, Q, G, P, L), tuple(sw.shape)))
+    if tuple(td.shape) != (B, T) or tuple(l2i.shape) != (B, T * N, 4, 4) or tuple(vel.shape) != (B, Q, 2):
+        raise RuntimeError('time_diff / lidar2img / velocity shape mismatch')
+    if out is None:
+        out = torch.empty(B, Q, G, T * P, C, device=pts.device, dtype=torch.float32)
+    loc = torch.empty(B * T * G, Q, P, 3, device=pts.device, dtype=torch.float32) if return_loc else None
+    with torch.cuda.device(pts.device):
+        _lib.check(lib.sbev_sampling4d_fwd(
+            _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
+            _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
+            pts.data_ptr(), vel.data_ptr(), td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
+            B, T, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
+            out.data_ptr(), _p(loc), _stream()), 'sbev_sampling4d_fwd')
+    return (out, loc) if return_loc else out
+
+
+class DenseWeight:
+    """Device-side cache of one nn.Linear's weight in the layout sbev_dense_fwd wants:
+    Wt[K][ldw] = W^T zero-padded to a multiple of 4 columns.  Rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.wt = None
+        self.ldw = 0
+
+    def get(self, weight):
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+        if key != self.key:
+            N, K = weight.shape
+            ldw = (N + 3) // 4 * 4
+            wt = torch.zeros(K, ldw, device=weight.device, dtype=torch.float32)
+            wt[:, :N] = weight.detach().t()
+            self.wt, self.ldw, self.key = wt, ldw, key
+        return self.wt, self.ldw
+
+
+def dense(x, wt, ldw, n_out, bias=None, ln_w=None, ln_b=None, residual=None, relu=False, res_pre_ln=False, out=None, k=None):
+    """y[M,N] = epilogue(x[M,K] @ W^T) with W given pre-transposed (see DenseWeight)."""
+    lib = _lib.load()
+    if k is None:
+        x = _chk(x, 'x')
+        M, K = x.shape
+        ldx = K
+    else:                       # use the first k columns of a wider row-major matrix without copying
+        _chk(x, 'x')
+        M, ldx = x.shape
+        K = k
+    if out is None:
+        out = torch.empty(M, n_out, device=x.device, dtype=torch.float32)
+    flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_dense_fwd(x.data_ptr(), ldx, wt.data_ptr(), ldw, _p(bias), _p(ln_w), _p(ln_b), _p(residual),
+                                      M, K, n_out, flags, out.data_ptr(), _stream()), 'sbev_dense_fwd')
+    return out
+
+
+def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels):
+    """query_bbox [B,Q,10], offset [B,Q,GP*3], scale_logits [B,Q,GP*L] -> points [B,Q,GP,3], scale_w [B,Q,GP,L] (GP = G*P, group-major)."""
+    lib = _lib.load()
+    qb = _chk(query_bbox, 'query_bbox')
+    off = _chk(offset, 'offset')
+    lg = _chk(scale_logits, 'scale_logits')
+    B, Q, _ = qb.shape
+    GP = off.shape[-1] // 3
+    L = num_levels
+    pts = torch.empty(B, Q, GP, 3, device=qb.device, dtype=torch.float32)
+    sw = torch.empty(B, Q, GP, L, device=qb.device, dtype=torch.float32)
+    with torch.cuda.device(qb.device):
+        _lib.check(lib.sbev_sample_points_fwd(qb.data_ptr(), off.data_ptr(), lg.data_ptr(),
+                                              _lib.f32_array([float(v) for v in pc_range]), B * Q, GP, L,
+                                              pts.data_ptr(), sw.data_ptr(), _stream()), 'sbev_sample_points_fwd')
+    return pts, sw
+
+
+def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None):
+    """qkv [B,Q,3D], query_bbox [B,Q,10], tau [B,Q,H] -> attention output [B,Q,D] (before out_proj)."""
+    lib = _lib.load()
+    qkv = _chk(qkv, 'qkv')
+    qb = _chk(query_bbox, 'query_bbox')
+    tau = _chk(tau, 'tau')
+    B, Q, D3 = qkv.shape
+    D = D3 // 3
+    m = None
+    if dn_mask is not None:
+        m = _chk(dn_mask.to(torch.uint8).contiguous(), 'dn_mask', torch.uint8)
+    out = torch.empty(B, Q, D, device=qkv.device, dtype=torch.float32)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.sbev_sasa_fwd(qkv.data_ptr(), qb.data_ptr(), tau.data_ptr(), _p(m),
+                                     _lib.f32_array([float(v) for v in pc_range]), B, Q, num_heads, D,
+                                     out.data_ptr(), _stream()), 'sbev_sasa_fwd')
+    return out
+
+
+def split_bf16(x, need_lo=True):
+    """fp32 -> (hi, lo) bf16 with x ~= hi + lo."""
+    lib = _lib.load()
+    x = _chk(x, 'x')
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if need_lo else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_split_bf16(x.data_ptr(), ctypes.c_int64(x.numel()), hi.data_ptr(), _p(lo), _stream()),
+                   'sbev_split_bf16')
+    return hi, lo
+
+
+def gemm_bf16_tn(a_list, b_list, M, N, K, bias=None, split_k=1, out=None):
+    """C[M,N] = sum_s A_s[M,K] @ B_s[N,K]^T (+bias) on tcgen05; returns [split_k, M, N] fp32 partials
+    (a plain [M,N] when split_k == 1)."""
+    lib = _lib.load()
+    for t in list(a_list) + list(b_list):
+        _chk(t, 'gemm operand', torch.bfloat16)
+    dev = a_list[0].device
+    if out is None:
+        out = torch.empty((split_k, M, N) if split_k > 1 else (M, N), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sbev_gemm_bf16_tn(_lib.ptr_array([t.data_ptr() for t in a_list]),
+                                         _lib.ptr_array([t.data_ptr() for t in b_list]), len(a_list),
+                                         _p(bias), M, N, K, split_k, out.data_ptr(), _stream()), 'sbev_gemm_bf16_tn')
+    return out
+
+
+def mix(params, x, want_f32=False, want_split=True):
+    """params [BQ, G*(C*C+Pout*Pin)], x [BQ,G,Pin,C] -> (y_hi, y_lo) bf16 [BQ, G*Pout*C] (and/or fp32 y)."""
+    lib = _lib.load()
+    params = _chk(params, 'params')
+    x = _chk(x, 'x')
+    BQ, G, Pin, C = x.shape
+    n = G * OUT_POINTS * C
+    hi = torch.empty(BQ, n, device=x.device, dtype=torch.bfloat16) if want_split else None
+    lo = torch.empty_like(hi) if want_split else None
+    yf = torch.empty(BQ, n, device=x.device, dtype=torch.float32) if want_f32 else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_mix_fwd(params.data_ptr(), x.data_ptr(), BQ, G, Pin, OUT_POINTS, C,
+                                    _p(hi), _p(lo), _p(yf), _stream()), 'sbev_mix_fwd')
+    return hi, lo, yf
+
+
+def reduce_ln(partial, bias=None, residual=None, ln_w=None, ln_b=None):
+    """[S,M,N] (or [M,N]) partials -> LN(sum + bias + residual) [M,N]."""
+    lib = _lib.load()
+    partial = _chk(partial, 'partial')
+    if partial.dim() == 2:
+        partial = partial[None]
+    S, M, N = partial.shape
+    out = torch.empty(M, N, device=partial.device, dtype=torch.float32)
+    with torch.cuda.device(partial.device):
+        _lib.check(lib.sbev_reduce_ln_fwd(partial.data_ptr(), S, _p(bias), _p(residual), _p(ln_w), _p(ln_b), M, N,
+                                          out.data_ptr(), _stream()), 'sbev_reduce_ln_fwd')
+    return out
+
+
+def refine_bbox(proposal, delta, time_diff):
+    """proposal/delta [B,Q,code], time_diff [B,T] -> refined boxes [B,Q,code]."""
+    lib = _lib.load()
+    proposal = _chk(proposal, 'proposal')
+    delta = _chk(delta, 'delta')
+    td = _chk(time_diff, 'time_diff')
+    B, Q, code = proposal.shape
+    out = torch.empty_like(proposal)
+    with torch.cuda.device(proposal.device):
+        _lib.check(lib.sbev_refine_bbox_fwd(proposal.data_ptr(), delta.data_ptr(), td.data_ptr(), B, Q, td.shape[1], code,
+                                            out.data_ptr(), _stream()), 'sbev_refine_bbox_fwd')
+    return out

@@ -1,0 +1,134 @@
+"""Whole-layer / whole-decoder parity of the module mirror against the CPU oracle's restatement of the
+reference decoder (oracle/ref_torch.py), same weights (reference state-dict keys), same inputs."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_torch as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name, T, B, Q=None, seed=0, num_layers=2, memory_format='nchw'):
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import synthetic as S
+    cfg = S.layer_cfg(name, T, num_layers=num_layers)
+    if Q is not None:
+        cfg['num_query'] = Q
+    sd = S.make_state_dict(cfg, seed=seed)
+    model = sb.SparseBEVTransformer(256, num_frames=T, num_points=cfg['num_points'], num_layers=num_layers,
+                                    num_levels=cfg['num_levels'], num_classes=10, code_size=10, pc_range=cfg['pc_range'])
+    model.load_state_dict({'decoder.decoder_layer.' + k: v for k, v in sd.items()})
+    model = model.cuda().eval()
+    feats = S.make_feats(name, T, batch=B, seed=seed + 1, memory_format=memory_format)
+    metas = S.make_metas(name, T, batch=B)
+    n = int(np.ceil(np.sqrt(cfg['num_query']))) ** 2
+    qb = S.init_query_bbox(n, seed=seed + 2)[:cfg['num_query']][None].repeat(B, 1, 1).contiguous()
+    qb[..., 8:10] = 0.3 * torch.randn(B, cfg['num_query'], 2, generator=torch.Generator().manual_seed(seed + 3))
+    qf = torch.randn(B, cfg['num_query'], 256, generator=torch.Generator().manual_seed(seed + 4))
+    return cfg, sd, model, feats, metas, qb, qf
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('T,B', [(2, 2), (8, 1)])
+def test_decoder_layer_vs_oracle(T, B):
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', T, B)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    taps = {}
+    grouped = R.regroup_feats(feats, channel_last=True)
+    want_q, want_cls, want_box = R.decoder_layer(qb, qf, grouped, sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics, taps=taps)
+
+    layer = model.decoder.decoder_layer
+    metas_gpu = copy.deepcopy(metas)
+    model.decoder.prepare_metas(metas_gpu, B, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    got_q, got_cls, got_box = layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
+    assert torch.equal(metas_gpu[0]['time_diff'].cpu(), td)
+    assert _rel(got_q, want_q) < 2e-4, 'query_feat rel err %.3e' % _rel(got_q, want_q)
+    assert _rel(got_cls, want_cls) < 2e-4, 'cls rel err %.3e' % _rel(got_cls, want_cls)
+    assert _rel(got_box, want_box) < 2e-4, 'bbox rel err %.3e' % _rel(got_box, want_box)
+
+
+def test_decoder_stages_vs_oracle():
+    """Stage-wise: SASA block, sampling block and mixing block each against the oracle taps."""
+    T, B = 4, 1
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', T, B, seed=5)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    taps = {}
+    grouped = R.regroup_feats(feats, channel_last=True)
+    R.decoder_layer(qb, qf, grouped, sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics, taps=taps)
+    layer = model.decoder.decoder_layer
+    metas_gpu = copy.deepcopy(metas)
+    model.decoder.prepare_metas(metas_gpu, B, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    q_in = taps['after_sasa'].cuda()
+    sampled = layer.sampling(qb.cuda(), q_in, gfeats, metas_gpu)
+    assert _rel(sampled, taps['sampled']) < 1e-4, 'sampling block rel err %.3e' % _rel(sampled, taps['sampled'])
+    mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), q_in, layer.norm2)
+    assert _rel(mixed, taps['mixed']) < 1e-4, 'mixing block rel err %.3e' % _rel(mixed, taps['mixed'])
+    layer.mixing.precision = 'bf16'
+    fast = layer.mixing.forward_fused(taps['sampled'].cuda(), q_in, layer.norm2)
+    layer.mixing.precision = 'bf16x3'
+    assert _rel(fast, taps['mixed']) < 3e-2       # single-pass bf16 is a documented fast mode, not the parity mode
+
+
+def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import synthetic as S
+    T, B, L = 2, 1, 3
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', T, B, seed=9, num_layers=L)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    want_cls, want_box = R.decoder(qb, qf, feats, sd, cfg, td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
+    got_cls, got_box = model(qb.cuda(), qf.cuda(), [f.cuda() for f in feats], None, copy.deepcopy(metas))
+    assert got_cls.shape == (L, B, cfg['num_query'], 10) and got_box.shape == (L, B, cfg['num_query'], 10)
+    assert _rel(got_cls, want_cls) < 1e-3 and _rel(got_box, want_box) < 1e-3, (_rel(got_cls, want_cls), _rel(got_box, want_box))
+    # channels-last features take the zero-copy 'nhwc' path and must agree exactly with the regrouped path
+    nhwc = [f.cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f in feats]
+    ptrs = [f.data_ptr() for f in nhwc]
+    got2 = model(qb.cuda(), qf.cuda(), nhwc, None, copy.deepcopy(metas))
+    assert model.decoder.decoder_layer.sampling.feat_layout == 'nhwc' and [f.data_ptr() for f in nhwc] == ptrs
+    assert torch.equal(got2[0], got_cls) and torch.equal(got2[1], got_box)
+    # head (eval path)
+    head = sb.SparseBEVHead(num_classes=10, in_channels=256, num_query=cfg['num_query'], pc_range=cfg['pc_range'],
+                            transformer=dict(type='SparseBEVTransformer', embed_dims=256, num_frames=T, num_points=4,
+                                             num_layers=L, num_levels=cfg['num_levels'], pc_range=cfg['pc_range'])).cuda().eval()
+    head.transformer.load_state_dict(model.state_dict())
+    outs = head([f.cuda() for f in feats], copy.deepcopy(metas))
+    want = R.head_forward(head.init_query_bbox.weight.detach().cpu(), head.label_enc.weight.detach().cpu(), feats, sd, cfg,
+                          td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
+    assert _rel(outs['all_cls_scores'], want['all_cls_scores']) < 1e-3
+    assert _rel(outs['all_bbox_preds'], want['all_bbox_preds']) < 1e-3
+
+
+def test_r50_t8_layer_runs_and_is_deterministic():
+    """Full-size r50-T8 (the bench workload): finite, deterministic, and the sampled block equals the
+    op-boundary path (sbev_msmv_fwd fed with the fused kernel's own loc) bit for bit."""
+    from sparsebev_b200 import ops
+    cfg, sd, model, feats, metas, qb, qf = _setup('r50_704x256', 8, 1, seed=1, num_layers=1)
+    layer = model.decoder.decoder_layer
+    model.decoder.prepare_metas(metas, 1, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    a = layer(qb.cuda(), qf.cuda(), gfeats, None, metas)
+    b = layer(qb.cuda(), qf.cuda(), gfeats, None, metas)
+    for x, y in zip(a, b):
+        assert torch.isfinite(x).all() and torch.equal(x, y)
+    B, Q, G, P, T, Lv = 1, 900, 4, 4, 8, 4
+    x = qf.cuda().reshape(Q, 256)
+    off, lg = layer.sampling._off(x), layer.sampling._sw(x)
+    pts, sw = ops.sample_points(qb.cuda(), off.reshape(1, Q, 48), lg.reshape(1, Q, 64), cfg['pc_range'], Lv)
+    out, loc = ops.sampling4d_fused(gfeats, pts, qb[..., 8:10].contiguous().cuda(), metas[0]['time_diff'], metas[0]['lidar2img'],
+                                    sw.reshape(1, Q, G, P, Lv), 256, 704, num_frames=T, return_loc=True)
+    i = torch.arange(T * G, device='cuda')
+    w_op = sw.reshape(1, Q, G, P, Lv)[0][:, (i // T)].permute(1, 0, 2, 3).contiguous()          # [T*G,Q,P,L], row (t*G+g) -> g'
+    ref = ops.msmv_forward(gfeats, loc, w_op)                                                   # [TG,Q,C,P]
+    ref = ref.reshape(1, T, G, Q, 64, P).permute(0, 3, 2, 1, 5, 4).reshape(1, Q, G, T * P, 64)
+    assert torch.equal(out, ref)

@@ -1,0 +1,391 @@
+"""GPU parity tests: every CUDA kernel (called through the C ABI) against the CPU oracle on the same
+seeded inputs, against the committed golden vectors of the real reference, and -- when the compiled
+reference op travelled with the snapshot (oracle/_ref) -- against the reference CUDA kernel itself.
+
+Tolerances (stated per north_star): sample INDICES bit-exact; sampled / mixed FEATURES within
+1e-4 relative with a 1e-5 absolute floor (gotcha 3).
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, ref_torch as R
+from oracle.synth import hashrand
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def _ops():
+    from sparsebev_b200 import ops
+    return ops
+
+
+def _close(a, b, rtol=RTOL, atol=ATOL, what=''):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), '%s: %d / %d elements off, max abs err %.3e (max ref %.3e)' % (
+        what, int(bad.sum()), bad.numel(), float(err.max()), float(b.abs().max()))
+
+
+def _rand_case(Bp, N, hw, Q, P, C=64, seed=0, spread=0.15):
+    feats = [hashrand((Bp, N, h, w, C), seed * 10 + i, -1, 1) for i, (h, w) in enumerate(hw)]
+    loc = hashrand((Bp, Q, P, 3), seed * 10 + 7, -spread, 1 + spread)
+    loc[..., 2] = torch.from_numpy(np.random.RandomState(seed).randint(0, N, size=(Bp, Q, P))).float() / max(N - 1, 1)
+    w = torch.softmax(hashrand((Bp, Q, P, len(hw)), seed * 10 + 8, -2, 2), dim=-1)
+    return feats, loc, w
+
+
+def _ref_cuda():
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', '_msmv_sampling_cuda.so')
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location('_msmv_sampling_cuda', so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------ op
+@pytest.mark.parametrize('name', ['op_small.npz', 'op_cfg1.npz'])
+def test_msmv_fwd_matches_golden_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    Bp, C, N, Q, P = [int(v) for v in g['shape']]
+    feats = [hashrand((Bp, C, N, int(h), int(w)), int(s), -1, 1).permute(0, 2, 3, 4, 1).contiguous().to(dev())
+             for (h, w), s in zip(g['hw'], g['feat_seeds'])]
+    out = _ops().msmv_forward(feats, torch.from_numpy(g['loc']).to(dev()), torch.from_numpy(g['w']).to(dev()))
+    _close(out, torch.from_numpy(g['out']), what='vs reference msmv_sampling_pytorch (%s)' % name)
+
+
+@pytest.mark.parametrize('L,P,Q,C', [(4, 4, 37, 64), (5, 4, 20, 64), (1, 1, 9, 64), (2, 7, 11, 64), (3, 32, 5, 64),
+                                     (4, 4, 13, 16), (2, 3, 8, 8)])
+def test_msmv_fwd_vs_c_oracle(L, P, Q, C):
+    hw = [(12, 20), (6, 10), (3, 5), (2, 3), (1, 2)][:L]
+    feats, loc, w = _rand_case(3, 6, hw, Q, P, C=C, seed=L * 100 + P)
+    want = c_oracle.fwd(feats, loc, w)
+    got = _ops().msmv_forward([f.to(dev()) for f in feats], loc.to(dev()), w.to(dev()))
+    _close(got, want, what='fwd L=%d P=%d C=%d' % (L, P, C))
+
+
+def test_msmv_indices_bit_exact():
+    hw = [(64, 176), (32, 88), (16, 44), (8, 22)]
+    loc = hashrand((4, 900, 4, 3), 5, -0.2, 1.2)
+    loc[..., 2] = torch.from_numpy(np.random.RandomState(1).randint(0, 6, size=(4, 900, 4))).float() / 5
+    loc[0, :8, 0, 0] = torch.tensor([0.0, 1.0, 0.5, 1 / 175, 174.5 / 175, -1 / 175, 1 + 1 / 175, 0.999999])
+    want = c_oracle.indices(hw, loc, 6)
+    got = _ops().msmv_indices(hw, loc.to(dev()), 6)
+    for name, a, b in zip(('view', 'y0', 'x0', 'inside'), got, want):
+        assert torch.equal(a.cpu(), b), name + ' differs from the reference index arithmetic'
+
+
+def test_msmv_fwd_r50_t1_full_size_properties():
+    """BASELINE config 2 shape (r50 704x256, 4 levels, 6 cams, T=1 -> B'=4, 900 q): checked through
+    size-independent properties: linearity in the features and in the scale weights, zero outside."""
+    hw = [(64, 176), (32, 88), (16, 44), (8, 22)]
+    torch.manual_seed(0)
+    feats = [torch.randn(4, 6, h, w, 64, device=dev()) for h, w in hw]
+    loc = torch.rand(4, 900, 4, 3, device=dev())
+    loc[..., 2] = torch.randint(0, 6, (4, 900, 4), device=dev()).float() / 5
+    w = torch.softmax(torch.randn(4, 900, 4, 4, device=dev()), -1)
+    ops = _ops()
+    a = ops.msmv_forward(feats, loc, w)
+    b = ops.msmv_forward([2.5 * f for f in feats], loc, w)
+    _close(b, 2.5 * a, what='linearity in features')
+    c = ops.msmv_forward(feats, loc, 0.5 * w)
+    _close(c, 0.5 * a, what='linearity in weights')
+    far = loc.clone()
+    far[..., 0] = 3.0
+    assert float(ops.msmv_forward(feats, far, w).abs().max()) == 0.0
+    # sub-sample against the oracle (first batch slice, first 40 queries)
+    want = c_oracle.fwd([f[:1].cpu() for f in feats], loc[:1, :40].cpu(), w[:1, :40].cpu())
+    _close(a[:1, :40], want, what='r50-T1 subsample vs oracle')
+
+
+def test_msmv_empty_and_errors():
+    ops = _ops()
+    feats = [torch.zeros(2, 6, 4, 4, 64, device=dev())]
+    out = ops.msmv_forward(feats, torch.zeros(2, 0, 4, 3, device=dev()), torch.zeros(2, 0, 4, 1, device=dev()))
+    assert out.shape == (2, 0, 64, 4)
+    with pytest.raises(RuntimeError, match='num_point exceed limits'):      # reference: msmv_sampling.cpp:125
+        ops.msmv_forward(feats, torch.zeros(2, 1, 33, 3, device=dev()), torch.zeros(2, 1, 33, 1, device=dev()))
+    with pytest.raises(RuntimeError, match='contiguous'):                    # reference: msmv_sampling.cpp:106-111
+        ops.msmv_forward([feats[0].transpose(2, 3)], torch.zeros(2, 1, 4, 3, device=dev()), torch.zeros(2, 1, 4, 1, device=dev()))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.msmv_forward(feats, torch.zeros(2, 1, 4, 3), torch.zeros(2, 1, 4, 1, device=dev()))
+
+
+@pytest.mark.parametrize('L,P,C', [(4, 4, 64), (2, 3, 64), (5, 4, 64), (2, 2, 8)])
+def test_msmv_bwd_vs_c_oracle(L, P, C):
+    hw = [(7, 9), (4, 6), (3, 3), (2, 2), (1, 2)][:L]
+    feats, loc, w = _rand_case(2, 6, hw, 10, P, C=C, seed=40 + L)
+    go = hashrand((2, 10, C, P), 99, -1, 1)
+    gf, gl, gw = c_oracle.bwd(go, feats, loc, w)
+    f2, l2, w2 = _ops().msmv_backward(go.to(dev()), [f.to(dev()) for f in feats], loc.to(dev()), w.to(dev()))
+    for a, b in zip(f2, gf):
+        _close(a, b, atol=1e-4, what='grad feats')
+    _close(l2, gl, atol=1e-3, what='grad loc')
+    _close(w2, gw, atol=1e-4, what='grad w')
+    assert float(l2[..., 2].abs().max()) == 0.0
+
+
+def test_autograd_function_surface():
+    from sparsebev_b200 import wrapper
+    hw = [(6, 8), (3, 4), (2, 2), (1, 2)]
+    feats, loc, w = _rand_case(2, 6, hw, 6, 4, seed=3)
+    feats = [f.to(dev()).requires_grad_() for f in feats]
+    loc, w = loc.to(dev()).requires_grad_(), w.to(dev()).requires_grad_()
+    out = wrapper.msmv_sampling(feats, loc, w)
+    assert out.shape == (2, 6, 64, 4)
+    out.sum().backward()
+    assert all(f.grad is not None for f in feats) and loc.grad is not None and w.grad is not None
+    out2 = wrapper.MSMVSamplingC2345.apply(*[f.detach() for f in feats], loc.detach(), w.detach())
+    assert torch.equal(out2, out.detach())
+    with pytest.raises(RuntimeError, match='CUDA'):
+        wrapper.msmv_sampling([f.detach().cpu() for f in feats], loc.detach().cpu(), w.detach().cpu())
+
+
+def test_against_reference_cuda_kernel():
+    """O3 of SURVEY 8(c): our op vs the UNMODIFIED reference kernel compiled for sm_100a (oracle/_ref)."""
+    ref = _ref_cuda()
+    if ref is None:
+        pytest.skip('oracle/_ref/_msmv_sampling_cuda.so not present')
+    ops = _ops()
+    for L in (4, 5):
+        hw = [(64, 176), (32, 88), (16, 44), (8, 22), (4, 11)][:L]
+        torch.manual_seed(L)
+        feats = [torch.randn(4, 6, h, w, 64, device=dev()) for h, w in hw]
+        loc = torch.rand(4, 300, 4, 3, device=dev()) * 1.2 - 0.1
+        loc[..., 2] = torch.randint(0, 6, (4, 300, 4), device=dev()).float() / 5
+        w = torch.softmax(torch.randn(4, 300, 4, L, device=dev()), -1)
+        fwd = getattr(ref, '_ms_deform_attn_cuda_c2345_forward' if L == 4 else '_ms_deform_attn_cuda_c23456_forward')
+        bwd = getattr(ref, '_ms_deform_attn_cuda_c2345_backward' if L == 4 else '_ms_deform_attn_cuda_c23456_backward')
+        want = fwd(*feats, loc, w)
+        got = ops.msmv_forward(feats, loc, w)
+        _close(got, want, rtol=1e-5, atol=1e-6, what='fwd vs reference CUDA kernel L=%d' % L)
+        go = torch.randn_like(want)
+        rg = bwd(go, *feats, loc, w)
+        gf, gl, gw = ops.msmv_backward(go, feats, loc, w)
+        for a, b in zip(gf, rg[:L]):
+            _close(a, b, atol=1e-4, what='grad feats vs reference CUDA')
+        _close(gl, rg[L], atol=2e-3, what='grad loc vs reference CUDA')
+        _close(gw, rg[L + 1], atol=1e-4, what='grad w vs reference CUDA')
+
+
+# ---------------------------------------------------------------------------- fused sampling_4d
+def _sampling_inputs(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'sampling4d.npz'))
+    B, Q, T, G, P, L, C, ih, iw = [int(v) for v in g['dims']]
+    feats_cf = [hashrand((B * T * G, C, 6, int(h), int(w_)), int(s), -1, 1) for (h, w_), s in zip(g['hw'], g['feat_seeds'])]
+    return g, (B, Q, T, G, P, L, C, ih, iw), feats_cf
+
+
+def test_fused_sampling_matches_golden_reference(golden_dir):
+    g, (B, Q, T, G, P, L, C, ih, iw), feats_cf = _sampling_inputs(golden_dir)
+    ops = _ops()
+    feats = [f.permute(0, 2, 3, 4, 1).contiguous().to(dev()) for f in feats_cf]            # [BTG,N,H,W,C]
+    pts = torch.from_numpy(g['points']).to(dev())                                          # [B,Q,GP,3] un-warped
+    vel = torch.from_numpy(g['query_bbox'][..., 8:10]).contiguous().to(dev())
+    td = torch.from_numpy(g['time_diff']).to(dev())
+    l2i = torch.from_numpy(g['lidar2img']).to(dev())
+    sw = torch.from_numpy(g['scale_weights'][:, :, :, 0]).contiguous().to(dev())           # [B,Q,G,P,L]
+    out, loc = ops.sampling4d_fused(feats, pts, vel, td, l2i, sw, ih, iw, num_frames=T, return_loc=True)
+    # the reference's own loc (view choice identical, uv to fp32 round-off of its 4x4 matmul)
+    assert torch.equal(loc[..., 2].cpu(), torch.from_numpy(g['loc'][..., 2])), 'view selection differs from reference'
+    _close(loc[..., :2], torch.from_numpy(g['loc'][..., :2]), rtol=1e-5, atol=1e-5, what='loc vs reference sampling_4d')
+    _close(out, torch.from_numpy(g['out']), rtol=1e-4, atol=1e-4, what='fused sampling vs reference sampling_4d')
+    # drop-in sampling_4d signature (warped points per frame)
+    from sparsebev_b200 import sampling
+    out2 = sampling.sampling_4d(torch.from_numpy(g['points6']).to(dev()), feats, torch.from_numpy(g['scale_weights']).to(dev()),
+                                l2i, ih, iw)
+    _close(out2, torch.from_numpy(g['out']), rtol=1e-4, atol=1e-4, what='sampling_4d drop-in vs reference')
+    pts2 = sampling.make_sample_points(torch.from_numpy(g['query_bbox']).to(dev()), torch.from_numpy(g['offset']).to(dev()),
+                                       g['pc_range'].tolist())
+    _close(pts2, torch.from_numpy(g['points']), rtol=1e-5, atol=1e-5, what='make_sample_points vs reference')
+
+
+@pytest.mark.parametrize('T', [1, 2, 8])
+def test_fused_sampling_loc_bit_exact_vs_oracle_and_layouts(T):
+    """Given identical points, the fused kernel's (u, v, view) must equal the oracle's fixed-order fp32
+    projection BIT FOR BIT, and the two feature layouts must give identical samples."""
+    from sparsebev_b200 import synthetic as S
+    ops = _ops()
+    cfg = S.layer_cfg('tiny', T)
+    B, Q, G, P, L = 2, 36, 4, 4, cfg['num_levels']
+    l2i, stamps = S.camera_rig(T, cfg['image_h'], cfg['image_w'])
+    l2i = l2i[None].repeat(B, 1, 1, 1).contiguous()
+    td = R.time_diff_from_timestamps([stamps] * B)
+    qb = S.init_query_bbox(Q, seed=1)[None].repeat(B, 1, 1)
+    qb[..., 8:10] = hashrand((B, Q, 2), 3, -1, 1)
+    pts = R.make_sample_points(qb, hashrand((B, Q, G * P, 3), 4, -0.5, 0.5), cfg['pc_range'])
+    sw = torch.softmax(hashrand((B, Q, G, P, L), 5, -2, 2), -1)
+    feats_nchw = S.make_feats('tiny', T, batch=B, seed=2)
+    grouped = R.regroup_feats(feats_nchw, channel_last=True)
+    pts6 = pts.reshape(B, Q, 1, G, P, 3).expand(B, Q, T, G, P, 3)
+    shift = qb[..., 8:10][:, :, None, :] * td[:, None, :, None]
+    pts6 = torch.cat([pts6[..., 0:2] - shift[:, :, :, None, None, :], pts6[..., 2:3]], dim=-1)
+    sw6 = sw[:, :, :, None].expand(B, Q, G, T, P, L)
+    want_loc, _ = R.sampling_4d(pts6, None, sw6, l2i, cfg['image_h'], cfg['image_w'], return_loc=True)
+    want = R.sampling_4d(pts6, grouped, sw6, l2i, cfg['image_h'], cfg['image_w'], op=R.msmv_sampling_kernel_semantics)
+    args = (pts.to(dev()), qb[..., 8:10].contiguous().to(dev()), td.to(dev()), l2i.to(dev()), sw.to(dev()),
+            cfg['image_h'], cfg['image_w'])
+    out_g, loc = ops.sampling4d_fused([f.to(dev()) for f in grouped], *args, num_frames=T, return_loc=True)
+    assert torch.equal(loc.cpu(), want_loc), 'projected sample locations are not bit-exact'
+    _close(out_g, want, what='fused (grouped layout) vs oracle')
+    nhwc = [f.permute(0, 1, 3, 4, 2).contiguous().to(dev()) for f in feats_nchw]
+    out_n = ops.sampling4d_fused(nhwc, *args, num_frames=T, layout='nhwc')
+    assert torch.equal(out_n, out_g), 'nhwc and grouped layouts disagree'
+
+
+# ------------------------------------------------------------------------------- small dense ops
+@pytest.mark.parametrize('M,K,N,ln,relu,res', [(900, 256, 256, True, True, 'post'), (37, 3, 256, True, True, None),
+                                              (900, 256, 768, False, False, None), (123, 512, 256, True, False, 'pre'),
+                                              (900, 256, 10, False, False, None), (64, 256, 48, False, True, None),
+                                              (5, 256, 512, False, True, None)])
+def test_dense_vs_torch(M, K, N, ln, relu, res):
+    ops = _ops()
+    torch.manual_seed(M + K + N)
+    x, W, b = torch.randn(M, K), torch.randn(N, K) * 0.1, torch.randn(N) * 0.1
+    lw, lb, r = 1 + 0.1 * torch.randn(N), 0.1 * torch.randn(N), torch.randn(M, N)
+    y = torch.nn.functional.linear(x, W, b)
+    if res == 'pre':
+        y = y + r
+    if ln:
+        y = torch.nn.functional.layer_norm(y, (N,), lw, lb)
+    if relu:
+        y = torch.relu(y)
+    if res == 'post':
+        y = y + r
+    cache = ops.DenseWeight()
+    wt, ldw = cache.get(W.to(dev()))
+    got = ops.dense(x.to(dev()), wt, ldw, N, bias=b.to(dev()), ln_w=lw.to(dev()) if ln else None, ln_b=lb.to(dev()) if ln else None,
+                    residual=r.to(dev()) if res else None, relu=relu, res_pre_ln=res == 'pre')
+    _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
+
+
+def test_sample_points_and_refine_vs_oracle():
+    ops = _ops()
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    qb = R.init_query_bbox(900, seed=2)[None].repeat(2, 1, 1)
+    qb[..., 8:10] = hashrand((2, 900, 2), 1, -1, 1)
+    off = hashrand((2, 900, 16, 3), 2, -0.5, 0.5)
+    logits = hashrand((2, 900, 16, 4), 3, -3, 3)
+    pts, sw = ops.sample_points(qb.to(dev()), off.reshape(2, 900, 48).to(dev()), logits.reshape(2, 900, 64).to(dev()), pc, 4)
+    _close(pts, R.make_sample_points(qb, off, pc), rtol=1e-5, atol=2e-5, what='sample points')
+    _close(sw, torch.softmax(logits, -1), rtol=1e-5, atol=1e-6, what='scale weights')
+    delta = hashrand((2, 900, 10), 4, -2, 2)
+    td = torch.tensor([[0.0, 0.5, 1.0], [0.0, 1e-6, 1.0]])
+    want = R.refine_bbox(qb, delta)
+    t = td.clone()
+    t[t < 1e-5] = 1.0
+    want = torch.cat([want[..., :8], want[..., 8:] / t[:, 1:2, None]], -1)
+    _close(ops.refine_bbox(qb.to(dev()), delta.to(dev()), td.to(dev())), want, rtol=1e-5, atol=1e-6, what='refine_bbox')
+
+
+@pytest.mark.parametrize('Q', [900, 70, 64])
+def test_sasa_vs_oracle(Q):
+    ops = _ops()
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    B, D, H = 2, 256, 8
+    n = int(np.ceil(np.sqrt(Q))) ** 2
+    qb = R.init_query_bbox(n, seed=3)[:Q][None].repeat(B, 1, 1)
+    qb[1, :, :2] = hashrand((Q, 2), 8, 0, 1)
+    qkv = hashrand((B, Q, 3 * D), 5, -1.5, 1.5)
+    tau = hashrand((B, Q, H), 6, 0, 2)
+    q, k, v = [t.reshape(B, Q, H, 32).transpose(1, 2) for t in qkv.chunk(3, -1)]
+    bias = -R.pairwise_centre_dist(qb, pc)[:, None] * tau.permute(0, 2, 1)[..., None]
+    want = torch.softmax(q * (1 / np.sqrt(32)) @ k.transpose(-1, -2) + bias, -1) @ v
+    want = want.transpose(1, 2).reshape(B, Q, D)
+    got = ops.sasa(qkv.to(dev()), qb.to(dev()), tau.to(dev()), pc, H)
+    _close(got, want, rtol=1e-4, atol=1e-5, what='sasa core')
+    mask = torch.zeros(Q, Q, dtype=torch.bool)
+    mask[: Q // 2, Q // 2:] = True
+    want_m = torch.softmax((q * (1 / np.sqrt(32)) @ k.transpose(-1, -2) + bias).masked_fill(mask, float('-inf')), -1) @ v
+    got_m = ops.sasa(qkv.to(dev()), qb.to(dev()), tau.to(dev()), pc, H, dn_mask=mask.to(dev()))
+    _close(got_m, want_m.transpose(1, 2).reshape(B, Q, D), rtol=1e-4, atol=1e-5, what='sasa core with dn mask')
+
+
+# ------------------------------------------------------------------------- tcgen05 GEMM + mixing
+@pytest.mark.parametrize('M,N,K,split_k', [(128, 128, 64, 1), (900, 256, 256, 1), (900, 1024, 256, 1), (300, 256, 2048, 8),
+                                           (1, 128, 128, 2)])
+def test_gemm_bf16_single_segment(M, N, K, split_k):
+    ops = _ops()
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev()).bfloat16()
+    b = torch.randn(N, K, device=dev()).bfloat16()
+    bias = torch.randn(N, device=dev())
+    got = ops.gemm_bf16_tn([a], [b], M, N, K, bias=bias, split_k=split_k)
+    if split_k > 1:
+        got = got.sum(0)
+    want = a.double() @ b.double().t() + bias.double()
+    _close(got, want.float(), rtol=1e-5, atol=1e-4 * np.sqrt(K / 64), what='bf16 gemm (exact products, fp32 accumulate)')
+
+
+def test_gemm_bf16x3_is_fp32_grade():
+    ops = _ops()
+    torch.manual_seed(0)
+    M, N, K = 900, 512, 256
+    a, b = torch.randn(M, K, device=dev()), torch.randn(N, K, device=dev()) * 0.05
+    ah, al = ops.split_bf16(a)
+    bh, bl = ops.split_bf16(b)
+    _close(ah.float() + al.float(), a, rtol=2 ** -15, atol=0, what='bf16 split residual')
+    got = ops.gemm_bf16_tn([ah, ah, al], [bh, bl, bh], M, N, K)
+    want = (a.double() @ b.double().t()).float()
+    err = (got - want).abs().max() / want.abs().max()
+    assert float(err) < 2e-5, 'bf16x3 relative error %.3e' % float(err)
+    single = ops.gemm_bf16_tn([ah], [bh], M, N, K)
+    assert float((single - want).abs().max() / want.abs().max()) > float(err) * 10     # the split really matters
+
+
+def test_mix_kernel_and_full_mixing_vs_reference_golden(golden_dir):
+    """AdaptiveMixing end to end (param-gen GEMM -> mix -> out_proj GEMM -> +query) against the golden
+    output of the REAL reference class, and the middle stage alone against the oracle."""
+    import sparsebev_b200 as sb
+    g = np.load(os.path.join(golden_dir, 'mixing.npz'))
+    Bm, Qm, G, Pin, C = [int(v) for v in g['dims']]
+    s = [int(v) for v in g['seeds']]
+    mod = sb.AdaptiveMixing(in_dim=256, in_points=Pin, n_groups=4, out_points=128)
+    mod.load_state_dict({
+        'parameter_generator.weight': hashrand((G * (C * C + Pin * 128), 256), s[0], -0.04, 0.04),
+        'parameter_generator.bias': hashrand((G * (C * C + Pin * 128),), s[1], -0.1, 0.1),
+        'out_proj.weight': hashrand((256, G * 128 * C), s[2], -0.02, 0.02),
+        'out_proj.bias': hashrand((256,), s[3], -0.05, 0.05)})
+    mod = mod.to(dev())
+    x = hashrand((Bm, Qm, G, Pin, C), s[4], -2, 2).to(dev())
+    q = hashrand((Bm, Qm, 256), s[5], -1.5, 1.5).to(dev())
+    out = mod(x, q)
+    _close(out, torch.from_numpy(g['out']), rtol=1e-4, atol=1e-4, what='AdaptiveMixing (bf16x3) vs reference')
+
+
+@pytest.mark.parametrize('Pin', [32, 8, 60, 120])
+def test_mix_stage_vs_oracle(Pin):
+    ops = _ops()
+    BQ, G, C = 5, 4, 64
+    params = hashrand((BQ, G * (C * C + 128 * Pin)), 11 + Pin, -0.3, 0.3)
+    x = hashrand((BQ, G, Pin, C), 12 + Pin, -2, 2)
+    p3 = params.reshape(BQ, G, -1)
+    m = p3[..., :C * C].reshape(BQ, G, C, C)
+    sm = p3[..., C * C:].reshape(BQ, G, 128, Pin)
+    h = torch.relu(torch.nn.functional.layer_norm(x @ m, (Pin, C)))
+    want = torch.relu(torch.nn.functional.layer_norm(sm @ h, (128, C))).reshape(BQ, -1)
+    hi, lo, yf = ops.mix(params.to(dev()), x.to(dev()), want_f32=True)
+    _close(yf, want, rtol=1e-4, atol=1e-5, what='mix stage fp32')
+    _close(hi.float() + lo.float(), want, rtol=1e-4, atol=1e-5, what='mix stage bf16 hi+lo')
+
+
+def test_reduce_ln_vs_torch():
+    ops = _ops()
+    torch.manual_seed(0)
+    part, bias, res = torch.randn(16, 900, 256), torch.randn(256), torch.randn(900, 256)
+    lw, lb = torch.randn(256), torch.randn(256)
+    want = torch.nn.functional.layer_norm(part.sum(0) + bias + res, (256,), lw, lb)
+    got = ops.reduce_ln(part.to(dev()), bias.to(dev()), res.to(dev()), lw.to(dev()), lb.to(dev()))
+    _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
