@@ -293,8 +293,10 @@ def main():
 
     # ---- roofline of the dominant kernel (fused gather), timed alone with CUDA events on the launch stream
     x = qf.reshape(Q, 256)
-    off, lg = layer.sampling._off(x), layer.sampling._sw(x)
-    pts, sw = ops.sample_points(qb, off.reshape(1, Q, -1), lg.reshape(1, Q, -1), cfg['pc_range'], cfg['num_levels'])
+    heads = layer.sampling._heads(x)
+    GP = 4 * cfg['num_points']
+    pts, sw = ops.sample_points(qb, heads, heads[:, GP * 3:], cfg['pc_range'], cfg['num_levels'], num_points_total=GP,
+                                ld_off=heads.shape[1], ld_log=heads.shape[1])
     vel = qb[..., 8:10].contiguous()
     sw5 = sw.reshape(1, Q, 4, cfg['num_points'], cfg['num_levels'])
     out_buf = torch.empty(1, Q, 4, T * cfg['num_points'], 64, device=dev)
@@ -380,23 +382,30 @@ def stage_breakdown(layer, qb, qf, feats, metas, cfg, iters=20):
         return r
 
     x0 = qf.reshape(M, D).contiguous()
-    h = timeit('pos_enc', lambda: layer._pe1(layer._pe0(qb.reshape(M, -1), relu=True, k=3), relu=True, residual=x0))
+    def pos_enc():
+        q1 = torch.empty(M, D, device=qf.device)
+        ops.dense_chain(qb.reshape(M, -1), qb.shape[-1], M, [layer._pe0.layer(relu=True), layer._pe1.layer(relu=True, residual=x0, y=q1)])
+        return q1
+    h = timeit('pos_enc_chain', pos_enc)
     q1 = timeit('sasa_block', lambda: layer.self_attn.forward_fused(qb, h.reshape(B, Q, D), None, layer.norm1))
     sampled = timeit('sampling_block', lambda: layer.sampling(qb, q1, feats, metas))
     q2 = timeit('mixing_block', lambda: layer.mixing.forward_fused(sampled, q1, layer.norm2))
     x2 = q2.reshape(M, D)
-    q3 = timeit('ffn', lambda: layer._ffn1(layer._ffn0(x2, relu=True), residual=x2, res_pre_ln=True))
 
-    def heads():
-        c = q3
-        for l in layer._cls[:-1]:
-            c = l(c, relu=True)
-        c = layer._cls[-1](c)
-        r = q3
-        for l in layer._reg[:-1]:
-            r = l(r, relu=True)
-        return c, ops.refine_bbox(qb, layer._reg[-1](r).reshape(B, Q, -1), metas[0]['time_diff'])
-    timeit('heads', heads)
+    def ffn_cls():
+        q4, cls = torch.empty(M, D, device=qf.device), torch.empty(M, layer.num_classes, device=qf.device)
+        ch = [layer._ffn0.layer(relu=True), layer._ffn1.layer(residual=x2, res_pre_ln=True, y=q4)]
+        ch += [l.layer(relu=True) for l in layer._cls[:-1]] + [layer._cls[-1].layer(y=cls)]
+        ops.dense_chain(x2, D, M, ch)
+        return q4
+    q3 = timeit('ffn_cls_chain', ffn_cls)
+
+    def reg():
+        box = torch.empty(M, 10, device=qf.device)
+        td = metas[0]['time_diff']
+        ops.dense_chain(q3, D, M, [l.layer(relu=True) for l in layer._reg[:-1]] + [layer._reg[-1].layer(refine=True, y=box)],
+                        refine_proposal=qb, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
+    timeit('reg_refine_chain', reg)
     # finer split of the mixing block
     mix = layer.mixing
     qh, ql = ops.split_bf16(q1.reshape(M, D))
@@ -410,11 +419,11 @@ def stage_breakdown(layer, qb, qf, feats, metas, cfg, iters=20):
     part = timeit('mix.out_gemm', lambda: ops.gemm_bf16_tn(sa, sb_, M, D, mix.out_proj.in_features, split_k=mix.split_k))
     timeit('mix.reduce_ln', lambda: ops.reduce_ln(part, mix.out_proj.bias, q1.reshape(M, D), layer.norm2.weight, layer.norm2.bias))
     # SASA split
-    attn = layer.self_attn.attention.attn
-    wt, ldw = layer.self_attn._in.get(attn.in_proj_weight)
-    qkv = timeit('sasa.in_proj', lambda: ops.dense(h, wt, ldw, 3 * D, bias=attn.in_proj_bias))
-    tau = layer.self_attn._tau(h)
-    timeit('sasa.core', lambda: ops.sasa(qkv.reshape(B, Q, 3 * D), qb, tau.reshape(B, Q, 8), cfg['pc_range'], 8))
+    qkvt = torch.empty(M, 3 * D + 8, device=qf.device)
+    timeit('sasa.in_proj_tau', lambda: ops.dense_chain(h, D, M, [layer.self_attn.in_layer(qkvt)]))
+    timeit('sasa.core', lambda: ops.sasa(qkvt, qb, qkvt[:, 3 * D:], cfg['pc_range'], 8, ld_qkv=3 * D + 8, ld_tau=3 * D + 8, embed_dims=D))
+    heads = layer.sampling._heads(q1.reshape(M, D))
+    timeit('sampling.gather', lambda: layer.sampling.sample(qb, heads, feats, metas))
     return res
 
 

@@ -114,17 +114,43 @@ int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
  */
 #define SBEV_DENSE_RELU        1
 #define SBEV_DENSE_RES_PRE_LN  2
+#define SBEV_DENSE_REFINE      4   /* chain only: box refinement epilogue, see sbev_dense_chain_fwd */
 int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const float* bias,
                    const float* ln_w, const float* ln_b, const float* residual,
                    int M, int K, int N, int flags, float* y, void* stream);
 
+/* A CHAIN of 1..6 such layers in ONE kernel: a CTA owns 8 full rows through all layers (intermediate
+ * activations stay in shared memory), weights of all layers stream through a cp.async.bulk + mbarrier ring.
+ * Layer i consumes layer i-1's output (K_i == N_{i-1}); every layer may additionally store its result
+ * (y != NULL, row stride ldy); the last layer must.  With SBEV_DENSE_REFINE on the last layer the epilogue is
+ * refine_bbox + velocity rescale (models/sparsebev_transformer.py:155-160,179-183): columns 0..2 become
+ * sigmoid(v + inverse_sigmoid(refine_proposal[row, n])), columns >= 8 are divided by time_diff[b,1] (if T > 1).
+ * Used for: position_encoder (2 layers), in_proj+gen_tau (1, concatenated), out_proj+norm1 -> sampling heads (2),
+ * FFN+norm3 (2), cls_branch (3), reg_branch+refine (3).
+ */
+typedef struct sbev_dense_layer {
+    const float* Wt;        /* [K][ldw] pre-transposed weight, zero padded */
+    int ldw, K, N;
+    const float* bias;      /* [N] or NULL */
+    const float* ln_w;      /* [N] or NULL (with ln_b) */
+    const float* ln_b;
+    const float* residual;  /* [M][N] or NULL */
+    int flags;              /* SBEV_DENSE_* */
+    float* y;               /* [M][ldy] or NULL */
+    int ldy;
+} sbev_dense_layer;
+int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                         const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                         void* stream);
+
 /* Sampling head epilogue: box decode + offset scaling + yaw rotation + softmax over levels.
  * Replaces make_sample_points (models/sparsebev_sampling.py:8-24), decode_bbox (models/bbox/utils.py:63-77),
  * rotation_3d_in_axis (models/utils.py:49-84) and the softmax at sparsebev_transformer.py:298-299.
- *   query_bbox [BQ,10]; offset [BQ, GP*3] (Linear output); scale_logits [BQ, GP*L]; pc_range HOST[6]
+ *   query_bbox [BQ,10]; offset rows of GP*3 floats (row stride ld_off); scale_logits rows of GP*L floats (row
+ *   stride ld_log) -- both may be column blocks of one concatenated Linear output; pc_range HOST[6]
  *   points [BQ, GP, 3]; scale_w [BQ, GP, L]
  */
-int sbev_sample_points_fwd(const float* query_bbox, const float* offset, const float* scale_logits,
+int sbev_sample_points_fwd(const float* query_bbox, const float* offset, int ld_off, const float* scale_logits, int ld_log,
                            const float* pc_range, int BQ, int GP, int L,
                            float* points, float* scale_w, void* stream);
 
@@ -140,12 +166,13 @@ int sbev_refine_bbox_fwd(const float* proposal, const float* delta, const float*
  * Scale-adaptive self-attention core: softmax(q k^T / sqrt(hd) - tau_h * dist(c_i, c_j)) v.
  * Replaces SparseBEVSelfAttention.inner_forward's mask build + nn.MultiheadAttention core
  * (models/sparsebev_transformer.py:210-248); the [B*8,Q,Q] mask is never materialised.
- *   qkv [B,Q,3*D] (in_proj output, q|k|v), query_bbox [B,Q,10] (centres are decoded in-kernel with
- *   pc_range, HOST float[6]), tau [B,Q,H], dn_mask optional [Q,Q] uint8 (1 = blocked, query
- *   denoising), out [B,Q,D] (heads concatenated, before out_proj)
+ *   qkv [B*Q rows, row stride ld_qkv >= 3*D] (in_proj output, q|k|v), query_bbox [B,Q,10] (centres are decoded
+ *   in-kernel with pc_range, HOST float[6]), tau [B*Q rows, row stride ld_tau >= H] (may alias columns of the
+ *   same matrix as qkv when in_proj and gen_tau are run as one concatenated Linear), dn_mask optional [Q,Q]
+ *   uint8 (1 = blocked, query denoising), out [B,Q,D] (heads concatenated, before out_proj)
  */
-int sbev_sasa_fwd(const float* qkv, const float* query_bbox, const float* tau, const uint8_t* dn_mask,
-                  const float* pc_range, int B, int Q, int H, int D, float* out, void* stream);
+int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bbox, const float* tau, int ld_tau,
+                  const uint8_t* dn_mask, const float* pc_range, int B, int Q, int H, int D, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * AdaptiveMixing (models/sparsebev_transformer.py:351-381).

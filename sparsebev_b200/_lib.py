@@ -15,8 +15,17 @@ c_vp = ctypes.c_void_p
 c_int = ctypes.c_int
 c_vpp = ctypes.POINTER(c_vp)
 
+
+
+class DenseLayer(ctypes.Structure):
+    """struct sbev_dense_layer (include/sparsebev_b200.h)"""
+    _fields_ = [('Wt', c_vp), ('ldw', c_int), ('K', c_int), ('N', c_int), ('bias', c_vp), ('ln_w', c_vp), ('ln_b', c_vp),
+                ('residual', c_vp), ('flags', c_int), ('y', c_vp), ('ldy', c_int)]
+
+
 # name -> argtypes; every function returns int (SBEV_OK = 0)
 SIGNATURES = {
+    'sbev_dense_chain_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                       c_vpp, c_vp, c_vp, c_vp],
@@ -27,8 +36,8 @@ SIGNATURES = {
                             ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp],
     'sbev_dense_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_refine_bbox_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
-    'sbev_sample_points_fwd': [c_vp, c_vp, c_vp, c_f32p, c_int, c_int, c_int, c_vp, c_vp, c_vp],
-    'sbev_sasa_fwd': [c_vp, c_vp, c_vp, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_sample_points_fwd': [c_vp, c_vp, c_int, c_vp, c_int, c_f32p, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'sbev_sasa_fwd': [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_mix_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_split_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp],
     'sbev_gemm_bf16_tn': [c_vpp, c_vpp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],

@@ -13,89 +13,202 @@
 // pre-transposed [K, ldw] so every lane streams 16 B coalesced from L2, 113 CTAs cover Q=900.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <mutex>
 
 namespace sbev {
 
 constexpr int DENSE_ROWS = 8;
+constexpr int CHAIN_STAGES = 3;
+constexpr int CHAIN_STAGE_FLOATS = 8192;          // 32 KB weight chunk per pipeline stage
+constexpr int CHAIN_MAX_LAYERS = 6;
+constexpr int CHAIN_MAX_PASS = 4;                 // N <= 4 * 256
 
-// y[M,N] = epilogue(x[M,K] @ Wt[K,ldw])   (Wt = W^T, zero-padded to ldw = multiple of 4)
-__global__ void __launch_bounds__(256)
-dense_rows8_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ Wt, int ldw,
-                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                   const float* __restrict__ residual, int M, int K, int N, int flags, float* __restrict__ y) {
-    extern __shared__ float smem[];
-    const int Kp = (K + 3) & ~3;
-    float* xs = smem;                         // [8][Kp]
-    float* ys = smem + DENSE_ROWS * Kp;       // [8][ldw]
-    const int tid = threadIdx.x;
+struct ChainLayer {
+    const float* Wt; const float* bias; const float* ln_w; const float* ln_b; const float* residual; float* y;
+    int ldw, K, N, flags, ldy, kc;                // kc = weight rows per chunk
+};
+struct ChainParams {
+    const float* x; int ldx, M, n_layers, act_ld; // act_ld: row stride (floats) of the shared activation buffers
+    const float* aux_proposal; const float* aux_time_diff; int aux_Q, aux_T;   // SBEV_DENSE_REFINE epilogue
+    ChainLayer layer[CHAIN_MAX_LAYERS];
+};
+
+__device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(dsmem_u32(bar)), "r"(parity) : "memory");
+        if (!done && spins > (1u << 26)) __trap();
+    }
+}
+
+// A chain of up to 4 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers.  One CTA owns 8 full rows from the
+// first layer to the last (activations never leave shared memory, LayerNorm never leaves the CTA); the
+// pre-transposed weights of ALL layers are streamed back-to-back through a 3-stage ring of 32 KB chunks by
+// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), so the next layer's weights are already in flight
+// while the current layer's epilogue runs.  fp32 FFMA, 2 rows x (up to 4 x 4) columns per thread.
+__global__ void __launch_bounds__(256, 2)
+dense_chain_kernel(const __grid_constant__ ChainParams prm) {
+    extern __shared__ __align__(128) float smem[];
+    float* wbuf = smem;                                              // [STAGES][8192]
+    float* act0 = smem + CHAIN_STAGES * CHAIN_STAGE_FLOATS;           // [8][act_ld]
+    float* act1 = act0 + DENSE_ROWS * prm.act_ld;
+    __shared__ uint64_t full_bar[CHAIN_STAGES], empty_bar[CHAIN_STAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * DENSE_ROWS;
-    for (int i = tid; i < DENSE_ROWS * Kp; i += 256) {
-        const int r = i / Kp, k = i - r * Kp;
-        xs[i] = (row0 + r < M && k < K) ? __ldg(x + (long long)(row0 + r) * ldx + k) : 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < CHAIN_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&full_bar[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&empty_bar[s])), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // stage the input rows
+    {
+        const int K0 = prm.layer[0].K;
+        for (int i = tid; i < DENSE_ROWS * prm.act_ld; i += 256) {
+            const int r = i / prm.act_ld, k = i - r * prm.act_ld;
+            act0[i] = (row0 + r < prm.M && k < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k) : 0.f;
+        }
     }
     __syncthreads();
-    const int ncg = ldw >> 2;                 // column groups of 4
-    const int rg = tid >> 6;                  // 0..3 -> rows 2rg, 2rg+1
-    const float* x0 = xs + (2 * rg) * Kp;
-    const float* x1 = x0 + Kp;
-    for (int cg = tid & 63; cg < ncg; cg += 64) {
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        const float* wp = Wt + 4 * cg;
-        int k = 0;
-        for (; k + 4 <= K; k += 4) {
-            const float4 w0 = ldg4(wp + (long long)(k + 0) * ldw);
-            const float4 w1 = ldg4(wp + (long long)(k + 1) * ldw);
-            const float4 w2 = ldg4(wp + (long long)(k + 2) * ldw);
-            const float4 w3 = ldg4(wp + (long long)(k + 3) * ldw);
-            const float4 xa = *reinterpret_cast<const float4*>(x0 + k);
-            const float4 xb = *reinterpret_cast<const float4*>(x1 + k);
-#define SBEV_FMA4(acc, xv, wv) acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
-            SBEV_FMA4(a0, xa.x, w0) SBEV_FMA4(a0, xa.y, w1) SBEV_FMA4(a0, xa.z, w2) SBEV_FMA4(a0, xa.w, w3)
-            SBEV_FMA4(a1, xb.x, w0) SBEV_FMA4(a1, xb.y, w1) SBEV_FMA4(a1, xb.z, w2) SBEV_FMA4(a1, xb.w, w3)
-        }
-        for (; k < K; ++k) {
-            const float4 w0 = ldg4(wp + (long long)k * ldw);
-            SBEV_FMA4(a0, x0[k], w0) SBEV_FMA4(a1, x1[k], w0)
+
+    // producer state (thread 0): walks the global chunk sequence over all layers
+    int p_layer = 0, p_k0 = 0, p_idx = 0;
+    auto produce_one = [&]() {
+        if (p_layer >= prm.n_layers) return;
+        const ChainLayer& L = prm.layer[p_layer];
+        const int kc = min(L.kc, L.K - p_k0);
+        const int stage = p_idx % CHAIN_STAGES;
+        if (p_idx >= CHAIN_STAGES) chain_mbar_wait(&empty_bar[stage], ((p_idx / CHAIN_STAGES) - 1) & 1);
+        const uint32_t bytes = (uint32_t)kc * L.ldw * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(&full_bar[stage])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dsmem_u32(wbuf + stage * CHAIN_STAGE_FLOATS)), "l"(L.Wt + (long long)p_k0 * L.ldw), "r"(bytes),
+                       "r"(dsmem_u32(&full_bar[stage])) : "memory");
+        p_k0 += kc; ++p_idx;
+        if (p_k0 >= L.K) { p_k0 = 0; ++p_layer; }
+    };
+    if (tid == 0) { for (int s = 0; s < CHAIN_STAGES - 1; ++s) produce_one(); }
+
+    const int cg0 = tid & 63, rg = tid >> 6;                          // rows 2rg, 2rg+1; column groups cg0 + 64*pass
+    int c_idx = 0;                                                    // consumer chunk counter
+    float* xin = act0;
+    float* yout = act1;
+    for (int li = 0; li < prm.n_layers; ++li) {
+        const ChainLayer& L = prm.layer[li];
+        const int ncg = L.ldw >> 2;
+        float4 acc[CHAIN_MAX_PASS][2];
+#pragma unroll
+        for (int ps = 0; ps < CHAIN_MAX_PASS; ++ps) { acc[ps][0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[ps][1] = acc[ps][0]; }
+        const float* x0 = xin + (2 * rg) * prm.act_ld;
+        const float* x1 = x0 + prm.act_ld;
+        for (int k0 = 0; k0 < L.K; k0 += L.kc, ++c_idx) {
+            if (tid == 0) produce_one();
+            const int stage = c_idx % CHAIN_STAGES;
+            chain_mbar_wait(&full_bar[stage], (c_idx / CHAIN_STAGES) & 1);
+            const float* wch = wbuf + stage * CHAIN_STAGE_FLOATS;
+            const int kc = min(L.kc, L.K - k0);
+#define SBEV_FMA4(a, xv, wv) a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y); a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
+            int kk = 0;
+            for (; kk + 4 <= kc; kk += 4) {
+                const float4 xa = *reinterpret_cast<const float4*>(x0 + k0 + kk);
+                const float4 xb = *reinterpret_cast<const float4*>(x1 + k0 + kk);
+#pragma unroll
+                for (int ps = 0; ps < CHAIN_MAX_PASS; ++ps) {
+                    const int cg = cg0 + 64 * ps;
+                    if (cg < ncg) {
+                        const float* wp = wch + kk * L.ldw + 4 * cg;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wp + L.ldw);
+                        const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * L.ldw);
+                        const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * L.ldw);
+                        SBEV_FMA4(acc[ps][0], xa.x, w0) SBEV_FMA4(acc[ps][0], xa.y, w1) SBEV_FMA4(acc[ps][0], xa.z, w2) SBEV_FMA4(acc[ps][0], xa.w, w3)
+                        SBEV_FMA4(acc[ps][1], xb.x, w0) SBEV_FMA4(acc[ps][1], xb.y, w1) SBEV_FMA4(acc[ps][1], xb.z, w2) SBEV_FMA4(acc[ps][1], xb.w, w3)
+                    }
+                }
+            }
+            for (; kk < kc; ++kk) {
+                const float xa = x0[k0 + kk], xb = x1[k0 + kk];
+#pragma unroll
+                for (int ps = 0; ps < CHAIN_MAX_PASS; ++ps) {
+                    const int cg = cg0 + 64 * ps;
+                    if (cg < ncg) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wch + kk * L.ldw + 4 * cg);
+                        SBEV_FMA4(acc[ps][0], xa, w0) SBEV_FMA4(acc[ps][1], xb, w0)
+                    }
+                }
+            }
 #undef SBEV_FMA4
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
         }
-        *reinterpret_cast<float4*>(ys + (2 * rg) * ldw + 4 * cg) = a0;
-        *reinterpret_cast<float4*>(ys + (2 * rg + 1) * ldw + 4 * cg) = a1;
-    }
-    __syncthreads();
-    // epilogue: one warp per row
-    const int warp = tid >> 5, lane = tid & 31;
-    const int row = row0 + warp;
-    if (row >= M) return;
-    float* yr = ys + warp * ldw;
-    const bool pre_res = (flags & SBEV_DENSE_RES_PRE_LN) && residual != nullptr;
-    for (int n = lane; n < N; n += 32) {
-        float v = yr[n];
-        if (bias) v += __ldg(bias + n);
-        if (pre_res) v += __ldg(residual + (long long)row * N + n);
-        yr[n] = v;
-    }
-    float mean = 0.f, rstd = 1.f;
-    if (ln_w != nullptr) {
-        float s = 0.f;
-        for (int n = lane; n < N; n += 32) s += yr[n];
-        mean = warp_sum(s) / (float)N;
-        float ss = 0.f;
-        for (int n = lane; n < N; n += 32) { const float d = yr[n] - mean; ss += d * d; }
-        rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
-    }
-    for (int n = lane; n < N; n += 32) {
-        float v = yr[n];
-        if (ln_w != nullptr) v = (v - mean) * rstd * __ldg(ln_w + n) + __ldg(ln_b + n);
-        if (flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
-        if (!pre_res && residual != nullptr) v += __ldg(residual + (long long)row * N + n);
-        y[(long long)row * N + n] = v;
+#pragma unroll
+        for (int ps = 0; ps < CHAIN_MAX_PASS; ++ps) {
+            const int cg = cg0 + 64 * ps;
+            if (cg < ncg) {
+                *reinterpret_cast<float4*>(yout + (2 * rg) * prm.act_ld + 4 * cg) = acc[ps][0];
+                *reinterpret_cast<float4*>(yout + (2 * rg + 1) * prm.act_ld + 4 * cg) = acc[ps][1];
+            }
+        }
+        __syncthreads();
+        // epilogue: one warp per row; result stays in yout (next layer's input) and optionally goes to global
+        {
+            const int row = row0 + warp;
+            float* yr = yout + warp * prm.act_ld;
+            const int N = L.N;
+            const bool live = row < prm.M;
+            const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
+            for (int n = lane; n < N; n += 32) {
+                float v = yr[n];
+                if (L.bias) v += __ldg(L.bias + n);
+                if (pre_res && live) v += __ldg(L.residual + (long long)row * N + n);
+                yr[n] = v;
+            }
+            float mean = 0.f, rstd = 1.f;
+            if (L.ln_w != nullptr) {
+                float s = 0.f;
+                for (int n = lane; n < N; n += 32) s += yr[n];
+                mean = warp_sum(s) / (float)N;
+                float ss = 0.f;
+                for (int n = lane; n < N; n += 32) { const float d = yr[n] - mean; ss += d * d; }
+                rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
+            }
+            for (int n = lane; n < N; n += 32) {
+                float v = yr[n];
+                if (L.ln_w != nullptr) v = (v - mean) * rstd * __ldg(L.ln_w + n) + __ldg(L.ln_b + n);
+                if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
+                if (!pre_res && L.residual != nullptr && live) v += __ldg(L.residual + (long long)row * N + n);
+                if ((L.flags & SBEV_DENSE_REFINE) && live) {
+                    // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
+                    if (n < 3) {
+                        const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
+                        v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
+                        v = __fdiv_rn(1.f, 1.f + expf(-v));
+                    } else if (n >= 8 && prm.aux_T > 1) {
+                        float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
+                        if (td < 1e-5f) td = 1.0f;
+                        v = __fdiv_rn(v, td);
+                    }
+                }
+                yr[n] = v;
+                if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
+            }
+            // zero the K-padding of the next layer's input (its K may not be a multiple of 4)
+            if (li + 1 < prm.n_layers) for (int n = N + lane; n < ((N + 3) & ~3); n += 32) yr[n] = 0.f;
+        }
+        __syncthreads();
+        float* t = xin; xin = yout; yout = t;
     }
 }
 
 // Box decode + offsets -> lidar-frame sample points; softmax over levels.  Thread per point.
 __global__ void __launch_bounds__(128)
-sample_points_kernel(const float* __restrict__ query_bbox, const float* __restrict__ offset,
-                     const float* __restrict__ logits, float r0, float r1, float r2, float r3, float r4, float r5,
+sample_points_kernel(const float* __restrict__ query_bbox, const float* __restrict__ offset, int ld_off,
+                     const float* __restrict__ logits, int ld_log, float r0, float r1, float r2, float r3, float r4, float r5,
                      int BQ, int GP, int L, float* __restrict__ points, float* __restrict__ scale_w) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)BQ * GP) return;
@@ -108,7 +221,8 @@ sample_points_kernel(const float* __restrict__ query_bbox, const float* __restri
     const float sw = expf(__ldg(bb + 3)), sl = expf(__ldg(bb + 4)), sh = expf(__ldg(bb + 5));
     const float yaw = atan2f(__ldg(bb + 6), __ldg(bb + 7));
     const float s = sinf(yaw), c = cosf(yaw);
-    const float* op = offset + idx * 3;
+    const int gp = (int)(idx - bq * GP);
+    const float* op = offset + bq * ld_off + gp * 3;
     const float dx = __fmul_rn(sw, __ldg(op)), dy = __fmul_rn(sl, __ldg(op + 1)), dz = __fmul_rn(sh, __ldg(op + 2));
     // rotate counter-clockwise by yaw about z: x' = x*c + y*(-s), y' = x*s + y*c
     const float rx = __fadd_rn(__fmul_rn(dx, c), __fmul_rn(dy, -s));
@@ -117,7 +231,7 @@ sample_points_kernel(const float* __restrict__ query_bbox, const float* __restri
     points[idx * 3 + 1] = __fadd_rn(cy, ry);
     points[idx * 3 + 2] = __fadd_rn(cz, dz);
     // softmax over L
-    const float* lp = logits + idx * L;
+    const float* lp = logits + bq * ld_log + gp * L;
     float mx = -INFINITY;
     for (int l = 0; l < L; ++l) mx = fmaxf(mx, __ldg(lp + l));
     float e[SBEV_MAX_LEVELS], sum = 0.f;
@@ -145,41 +259,62 @@ split_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __res
     }
 }
 
-// out[row] = LN(sum_z partial[z][row] + bias + residual[row]); one warp per row, N <= 1024.
-__global__ void __launch_bounds__(256)
+// out[row] = LN(sum_z partial[z][row] + bias + residual[row]); one warp per row, N <= 1024, N % 4 == 0.
+// All split-K partials of a lane are requested before the first add (nsplit x 16 B loads in flight).
+__global__ void __launch_bounds__(128)
 reduce_ln_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
                  const float* __restrict__ residual, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                  int M, int N, float* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
+    const int row = blockIdx.x * 4 + warp;
     if (row >= M) return;
-    float v[32];
-    const int per = (N + 31) / 32;
+    float4 v[8];
+    const int per = (N / 4 + 31) / 32;          // float4 groups per lane (<= 8)
     float s = 0.f;
-    for (int i = 0; i < per; ++i) {
-        const int n = lane + 32 * i;
-        float a = 0.f;
-        if (n < N) {
-            for (int z = 0; z < nsplit; ++z) a += __ldg(partial + ((long long)z * M + row) * N + n);
-            if (bias) a += __ldg(bias + n);
-            if (residual) a += __ldg(residual + (long long)row * N + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = (lane + 32 * i) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < per && n < N) {
+            const float* p0 = partial + (long long)row * N + n;
+            const long long zs = (long long)M * N;
+            int z = 0;
+            for (; z + 8 <= nsplit; z += 8) {
+                float4 t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = ldg4(p0 + (z + u) * zs);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
+            }
+            for (; z < nsplit; ++z) { const float4 t = ldg4(p0 + z * zs); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (bias) { const float4 t = ldg4(bias + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (residual) { const float4 t = ldg4(residual + (long long)row * N + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            s += (a.x + a.y) + (a.z + a.w);
         }
         v[i] = a;
-        s += (n < N) ? a : 0.f;
     }
     float mean = 0.f, rstd = 1.f;
     if (ln_w != nullptr) {
         mean = warp_sum(s) / (float)N;
         float ss = 0.f;
-        for (int i = 0; i < per; ++i) { const int n = lane + 32 * i; if (n < N) { const float d = v[i] - mean; ss += d * d; } }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i < per && (lane + 32 * i) * 4 < N) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
         rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
     }
-    for (int i = 0; i < per; ++i) {
-        const int n = lane + 32 * i;
-        if (n < N) {
-            float a = v[i];
-            if (ln_w != nullptr) a = (a - mean) * rstd * __ldg(ln_w + n) + __ldg(ln_b + n);
-            out[(long long)row * N + n] = a;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = (lane + 32 * i) * 4;
+        if (i < per && n < N) {
+            float4 a = v[i];
+            if (ln_w != nullptr) {
+                const float4 g = ldg4(ln_w + n), b = ldg4(ln_b + n);
+                a.x = (a.x - mean) * rstd * g.x + b.x; a.y = (a.y - mean) * rstd * g.y + b.y;
+                a.z = (a.z - mean) * rstd * g.z + b.z; a.w = (a.w - mean) * rstd * g.w + b.w;
+            }
+            *reinterpret_cast<float4*>(out + (long long)row * N + n) = a;
         }
     }
 }
@@ -211,35 +346,67 @@ refine_bbox_kernel(const float* __restrict__ proposal, const float* __restrict__
 
 using namespace sbev;
 
+extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                                    const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                                    void* stream) {
+    SBEV_REQUIRE(x && layers, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
+    SBEV_REQUIRE(n_layers >= 1 && n_layers <= CHAIN_MAX_LAYERS, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_fwd: 1..%d layers", CHAIN_MAX_LAYERS);
+    SBEV_REQUIRE(M >= 0 && ldx >= layers[0].K, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: bad sizes");
+    ChainParams prm;
+    prm.x = x; prm.ldx = ldx; prm.M = M; prm.n_layers = n_layers;
+    prm.aux_proposal = refine_proposal; prm.aux_time_diff = refine_time_diff; prm.aux_Q = refine_Q > 0 ? refine_Q : 1; prm.aux_T = refine_T;
+    int act = 4;
+    for (int i = 0; i < n_layers; ++i) {
+        const sbev_dense_layer& l = layers[i];
+        SBEV_REQUIRE(l.Wt != nullptr && l.K > 0 && l.N > 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: bad weight/sizes", i);
+        SBEV_REQUIRE(l.ldw >= l.N && (l.ldw & 3) == 0 && l.ldw <= 256 * CHAIN_MAX_PASS, SBEV_ERR_UNSUPPORTED,
+                     "sbev_dense_chain_fwd: layer %d: ldw must be a multiple of 4, >= N and <= %d", i, 256 * CHAIN_MAX_PASS);
+        SBEV_REQUIRE((l.ln_w == nullptr) == (l.ln_b == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: ln_w and ln_b go together");
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(l.Wt) & 15) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: Wt not 16-byte aligned");
+        SBEV_REQUIRE(i == 0 || l.K == layers[i - 1].N, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d K != previous N", i);
+        SBEV_REQUIRE(l.y == nullptr || l.ldy >= l.N, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: ldy < N", i);
+        if (l.flags & SBEV_DENSE_REFINE)
+            SBEV_REQUIRE(refine_proposal && refine_time_diff && l.N >= 10 && refine_T >= 1, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: refine needs proposal/time_diff");
+        ChainLayer& c = prm.layer[i];
+        c.Wt = l.Wt; c.bias = l.bias; c.ln_w = l.ln_w; c.ln_b = l.ln_b; c.residual = l.residual; c.y = l.y;
+        c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags; c.ldy = l.ldy;
+        int kc = CHAIN_STAGE_FLOATS / l.ldw;
+        if (kc >= 4) kc &= ~3;
+        if (kc > l.K) kc = l.K;
+        c.kc = kc;
+        act = act > ((l.K + 3) & ~3) ? act : ((l.K + 3) & ~3);
+        act = act > l.ldw ? act : l.ldw;
+    }
+    SBEV_REQUIRE(layers[n_layers - 1].y != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: last layer needs an output pointer");
+    prm.act_ld = act + 4;
+    if (M == 0) return SBEV_OK;
+    const size_t smem = sizeof(float) * ((size_t)CHAIN_STAGES * CHAIN_STAGE_FLOATS + 2 * (size_t)DENSE_ROWS * prm.act_ld);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    dense_chain_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 256, smem, (cudaStream_t)stream>>>(prm);
+    return check_launch("sbev_dense_chain_fwd");
+}
+
 extern "C" int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const float* bias,
                               const float* ln_w, const float* ln_b, const float* residual,
                               int M, int K, int N, int flags, float* y, void* stream) {
-    SBEV_REQUIRE(x && Wt && y, SBEV_ERR_INVALID, "sbev_dense_fwd: null pointer");
-    SBEV_REQUIRE(M >= 0 && K > 0 && N > 0 && ldx >= K, SBEV_ERR_INVALID, "sbev_dense_fwd: bad sizes");
-    SBEV_REQUIRE(ldw >= N && (ldw & 3) == 0, SBEV_ERR_INVALID, "sbev_dense_fwd: ldw must be a multiple of 4 and >= N");
-    SBEV_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), SBEV_ERR_INVALID, "sbev_dense_fwd: ln_w and ln_b go together");
-    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(Wt) & 15) == 0, SBEV_ERR_INVALID, "sbev_dense_fwd: Wt not 16-byte aligned");
-    if (M == 0) return SBEV_OK;
-    const int Kp = (K + 3) & ~3;
-    const size_t smem = sizeof(float) * (size_t)DENSE_ROWS * (Kp + ldw);
-    SBEV_REQUIRE(smem <= 200 * 1024, SBEV_ERR_UNSUPPORTED, "sbev_dense_fwd: K + N too large (%d + %d)", K, N);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(dense_rows8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dense_rows8_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 256, smem, (cudaStream_t)stream>>>(
-        x, ldx, Wt, ldw, bias, ln_w, ln_b, residual, M, K, N, flags, y);
-    return check_launch("sbev_dense_fwd");
+    SBEV_REQUIRE(y != nullptr, SBEV_ERR_INVALID, "sbev_dense_fwd: null pointer");
+    sbev_dense_layer l;
+    l.Wt = Wt; l.ldw = ldw; l.K = K; l.N = N; l.bias = bias; l.ln_w = ln_w; l.ln_b = ln_b; l.residual = residual;
+    l.flags = flags & (SBEV_DENSE_RELU | SBEV_DENSE_RES_PRE_LN); l.y = y; l.ldy = N;
+    return sbev_dense_chain_fwd(x, ldx, M, 1, &l, nullptr, nullptr, 0, 0, stream);
 }
 
-extern "C" int sbev_sample_points_fwd(const float* query_bbox, const float* offset, const float* scale_logits,
+extern "C" int sbev_sample_points_fwd(const float* query_bbox, const float* offset, int ld_off, const float* scale_logits, int ld_log,
                                       const float* pc_range, int BQ, int GP, int L,
                                       float* points, float* scale_w, void* stream) {
     SBEV_REQUIRE(query_bbox && offset && scale_logits && pc_range && points && scale_w, SBEV_ERR_INVALID,
                  "sbev_sample_points_fwd: null pointer");
-    SBEV_REQUIRE(BQ >= 0 && GP > 0 && L >= 1 && L <= SBEV_MAX_LEVELS, SBEV_ERR_INVALID, "sbev_sample_points_fwd: bad sizes");
+    SBEV_REQUIRE(BQ >= 0 && GP > 0 && L >= 1 && L <= SBEV_MAX_LEVELS && ld_off >= GP * 3 && ld_log >= GP * L, SBEV_ERR_INVALID, "sbev_sample_points_fwd: bad sizes");
     const long long total = (long long)BQ * GP;
     if (total == 0) return SBEV_OK;
     sample_points_kernel<<<(int)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        query_bbox, offset, scale_logits, pc_range[0], pc_range[1], pc_range[2], pc_range[3], pc_range[4], pc_range[5],
+        query_bbox, offset, ld_off, scale_logits, ld_log, pc_range[0], pc_range[1], pc_range[2], pc_range[3], pc_range[4], pc_range[5],
         BQ, GP, L, points, scale_w);
     return check_launch("sbev_sample_points_fwd");
 }
@@ -258,10 +425,10 @@ extern "C" int sbev_split_bf16(const float* x, int64_t n, uint16_t* hi, uint16_t
 extern "C" int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
                                   const float* ln_w, const float* ln_b, int M, int N, float* out, void* stream) {
     SBEV_REQUIRE(partial && out && nsplit >= 1, SBEV_ERR_INVALID, "sbev_reduce_ln_fwd: bad arguments");
-    SBEV_REQUIRE(N > 0 && N <= 1024, SBEV_ERR_UNSUPPORTED, "sbev_reduce_ln_fwd: N must be in (0,1024]");
+    SBEV_REQUIRE(N > 0 && N <= 1024 && (N & 3) == 0, SBEV_ERR_UNSUPPORTED, "sbev_reduce_ln_fwd: N must be a multiple of 4 in (0,1024]");
     SBEV_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), SBEV_ERR_INVALID, "sbev_reduce_ln_fwd: ln_w and ln_b go together");
     if (M <= 0) return SBEV_OK;
-    reduce_ln_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
+    reduce_ln_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
     return check_launch("sbev_reduce_ln_fwd");
 }
 

@@ -16,6 +16,7 @@
 // of the feature pyramid in L2.  Outputs are written as whole 256 B (fused layout) or
 // 64*P*4 B (op layout, transposed through shared memory) contiguous segments.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace sbev {
 
@@ -59,33 +60,42 @@ __device__ __forceinline__ int view_from_coord(float z, int N) {
 }
 
 // Gather all L levels for 4 consecutive channels.  base[l] already points at
-// (slice, view, channel lane); pxs[l] = floats between neighbouring pixels.
-template <int L>
+// (slice, view, channel lane); pxs[l] = floats between neighbouring pixels (pixel offsets fit 32 bits).
+// LB = levels whose 4*LB loads are in flight together (LB == L: maximum memory-level parallelism;
+// smaller LB: fewer live registers -> more resident warps).
+template <int L, int LB>
 __device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], const int (&H)[L],
-                                                const int (&W)[L], const long long (&pxs)[L],
+                                                const int (&W)[L], const int (&pxs)[L],
                                                 float u, float v, const float (&wt)[L], bool live) {
-    Tap tp[L];
-    float4 c1[L], c2[L], c3[L], c4[L];
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-        tp[l] = make_tap(u, v, H[l], W[l]);
-        const float* p = base[l] + ((long long)tp[l].y0 * W[l] + tp[l].x0) * pxs[l];
-        const long long row = (long long)W[l] * pxs[l];
-        c1[l] = (live && tp[l].ok1) ? ldg4(p) : zero;
-        c2[l] = (live && tp[l].ok2) ? ldg4(p + pxs[l]) : zero;
-        c3[l] = (live && tp[l].ok3) ? ldg4(p + row) : zero;
-        c4[l] = (live && tp[l].ok4) ? ldg4(p + row + pxs[l]) : zero;
-    }
     float4 acc = zero;
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-        if (tp[l].inside) {
-            const Tap& t = tp[l];
-            acc.x += (t.w1 * c1[l].x + t.w2 * c2[l].x + t.w3 * c3[l].x + t.w4 * c4[l].x) * wt[l];
-            acc.y += (t.w1 * c1[l].y + t.w2 * c2[l].y + t.w3 * c3[l].y + t.w4 * c4[l].y) * wt[l];
-            acc.z += (t.w1 * c1[l].z + t.w2 * c2[l].z + t.w3 * c3[l].z + t.w4 * c4[l].z) * wt[l];
-            acc.w += (t.w1 * c1[l].w + t.w2 * c2[l].w + t.w3 * c3[l].w + t.w4 * c4[l].w) * wt[l];
+    for (int l0 = 0; l0 < L; l0 += LB) {
+        Tap tp[LB];
+        float4 c1[LB], c2[LB], c3[LB], c4[LB];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int l = l0 + i;
+            if (l < L) {
+                tp[i] = make_tap(u, v, H[l], W[l]);
+                const int row = W[l] * pxs[l];
+                const float* p = base[l] + (tp[i].y0 * row + tp[i].x0 * pxs[l]);
+                c1[i] = (live && tp[i].ok1) ? ldg4(p) : zero;
+                c2[i] = (live && tp[i].ok2) ? ldg4(p + pxs[l]) : zero;
+                c3[i] = (live && tp[i].ok3) ? ldg4(p + row) : zero;
+                c4[i] = (live && tp[i].ok4) ? ldg4(p + row + pxs[l]) : zero;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int l = l0 + i;
+            if (l < L && tp[i].inside) {
+                const Tap& t = tp[i];
+                acc.x += (t.w1 * c1[i].x + t.w2 * c2[i].x + t.w3 * c3[i].x + t.w4 * c4[i].x) * wt[l];
+                acc.y += (t.w1 * c1[i].y + t.w2 * c2[i].y + t.w3 * c3[i].y + t.w4 * c4[i].y) * wt[l];
+                acc.z += (t.w1 * c1[i].z + t.w2 * c2[i].z + t.w3 * c3[i].z + t.w4 * c4[i].z) * wt[l];
+                acc.w += (t.w1 * c1[i].w + t.w2 * c2[i].w + t.w3 * c3[i].w + t.w4 * c4[i].w) * wt[l];
+            }
         }
     }
     return acc;
@@ -104,16 +114,16 @@ msmv_fwd_c64_kernel(LevelSet lv, const float* __restrict__ loc, const float* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, j = lane & 15;
     float* tile = smem + warp * (64 * P);
-    const long long items = (long long)Bp * Q;
-    for (long long item = (long long)blockIdx.x * 8 + warp; item < items; item += (long long)gridDim.x * 8) {
-        const int b = (int)(item / Q);
+    const int items = Bp * Q;
+    for (int item = blockIdx.x * 8 + warp; item < items; item += gridDim.x * 8) {
+        const int b = item / Q;
         float lu = 0.f, lvv = 0.f, lz = 0.f, lw[L];
 #pragma unroll
         for (int l = 0; l < L; ++l) lw[l] = 0.f;
         if (lane < P) {
-            const float* lp = loc + (item * P + lane) * 3;
+            const float* lp = loc + ((long long)item * P + lane) * 3;
             lu = __ldg(lp); lvv = __ldg(lp + 1); lz = __ldg(lp + 2);
-            const float* wp = wgt + (item * P + lane) * L;
+            const float* wp = wgt + ((long long)item * P + lane) * L;
 #pragma unroll
             for (int l = 0; l < L; ++l) lw[l] = __ldg(wp + l);
         }
@@ -129,17 +139,17 @@ msmv_fwd_c64_kernel(LevelSet lv, const float* __restrict__ loc, const float* __r
             for (int l = 0; l < L; ++l) wt[l] = __shfl_sync(0xffffffffu, lw[l], src);
             const int view = view_from_coord(z, N);
             const bool view_ok = (view >= 0) && (view < N);
-            const float* base[L]; int H[L], W[L]; long long pxs[L];
+            const float* base[L]; int H[L], W[L]; int pxs[L];
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = 64;
                 base[l] = lv.ptr[l] + ((long long)b * N + (view_ok ? view : 0)) * H[l] * W[l] * 64 + 4 * j;
             }
-            const float4 acc = gather_levels<L>(base, H, W, pxs, u, v, wt, live && view_ok);
+            const float4 acc = gather_levels<L, L>(base, H, W, pxs, u, v, wt, live && view_ok);
             if (live) *reinterpret_cast<float4*>(tile + p * 64 + 4 * j) = acc;
         }
         __syncwarp();
-        float* dst = out + item * 64 * P;
+        float* dst = out + (long long)item * 64 * P;
         for (int i = lane * 4; i < 64 * P; i += 128) {
             float4 o;
             o.x = tile[((i + 0) % P) * 64 + (i + 0) / P];
@@ -352,76 +362,68 @@ struct FusedParams {
     float image_h, image_w, eps;
 };
 
-template <int L>
-__global__ void __launch_bounds__(256)
+template <int L, int LB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
     const int T = prm.T, G = prm.G, N = prm.N, Q = prm.Q, P = prm.P;
-    const long long total = (long long)prm.B * T * G * Q * P;
-    const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const long long hw_stride = ((long long)gridDim.x * blockDim.x) >> 4;
-    const long long iters = (total + hw_stride - 1) / hw_stride;
-    for (long long it = 0; it < iters; ++it) {
-        const long long i_raw = hw_id + it * hw_stride;
-        const bool live = i_raw < total;
-        const long long i = live ? i_raw : total - 1;
-        const int p = (int)(i % P);
-        const int q = (int)((i / P) % Q);
-        const int s = (int)(i / ((long long)P * Q));       // (b*T + t)*G + g
-        const int g = s % G;
-        const int bt = s / G;
-        const int t = bt % T;
-        const int b = bt / T;
-        const long long bq = (long long)b * Q + q;
+    // slice (b,t,g) = blockIdx.y (uniform); sample (q,p) inside the slice from blockIdx.x: all 32-bit, no 64-bit div/mod
+    const int s = blockIdx.y;
+    const int g = s % G, bt = s / G, t = bt % T, b = bt / T;
+    const int idx_raw = blockIdx.x * 16 + (threadIdx.x >> 4);
+    const bool live = idx_raw < Q * P;
+    const int idx = live ? idx_raw : Q * P - 1;
+    const int q = (P == 4) ? (idx >> 2) : (idx / P);
+    const int p = idx - q * P;
+    const long long bq = (long long)b * Q + q;
 
-        // motion warp (sparsebev_transformer.py:286-295): xy -= vel * time_diff[t]; no FMA contraction
-        const float* pp = prm.points + (bq * G * P + g * P + p) * 3;
-        const float td = __ldg(prm.time_diff + b * T + t);
-        const float px = __fsub_rn(__ldg(pp), __fmul_rn(__ldg(prm.velocity + bq * 2), td));
-        const float py = __fsub_rn(__ldg(pp + 1), __fmul_rn(__ldg(prm.velocity + bq * 2 + 1), td));
-        const float pz = __ldg(pp + 2);
+    // motion warp (sparsebev_transformer.py:286-295): xy -= vel * time_diff[t]; no FMA contraction
+    const float* pp = prm.points + (bq * G * P + g * P + p) * 3;
+    const float td = __ldg(prm.time_diff + bt);
+    const float px = __fsub_rn(__ldg(pp), __fmul_rn(__ldg(prm.velocity + bq * 2), td));
+    const float py = __fsub_rn(__ldg(pp + 1), __fmul_rn(__ldg(prm.velocity + bq * 2 + 1), td));
+    const float pz = __ldg(pp + 2);
 
-        // projection to view j (sparsebev_sampling.py:50-79), fixed order ((x*m0 + y*m1) + z*m2) + m3
-        float un = 0.f, vn = 0.f;
-        bool valid = false;
-        if (j < N) {
-            const float4* m = reinterpret_cast<const float4*>(prm.lidar2img + ((long long)bt * N + j) * 16);
-            const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
-            const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r0.x), __fmul_rn(py, r0.y)), __fmul_rn(pz, r0.z)), r0.w);
-            const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r1.x), __fmul_rn(py, r1.y)), __fmul_rn(pz, r1.z)), r1.w);
-            const float dz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r2.x), __fmul_rn(py, r2.y)), __fmul_rn(pz, r2.z)), r2.w);
-            const float safe = fmaxf(dz, prm.eps);
-            un = __fdiv_rn(__fdiv_rn(cx, safe), prm.image_w);
-            vn = __fdiv_rn(__fdiv_rn(cy, safe), prm.image_h);
-            valid = (dz > prm.eps) && (vn > 0.f) && (vn < 1.f) && (un > 0.f) && (un < 1.f);
-        }
-        const unsigned ball = (__ballot_sync(0xffffffffu, valid) >> (16 * half)) & 0xffffu;
-        const int view = ball ? (__ffs(ball) - 1) : 0;          // argmax of 0/1 flags: first valid, else 0
-        const float u = __shfl_sync(0xffffffffu, un, 16 * half + view);
-        const float v = __shfl_sync(0xffffffffu, vn, 16 * half + view);
-
-        // scale weights: the reference pairs loc slice (b,t,g) with weight slice (b,g',t'),
-        // (g',t') = divmod(t*G+g, T)  (sparsebev_sampling.py:112-119); weights do not depend on t'.
-        const int gw = (t * G + g) / T;
-        const float* wp = prm.scale_w + ((bq * G + gw) * P + p) * L;
-        float wt[L];
+    // scale weights: the reference pairs loc slice (b,t,g) with weight slice (b,g',t'),
+    // (g',t') = divmod(t*G+g, T)  (sparsebev_sampling.py:112-119); weights do not depend on t'.
+    const int gw = (t * G + g) / T;
+    const float* wp = prm.scale_w + ((bq * G + gw) * P + p) * L;
+    float wt[L];
 #pragma unroll
-        for (int l = 0; l < L; ++l) wt[l] = __ldg(wp + l);
+    for (int l = 0; l < L; ++l) wt[l] = __ldg(wp + l);
 
-        const float* base[L]; int H[L], W[L]; long long pxs[L];
+    // projection to view j (sparsebev_sampling.py:50-79), fixed order ((x*m0 + y*m1) + z*m2) + m3
+    float un = 0.f, vn = 0.f;
+    bool valid = false;
+    if (j < N) {
+        const float4* m = reinterpret_cast<const float4*>(prm.lidar2img + ((long long)bt * N + j) * 16);
+        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+        const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r0.x), __fmul_rn(py, r0.y)), __fmul_rn(pz, r0.z)), r0.w);
+        const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r1.x), __fmul_rn(py, r1.y)), __fmul_rn(pz, r1.z)), r1.w);
+        const float dz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, r2.x), __fmul_rn(py, r2.y)), __fmul_rn(pz, r2.z)), r2.w);
+        const float safe = fmaxf(dz, prm.eps);
+        un = __fdiv_rn(__fdiv_rn(cx, safe), prm.image_w);
+        vn = __fdiv_rn(__fdiv_rn(cy, safe), prm.image_h);
+        valid = (dz > prm.eps) && (vn > 0.f) && (vn < 1.f) && (un > 0.f) && (un < 1.f);
+    }
+    const unsigned ball = (__ballot_sync(0xffffffffu, valid) >> (16 * half)) & 0xffffu;
+    const int view = ball ? (__ffs(ball) - 1) : 0;          // argmax of 0/1 flags: first valid, else 0
+    const float u = __shfl_sync(0xffffffffu, un, 16 * half + view);
+    const float v = __shfl_sync(0xffffffffu, vn, 16 * half + view);
+
+    const float* base[L]; int H[L], W[L]; int pxs[L];
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-            H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = lv.s_px[l];
-            base[l] = lv.ptr[l] + (long long)bt * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j;
-        }
-        const float4 acc = gather_levels<L>(base, H, W, pxs, u, v, wt, live);
-        if (live) {
-            float* dst = prm.out + ((bq * G + g) * ((long long)T * P) + (long long)t * P + p) * 64 + 4 * j;
-            *reinterpret_cast<float4*>(dst) = acc;
-            if (prm.loc_out != nullptr && j == 0) {
-                float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
-                lo[0] = u; lo[1] = v; lo[2] = __fdiv_rn((float)view, (float)(N - 1));
-            }
+    for (int l = 0; l < L; ++l) {
+        H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = (int)lv.s_px[l];
+        base[l] = lv.ptr[l] + ((long long)bt * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
+    }
+    const float4 acc = gather_levels<L, LB>(base, H, W, pxs, u, v, wt, live);
+    if (live) {
+        float* dst = prm.out + ((bq * G + g) * (T * P) + (t * P + p)) * 64 + 4 * j;
+        *reinterpret_cast<float4*>(dst) = acc;
+        if (prm.loc_out != nullptr && j == 0) {
+            float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
+            lo[0] = u; lo[1] = v; lo[2] = __fdiv_rn((float)view, (float)(N - 1));
         }
     }
 }
@@ -459,9 +461,12 @@ using namespace sbev;
 
 extern "C" int sbev_msmv_fwd(const float* const* feats, const int* hw, int L, const float* loc, const float* w,
                              int Bp, int N, int C, int Q, int P, float* out, void* stream) {
-    SBEV_REQUIRE(feats && loc && w && out, SBEV_ERR_INVALID, "sbev_msmv_fwd: null pointer");
     SBEV_REQUIRE(Bp >= 0 && Q >= 0 && N > 0 && C > 0 && P > 0, SBEV_ERR_INVALID, "sbev_msmv_fwd: bad sizes");
     SBEV_REQUIRE(P <= SBEV_MAX_POINTS, SBEV_ERR_INVALID, "num_point exceed limits (%d > %d)", P, SBEV_MAX_POINTS);
+    SBEV_REQUIRE(L >= 1 && L <= SBEV_MAX_LEVELS, SBEV_ERR_UNSUPPORTED, "num levels %d outside [1,%d]", L, SBEV_MAX_LEVELS);
+    if ((long long)Bp * Q == 0) return SBEV_OK;          // empty problem: nothing to read or write (buffers may be null)
+    SBEV_REQUIRE(feats && loc && w && out, SBEV_ERR_INVALID, "sbev_msmv_fwd: null pointer");
+    SBEV_REQUIRE((long long)Bp * Q < (1ll << 31), SBEV_ERR_UNSUPPORTED, "sbev_msmv_fwd: Bp*Q too large");
     LevelSet lv;
     int rc = fill_levels(lv, feats, hw, L);
     if (rc) return rc;
@@ -552,9 +557,18 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
     }
     const long long total = (long long)B * T * G * Q * P;
     if (total == 0) return SBEV_OK;
+    SBEV_REQUIRE((long long)B * T * G <= 65535 && (long long)Q * P < (1ll << 30), SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: too many slices / samples per slice");
+    for (int l = 0; l < L; ++l)
+        SBEV_REQUIRE((long long)lv.H[l] * lv.W[l] * stride_px[l] < (1ll << 31), SBEV_ERR_UNSUPPORTED, "level %d too large for 32-bit pixel offsets", l);
     FusedParams prm{points, velocity, time_diff, lidar2img, scale_w, out, loc_out, B, T, G, N, Q, P, image_h, image_w, eps};
-    const int grid = grid_for(total, 16, 1 << 30);
-#define SBEV_LAUNCH_FUSED(LL) case LL: sampling4d_c64_kernel<LL><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm); break;
+    const dim3 grid((Q * P + 15) / 16, B * T * G);
+    static int variant = -1;        // SBEV_GATHER_VARIANT: 0 = all levels in flight (default), 1 = two levels at a time, 3 CTAs/SM
+    if (variant < 0) { const char* e = getenv("SBEV_GATHER_VARIANT"); variant = e ? atoi(e) : 0; }
+#define SBEV_LAUNCH_FUSED(LL)                                                                                     \
+    case LL:                                                                                                      \
+        if (variant == 1 && LL >= 3) sampling4d_c64_kernel<LL, 2, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);   \
+        else sampling4d_c64_kernel<LL, LL, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);                   \
+        break;
     switch (L) { SBEV_LAUNCH_FUSED(1) SBEV_LAUNCH_FUSED(2) SBEV_LAUNCH_FUSED(3) SBEV_LAUNCH_FUSED(4) SBEV_LAUNCH_FUSED(5) }
 #undef SBEV_LAUNCH_FUSED
     return check_launch("sbev_sampling4d_fwd");

@@ -19,7 +19,7 @@ constexpr int SA_BK = 64;   // keys per tile
 constexpr int SA_HD = 32;   // head dim (embed 256 / 8 heads)
 
 __global__ void __launch_bounds__(256)
-sasa_hd32_kernel(const float* __restrict__ qkv, const float* __restrict__ query_bbox, const float* __restrict__ tau,
+sasa_hd32_kernel(const float* __restrict__ qkv, int ld_qkv, const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
                  const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
                  int B, int Q, int H, float* __restrict__ out) {
     __shared__ __align__(16) float Qt[SA_HD][SA_BQ];        // [d][q]   (q pre-scaled)
@@ -33,13 +33,13 @@ sasa_hd32_kernel(const float* __restrict__ qkv, const float* __restrict__ query_
     const int q0 = blockIdx.x * SA_BQ;
     const int h = blockIdx.y, b = blockIdx.z;
     const float scale = 0.17677669529663687f;               // 1/sqrt(32) rounded to fp32, as math.sqrt(1/E) -> float
-    const float* base = qkv + (long long)b * Q * 3 * D;
+    const float* base = qkv + (long long)b * Q * ld_qkv;
 
     // stage the query tile (transposed, scaled), centres and tau
     for (int i = tid; i < SA_BQ * SA_HD; i += 256) {
         const int q = i >> 5, d = i & 31;
         const int gq = q0 + q;
-        Qt[d][q] = (gq < Q) ? __ldg(base + (long long)gq * 3 * D + h * SA_HD + d) * scale : 0.f;
+        Qt[d][q] = (gq < Q) ? __ldg(base + (long long)gq * ld_qkv + h * SA_HD + d) * scale : 0.f;
     }
     if (tid < SA_BQ) {
         const int gq = q0 + tid;
@@ -47,7 +47,7 @@ sasa_hd32_kernel(const float* __restrict__ qkv, const float* __restrict__ query_
         // decode_bbox centre (bbox/utils.py:63-71): c*(hi-lo)+lo, separate multiply and add
         qcx[tid] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gq) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
         qcy[tid] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gq) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
-        qtau[tid] = ok ? __ldg(tau + ((long long)b * Q + gq) * H + h) : 0.f;
+        qtau[tid] = ok ? __ldg(tau + ((long long)b * Q + gq) * ld_tau + h) : 0.f;
     }
 
     const int ty = tid >> 4, tx = tid & 15;       // S rows 4ty..4ty+3, S cols 4tx..4tx+3, O cols 2tx..2tx+1
@@ -61,7 +61,7 @@ sasa_hd32_kernel(const float* __restrict__ qkv, const float* __restrict__ query_
             const int k = i >> 5, d = i & 31;
             const int gk = k0 + k;
             const bool ok = gk < Q;
-            const float* row = base + (long long)gk * 3 * D + h * SA_HD + d;
+            const float* row = base + (long long)gk * ld_qkv + h * SA_HD + d;
             Kt[d][k] = ok ? __ldg(row + D) : 0.f;
             Vs[k][d] = ok ? __ldg(row + 2 * D) : 0.f;
         }
@@ -151,13 +151,14 @@ sasa_hd32_kernel(const float* __restrict__ qkv, const float* __restrict__ query_
 
 using namespace sbev;
 
-extern "C" int sbev_sasa_fwd(const float* qkv, const float* query_bbox, const float* tau, const uint8_t* dn_mask,
-                             const float* pc_range, int B, int Q, int H, int D, float* out, void* stream) {
+extern "C" int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bbox, const float* tau, int ld_tau,
+                             const uint8_t* dn_mask, const float* pc_range, int B, int Q, int H, int D, float* out, void* stream) {
     SBEV_REQUIRE(qkv && query_bbox && tau && pc_range && out, SBEV_ERR_INVALID, "sbev_sasa_fwd: null pointer");
     SBEV_REQUIRE(B >= 0 && Q >= 0 && H > 0, SBEV_ERR_INVALID, "sbev_sasa_fwd: bad sizes");
+    SBEV_REQUIRE(ld_qkv >= 3 * D && ld_tau >= H, SBEV_ERR_INVALID, "sbev_sasa_fwd: row strides too small");
     SBEV_REQUIRE(D == H * SA_HD, SBEV_ERR_UNSUPPORTED, "sbev_sasa_fwd: head dim must be 32 (D=%d, H=%d)", D, H);
     if (B == 0 || Q == 0) return SBEV_OK;
     dim3 grid((Q + SA_BQ - 1) / SA_BQ, H, B);
-    sasa_hd32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, query_bbox, tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+    sasa_hd32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
     return check_launch("sbev_sasa_fwd");
 }

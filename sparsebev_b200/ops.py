@@ -13,6 +13,7 @@ GROUPS = 4          # reference: num_groups hard-coded, sparsebev_transformer.py
 OUT_POINTS = 128    # reference: out_points hard-coded, sparsebev_transformer.py:124
 DENSE_RELU = 1
 DENSE_RES_PRE_LN = 2
+DENSE_REFINE = 4
 
 
 def _stream():
@@ -151,23 +152,56 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
 
 
 class DenseWeight:
-    """Device-side cache of one nn.Linear's weight in the layout sbev_dense_fwd wants:
-    Wt[K][ldw] = W^T zero-padded to a multiple of 4 columns.  Rebuilt when the parameter changes."""
+    """Device-side cache of one (or several, concatenated along the output dim) nn.Linear weights in the layout
+    the dense kernels want: Wt[K][ldw] = W^T zero-padded to a multiple of 4 columns (+ the concatenated bias).
+    Rebuilt when any parameter changes (data_ptr / version / device)."""
 
     def __init__(self):
         self.key = None
         self.wt = None
+        self.bias = None
         self.ldw = 0
+        self.n = 0
 
-    def get(self, weight):
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    def get(self, weight, *more_weights):
+        return self.get_with_bias([weight] + list(more_weights), None)[:2]
+
+    def get_with_bias(self, weights, biases):
+        key = tuple((w.data_ptr(), w._version, tuple(w.shape), w.device) for w in weights)
+        if biases is not None:
+            key += tuple((b.data_ptr(), b._version) for b in biases if b is not None)
         if key != self.key:
-            N, K = weight.shape
+            K = weights[0].shape[1]
+            N = sum(w.shape[0] for w in weights)
             ldw = (N + 3) // 4 * 4
-            wt = torch.zeros(K, ldw, device=weight.device, dtype=torch.float32)
-            wt[:, :N] = weight.detach().t()
-            self.wt, self.ldw, self.key = wt, ldw, key
-        return self.wt, self.ldw
+            wt = torch.zeros(K, ldw, device=weights[0].device, dtype=torch.float32)
+            wt[:, :N] = torch.cat([w.detach() for w in weights], dim=0).t()
+            self.bias = None
+            if biases is not None and any(b is not None for b in biases):
+                self.bias = torch.cat([b.detach() if b is not None else torch.zeros(w.shape[0], device=w.device)
+                                       for w, b in zip(weights, biases)]).contiguous()
+            self.wt, self.ldw, self.n, self.key = wt, ldw, N, key
+        return self.wt, self.ldw, self.bias
+
+
+def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None):
+    """One entry of a dense chain (see dense_chain)."""
+    flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
+    keep = [t for t in (wt, bias, residual, y) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
+    return _lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
+                           _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
+                           (ldy if ldy is not None else N) if y is not None else 0), keep
+
+
+def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):
+    """Run 1..6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers in ONE kernel (sbev_dense_chain_fwd).
+    `layers` = list of chain_layer(...) results; outputs are the `y` tensors given to them."""
+    lib = _lib.load()
+    _chk(x, 'x')
+    arr = (_lib.DenseLayer * len(layers))(*[l[0] for l in layers])
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_dense_chain_fwd(x.data_ptr(), ldx, M, len(layers), arr, _p(refine_proposal), _p(refine_time_diff),
+                                            refine_Q, refine_T, _stream()), 'sbev_dense_chain_fwd')
 
 
 def dense(x, wt, ldw, n_out, bias=None, ln_w=None, ln_b=None, residual=None, relu=False, res_pre_ln=False, out=None, k=None):
@@ -190,38 +224,49 @@ def dense(x, wt, ldw, n_out, bias=None, ln_w=None, ln_b=None, residual=None, rel
     return out
 
 
-def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels):
-    """query_bbox [B,Q,10], offset [B,Q,GP*3], scale_logits [B,Q,GP*L] -> points [B,Q,GP,3], scale_w [B,Q,GP,L] (GP = G*P, group-major)."""
+def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels, num_points_total=None, ld_off=None, ld_log=None):
+    """query_bbox [B,Q,10]; offset rows of GP*3 floats, scale_logits rows of GP*L floats (either plain [B,Q,GP*3] /
+    [B,Q,GP*L] tensors, or column blocks of a wider matrix given with explicit row strides ld_off / ld_log)
+    -> points [B,Q,GP,3], scale_w [B,Q,GP,L] (GP = G*P, group-major)."""
     lib = _lib.load()
     qb = _chk(query_bbox, 'query_bbox')
-    off = _chk(offset, 'offset')
-    lg = _chk(scale_logits, 'scale_logits')
     B, Q, _ = qb.shape
-    GP = off.shape[-1] // 3
     L = num_levels
+    if ld_off is None:
+        off = _chk(offset, 'offset')
+        lg = _chk(scale_logits, 'scale_logits')
+        GP = off.shape[-1] // 3
+        ld_off, ld_log = GP * 3, GP * L
+    else:
+        off, lg, GP = offset, scale_logits, num_points_total
     pts = torch.empty(B, Q, GP, 3, device=qb.device, dtype=torch.float32)
     sw = torch.empty(B, Q, GP, L, device=qb.device, dtype=torch.float32)
     with torch.cuda.device(qb.device):
-        _lib.check(lib.sbev_sample_points_fwd(qb.data_ptr(), off.data_ptr(), lg.data_ptr(),
+        _lib.check(lib.sbev_sample_points_fwd(qb.data_ptr(), off.data_ptr(), ld_off, lg.data_ptr(), ld_log,
                                               _lib.f32_array([float(v) for v in pc_range]), B * Q, GP, L,
                                               pts.data_ptr(), sw.data_ptr(), _stream()), 'sbev_sample_points_fwd')
     return pts, sw
 
 
-def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None):
-    """qkv [B,Q,3D], query_bbox [B,Q,10], tau [B,Q,H] -> attention output [B,Q,D] (before out_proj)."""
+def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None, ld_qkv=None, ld_tau=None, embed_dims=None):
+    """qkv [B,Q,3D] and tau [B,Q,H] (or column blocks of one wider [B*Q, ld] matrix, with explicit row strides)
+    + query_bbox [B,Q,10] -> attention output [B,Q,D] (before out_proj)."""
     lib = _lib.load()
-    qkv = _chk(qkv, 'qkv')
     qb = _chk(query_bbox, 'query_bbox')
-    tau = _chk(tau, 'tau')
-    B, Q, D3 = qkv.shape
-    D = D3 // 3
+    B, Q, _ = qb.shape
+    if ld_qkv is None:
+        qkv = _chk(qkv, 'qkv')
+        tau = _chk(tau, 'tau')
+        D = qkv.shape[-1] // 3
+        ld_qkv, ld_tau = 3 * D, num_heads
+    else:
+        D = embed_dims
     m = None
     if dn_mask is not None:
         m = _chk(dn_mask.to(torch.uint8).contiguous(), 'dn_mask', torch.uint8)
-    out = torch.empty(B, Q, D, device=qkv.device, dtype=torch.float32)
-    with torch.cuda.device(qkv.device):
-        _lib.check(lib.sbev_sasa_fwd(qkv.data_ptr(), qb.data_ptr(), tau.data_ptr(), _p(m),
+    out = torch.empty(B, Q, D, device=qb.device, dtype=torch.float32)
+    with torch.cuda.device(qb.device):
+        _lib.check(lib.sbev_sasa_fwd(qkv.data_ptr(), ld_qkv, qb.data_ptr(), tau.data_ptr(), ld_tau, _p(m),
                                      _lib.f32_array([float(v) for v in pc_range]), B, Q, num_heads, D,
                                      out.data_ptr(), _stream()), 'sbev_sasa_fwd')
     return out

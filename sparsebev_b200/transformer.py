@@ -13,8 +13,8 @@ Same class names, constructor kwargs, call signatures, side effects and state-di
     AdaptiveMixing                  :320-387
 
 The nn.Modules only HOLD parameters (so names/shapes match the checkpoint); every forward runs the
-hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- about two dozen launches per layer,
-capturable in one CUDA graph (see `SparseBEVTransformerDecoder.forward_graphed`).  Forward only: this
+hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- 13 launches per layer, capturable in one
+CUDA graph (bench.py does).  Forward only: this
 is the eval path (dropout = identity, no activation checkpointing); training the decoder through these
 modules is out of scope (the op-level autograd Functions in `wrapper.py` do have a backward).
 """
@@ -41,16 +41,24 @@ NUM_VIEWS = 6     # hard-coded in the reference (sparsebev_transformer.py:61,75)
 
 
 class _Dense:
-    """Linear (+LN +ReLU +residual) launcher bound to the parameters of one nn.Linear."""
+    """One nn.Linear (or several sharing the input, concatenated along the output dim) + optional LayerNorm,
+    bound to the cached device layout the dense kernels want.  `layer(...)` builds a chain entry."""
 
-    def __init__(self, linear, ln=None):
-        self.linear, self.ln, self.cache = linear, ln, ops.DenseWeight()
+    def __init__(self, linear, ln=None, extra=()):
+        self.linears, self.ln, self.cache = [linear] + list(extra), ln, ops.DenseWeight()
+        self.in_features = linear.in_features
+        self.out_features = sum(l.out_features for l in self.linears)
+
+    def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None):
+        wt, ldw, bias = self.cache.get_with_bias([l.weight for l in self.linears], [l.bias for l in self.linears])
+        return ops.chain_layer(wt, ldw, self.in_features, self.out_features, bias=bias, ln=self.ln, residual=residual,
+                               relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy)
 
     def __call__(self, x, relu=False, residual=None, res_pre_ln=False, k=None):
-        wt, ldw = self.cache.get(self.linear.weight)
-        return ops.dense(x, wt, ldw, self.linear.out_features, bias=self.linear.bias,
-                         ln_w=None if self.ln is None else self.ln.weight, ln_b=None if self.ln is None else self.ln.bias,
-                         residual=residual, relu=relu, res_pre_ln=res_pre_ln, k=k)
+        M = x.shape[0]
+        y = torch.empty(M, self.out_features, device=x.device, dtype=torch.float32)
+        ops.dense_chain(x, x.shape[1], M, [self.layer(relu=relu, residual=residual, res_pre_ln=res_pre_ln, y=y)])
+        return y
 
 
 class _SplitWeight:
@@ -144,26 +152,41 @@ class SparseBEVSelfAttention(BaseModule):
         self.num_heads = num_heads
         self.attention = _MHAParams(embed_dims, num_heads, dropout)
         self.gen_tau = nn.Linear(embed_dims, num_heads)
-        self._in, self._out, self._tau = ops.DenseWeight(), ops.DenseWeight(), _Dense(self.gen_tau)
+        self._cache_in, self._cache_out = ops.DenseWeight(), ops.DenseWeight()
 
     @torch.no_grad()
     def init_weights(self):
         nn.init.zeros_(self.gen_tau.weight)
         nn.init.uniform_(self.gen_tau.bias, 0.0, 2.0)
 
+    def in_layer(self, y):
+        """in_proj and gen_tau as ONE concatenated Linear: columns [0,3D) = q|k|v, [3D,3D+H) = tau."""
+        attn = self.attention.attn
+        wt, ldw, bias = self._cache_in.get_with_bias([attn.in_proj_weight, self.gen_tau.weight], [attn.in_proj_bias, self.gen_tau.bias])
+        return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y)
+
+    def out_layer(self, residual, norm, y):
+        attn = self.attention.attn
+        wt, ldw, bias = self._cache_out.get_with_bias([attn.out_proj.weight], [attn.out_proj.bias])
+        return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y)
+
+    def attention_core(self, query_bbox, x, pre_attn_mask=None):
+        """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj)."""
+        B, Q = query_bbox.shape[:2]
+        D, H = self.attention.attn.embed_dim, self.num_heads
+        qkvt = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.float32)
+        ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt)])
+        o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
+                     ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
+        return o.reshape(B * Q, D)
+
     def forward_fused(self, query_bbox, query_feat, pre_attn_mask=None, norm=None):
         """-> norm(query_feat + out_proj(attention)) ; the [B*8,Q,Q] mask is never built."""
         B, Q, D = query_feat.shape
         x = query_feat.reshape(B * Q, D)
-        attn = self.attention.attn
-        wt, ldw = self._in.get(attn.in_proj_weight)
-        qkv = ops.dense(x, wt, ldw, 3 * D, bias=attn.in_proj_bias)
-        tau = self._tau(x)
-        o = ops.sasa(qkv.reshape(B, Q, 3 * D), query_bbox, tau.reshape(B, Q, self.num_heads), self.pc_range,
-                     self.num_heads, dn_mask=pre_attn_mask)
-        wt, ldw = self._out.get(attn.out_proj.weight)
-        out = ops.dense(o.reshape(B * Q, D), wt, ldw, D, bias=attn.out_proj.bias, residual=x, res_pre_ln=True,
-                        ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
+        o = self.attention_core(query_bbox, x, pre_attn_mask)
+        out = torch.empty(B * Q, D, device=x.device, dtype=torch.float32)
+        ops.dense_chain(o, D, B * Q, [self.out_layer(x, norm, out)])
         return out.reshape(B, Q, D)
 
     def forward(self, query_bbox, query_feat, pre_attn_mask):
@@ -180,7 +203,7 @@ class SparseBEVSampling(BaseModule):
         self.pc_range = pc_range
         self.sampling_offset = nn.Linear(embed_dims, num_groups * num_points * 3)
         self.scale_weights = nn.Linear(embed_dims, num_groups * num_points * num_levels)
-        self._off, self._sw = _Dense(self.sampling_offset), _Dense(self.scale_weights)
+        self._heads = _Dense(self.sampling_offset, extra=[self.scale_weights])      # one Linear: [offset | scale logits]
         self.feat_layout = 'grouped'
 
     def init_weights(self):
@@ -188,19 +211,27 @@ class SparseBEVSampling(BaseModule):
         nn.init.zeros_(self.sampling_offset.weight)
         nn.init.uniform_(bias[:, 0:3], -0.5, 0.5)
 
-    def forward(self, query_bbox, query_feat, mlvl_feats, img_metas):
-        B, Q, D = query_feat.shape
+    def heads_layer(self, y):
+        return self._heads.layer(y=y)
+
+    def sample(self, query_bbox, heads_out, mlvl_feats, img_metas):
+        """heads_out [B*Q, G*P*3 + G*P*L] = the concatenated sampling_offset | scale_weights Linear output."""
+        B, Q = query_bbox.shape[:2]
         image_h, image_w, _ = img_metas[0]['img_shape'][0]
-        x = query_feat.reshape(B * Q, D)
-        offset = self._off(x)                                   # [BQ, G*P*3]
-        logits = self._sw(x)                                    # [BQ, G*P*L]
         G, P, L = self.num_groups, self.num_points, self.num_levels
-        pts, sw = ops.sample_points(query_bbox, offset.reshape(B, Q, G * P * 3), logits.reshape(B, Q, G * P * L),
-                                    self.pc_range, L)
+        ld = heads_out.shape[1]
+        pts, sw = ops.sample_points(query_bbox, heads_out, heads_out[:, G * P * 3:], self.pc_range, L,
+                                    num_points_total=G * P, ld_off=ld, ld_log=ld)
         vel = query_bbox[..., 8:10].contiguous()
         return ops.sampling4d_fused(mlvl_feats, pts, vel, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
                                     sw.reshape(B, Q, G, P, L), image_h, image_w, num_frames=self.num_frames,
                                     num_views=NUM_VIEWS, layout=self.feat_layout)       # [B,Q,G,T*P,C]
+
+    def forward(self, query_bbox, query_feat, mlvl_feats, img_metas):
+        B, Q, D = query_feat.shape
+        heads = torch.empty(B * Q, self._heads.out_features, device=query_feat.device, dtype=torch.float32)
+        ops.dense_chain(query_feat.reshape(B * Q, D), D, B * Q, [self.heads_layer(heads)])
+        return self.sample(query_bbox, heads, mlvl_feats, img_metas)
 
 
 class _FFNParams(nn.Module):
@@ -256,28 +287,38 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
     @torch.no_grad()
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
-        -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193)."""
+        -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
+
+        13 kernel launches: 5 dense chains, SASA core, sample_points, fused gather, bf16 split, 2 tcgen05 GEMMs,
+        mix, split-K reduce + norm2."""
         B, Q, D = query_feat.shape
-        M = B * Q
+        M, dev = B * Q, query_feat.device
         query_bbox = query_bbox.contiguous()
         qf = query_feat.reshape(M, D).contiguous()
-        h = self._pe0(query_bbox.reshape(M, -1), relu=True, k=3)                  # Linear(3,D) on bbox[..., :3] + LN + ReLU
-        qf = self._pe1(h, relu=True, residual=qf)                                  # + LN + ReLU, then query_feat + query_pos
-        qf = self.self_attn.forward_fused(query_bbox, qf.reshape(B, Q, D), attn_mask, self.norm1)
-        sampled = self.sampling(query_bbox, qf, mlvl_feats, img_metas)
-        qf = self.mixing.forward_fused(sampled, qf, self.norm2).reshape(M, D)
-        h = self._ffn0(qf, relu=True)
-        qf = self._ffn1(h, residual=qf, res_pre_ln=True)                           # identity + ffn, then norm3
-        c = qf
-        for layer in self._cls[:-1]:
-            c = layer(c, relu=True)
-        cls_score = self._cls[-1](c).reshape(B, Q, self.num_classes)
-        r = qf
-        for layer in self._reg[:-1]:
-            r = layer(r, relu=True)
-        delta = self._reg[-1](r).reshape(B, Q, self.code_size)
-        bbox_pred = self.refine_bbox(query_bbox, delta, img_metas[0]['time_diff'])
-        return qf.reshape(B, Q, D), cls_score, bbox_pred
+        new = lambda n: torch.empty(M, n, device=dev, dtype=torch.float32)      # noqa: E731
+        # (1) position encoder, + query_feat                                     [Linear(3,D) LN ReLU Linear LN ReLU] + residual
+        q1 = new(D)
+        ops.dense_chain(query_bbox.reshape(M, -1), query_bbox.shape[-1], M,
+                        [self._pe0.layer(relu=True), self._pe1.layer(relu=True, residual=qf, y=q1)])
+        # (2) scale-adaptive self-attention; out_proj + identity + norm1 chained with the sampling heads
+        o = self.self_attn.attention_core(query_bbox, q1, attn_mask)
+        q2, heads = new(D), new(self.sampling._heads.out_features)
+        ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2), self.sampling.heads_layer(heads)])
+        # (3) adaptive spatio-temporal sampling
+        sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+        # (4) adaptive mixing (+ identity + norm2)
+        q3 = self.mixing.forward_fused(sampled, q2.reshape(B, Q, D), self.norm2).reshape(M, D)
+        # (5) FFN (+ identity + norm3) chained with the classification branch
+        q4, cls_score = new(D), new(self.num_classes)
+        chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
+        chain += [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
+        ops.dense_chain(q3, D, M, chain)
+        # (6) regression branch with the box refinement / velocity rescale as its epilogue
+        bbox_pred = new(self.code_size)
+        td = img_metas[0]['time_diff']
+        ops.dense_chain(q4, D, M, [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)],
+                        refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
+        return q4.reshape(B, Q, D), cls_score.reshape(B, Q, self.num_classes), bbox_pred.reshape(B, Q, self.code_size)
 
 
 class SparseBEVTransformerDecoder(BaseModule):

@@ -22,7 +22,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert os.path.exists(so)
     lib = _lib.load()
     declared = _declared_symbols()
-    assert len(declared) >= 14
+    assert len(declared) >= 15
     for name in declared:
         assert hasattr(lib, name), 'libsparsebev_b200.so does not export %s' % name
     assert sorted(_lib.exported_symbols()) == declared, 'ctypes signature table and header disagree'
@@ -43,7 +43,7 @@ def test_argument_validation_without_gpu():
     assert lib.sbev_gemm_bf16_tn(one, one, 1, None, 128, 100, 64, 1, 16, None) == -2      # N % 128
     assert lib.sbev_gemm_bf16_tn(one, one, 4, None, 128, 128, 64, 1, 16, None) == -1      # nseg > 3
     assert lib.sbev_mix_fwd(16, 16, 1, 4, 32, 64, 64, 16, 16, None, None) == -2           # out_points != 128
-    assert lib.sbev_sasa_fwd(16, 16, 16, None, _lib.f32_array([0] * 6), 1, 4, 8, 128, 16, None) == -2   # head dim != 32
+    assert lib.sbev_sasa_fwd(16, 384, 16, 16, 8, None, _lib.f32_array([0] * 6), 1, 4, 8, 128, 16, None) == -2   # head dim != 32
     # zero-sized problems are a no-op that never touches CUDA
     assert lib.sbev_msmv_fwd(one, hw, 1, 16, 16, 0, 6, 64, 0, 4, 16, None) == 0
 

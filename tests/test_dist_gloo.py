@@ -1,0 +1,54 @@
+"""N>1 host logic on CPU: world_size-2 gloo process group (rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    from sparsebev_b200 import dist as D
+    r, w = D.init(backend='gloo')
+    assert (r, w) == (rank, world)
+    D.barrier()
+    mx = D.max_over_ranks(10.0 + rank)
+    t0, t1 = D.frame_partition(8, rank, world)
+    local = torch.arange(t0, t1, dtype=torch.float32)[:, None].repeat(1, 3)          # [T_local, 3], value = global frame id
+    full = D.all_gather_frames(local)
+    scenes = D.scene_partition(5, rank, world)
+    q.put((rank, mx, full[:, 0].tolist(), scenes))
+    torch.distributed.destroy_process_group()
+
+
+def test_gloo_world2_partitions_and_timing_reduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] == 11.0 for r in res)                       # max over ranks
+    assert all(r[2] == [0, 1, 2, 3, 4, 5, 6, 7] for r in res)   # frame-major all-gather in rank order
+    assert res[0][3] == [0, 1, 2] and res[1][3] == [3, 4]       # scene partition covers everything once
+
+
+def test_partitions_single_process():
+    from sparsebev_b200 import dist as D
+    assert D.frame_partition(8, 3, 4) == (6, 8)
+    assert sum((D.scene_partition(7, r, 3) for r in range(3)), []) == list(range(7))
+    assert D.max_over_ranks(3.5) == 3.5
+    x = torch.ones(2, 4)
+    assert D.all_gather_frames(x) is x

@@ -123,8 +123,11 @@ def test_r50_t8_layer_runs_and_is_deterministic():
         assert torch.isfinite(x).all() and torch.equal(x, y)
     B, Q, G, P, T, Lv = 1, 900, 4, 4, 8, 4
     x = qf.cuda().reshape(Q, 256)
-    off, lg = layer.sampling._off(x), layer.sampling._sw(x)
-    pts, sw = ops.sample_points(qb.cuda(), off.reshape(1, Q, 48), lg.reshape(1, Q, 64), cfg['pc_range'], Lv)
+    heads = layer.sampling._heads(x)                                   # [Q, 48 + 64] = offset | scale logits
+    pts, sw = ops.sample_points(qb.cuda(), heads, heads[:, 48:], cfg['pc_range'], Lv, num_points_total=16, ld_off=112, ld_log=112)
+    pts_b, sw_b = ops.sample_points(qb.cuda(), heads[:, :48].contiguous().reshape(1, Q, 48), heads[:, 48:].contiguous().reshape(1, Q, 64),
+                                    cfg['pc_range'], Lv)
+    assert torch.equal(pts, pts_b) and torch.equal(sw, sw_b)           # strided and packed forms agree
     out, loc = ops.sampling4d_fused(gfeats, pts, qb[..., 8:10].contiguous().cuda(), metas[0]['time_diff'], metas[0]['lidar2img'],
                                     sw.reshape(1, Q, G, P, Lv), 256, 704, num_frames=T, return_loc=True)
     i = torch.arange(T * G, device='cuda')

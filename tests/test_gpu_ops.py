@@ -271,6 +271,55 @@ def test_dense_vs_torch(M, K, N, ln, relu, res):
     _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
 
 
+def test_dense_chain_vs_torch():
+    """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored."""
+    ops = _ops()
+    torch.manual_seed(1)
+    M, D = 901, 256
+    x = torch.randn(M, D)
+    lin = [torch.nn.Linear(256, 512), torch.nn.Linear(512, 256), torch.nn.Linear(256, 256), torch.nn.Linear(256, 256), torch.nn.Linear(256, 10)]
+    lns = [None, torch.nn.LayerNorm(256), torch.nn.LayerNorm(256), torch.nn.LayerNorm(256), None]
+    for ln in lns:
+        if ln is not None:
+            torch.nn.init.normal_(ln.weight, 1, 0.1); torch.nn.init.normal_(ln.bias, 0, 0.1)
+    with torch.no_grad():
+        h = torch.relu(lin[0](x))
+        q4 = lns[1](x + lin[1](h))
+        c = torch.relu(lns[2](lin[2](q4)))
+        c = torch.relu(lns[3](lin[3](c)))
+        want_cls = lin[4](c)
+    caches = [ops.DenseWeight() for _ in lin]
+    xd = x.to(dev())
+    q4d, clsd = torch.empty(M, 256, device=dev()), torch.empty(M, 10, device=dev())
+    mods = [m.to(dev()) for m in lin]
+    lnd = [None if l is None else l.to(dev()) for l in lns]
+
+    def entry(i, **kw):
+        wt, ldw, bias = caches[i].get_with_bias([mods[i].weight], [mods[i].bias])
+        return ops.chain_layer(wt, ldw, mods[i].in_features, mods[i].out_features, bias=bias, ln=lnd[i], **kw)
+    ops.dense_chain(xd, D, M, [entry(0, relu=True), entry(1, residual=xd, res_pre_ln=True, y=q4d), entry(2, relu=True),
+                               entry(3, relu=True), entry(4, y=clsd)])
+    _close(q4d, q4, rtol=1e-4, atol=2e-5, what='chain intermediate (ffn + norm3)')
+    _close(clsd, want_cls, rtol=1e-4, atol=2e-5, what='chain final (cls)')
+    # concatenated Linear (two heads sharing the input) == the two separate Linears
+    cat = ops.DenseWeight()
+    wt, ldw, bias = cat.get_with_bias([mods[2].weight, mods[4].weight], [mods[2].bias, mods[4].bias])
+    both = torch.empty(M, 266, device=dev())
+    ops.dense_chain(q4d, D, M, [ops.chain_layer(wt, ldw, 256, 266, bias=bias, y=both)])
+    with torch.no_grad():
+        _close(both[:, :256], lin[2](q4), rtol=1e-4, atol=2e-5, what='concat head A')
+        _close(both[:, 256:], lin[4](q4), rtol=1e-4, atol=2e-5, what='concat head B')
+    # refine epilogue
+    qb = R.init_query_bbox(961, seed=2)[:M][None].contiguous()
+    td = torch.tensor([[0.0, 0.5, 1.0]])
+    box = torch.empty(M, 10, device=dev())
+    ops.dense_chain(q4d, D, M, [entry(4, refine=True, y=box)], refine_proposal=qb.to(dev()), refine_time_diff=td.to(dev()), refine_Q=M, refine_T=3)
+    with torch.no_grad():
+        wb = R.refine_bbox(qb, lin[4](q4)[None])
+        wb = torch.cat([wb[..., :8], wb[..., 8:] / 0.5], -1)
+    _close(box, wb[0], rtol=1e-4, atol=2e-5, what='refine epilogue')
+
+
 def test_sample_points_and_refine_vs_oracle():
     ops = _ops()
     pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
@@ -306,6 +355,9 @@ def test_sasa_vs_oracle(Q):
     want = want.transpose(1, 2).reshape(B, Q, D)
     got = ops.sasa(qkv.to(dev()), qb.to(dev()), tau.to(dev()), pc, H)
     _close(got, want, rtol=1e-4, atol=1e-5, what='sasa core')
+    packed = torch.cat([qkv, tau], -1).reshape(B * Q, 3 * D + H).contiguous().to(dev())       # strided (concatenated-Linear) form
+    got_s = ops.sasa(packed, qb.to(dev()), packed[:, 3 * D:], pc, H, ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
+    assert torch.equal(got_s, got)
     mask = torch.zeros(Q, Q, dtype=torch.bool)
     mask[: Q // 2, Q // 2:] = True
     want_m = torch.softmax((q * (1 / np.sqrt(32)) @ k.transpose(-1, -2) + bias).masked_fill(mask, float('-inf')), -1) @ v
