@@ -25,6 +25,7 @@ class DenseLayer(ctypes.Structure):
 
 # name -> argtypes; every function returns int (SBEV_OK = 0)
 SIGNATURES = {
+    'sbev_set_option': [ctypes.c_char_p, c_int],
     'sbev_dense_chain_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
@@ -72,6 +73,12 @@ def load():
 
 
 launch_count = 0      # number of successful C-ABI launches (each enqueues exactly one of OUR kernels)
+
+
+def set_option(name, value):
+    rc = load().sbev_set_option(name.encode(), int(value))
+    if rc != 0:
+        raise RuntimeError('sbev_set_option(%s) failed' % name)
 
 
 def check(rc, what):

@@ -1,6 +1,8 @@
 // Error reporting + ABI version for libsparsebev_b200.so.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace sbev {
 static thread_local char g_err[512] = "";
@@ -11,7 +13,32 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+// Implementation selectors (A/B testing of kernel variants).  Defaults come from the environment
+// (SBEV_GEMM_IMPL, SBEV_MIX_IMPL, SBEV_SASA_IMPL, SBEV_GATHER_VARIANT), sbev_set_option overrides.
+static const char* kOptNames[OPT_COUNT] = {"gemm_impl", "mix_impl", "sasa_impl", "gather_variant"};
+static const char* kOptEnv[OPT_COUNT] = {"SBEV_GEMM_IMPL", "SBEV_MIX_IMPL", "SBEV_SASA_IMPL", "SBEV_GATHER_VARIANT"};
+static const int kOptDefault[OPT_COUNT] = {1, 0, 0, 0};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1};
+
+int get_option(int id) {
+    if (g_opt[id] < 0) {
+        const char* e = getenv(kOptEnv[id]);
+        g_opt[id] = e ? atoi(e) : kOptDefault[id];
+    }
+    return g_opt[id];
+}
+int set_option(const char* name, int value) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) { g_opt[i] = value; return SBEV_OK; }
+    set_error("unknown option '%s'", name);
+    return SBEV_ERR_INVALID;
+}
 }  // namespace sbev
 
 extern "C" int sbev_abi_version(void) { return 1; }
 extern "C" const char* sbev_last_error(void) { return sbev::g_err; }
+extern "C" int sbev_set_option(const char* name, int value) {
+    if (!name || value < 0) { sbev::set_error("sbev_set_option: bad arguments"); return SBEV_ERR_INVALID; }
+    return sbev::set_option(name, value);
+}

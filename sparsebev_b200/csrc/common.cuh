@@ -8,6 +8,9 @@
 namespace sbev {
 
 void set_error(const char* fmt, ...);
+enum { OPT_GEMM_IMPL = 0, OPT_MIX_IMPL = 1, OPT_SASA_IMPL = 2, OPT_GATHER_VARIANT = 3, OPT_COUNT = 4 };
+int get_option(int id);
+int set_option(const char* name, int value);
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

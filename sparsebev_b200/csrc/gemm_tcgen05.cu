@@ -220,6 +220,141 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int nseg, int kb_per_
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
+// ------------------------------------------------------------------------------- v2: persistent
+// Differences from the one-tile-per-CTA kernel above:
+//   * persistent CTAs (grid = min(#tiles, #SMs)) walk a static tile schedule, M-tile fastest so the CTAs that run
+//     concurrently share the same B (weight) tiles in L2;
+//   * TWO TMEM accumulators: the epilogue of tile i drains accumulator i&1 while the MMA warp already fills the
+//     other one for tile i+1 (tmem_full / tmem_empty mbarriers);
+//   * in bf16x3 mode one pipeline stage holds {A_hi, A_lo, B_hi, B_lo} for a k-block and the MMA warp issues the
+//     three products hi.hi, hi.lo, lo.hi from them -> every operand tile is fetched once, not 1.5x.
+//   * epilogue goes TMEM -> registers -> global directly (each thread owns one output row: 128 B runs).
+struct GemmMapsV2 {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+template <int BN, int STAGES, bool X3>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_per_split, int m_tiles, int n_tiles, int num_tiles,
+                               const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
+    constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    constexpr int B_BYTES = BN * GEMM_BK * 2;
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+            if (X3) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+            }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile % m_tiles) * GEMM_BM;
+                const int rest = tile / m_tiles;
+                const int n0 = (rest % n_tiles) * BN;
+                const int kb0 = (rest / n_tiles) * kb_per_split;
+                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    const int kc = (kb0 + kb) * GEMM_BK;
+                    tma_load_2d(st, &maps.a_hi, &full_bar[stage], kc, m0);
+                    tma_load_2d(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0);
+                    if (X3) {
+                        tma_load_2d(st + A_BYTES + B_BYTES, &maps.a_lo, &full_bar[stage], kc, m0);
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int as = lt & 1;
+                mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_k_sw128(st), b_hi = umma_desc_k_sw128(st + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    if (X3) {
+                        const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES + B_BYTES);
+                        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                }
+                umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile % m_tiles) * GEMM_BM;
+            const int rest = tile / m_tiles;
+            const int n0 = (rest % n_tiles) * BN;
+            const int z = rest / n_tiles;
+            const int as = lt & 1;
+            mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            float* crow = C + ((long long)z * M + row) * N + n0;
+            const bool add_bias = (bias != nullptr) && (z == 0);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+                if (row < M) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (add_bias) { const float4 bv = ldg4(bias + n0 + c * 32 + i); o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w; }
+                        *reinterpret_cast<float4*>(crow + c * 32 + i) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -267,25 +402,42 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
     SBEV_REQUIRE((K / GEMM_BK) % split_k == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: K/64 must be divisible by split_k");
     SBEV_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                  SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: C / bias must be 16-byte aligned");
+    for (int sg = 0; sg < nseg; ++sg) {
+        SBEV_REQUIRE(A[sg] && B[sg], SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: null operand in segment %d", sg);
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(A[sg]) & 15) == 0 && (reinterpret_cast<uintptr_t>(B[sg]) & 15) == 0,
+                     SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: operands must be 16-byte aligned");
+    }
+    const bool x3_pattern = nseg == 3 && A[0] == A[1] && B[0] == B[2];
+    if (get_option(OPT_GEMM_IMPL) == 1 && (nseg == 1 || x3_pattern)) {
+        // ---- v2: persistent, double-buffered TMEM, shared operand tiles for the three bf16x3 products
+        const bool wide = (N % 256 == 0);
+        const int BNv = wide ? 256 : 128;
+        GemmMapsV2 mp;
+        int rc = make_map(&mp.a_hi, A[0], M, K, GEMM_BM);            if (rc) return rc;
+        rc = make_map(&mp.b_hi, B[0], N, K, BNv);                    if (rc) return rc;
+        rc = make_map(&mp.a_lo, x3_pattern ? A[2] : A[0], M, K, GEMM_BM); if (rc) return rc;
+        rc = make_map(&mp.b_lo, x3_pattern ? B[1] : B[0], N, K, BNv);     if (rc) return rc;
+        const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / BNv;
+        const int num_tiles = m_tiles * n_tiles * split_k;
+        static int num_sms = 0;
+        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+        const int kbs = (K / GEMM_BK) / split_k;
+        cudaStream_t st = (cudaStream_t)stream;
+#define SBEV_GEMM_V2(BNN, STG, XX)                                                                                               \
+        do {                                                                                                                     \
+            constexpr size_t smem_v2 = (size_t)STG * (XX ? 2 : 1) * (GEMM_BM * GEMM_BK * 2 + BNN * GEMM_BK * 2) + 1024;          \
+            static std::once_flag once;                                                                                          \
+            std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \
+            gemm_bf16_tn_persistent_kernel<BNN, STG, XX><<<grid, GEMM_THREADS, smem_v2, st>>>(mp, kbs, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
+        } while (0)
+        if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
+        else            { if (wide) SBEV_GEMM_V2(256, 4, false); else SBEV_GEMM_V2(128, 6, false); }
+#undef SBEV_GEMM_V2
+        return check_launch("sbev_gemm_bf16_tn(v2)");
+    }
     constexpr int BN = 128, STAGES = 3;
     GemmMaps maps;
-    for (int s = 0; s < nseg; ++s) {
-        SBEV_REQUIRE(A[s] && B[s], SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: null operand in segment %d", s);
-        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(A[s]) & 15) == 0 && (reinterpret_cast<uintptr_t>(B[s]) & 15) == 0,
-                     SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: operands must be 16-byte aligned");
-        int rc = make_map(&maps.a[s], A[s], M, K, GEMM_BM);
-        if (rc) return rc;
-        rc = make_map(&maps.b[s], B[s], N, K, BN);
-        if (rc) return rc;
-    }
-    for (int s = nseg; s < GEMM_MAX_SEG; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
-    const size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
-    static std::once_flag attr_once;
-    std::call_once(attr_once, [&] {
-        cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
-    dim3 grid(N / BN, (M + GEMM_BM - 1) / GEMM_BM, split_k);
-    gemm_bf16_tn_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-        maps, nseg, (K / GEMM_BK) / split_k, bias, C, M, N);
     return check_launch("sbev_gemm_bf16_tn");
 }

@@ -12,6 +12,7 @@
 // bf16 (hi, lo) pair the bf16x3 out_proj GEMM consumes -- the same bytes as one fp32 copy.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace sbev {
 
@@ -155,6 +156,211 @@ mix_kernel(const float* __restrict__ params, const float* __restrict__ x, int G,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version: both small matmuls on mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) with the
+// bf16x3 split (a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, ~2^-17 relative) so the result stays fp32-grade.
+// Every operand is split ONCE while it is staged into shared memory (hi and lo bf16 copies, rows padded so
+// ldmatrix is bank-conflict free); stage 1 = x[PK x 64] . M[64 x 64] with warp w owning output columns
+// 8w..8w+7; stage 2 = S[128 x PK] . h[PK x 64] with warp w owning rows 16w..16w+15; both LayerNorms are
+// block reductions over the accumulator fragments; the result leaves through shared memory as 128 B rows.
+constexpr int MX_LD = 72;            // bf16 row stride of the K=64 operands (x, M^T): 144 B, == 4 words mod 32
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_bf16(d, al, bh);
+    mma_bf16(d, ah, bl);
+    mma_bf16(d, ah, bh);
+}
+
+// NM = number of 16-row tiles of the in_points dimension (PK = 16*NM >= Pin)
+template <int NM>
+__global__ void __launch_bounds__(256)
+mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, int G, int Pin,
+               __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, float* __restrict__ y_f32) {
+    constexpr int PK = 16 * NM;
+    constexpr int PS = PK + 8;                       // bf16 row stride of the K=PK operands (S, h^T)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(smem_raw);        // [PK][72]
+    __nv_bfloat16* xl = xh + PK * MX_LD;
+    __nv_bfloat16* mh = xl + PK * MX_LD;                                   // M^T [64 c'][72 (c)]
+    __nv_bfloat16* ml = mh + MIX_C * MX_LD;
+    __nv_bfloat16* sh = ml + MIX_C * MX_LD;                                // S [128][PS]
+    __nv_bfloat16* sl = sh + MIX_POUT * PS;
+    __nv_bfloat16* hh = sl + MIX_POUT * PS;                                // h^T [64 c'][PS (p)]
+    __nv_bfloat16* hl = hh + MIX_C * PS;
+    __shared__ float red[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const long long qg = blockIdx.x;
+    const long long per_group = (long long)MIX_C * MIX_C + (long long)MIX_POUT * Pin;
+    const float* pm = params + qg * per_group;
+    const float* ps = pm + MIX_C * MIX_C;
+    const float* px = x + qg * Pin * MIX_C;
+
+    // ---- stage operands as bf16 (hi, lo)
+    for (int i = tid; i < PK * 16; i += 256) {                  // x: rows p (zero beyond Pin), 4 channels per thread
+        const int p = i >> 4, c = (i & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < Pin) v = ldg4(px + p * MIX_C + c);
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(xh + p * MX_LD + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(xl + p * MX_LD + c) = make_uint2(l0, l1);
+    }
+    for (int i = tid; i < MIX_C * 16; i += 256) {               // M[c][c'] -> M^T[c'][c]
+        const int c = i >> 4, n = (i & 15) * 4;
+        const float4 v = ldg4(pm + c * MIX_C + n);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(f[k]);
+            mh[(n + k) * MX_LD + c] = h;
+            ml[(n + k) * MX_LD + c] = __float2bfloat16_rn(f[k] - __bfloat162float(h));
+        }
+    }
+    {
+        const int q4 = Pin >> 2;                                // float4 groups per S row (Pin % 4 == 0)
+        for (int i = tid; i < MIX_POUT * (PK / 4); i += 256) {
+            const int o = i / (PK / 4), pq = i - o * (PK / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pq < q4) v = ldg4(ps + (long long)o * Pin + pq * 4);
+            uint32_t h0, l0, h1, l1;
+            split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2*>(sh + o * PS + pq * 4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(sl + o * PS + pq * 4) = make_uint2(l0, l1);
+        }
+    }
+    __syncthreads();
+
+    // ldmatrix lane addressing: A (16x16): row = r + 8*(id&1), col = 8*(id>>1); B (8 n x 16 k): row = r, col = 8*(id&1)
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
+    const int b_row = lm_r, b_col = 8 * (lm_id & 1);
+
+    // ---- stage 1: h[p][c'] = sum_c x[p][c] M[c][c'], warp w owns columns c' = 8w..8w+7, all NM row tiles
+    float acc1[NM][4];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) { acc1[m][0] = acc1[m][1] = acc1[m][2] = acc1[m][3] = 0.f; }
+#pragma unroll
+    for (int k0 = 0; k0 < MIX_C; k0 += 16) {
+        uint32_t bh[2], bl[2];
+        ldsm_x2(bh, mh + (8 * warp + b_row) * MX_LD + k0 + b_col);
+        ldsm_x2(bl, ml + (8 * warp + b_row) * MX_LD + k0 + b_col);
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            uint32_t ah[4], al[4];
+            ldsm_x4(ah, xh + (16 * m + a_row) * MX_LD + k0 + a_col);
+            ldsm_x4(al, xl + (16 * m + a_row) * MX_LD + k0 + a_col);
+            mma3(acc1[m], ah, al, bh, bl);
+        }
+    }
+    {   // LayerNorm over the valid Pin x 64 block + ReLU, written as h^T (hi, lo)
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            if (16 * m + g8 < Pin) s += acc1[m][0] + acc1[m][1];
+            if (16 * m + g8 + 8 < Pin) s += acc1[m][2] + acc1[m][3];
+        }
+        const float n = (float)(Pin * MIX_C);
+        const float mean = block_sum_256(s, red) / n;
+        float ss = 0.f;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            if (16 * m + g8 < Pin) { const float a = acc1[m][0] - mean, b = acc1[m][1] - mean; ss += a * a + b * b; }
+            if (16 * m + g8 + 8 < Pin) { const float a = acc1[m][2] - mean, b = acc1[m][3] - mean; ss += a * a + b * b; }
+        }
+        const float rstd = rsqrtf(block_sum_256(ss, red) / n + 1e-5f);
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = 16 * m + g8 + 8 * (i >> 1), c = 8 * warp + 2 * t4 + (i & 1);
+                const float v = (p < Pin) ? fmaxf((acc1[m][i] - mean) * rstd, 0.f) : 0.f;
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                hh[c * PS + p] = h;
+                hl[c * PS + p] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+    }
+    __syncthreads();
+
+    // ---- stage 2: y[o][c'] = sum_p S[o][p] h[p][c'], warp w owns rows o = 16w..16w+15, all 8 column tiles
+    float acc2[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f; }
+#pragma unroll
+    for (int k0 = 0; k0 < PK; k0 += 16) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, sh + (16 * warp + a_row) * PS + k0 + a_col);
+        ldsm_x4(al, sl + (16 * warp + a_row) * PS + k0 + a_col);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            uint32_t bh[2], bl[2];
+            ldsm_x2(bh, hh + (8 * n + b_row) * PS + k0 + b_col);
+            ldsm_x2(bl, hl + (8 * n + b_row) * PS + k0 + b_col);
+            mma3(acc2[n], ah, al, bh, bl);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s += (acc2[n][0] + acc2[n][1]) + (acc2[n][2] + acc2[n][3]);
+    const float cnt = (float)(MIX_POUT * MIX_C);
+    const float mean = block_sum_256(s, red) / cnt;
+    float ss = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float d = acc2[n][i] - mean; ss += d * d; }
+    const float rstd = rsqrtf(block_sum_256(ss, red) / cnt + 1e-5f);      // (block_sum's barriers also fence the smem reuse below)
+
+    // ---- epilogue: ReLU(LN) -> (hi, lo) staged in shared memory (operands are dead now) -> 16 B coalesced stores
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(smem_raw);       // [128][72]
+    __nv_bfloat16* ol = oh + MIX_POUT * MX_LD;
+    const long long obase = qg * (MIX_POUT * MIX_C);
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int o = 16 * warp + g8 + 8 * hrow, c = 8 * n + 2 * t4;
+            const float v0 = fmaxf((acc2[n][2 * hrow] - mean) * rstd, 0.f), v1 = fmaxf((acc2[n][2 * hrow + 1] - mean) * rstd, 0.f);
+            uint32_t h, l;
+            split2(v0, v1, h, l);
+            *reinterpret_cast<uint32_t*>(oh + o * MX_LD + c) = h;
+            *reinterpret_cast<uint32_t*>(ol + o * MX_LD + c) = l;
+            if (y_f32) *reinterpret_cast<float2*>(y_f32 + obase + o * MIX_C + c) = make_float2(v0, v1);
+        }
+    __syncthreads();
+    if (y_hi) {
+        for (int i = tid; i < MIX_POUT * 8; i += 256) {
+            const int o = i >> 3, ch = (i & 7) * 8;
+            *reinterpret_cast<uint4*>(y_hi + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(oh + o * MX_LD + ch);
+            if (y_lo) *reinterpret_cast<uint4*>(y_lo + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(ol + o * MX_LD + ch);
+        }
+    }
+}
+
 }  // namespace sbev
 
 using namespace sbev;
@@ -167,11 +373,30 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
     SBEV_REQUIRE(BQ >= 0 && G > 0, SBEV_ERR_INVALID, "sbev_mix_fwd: bad sizes");
     SBEV_REQUIRE((((long long)MIX_C * MIX_C + (long long)Pout * Pin) & 3) == 0, SBEV_ERR_UNSUPPORTED, "sbev_mix_fwd: in_points must be a multiple of 4... (C*C + Pout*Pin) % 4 != 0");
     if (BQ == 0) return SBEV_OK;
-    const size_t smem = sizeof(float) * ((size_t)MIX_C * MIX_C + (size_t)Pin * MIX_C * 2 + (size_t)Pin * MIX_ST_LD);
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(y_hi);
     __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
     const int grid = BQ * G;
+    const int impl = get_option(OPT_MIX_IMPL);   // 1 selects the fp32 FFMA kernel (exact fp32 like the reference)
+    if (impl == 0 && (Pin & 3) == 0) {
+        const int NM = (Pin + 15) / 16;
+        const int PK = 16 * (NM <= 1 ? 1 : NM <= 2 ? 2 : NM <= 4 ? 4 : 8);
+        size_t smem = 2 * ((size_t)PK * MX_LD + (size_t)MIX_C * MX_LD + (size_t)MIX_POUT * (PK + 8) + (size_t)MIX_C * (PK + 8)) * 2;
+        const size_t out_stage = 2 * (size_t)MIX_POUT * MX_LD * 2;
+        if (smem < out_stage) smem = out_stage;
+#define SBEV_LAUNCH_MMA(R)                                                                                          \
+        do {                                                                                                        \
+            if (smem > 48 * 1024) cudaFuncSetAttribute(mix_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            mix_mma_kernel<R><<<grid, 256, smem, st>>>(params, x, G, Pin, hi, lo, y_f32);                           \
+        } while (0)
+        if (PK == 16) SBEV_LAUNCH_MMA(1);
+        else if (PK == 32) SBEV_LAUNCH_MMA(2);
+        else if (PK == 64) SBEV_LAUNCH_MMA(4);
+        else SBEV_LAUNCH_MMA(8);
+#undef SBEV_LAUNCH_MMA
+        return check_launch("sbev_mix_fwd(mma)");
+    }
+    const size_t smem = sizeof(float) * ((size_t)MIX_C * MIX_C + (size_t)Pin * MIX_C * 2 + (size_t)Pin * MIX_ST_LD);
 #define SBEV_LAUNCH_MIX(R)                                                                                         \
     do {                                                                                                           \
         if (smem > 48 * 1024) cudaFuncSetAttribute(mix_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -562,8 +562,7 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
         SBEV_REQUIRE((long long)lv.H[l] * lv.W[l] * stride_px[l] < (1ll << 31), SBEV_ERR_UNSUPPORTED, "level %d too large for 32-bit pixel offsets", l);
     FusedParams prm{points, velocity, time_diff, lidar2img, scale_w, out, loc_out, B, T, G, N, Q, P, image_h, image_w, eps};
     const dim3 grid((Q * P + 15) / 16, B * T * G);
-    static int variant = -1;        // SBEV_GATHER_VARIANT: 0 = all levels in flight (default), 1 = two levels at a time, 3 CTAs/SM
-    if (variant < 0) { const char* e = getenv("SBEV_GATHER_VARIANT"); variant = e ? atoi(e) : 0; }
+    const int variant = get_option(OPT_GATHER_VARIANT);   // 0 = all levels in flight (default), 1 = two levels at a time, 3 CTAs/SM
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
         if (variant == 1 && LL >= 3) sampling4d_c64_kernel<LL, 2, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);   \

@@ -10,7 +10,9 @@
 // 64-query tile of one (batch, head); keys/values stream through shared memory in tiles of 64; S and
 // O are register-tiled 4x4 / 4x2 per thread with operands read as float4 from d-major shared tiles.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace sbev {
 
@@ -147,6 +149,207 @@ sasa_hd32_kernel(const float* __restrict__ qkv, int ld_qkv, const float* __restr
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version (default): flash-attention-2 structure on mma.sync.m16n8k16 with the bf16x3 split
+// (q.k and p.v each as hi.hi + hi.lo + lo.hi, fp32 accumulate) so logits / outputs stay fp32-grade.
+// CTA = 4 warps x 16 query rows = 64 queries of one (batch, head); keys / values stream through shared
+// memory in tiles of 64, split into bf16 (hi, lo) as they are staged; S = QK^T and O += PV never leave
+// registers (the C fragments of S are re-used in place as the A fragments of P).
+constexpr int SM_LD = 40;      // bf16 row stride of the 32-wide head-dim tiles: 80 B = 20 words (ldmatrix conflict-free)
+
+__device__ __forceinline__ void sa_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void sa_ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void sa_ldsm_x2(uint32_t (&r)[2], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void sa_ldsm_x2_trans(uint32_t (&r)[2], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void sa_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void sa_mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                        const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    sa_mma(d, al, bh);
+    sa_mma(d, ah, bl);
+    sa_mma(d, ah, bh);
+}
+
+__global__ void __launch_bounds__(128)
+sasa_mma_kernel(const float* __restrict__ qkv, int ld_qkv, const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
+                const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
+                int B, int Q, int H, float* __restrict__ out) {
+    __shared__ __align__(16) __nv_bfloat16 Qh[SA_BQ * SM_LD], Ql[SA_BQ * SM_LD];
+    __shared__ __align__(16) __nv_bfloat16 Kh[SA_BK * SM_LD], Kl[SA_BK * SM_LD];
+    __shared__ __align__(16) __nv_bfloat16 Vh[SA_BK * SM_LD], Vl[SA_BK * SM_LD];
+    __shared__ float kcx[SA_BK], kcy[SA_BK];
+
+    const int D = H * SA_HD;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int q0 = blockIdx.x * SA_BQ;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const float scale = 0.17677669529663687f;
+    const float* base = qkv + (long long)b * Q * ld_qkv;
+
+    for (int i = tid; i < SA_BQ * 8; i += 128) {                 // Q tile, pre-scaled like nn.MultiheadAttention
+        const int q = i >> 3, d4 = (i & 7) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + q < Q) v = ldg4(base + (long long)(q0 + q) * ld_qkv + h * SA_HD + d4);
+        uint32_t h0, l0, h1, l1;
+        sa_split2(v.x * scale, v.y * scale, h0, l0); sa_split2(v.z * scale, v.w * scale, h1, l1);
+        *reinterpret_cast<uint2*>(Qh + q * SM_LD + d4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(Ql + q * SM_LD + d4) = make_uint2(l0, l1);
+    }
+    // this thread's two query rows: centres and tau
+    float rcx[2], rcy[2], rtau[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int gq = q0 + 16 * warp + g8 + 8 * r;
+        const bool ok = gq < Q;
+        rcx[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gq) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+        rcy[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gq) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        rtau[r] = ok ? __ldg(tau + ((long long)b * Q + gq) * ld_tau + h) : 0.f;
+    }
+    __syncthreads();
+
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
+    const int b_row = lm_r, b_col = 8 * (lm_id & 1);
+    uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        sa_ldsm_x4(qh[ks], Qh + (16 * warp + a_row) * SM_LD + 16 * ks + a_col);
+        sa_ldsm_x4(ql[ks], Ql + (16 * warp + a_row) * SM_LD + 16 * ks + a_col);
+    }
+
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float oacc[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+
+    for (int k0 = 0; k0 < Q; k0 += SA_BK) {
+        __syncthreads();                                          // previous K/V tile fully consumed
+        for (int i = tid; i < SA_BK * 8; i += 128) {
+            const int k = i >> 3, d4 = (i & 7) * 4;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + k < Q) {
+                const float* row = base + (long long)(k0 + k) * ld_qkv + h * SA_HD + d4;
+                kv = ldg4(row + D); vv = ldg4(row + 2 * D);
+            }
+            uint32_t h0, l0, h1, l1;
+            sa_split2(kv.x, kv.y, h0, l0); sa_split2(kv.z, kv.w, h1, l1);
+            *reinterpret_cast<uint2*>(Kh + k * SM_LD + d4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Kl + k * SM_LD + d4) = make_uint2(l0, l1);
+            sa_split2(vv.x, vv.y, h0, l0); sa_split2(vv.z, vv.w, h1, l1);
+            *reinterpret_cast<uint2*>(Vh + k * SM_LD + d4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Vl + k * SM_LD + d4) = make_uint2(l0, l1);
+        }
+        if (tid < SA_BK) {
+            const int gk = k0 + tid;
+            const bool ok = gk < Q;
+            kcx[tid] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gk) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+            kcy[tid] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + ((long long)b * Q + gk) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        }
+        __syncthreads();
+
+        // S = (q*scale) . k^T   (16 rows x 64 keys per warp)
+        float sacc[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                uint32_t bh[2], bl[2];
+                sa_ldsm_x2(bh, Kh + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                sa_ldsm_x2(bl, Kl + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                sa_mma3(sacc[n], qh[ks], ql[ks], bh, bl);
+            }
+        // + distance bias, masks, online softmax (row r of this thread = g8 + 8r; a row lives in one quad)
+        float alpha[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * n + 2 * t4 + e;
+                    const float dx = rcx[r] - kcx[k], dy = rcy[r] - kcy[k];
+                    float v = sacc[n][2 * r + e] + (-sqrtf(dx * dx + dy * dy)) * rtau[r];
+                    const int gq = q0 + 16 * warp + g8 + 8 * r;
+                    if (dn_mask != nullptr && gq < Q && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
+                    if (k0 + k >= Q) v = -INFINITY;
+                    sacc[n][2 * r + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[r], mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            alpha[r] = expf(m_run[r] - m_use);
+            float rs = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float pv = expf(sacc[n][2 * r + e] - m_use);
+                    sacc[n][2 * r + e] = pv;
+                    rs += pv;
+                }
+            l_run[r] = l_run[r] * alpha[r] + rs;                 // per-thread partial; quad-reduced once at the end
+            m_run[r] = m_new;
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { oacc[n][0] *= alpha[0]; oacc[n][1] *= alpha[0]; oacc[n][2] *= alpha[1]; oacc[n][3] *= alpha[1]; }
+        // O += P . V : the C fragments of S tiles (2j, 2j+1) are exactly the A fragment of key block j
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t ph[4], pl[4];
+            sa_split2(sacc[2 * j][0], sacc[2 * j][1], ph[0], pl[0]);
+            sa_split2(sacc[2 * j][2], sacc[2 * j][3], ph[1], pl[1]);
+            sa_split2(sacc[2 * j + 1][0], sacc[2 * j + 1][1], ph[2], pl[2]);
+            sa_split2(sacc[2 * j + 1][2], sacc[2 * j + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                uint32_t bh[2], bl[2];
+                sa_ldsm_x2_trans(bh, Vh + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
+                sa_ldsm_x2_trans(bl, Vl + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
+                sa_mma3(oacc[nd], ph, pl, bh, bl);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float l = l_run[r];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const int gq = q0 + 16 * warp + g8 + 8 * r;
+        if (gq < Q) {
+            const float inv = 1.f / l;
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd)
+                *reinterpret_cast<float2*>(out + ((long long)b * Q + gq) * D + h * SA_HD + 8 * nd + 2 * t4) =
+                    make_float2(oacc[nd][2 * r] * inv, oacc[nd][2 * r + 1] * inv);
+        }
+    }
+}
+
 }  // namespace sbev
 
 using namespace sbev;
@@ -159,6 +362,11 @@ extern "C" int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bb
     SBEV_REQUIRE(D == H * SA_HD, SBEV_ERR_UNSUPPORTED, "sbev_sasa_fwd: head dim must be 32 (D=%d, H=%d)", D, H);
     if (B == 0 || Q == 0) return SBEV_OK;
     dim3 grid((Q + SA_BQ - 1) / SA_BQ, H, B);
-    sasa_hd32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+    const int impl = get_option(OPT_SASA_IMPL);  // 1 selects the fp32 FFMA kernel
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (ld_qkv & 3) == 0, SBEV_ERR_INVALID, "sbev_sasa_fwd: qkv must be 16-byte aligned with ld_qkv % 4 == 0");
+    if (impl == 0)
+        sasa_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+    else
+        sasa_hd32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
     return check_launch("sbev_sasa_fwd");
 }

@@ -28,6 +28,19 @@ def _ops():
     return ops
 
 
+@pytest.fixture
+def option():
+    """Select a kernel variant for one test, restore the defaults afterwards."""
+    from sparsebev_b200 import _lib
+    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 0}
+
+    def setter(name, value):
+        _lib.set_option(name, value)
+    yield setter
+    for k, v in defaults.items():
+        _lib.set_option(k, v)
+
+
 def _close(a, b, rtol=RTOL, atol=ATOL, what=''):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     err = (a - b).abs()
@@ -288,11 +301,14 @@ def test_dense_chain_vs_torch():
         c = torch.relu(lns[2](lin[2](q4)))
         c = torch.relu(lns[3](lin[3](c)))
         want_cls = lin[4](c)
+        want_a, want_b = lin[2](q4), lin[4](q4)
+        want_delta = lin[4](q4)
     caches = [ops.DenseWeight() for _ in lin]
     xd = x.to(dev())
     q4d, clsd = torch.empty(M, 256, device=dev()), torch.empty(M, 10, device=dev())
-    mods = [m.to(dev()) for m in lin]
-    lnd = [None if l is None else l.to(dev()) for l in lns]
+    import copy
+    mods = [copy.deepcopy(m).to(dev()) for m in lin]
+    lnd = [None if l is None else copy.deepcopy(l).to(dev()) for l in lns]
 
     def entry(i, **kw):
         wt, ldw, bias = caches[i].get_with_bias([mods[i].weight], [mods[i].bias])
@@ -306,17 +322,15 @@ def test_dense_chain_vs_torch():
     wt, ldw, bias = cat.get_with_bias([mods[2].weight, mods[4].weight], [mods[2].bias, mods[4].bias])
     both = torch.empty(M, 266, device=dev())
     ops.dense_chain(q4d, D, M, [ops.chain_layer(wt, ldw, 256, 266, bias=bias, y=both)])
-    with torch.no_grad():
-        _close(both[:, :256], lin[2](q4), rtol=1e-4, atol=2e-5, what='concat head A')
-        _close(both[:, 256:], lin[4](q4), rtol=1e-4, atol=2e-5, what='concat head B')
+    _close(both[:, :256], want_a, rtol=1e-4, atol=2e-5, what='concat head A')
+    _close(both[:, 256:], want_b, rtol=1e-4, atol=2e-5, what='concat head B')
     # refine epilogue
     qb = R.init_query_bbox(961, seed=2)[:M][None].contiguous()
     td = torch.tensor([[0.0, 0.5, 1.0]])
     box = torch.empty(M, 10, device=dev())
     ops.dense_chain(q4d, D, M, [entry(4, refine=True, y=box)], refine_proposal=qb.to(dev()), refine_time_diff=td.to(dev()), refine_Q=M, refine_T=3)
-    with torch.no_grad():
-        wb = R.refine_bbox(qb, lin[4](q4)[None])
-        wb = torch.cat([wb[..., :8], wb[..., 8:] / 0.5], -1)
+    wb = R.refine_bbox(qb, want_delta[None])
+    wb = torch.cat([wb[..., :8], wb[..., 8:] / 0.5], -1)
     _close(box, wb[0], rtol=1e-4, atol=2e-5, what='refine epilogue')
 
 
@@ -339,8 +353,10 @@ def test_sample_points_and_refine_vs_oracle():
     _close(ops.refine_bbox(qb.to(dev()), delta.to(dev()), td.to(dev())), want, rtol=1e-5, atol=1e-6, what='refine_bbox')
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('Q', [900, 70, 64])
-def test_sasa_vs_oracle(Q):
+def test_sasa_vs_oracle(Q, impl, option):
+    option('sasa_impl', impl)            # 0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
     ops = _ops()
     pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
     B, D, H = 2, 256, 8
@@ -366,9 +382,11 @@ def test_sasa_vs_oracle(Q):
 
 
 # ------------------------------------------------------------------------- tcgen05 GEMM + mixing
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('M,N,K,split_k', [(128, 128, 64, 1), (900, 256, 256, 1), (900, 1024, 256, 1), (300, 256, 2048, 8),
-                                           (1, 128, 128, 2)])
-def test_gemm_bf16_single_segment(M, N, K, split_k):
+                                           (1, 128, 128, 2), (900, 384, 512, 2), (2000, 2560, 128, 1)])
+def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
+    option('gemm_impl', impl)            # 1 = persistent double-buffered kernel (default), 0 = one tile per CTA
     ops = _ops()
     torch.manual_seed(M + N + K)
     a = torch.randn(M, K, device=dev()).bfloat16()
@@ -381,15 +399,19 @@ def test_gemm_bf16_single_segment(M, N, K, split_k):
     _close(got, want.float(), rtol=1e-5, atol=1e-4 * np.sqrt(K / 64), what='bf16 gemm (exact products, fp32 accumulate)')
 
 
-def test_gemm_bf16x3_is_fp32_grade():
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('M,N,K,split_k', [(900, 512, 256, 1), (900, 256, 4096, 8), (900, 384, 256, 1)])
+def test_gemm_bf16x3_is_fp32_grade(M, N, K, split_k, impl, option):
+    option('gemm_impl', impl)
     ops = _ops()
     torch.manual_seed(0)
-    M, N, K = 900, 512, 256
     a, b = torch.randn(M, K, device=dev()), torch.randn(N, K, device=dev()) * 0.05
     ah, al = ops.split_bf16(a)
     bh, bl = ops.split_bf16(b)
     _close(ah.float() + al.float(), a, rtol=2 ** -15, atol=0, what='bf16 split residual')
-    got = ops.gemm_bf16_tn([ah, ah, al], [bh, bl, bh], M, N, K)
+    got = ops.gemm_bf16_tn([ah, ah, al], [bh, bl, bh], M, N, K, split_k=split_k)
+    if split_k > 1:
+        got = got.sum(0)
     want = (a.double() @ b.double().t()).float()
     err = (got - want).abs().max() / want.abs().max()
     assert float(err) < 2e-5, 'bf16x3 relative error %.3e' % float(err)
@@ -417,8 +439,10 @@ def test_mix_kernel_and_full_mixing_vs_reference_golden(golden_dir):
     _close(out, torch.from_numpy(g['out']), rtol=1e-4, atol=1e-4, what='AdaptiveMixing (bf16x3) vs reference')
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('Pin', [32, 8, 60, 120])
-def test_mix_stage_vs_oracle(Pin):
+def test_mix_stage_vs_oracle(Pin, impl, option):
+    option('mix_impl', impl)             # 0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
     ops = _ops()
     BQ, G, C = 5, 4, 64
     params = hashrand((BQ, G * (C * C + 128 * Pin)), 11 + Pin, -0.3, 0.3)
