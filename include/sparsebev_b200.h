@@ -34,10 +34,10 @@ extern "C" {
 int         sbev_abi_version(void);
 const char* sbev_last_error(void);
 /* Kernel-variant selectors for A/B measurements (process-wide; defaults from the environment):
- *   "gemm_impl"      1 = persistent, double-buffered-TMEM tcgen05 GEMM (default), 0 = one-tile-per-CTA version
+ *   "gemm_impl"      reserved
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
- *   "gather_variant" 0 = all levels' loads in flight (default), 1 = two levels at a time, 3 CTAs/SM */
+ *   "gather_variant" 1 = two levels' loads in flight at a time, 3 CTAs/SM (default), 0 = all levels in flight, 2 CTAs/SM */
 int         sbev_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------

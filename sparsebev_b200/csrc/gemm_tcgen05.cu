@@ -7,17 +7,15 @@
 // expressed as three operand-pair "segments" that accumulate into the SAME TMEM accumulator, so the
 // split costs tensor-core time only -- no extra passes over C.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D loads of 128x64 (A) and BNx64 (B) bf16 boxes,
-//            128-byte swizzled, into a STAGES-deep shared-memory ring, completion on mbarriers.
-//   warp 1   allocates TMEM (BN fp32 columns x 128 lanes), then ONE thread issues
-//            tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage and
-//            tcgen05.commit's the stage's "empty" barrier; a final commit signals the epilogue.
-//   warps 2-5  epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quarter) -> registers ->
-//            padded shared staging (re-using the operand ring) -> +bias -> 512 B-per-row coalesced
-//            fp32 stores (split-K partials go to C + z*M*N).
-// Two CTAs fit per SM (96 KB smem, 128 TMEM columns each) so one CTA's epilogue overlaps the other's
-// main loop.  All mbarrier waits are bounded: a protocol bug traps instead of hanging the GPU.
+// Structure (persistent CTAs, 192 threads, one CTA per SM):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D loads of 128x64 (A) and BNx64 (B) bf16 boxes, 128-byte swizzled,
+//            into a shared-memory ring, completion on mbarriers.  In bf16x3 mode one stage holds {A_hi, B_hi, A_lo, B_lo}.
+//   warp 1   allocates TMEM (2 accumulators x BN fp32 columns x 128 lanes); ONE thread issues
+//            tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16): hi.hi, hi.lo, lo.hi per k-block, then
+//            tcgen05.commit's the stage's "empty" barrier; a commit per tile signals the epilogue.
+//   warps 2-5  epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quarter) -> +bias -> global, overlapping the
+//            next tile's MMAs thanks to the second accumulator.
+// All mbarrier waits are bounded: a protocol bug traps instead of hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -111,117 +109,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct GemmMaps {
-    CUtensorMap a[GEMM_MAX_SEG];
-    CUtensorMap b[GEMM_MAX_SEG];
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
-gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int nseg, int kb_per_split,
-                    const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
-    constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;     // 16 KB
-    constexpr int B_BYTES = BN * GEMM_BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int STG_LD = BN + 4;                     // staging row stride (floats)
-    static_assert(GEMM_BM * STG_LD * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
-    __shared__ uint32_t tmem_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GEMM_BM, z = blockIdx.z;
-    const int iters = nseg * kb_per_split;
-    const int kb0 = z * kb_per_split;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(&tmem_slot, BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int s = 0; s < nseg; ++s) {
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[s]) : "memory");
-            }
-            for (int it = 0; it < iters; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                const int seg = it / kb_per_split;
-                const int kb = kb0 + (it - seg * kb_per_split);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                tma_load_2d(sa, &maps.a[seg], &full_bar[stage], kb * GEMM_BK, m0);
-                tma_load_2d(sa + A_BYTES, &maps.b[seg], &full_bar[stage], kb * GEMM_BK, n0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
-            for (int it = 0; it < iters; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const uint64_t adesc = umma_desc_k_sw128(sa);
-                const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
-#pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k)     // advance 16 bf16 = 32 B = 2 descriptor units along K
-                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty_bar[stage]);            // frees the smem slot once these MMAs have read it
-            }
-            umma_commit(&tmem_full_bar);                   // accumulator complete
-        }
-    } else {
-        // ---- epilogue warps 2..5; TMEM lane quarter = warp % 4
-        const int quarter = warp & 3;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        float* stg = reinterpret_cast<float*>(smem);
-        const int row_local = quarter * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-            float* dst = stg + row_local * STG_LD + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        __syncwarp();
-        float* Cz = C + (long long)z * M * N;
-        const bool add_bias = (bias != nullptr) && (z == 0);
-        for (int col = lane * 4; col < BN; col += 128) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add_bias) bv = ldg4(bias + n0 + col);
-            for (int r = 0; r < 32; ++r) {
-                const int row = m0 + quarter * 32 + r;
-                if (row < M) {
-                    float4 o = *reinterpret_cast<const float4*>(stg + (quarter * 32 + r) * STG_LD + col);
-                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                    *reinterpret_cast<float4*>(Cz + (long long)row * N + n0 + col) = o;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
-}
-
-// ------------------------------------------------------------------------------- v2: persistent
-// Differences from the one-tile-per-CTA kernel above:
+// ------------------------------------------------------------------------------- kernel
 //   * persistent CTAs (grid = min(#tiles, #SMs)) walk a static tile schedule, M-tile fastest so the CTAs that run
 //     concurrently share the same B (weight) tiles in L2;
 //   * TWO TMEM accumulators: the epilogue of tile i drains accumulator i&1 while the MMA warp already fills the
@@ -408,7 +296,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
                      SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: operands must be 16-byte aligned");
     }
     const bool x3_pattern = nseg == 3 && A[0] == A[1] && B[0] == B[2];
-    if (get_option(OPT_GEMM_IMPL) == 1 && (nseg == 1 || x3_pattern)) {
+    if (nseg == 1 || x3_pattern) {
         // ---- v2: persistent, double-buffered TMEM, shared operand tiles for the three bf16x3 products
         const bool wide = (N % 256 == 0);
         const int BNv = wide ? 256 : 128;
@@ -437,7 +325,6 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
 #undef SBEV_GEMM_V2
         return check_launch("sbev_gemm_bf16_tn(v2)");
     }
-    constexpr int BN = 128, STAGES = 3;
-    GemmMaps maps;
+    SBEV_REQUIRE(false, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: nseg must be 1, or 3 with the (A0,B0),(A0,B1),(A1,B0) bf16x3 pattern");
     return check_launch("sbev_gemm_bf16_tn");
 }

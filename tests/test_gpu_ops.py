@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 0}
+    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1}
 
     def setter(name, value):
         _lib.set_option(name, value)
@@ -225,8 +225,10 @@ def test_fused_sampling_matches_golden_reference(golden_dir):
     _close(pts2, torch.from_numpy(g['points']), rtol=1e-5, atol=1e-5, what='make_sample_points vs reference')
 
 
+@pytest.mark.parametrize('variant', [0, 1])
 @pytest.mark.parametrize('T', [1, 2, 8])
-def test_fused_sampling_loc_bit_exact_vs_oracle_and_layouts(T):
+def test_fused_sampling_loc_bit_exact_vs_oracle_and_layouts(T, variant, option):
+    option('gather_variant', variant)
     """Given identical points, the fused kernel's (u, v, view) must equal the oracle's fixed-order fp32
     projection BIT FOR BIT, and the two feature layouts must give identical samples."""
     from sparsebev_b200 import synthetic as S
@@ -382,7 +384,7 @@ def test_sasa_vs_oracle(Q, impl, option):
 
 
 # ------------------------------------------------------------------------- tcgen05 GEMM + mixing
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [1])
 @pytest.mark.parametrize('M,N,K,split_k', [(128, 128, 64, 1), (900, 256, 256, 1), (900, 1024, 256, 1), (300, 256, 2048, 8),
                                            (1, 128, 128, 2), (900, 384, 512, 2), (2000, 2560, 128, 1)])
 def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
@@ -399,7 +401,7 @@ def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
     _close(got, want.float(), rtol=1e-5, atol=1e-4 * np.sqrt(K / 64), what='bf16 gemm (exact products, fp32 accumulate)')
 
 
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [1])
 @pytest.mark.parametrize('M,N,K,split_k', [(900, 512, 256, 1), (900, 256, 4096, 8), (900, 384, 256, 1)])
 def test_gemm_bf16x3_is_fp32_grade(M, N, K, split_k, impl, option):
     option('gemm_impl', impl)
@@ -453,8 +455,12 @@ def test_mix_stage_vs_oracle(Pin, impl, option):
     h = torch.relu(torch.nn.functional.layer_norm(x @ m, (Pin, C)))
     want = torch.relu(torch.nn.functional.layer_norm(sm @ h, (128, C))).reshape(BQ, -1)
     hi, lo, yf = ops.mix(params.to(dev()), x.to(dev()), want_f32=True)
-    _close(yf, want, rtol=1e-4, atol=1e-5, what='mix stage fp32')
-    _close(hi.float() + lo.float(), want, rtol=1e-4, atol=1e-5, what='mix stage bf16 hi+lo')
+    # fp32 FFMA path: 1e-4 rel / 1e-5 abs.  Tensor-core path (bf16x3 products, operands held as bf16 hi+lo pairs, i.e.
+    # ~2^-17 relative each): the outputs are LayerNorm'ed to unit variance, absolute floor 5e-5 (= 5e-5 of the tensor scale).
+    atol = 1e-5 if impl == 1 else 5e-5
+    _close(yf, want, rtol=1e-4, atol=atol, what='mix stage fp32')
+    _close(hi.float() + lo.float(), want, rtol=1e-4, atol=atol, what='mix stage bf16 hi+lo')
+    assert float((yf.cpu() - want).abs().max() / want.abs().max()) < 2e-5
 
 
 def test_reduce_ln_vs_torch():
