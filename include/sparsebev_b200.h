@@ -37,6 +37,7 @@ const char* sbev_last_error(void);
  *   "gemm_impl"      reserved
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
+ *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
  *   "gather_variant" 1 = two levels' loads in flight at a time, 3 CTAs/SM (default), 0 = all levels in flight, 2 CTAs/SM */
 int         sbev_set_option(const char* name, int value);
 
@@ -126,7 +127,8 @@ int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const floa
                    int M, int K, int N, int flags, float* y, void* stream);
 
 /* A CHAIN of 1..6 such layers in ONE kernel: a CTA owns 8 full rows through all layers (intermediate
- * activations stay in shared memory), weights of all layers stream through a cp.async.bulk + mbarrier ring.
+ * activations stay in shared memory), weights of all layers stream through a TMA / cp.async.bulk + mbarrier ring;
+ * the matmuls run on the tensor cores (mma.sync, bf16x3 split, fp32 accumulate) when W_hi/W_lo are given.
  * Layer i consumes layer i-1's output (K_i == N_{i-1}); every layer may additionally store its result
  * (y != NULL, row stride ldy); the last layer must.  With SBEV_DENSE_REFINE on the last layer the epilogue is
  * refine_bbox + velocity rescale (models/sparsebev_transformer.py:155-160,179-183): columns 0..2 become
@@ -144,6 +146,9 @@ typedef struct sbev_dense_layer {
     int flags;              /* SBEV_DENSE_* */
     float* y;               /* [M][ldy] or NULL */
     int ldy;
+    const uint16_t* W_hi;   /* tensor-core path: bf16 (hi, lo) split of W in the nn.Linear layout [N][Kpad], zero padded */
+    const uint16_t* W_lo;   /*   (Kpad = K rounded up to 64); NULL selects the fp32 FFMA path, which needs Wt instead   */
+    int Kpad;
 } sbev_dense_layer;
 int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
                          const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,

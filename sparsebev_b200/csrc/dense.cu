@@ -43,7 +43,50 @@ __device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) 
     }
 }
 
-// A chain of up to 4 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers.  One CTA owns 8 full rows from the
+// Row epilogue shared by the FFMA and the tensor-core chain kernels: one warp finishes one output row held in
+// shared memory (yr[0..N)): + bias -> (+ residual) -> LayerNorm -> ReLU -> (+ residual) -> (refine) -> yr and global.
+__device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane) {
+    const int N = L.N;
+    const bool live = row < prm.M;
+    const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
+    for (int n = lane; n < N; n += 32) {
+        float v = yr[n];
+        if (L.bias) v += __ldg(L.bias + n);
+        if (pre_res && live) v += __ldg(L.residual + (long long)row * N + n);
+        yr[n] = v;
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (L.ln_w != nullptr) {
+        float s = 0.f;
+        for (int n = lane; n < N; n += 32) s += yr[n];
+        mean = warp_sum(s) / (float)N;
+        float ss = 0.f;
+        for (int n = lane; n < N; n += 32) { const float d = yr[n] - mean; ss += d * d; }
+        rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
+    }
+    for (int n = lane; n < N; n += 32) {
+        float v = yr[n];
+        if (L.ln_w != nullptr) v = (v - mean) * rstd * __ldg(L.ln_w + n) + __ldg(L.ln_b + n);
+        if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
+        if (!pre_res && L.residual != nullptr && live) v += __ldg(L.residual + (long long)row * N + n);
+        if ((L.flags & SBEV_DENSE_REFINE) && live) {
+            // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
+            if (n < 3) {
+                const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
+                v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
+                v = __fdiv_rn(1.f, 1.f + expf(-v));
+            } else if (n >= 8 && prm.aux_T > 1) {
+                float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
+                if (td < 1e-5f) td = 1.0f;
+                v = __fdiv_rn(v, td);
+            }
+        }
+        yr[n] = v;
+        if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
+    }
+}
+
+// A chain of up to 6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers (fp32 FFMA version; exact fp32).  One CTA owns 8 full rows from the
 // first layer to the last (activations never leave shared memory, LayerNorm never leaves the CTA); the
 // pre-transposed weights of ALL layers are streamed back-to-back through a 3-stage ring of 32 KB chunks by
 // 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), so the next layer's weights are already in flight
@@ -156,52 +199,171 @@ dense_chain_kernel(const __grid_constant__ ChainParams prm) {
         }
         __syncthreads();
         // epilogue: one warp per row; result stays in yout (next layer's input) and optionally goes to global
-        {
-            const int row = row0 + warp;
+        chain_row_epilogue(prm, L, row0 + warp, yout + warp * prm.act_ld, lane);
+        if (li + 1 < prm.n_layers) {   // zero the K-padding of the next layer's input (its K may not be a multiple of 4)
             float* yr = yout + warp * prm.act_ld;
-            const int N = L.N;
-            const bool live = row < prm.M;
-            const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
-            for (int n = lane; n < N; n += 32) {
-                float v = yr[n];
-                if (L.bias) v += __ldg(L.bias + n);
-                if (pre_res && live) v += __ldg(L.residual + (long long)row * N + n);
-                yr[n] = v;
-            }
-            float mean = 0.f, rstd = 1.f;
-            if (L.ln_w != nullptr) {
-                float s = 0.f;
-                for (int n = lane; n < N; n += 32) s += yr[n];
-                mean = warp_sum(s) / (float)N;
-                float ss = 0.f;
-                for (int n = lane; n < N; n += 32) { const float d = yr[n] - mean; ss += d * d; }
-                rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
-            }
-            for (int n = lane; n < N; n += 32) {
-                float v = yr[n];
-                if (L.ln_w != nullptr) v = (v - mean) * rstd * __ldg(L.ln_w + n) + __ldg(L.ln_b + n);
-                if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
-                if (!pre_res && L.residual != nullptr && live) v += __ldg(L.residual + (long long)row * N + n);
-                if ((L.flags & SBEV_DENSE_REFINE) && live) {
-                    // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
-                    if (n < 3) {
-                        const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
-                        v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
-                        v = __fdiv_rn(1.f, 1.f + expf(-v));
-                    } else if (n >= 8 && prm.aux_T > 1) {
-                        float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
-                        if (td < 1e-5f) td = 1.0f;
-                        v = __fdiv_rn(v, td);
-                    }
-                }
-                yr[n] = v;
-                if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
-            }
-            // zero the K-padding of the next layer's input (its K may not be a multiple of 4)
-            if (li + 1 < prm.n_layers) for (int n = N + lane; n < ((N + 3) & ~3); n += 32) yr[n] = 0.f;
+            for (int n = L.N + lane; n < ((L.N + 3) & ~3); n += 32) yr[n] = 0.f;
         }
         __syncthreads();
         float* t = xin; xin = yout; yout = t;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core chain (default).  Same contract as dense_chain_kernel, but the matmuls run on
+// mma.sync.m16n8k16 with the bf16x3 split and fp32 accumulation.  The problem is transposed so that the 8 rows a
+// CTA owns sit on the MMA N dimension: y^T[n][row] = sum_k W[n][k] x[row][k] -- A = W (the nn.Linear layout, no
+// transpose needed), B = x.  Pre-split bf16 (hi, lo) weights [Npad][Kpad] are streamed as 128-row x 64-k tiles by
+// 2-D TMA (128-byte swizzle, so ldmatrix is conflict free) through a 4-stage mbarrier ring fed by a dedicated
+// producer warp; warp w of the 8 consumer warps owns output features 16w..16w+15 of the current 128-wide block.
+constexpr int MC_STAGES = 4;
+constexpr int MC_TILE_BYTES = 128 * 64 * 2;            // one (hi or lo) 128 x 64 bf16 tile
+constexpr int MC_XLD = 512 + 8;                        // bf16 row stride of the activation operand (K <= 512)
+constexpr int MC_YLD = 1024 + 4;                       // fp32 row stride of the layer output (N <= 1024)
+
+struct ChainMaps { CUtensorMap hi[CHAIN_MAX_LAYERS]; CUtensorMap lo[CHAIN_MAX_LAYERS]; };
+
+__device__ __forceinline__ void mc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mc_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mc_ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(288, 1)
+dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_constant__ ChainMaps maps) {
+    extern __shared__ uint8_t mc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wring = smem;                                                             // [STAGES][hi tile | lo tile]
+    __nv_bfloat16* xbuf = reinterpret_cast<__nv_bfloat16*>(smem + MC_STAGES * 2 * MC_TILE_BYTES);   // [2 ping-pong][hi,lo][8][MC_XLD]
+    float* ys = reinterpret_cast<float*>(xbuf + 2 * 2 * DENSE_ROWS * MC_XLD);          // [8][MC_YLD]
+    __shared__ uint64_t full_bar[MC_STAGES], empty_bar[MC_STAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * DENSE_ROWS;
+    if (tid == 0) {
+        for (int s = 0; s < MC_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&full_bar[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&empty_bar[s])), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // stage the input rows as bf16 (hi, lo), zero-padded to the first layer's K rounded up to 64
+    {
+        const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
+        __nv_bfloat16* xh = xbuf;
+        __nv_bfloat16* xl = xbuf + DENSE_ROWS * MC_XLD;
+        for (int i = tid; i < DENSE_ROWS * (K0p / 2); i += 288) {
+            const int r = i / (K0p / 2), k = (i - r * (K0p / 2)) * 2;
+            const bool ok = row0 + r < prm.M;
+            const float a = (ok && k < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k) : 0.f;
+            const float b = (ok && k + 1 < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k + 1) : 0.f;
+            uint32_t h, l;
+            mc_split2(a, b, h, l);
+            *reinterpret_cast<uint32_t*>(xh + r * MC_XLD + k) = h;
+            *reinterpret_cast<uint32_t*>(xl + r * MC_XLD + k) = l;
+        }
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ---- producer warp: stream every layer's weight tiles in consumption order
+        if (lane == 0) {
+            int it = 0;
+            for (int li = 0; li < prm.n_layers; ++li) {
+                const ChainLayer& L = prm.layer[li];
+                const int kchunks = (L.K + 63) >> 6, nblocks = (L.N + 127) >> 7;
+                for (int nb = 0; nb < nblocks; ++nb)
+                    for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                        const int stage = it % MC_STAGES;
+                        if (it >= MC_STAGES) chain_mbar_wait(&empty_bar[stage], ((it / MC_STAGES) - 1) & 1);
+                        uint8_t* dst = wring + stage * 2 * MC_TILE_BYTES;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(&full_bar[stage])), "r"(2 * MC_TILE_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(dsmem_u32(dst)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(dsmem_u32(dst + MC_TILE_BYTES)), "l"(&maps.lo[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
+                    }
+            }
+        }
+        return;          // the producer warp takes no part in the consumer barriers below (named barrier 1, 256 threads)
+    }
+    // ---- consumers (warps 0..7)
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int a_row = 16 * warp + lm_r + 8 * (lm_id & 1);               // row of the 128-row weight tile this lane addresses
+    const int a_chunk = lm_id >> 1;                                     // + 2*kstep = 16-byte chunk inside the 128 B row
+    int it = 0, ping = 0;
+    for (int li = 0; li < prm.n_layers; ++li) {
+        const ChainLayer& L = prm.layer[li];
+        const int kchunks = (L.K + 63) >> 6, nblocks = (L.N + 127) >> 7;
+        const __nv_bfloat16* xh = xbuf + ping * 2 * DENSE_ROWS * MC_XLD;
+        const __nv_bfloat16* xl = xh + DENSE_ROWS * MC_XLD;
+        {
+            const uint32_t xh_addr = dsmem_u32(xh + lm_r * MC_XLD + 8 * (lm_id & 1));
+            const uint32_t xl_addr = dsmem_u32(xl + lm_r * MC_XLD + 8 * (lm_id & 1));
+            for (int nb = 0; nb < nblocks; ++nb) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                    const int stage = it % MC_STAGES;
+                    chain_mbar_wait(&full_bar[stage], (it / MC_STAGES) & 1);
+                    const uint32_t wh = dsmem_u32(wring + stage * 2 * MC_TILE_BYTES) + a_row * 128;
+                    const uint32_t wl = wh + MC_TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t ah[4], al[4], bh[2], bl[2];
+                        const uint32_t sw = (uint32_t)(((2 * ks + a_chunk) ^ (a_row & 7)) << 4);      // TMA 128-byte swizzle
+                        mc_ldsm_x4(ah, wh + sw);
+                        mc_ldsm_x4(al, wl + sw);
+                        const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
+                        mc_ldsm_x2(bh, xh_addr + xo);
+                        mc_ldsm_x2(bl, xl_addr + xo);
+                        mc_mma(acc, al, bh);
+                        mc_mma(acc, ah, bl);
+                        mc_mma(acc, ah, bh);
+                    }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
+                }
+                // D fragment: (feature 16w+g8 [+8], row 2t4 [+1])
+                const int n = nb * 128 + 16 * warp + g8;
+                if (n < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n] = acc[0]; ys[(2 * t4 + 1) * MC_YLD + n] = acc[1]; }
+                if (n + 8 < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n + 8] = acc[2]; ys[(2 * t4 + 1) * MC_YLD + n + 8] = acc[3]; }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+            float* yr = ys + warp * MC_YLD;
+            chain_row_epilogue(prm, L, row0 + warp, yr, lane);
+            __syncwarp();
+            if (li + 1 < prm.n_layers) {          // next layer's activation operand: bf16 (hi, lo), zero beyond N up to its padded K
+                __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD;
+                __nv_bfloat16* nl = nh + DENSE_ROWS * MC_XLD;
+                const int Kn = (prm.layer[li + 1].K + 63) & ~63;
+                for (int k = 2 * lane; k < Kn; k += 64) {
+                    const float a = (k < L.N) ? yr[k] : 0.f, b = (k + 1 < L.N) ? yr[k + 1] : 0.f;
+                    uint32_t h, l;
+                    mc_split2(a, b, h, l);
+                    *reinterpret_cast<uint32_t*>(nh + k) = h;
+                    *reinterpret_cast<uint32_t*>(nl + k) = l;
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ping ^= 1;
     }
 }
 
@@ -353,12 +515,13 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
     SBEV_REQUIRE(n_layers >= 1 && n_layers <= CHAIN_MAX_LAYERS, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_fwd: 1..%d layers", CHAIN_MAX_LAYERS);
     SBEV_REQUIRE(M >= 0 && ldx >= layers[0].K, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: bad sizes");
     ChainParams prm;
+    bool use_mma = get_option(OPT_DENSE_IMPL) == 0;
     prm.x = x; prm.ldx = ldx; prm.M = M; prm.n_layers = n_layers;
     prm.aux_proposal = refine_proposal; prm.aux_time_diff = refine_time_diff; prm.aux_Q = refine_Q > 0 ? refine_Q : 1; prm.aux_T = refine_T;
     int act = 4;
     for (int i = 0; i < n_layers; ++i) {
         const sbev_dense_layer& l = layers[i];
-        SBEV_REQUIRE(l.Wt != nullptr && l.K > 0 && l.N > 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: bad weight/sizes", i);
+        SBEV_REQUIRE((l.Wt != nullptr || l.W_hi != nullptr) && l.K > 0 && l.N > 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: bad weight/sizes", i);
         SBEV_REQUIRE(l.ldw >= l.N && (l.ldw & 3) == 0 && l.ldw <= 256 * CHAIN_MAX_PASS, SBEV_ERR_UNSUPPORTED,
                      "sbev_dense_chain_fwd: layer %d: ldw must be a multiple of 4, >= N and <= %d", i, 256 * CHAIN_MAX_PASS);
         SBEV_REQUIRE((l.ln_w == nullptr) == (l.ln_b == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: ln_w and ln_b go together");
@@ -367,6 +530,7 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
         SBEV_REQUIRE(l.y == nullptr || l.ldy >= l.N, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: ldy < N", i);
         if (l.flags & SBEV_DENSE_REFINE)
             SBEV_REQUIRE(refine_proposal && refine_time_diff && l.N >= 10 && refine_T >= 1, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: refine needs proposal/time_diff");
+        if (l.W_hi == nullptr || l.W_lo == nullptr || l.K > 512 || l.N > 1024) use_mma = false;
         ChainLayer& c = prm.layer[i];
         c.Wt = l.Wt; c.bias = l.bias; c.ln_w = l.ln_w; c.ln_b = l.ln_b; c.residual = l.residual; c.y = l.y;
         c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags; c.ldy = l.ldy;
@@ -380,6 +544,25 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
     SBEV_REQUIRE(layers[n_layers - 1].y != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: last layer needs an output pointer");
     prm.act_ld = act + 4;
     if (M == 0) return SBEV_OK;
+    if (use_mma) {
+        // tensor-core path: pre-split bf16 weights [N][Kpad] streamed by TMA (box 64 k x 128 rows, 128-byte swizzle)
+        ChainMaps maps;
+        for (int i = 0; i < CHAIN_MAX_LAYERS; ++i) {
+            const sbev_dense_layer& l = layers[i < n_layers ? i : 0];
+            SBEV_REQUIRE(l.Kpad >= l.K && (l.Kpad & 63) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: Kpad must be a multiple of 64 >= K", i);
+            int rc = make_bf16_map(&maps.hi[i], l.W_hi, l.N, l.Kpad, 128);
+            if (rc) return rc;
+            rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, 128);
+            if (rc) return rc;
+        }
+        const size_t smem_mma = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * DENSE_ROWS * MC_XLD * 2 + (size_t)DENSE_ROWS * MC_YLD * 4 + 1024;
+        static std::once_flag once_mma;
+        std::call_once(once_mma, [&] { cudaFuncSetAttribute(dense_chain_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma); });
+        dense_chain_mma_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 288, smem_mma, (cudaStream_t)stream>>>(prm, maps);
+        return check_launch("sbev_dense_chain_fwd(mma)");
+    }
+    for (int i = 0; i < n_layers; ++i)
+        SBEV_REQUIRE(layers[i].Wt != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: fp32 weight missing for the FFMA path", i);
     const size_t smem = sizeof(float) * ((size_t)CHAIN_STAGES * CHAIN_STAGE_FLOATS + 2 * (size_t)DENSE_ROWS * prm.act_ld);
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
@@ -394,6 +577,7 @@ extern "C" int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw,
     sbev_dense_layer l;
     l.Wt = Wt; l.ldw = ldw; l.K = K; l.N = N; l.bias = bias; l.ln_w = ln_w; l.ln_b = ln_b; l.residual = residual;
     l.flags = flags & (SBEV_DENSE_RELU | SBEV_DENSE_RES_PRE_LN); l.y = y; l.ldy = N;
+    l.W_hi = nullptr; l.W_lo = nullptr; l.Kpad = 0;
     return sbev_dense_chain_fwd(x, ldx, M, 1, &l, nullptr, nullptr, 0, 0, stream);
 }
 

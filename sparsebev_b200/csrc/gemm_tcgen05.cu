@@ -116,9 +116,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
 //     other one for tile i+1 (tmem_full / tmem_empty mbarriers);
 //   * in bf16x3 mode one pipeline stage holds {A_hi, A_lo, B_hi, B_lo} for a k-block and the MMA warp issues the
 //     three products hi.hi, hi.lo, lo.hi from them -> every operand tile is fetched once, not 1.5x.
-//   * epilogue goes TMEM -> registers -> global directly (each thread owns one output row: 128 B runs).
+//   * epilogue: TMEM -> registers (+bias) -> 128-byte-swizzled shared staging -> TMA tensor stores of 32x32 fp32
+//     boxes (full 128 B row segments, rows beyond M clipped by the tensor map), double-buffered per warp.
 struct GemmMapsV2 {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap c;          // fp32 [split_k][M][N], box {32 cols, 32 rows, 1}, 128-byte swizzle (epilogue TMA stores)
 };
 
 template <int BN, int STAGES, bool X3>
@@ -130,6 +132,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
     constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stg_base = smem + STAGES * STAGE_BYTES;          // epilogue staging: 4 warps x 2 buffers x [32 rows][128 B], swizzled
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
 
@@ -208,7 +211,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
         }
     } else {
         const int quarter = warp & 3;
-        int lt = 0;
+        int lt = 0, chunk_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const int m0 = (tile % m_tiles) * GEMM_BM;
             const int rest = tile / m_tiles;
@@ -217,26 +220,37 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
             const int as = lt & 1;
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
             tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
-            float* crow = C + ((long long)z * M + row) * N + n0;
             const bool add_bias = (bias != nullptr) && (z == 0);
+            uint8_t* my_stg = stg_base + (warp - 2) * 2 * 4096;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-                if (row < M) {
+                uint8_t* buf = my_stg + (chunk_ctr & 1) * 4096;
+                // the TMA store that last read this buffer (two chunks ago) must have finished reading shared memory
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (add_bias) { const float4 bv = ldg4(bias + n0 + c * 32 + i); o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w; }
-                        *reinterpret_cast<float4*>(crow + c * 32 + i) = o;
-                    }
+                for (int i = 0; i < 32; i += 4) {
+                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    if (add_bias) { const float4 bv = ldg4(bias + n0 + c * 32 + i); o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w; }
+                    // row = lane (128 B per row), 16-byte chunk j = i/4 stored at j ^ (row & 7): the layout the swizzled tensor map expects
+                    *reinterpret_cast<float4*>(buf + lane * 128 + ((((i >> 2) ^ (lane & 7))) << 4)) = o;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(&maps.c), "r"(smem_u32(buf)), "r"(n0 + c * 32), "r"(m0 + quarter * 32), "r"(z) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++chunk_ctr;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // all output tiles written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -262,7 +276,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128 B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
+int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -273,6 +287,21 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] box %d", (int)r, rows, cols, box_rows);
+    return SBEV_OK;
+}
+
+// fp32 [Z][M][N] output, box = {32 cols, 32 rows, 1}, 128-byte swizzle on the shared-memory side (TMA stores).
+static int make_f32_store_map(CUtensorMap* out, const void* ptr, long long N, long long M, long long Z) {
+    EncodeTiledFn enc = get_encode_fn();
+    SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)Z};
+    cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * M * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled(C) failed (%d)", (int)r);
     return SBEV_OK;
 }
 
@@ -301,10 +330,11 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
         const bool wide = (N % 256 == 0);
         const int BNv = wide ? 256 : 128;
         GemmMapsV2 mp;
-        int rc = make_map(&mp.a_hi, A[0], M, K, GEMM_BM);            if (rc) return rc;
-        rc = make_map(&mp.b_hi, B[0], N, K, BNv);                    if (rc) return rc;
-        rc = make_map(&mp.a_lo, x3_pattern ? A[2] : A[0], M, K, GEMM_BM); if (rc) return rc;
-        rc = make_map(&mp.b_lo, x3_pattern ? B[1] : B[0], N, K, BNv);     if (rc) return rc;
+        int rc = make_bf16_map(&mp.a_hi, A[0], M, K, GEMM_BM);            if (rc) return rc;
+        rc = make_bf16_map(&mp.b_hi, B[0], N, K, BNv);                    if (rc) return rc;
+        rc = make_bf16_map(&mp.a_lo, x3_pattern ? A[2] : A[0], M, K, GEMM_BM); if (rc) return rc;
+        rc = make_bf16_map(&mp.b_lo, x3_pattern ? B[1] : B[0], N, K, BNv);     if (rc) return rc;
+        rc = make_f32_store_map(&mp.c, C, N, M, split_k);                 if (rc) return rc;
         const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / BNv;
         const int num_tiles = m_tiles * n_tiles * split_k;
         static int num_sms = 0;
@@ -314,7 +344,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
         cudaStream_t st = (cudaStream_t)stream;
 #define SBEV_GEMM_V2(BNN, STG, XX)                                                                                               \
         do {                                                                                                                     \
-            constexpr size_t smem_v2 = (size_t)STG * (XX ? 2 : 1) * (GEMM_BM * GEMM_BK * 2 + BNN * GEMM_BK * 2) + 1024;          \
+            constexpr size_t smem_v2 = (size_t)STG * (XX ? 2 : 1) * (GEMM_BM * GEMM_BK * 2 + BNN * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;          \
             static std::once_flag once;                                                                                          \
             std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \

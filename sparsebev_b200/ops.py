@@ -162,6 +162,8 @@ class DenseWeight:
         self.bias = None
         self.ldw = 0
         self.n = 0
+        self.w_hi = self.w_lo = None
+        self.kpad = 0
 
     def get(self, weight, *more_weights):
         return self.get_with_bias([weight] + list(more_weights), None)[:2]
@@ -180,17 +182,24 @@ class DenseWeight:
             if biases is not None and any(b is not None for b in biases):
                 self.bias = torch.cat([b.detach() if b is not None else torch.zeros(w.shape[0], device=w.device)
                                        for w, b in zip(weights, biases)]).contiguous()
+            # tensor-core operand: bf16 (hi, lo) split in the nn.Linear layout [N][Kpad], K zero-padded to a multiple of 64
+            kpad = (K + 63) // 64 * 64
+            wpad = torch.zeros(N, kpad, device=weights[0].device, dtype=torch.float32)
+            wpad[:, :K] = torch.cat([w.detach() for w in weights], dim=0)
+            self.w_hi, self.w_lo = split_bf16(wpad) if wpad.is_cuda else (None, None)
+            self.kpad = kpad
             self.wt, self.ldw, self.n, self.key = wt, ldw, N, key
         return self.wt, self.ldw, self.bias
 
 
-def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None):
-    """One entry of a dense chain (see dense_chain)."""
+def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None,
+                w_hi=None, w_lo=None, kpad=0):
+    """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path."""
     flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
-    keep = [t for t in (wt, bias, residual, y) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
+    keep = [t for t in (wt, bias, residual, y, w_hi, w_lo) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
     return _lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
                            _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
-                           (ldy if ldy is not None else N) if y is not None else 0), keep
+                           (ldy if ldy is not None else N) if y is not None else 0, _p(w_hi), _p(w_lo), kpad), keep
 
 
 def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):

@@ -51,8 +51,9 @@ class _Dense:
 
     def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None):
         wt, ldw, bias = self.cache.get_with_bias([l.weight for l in self.linears], [l.bias for l in self.linears])
+        c = self.cache
         return ops.chain_layer(wt, ldw, self.in_features, self.out_features, bias=bias, ln=self.ln, residual=residual,
-                               relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy)
+                               relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
 
     def __call__(self, x, relu=False, residual=None, res_pre_ln=False, k=None):
         M = x.shape[0]
@@ -163,12 +164,15 @@ class SparseBEVSelfAttention(BaseModule):
         """in_proj and gen_tau as ONE concatenated Linear: columns [0,3D) = q|k|v, [3D,3D+H) = tau."""
         attn = self.attention.attn
         wt, ldw, bias = self._cache_in.get_with_bias([attn.in_proj_weight, self.gen_tau.weight], [attn.in_proj_bias, self.gen_tau.bias])
-        return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y)
+        c = self._cache_in
+        return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
 
     def out_layer(self, residual, norm, y):
         attn = self.attention.attn
         wt, ldw, bias = self._cache_out.get_with_bias([attn.out_proj.weight], [attn.out_proj.bias])
-        return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y)
+        c = self._cache_out
+        return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y,
+                               w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
 
     def attention_core(self, query_bbox, x, pre_attn_mask=None):
         """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj)."""

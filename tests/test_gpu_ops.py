@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1}
+    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1, 'dense_impl': 0}
 
     def setter(name, value):
         _lib.set_option(name, value)
@@ -286,8 +286,12 @@ def test_dense_vs_torch(M, K, N, ln, relu, res):
     _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
 
 
-def test_dense_chain_vs_torch():
-    """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored."""
+@pytest.mark.parametrize('impl', [0, 1])
+def test_dense_chain_vs_torch(impl, option):
+    """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored.
+    impl 0 = tensor-core chain (mma.sync bf16x3, TMA-streamed weights), impl 1 = fp32 FFMA chain."""
+    option('dense_impl', impl)
+    atol = 2e-5 if impl == 1 else 1e-4
     ops = _ops()
     torch.manual_seed(1)
     M, D = 901, 256
@@ -314,18 +318,19 @@ def test_dense_chain_vs_torch():
 
     def entry(i, **kw):
         wt, ldw, bias = caches[i].get_with_bias([mods[i].weight], [mods[i].bias])
-        return ops.chain_layer(wt, ldw, mods[i].in_features, mods[i].out_features, bias=bias, ln=lnd[i], **kw)
+        return ops.chain_layer(wt, ldw, mods[i].in_features, mods[i].out_features, bias=bias, ln=lnd[i],
+                               w_hi=caches[i].w_hi, w_lo=caches[i].w_lo, kpad=caches[i].kpad, **kw)
     ops.dense_chain(xd, D, M, [entry(0, relu=True), entry(1, residual=xd, res_pre_ln=True, y=q4d), entry(2, relu=True),
                                entry(3, relu=True), entry(4, y=clsd)])
-    _close(q4d, q4, rtol=1e-4, atol=2e-5, what='chain intermediate (ffn + norm3)')
-    _close(clsd, want_cls, rtol=1e-4, atol=2e-5, what='chain final (cls)')
+    _close(q4d, q4, rtol=1e-4, atol=atol, what='chain intermediate (ffn + norm3)')
+    _close(clsd, want_cls, rtol=1e-4, atol=atol, what='chain final (cls)')
     # concatenated Linear (two heads sharing the input) == the two separate Linears
     cat = ops.DenseWeight()
     wt, ldw, bias = cat.get_with_bias([mods[2].weight, mods[4].weight], [mods[2].bias, mods[4].bias])
     both = torch.empty(M, 266, device=dev())
-    ops.dense_chain(q4d, D, M, [ops.chain_layer(wt, ldw, 256, 266, bias=bias, y=both)])
-    _close(both[:, :256], want_a, rtol=1e-4, atol=2e-5, what='concat head A')
-    _close(both[:, 256:], want_b, rtol=1e-4, atol=2e-5, what='concat head B')
+    ops.dense_chain(q4d, D, M, [ops.chain_layer(wt, ldw, 256, 266, bias=bias, y=both, w_hi=cat.w_hi, w_lo=cat.w_lo, kpad=cat.kpad)])
+    _close(both[:, :256], want_a, rtol=1e-4, atol=atol, what='concat head A')
+    _close(both[:, 256:], want_b, rtol=1e-4, atol=atol, what='concat head B')
     # refine epilogue
     qb = R.init_query_bbox(961, seed=2)[:M][None].contiguous()
     td = torch.tensor([[0.0, 0.5, 1.0]])
@@ -333,7 +338,22 @@ def test_dense_chain_vs_torch():
     ops.dense_chain(q4d, D, M, [entry(4, refine=True, y=box)], refine_proposal=qb.to(dev()), refine_time_diff=td.to(dev()), refine_Q=M, refine_T=3)
     wb = R.refine_bbox(qb, want_delta[None])
     wb = torch.cat([wb[..., :8], wb[..., 8:] / 0.5], -1)
-    _close(box, wb[0], rtol=1e-4, atol=2e-5, what='refine epilogue')
+    _close(box, wb[0], rtol=1e-4, atol=atol, what='refine epilogue')
+    # K = 3 first layer (position encoder) and a wide N = 776 single layer
+    torch.manual_seed(5)
+    l3, l776 = torch.nn.Linear(3, 256), torch.nn.Linear(256, 776)
+    x10 = torch.randn(M, 10)
+    with torch.no_grad():
+        w3, w776 = torch.relu(l3(x10[:, :3])), l776(q4)
+    c3, c776 = ops.DenseWeight(), ops.DenseWeight()
+    y3, y776 = torch.empty(M, 256, device=dev()), torch.empty(M, 776, device=dev())
+    l3d, l776d = copy.deepcopy(l3).to(dev()), copy.deepcopy(l776).to(dev())
+    wt, ldw, bias = c3.get_with_bias([l3d.weight], [l3d.bias])
+    ops.dense_chain(x10.to(dev()), 10, M, [ops.chain_layer(wt, ldw, 3, 256, bias=bias, relu=True, y=y3, w_hi=c3.w_hi, w_lo=c3.w_lo, kpad=c3.kpad)])
+    _close(y3, w3, rtol=1e-4, atol=atol, what='K=3 layer')
+    wt, ldw, bias = c776.get_with_bias([l776d.weight], [l776d.bias])
+    ops.dense_chain(q4d, D, M, [ops.chain_layer(wt, ldw, 256, 776, bias=bias, y=y776, w_hi=c776.w_hi, w_lo=c776.w_lo, kpad=c776.kpad)])
+    _close(y776, w776, rtol=1e-4, atol=atol, what='N=776 layer')
 
 
 def test_sample_points_and_refine_vs_oracle():
