@@ -421,7 +421,8 @@ def stage_breakdown(layer, qb, qf, feats, metas, cfg, iters=20):
     # SASA split
     qkvt = torch.empty(M, 3 * D + 8, device=qf.device)
     timeit('sasa.in_proj_tau', lambda: ops.dense_chain(h, D, M, [layer.self_attn.in_layer(qkvt)]))
-    timeit('sasa.core', lambda: ops.sasa(qkvt, qb, qkvt[:, 3 * D:], cfg['pc_range'], 8, ld_qkv=3 * D + 8, ld_tau=3 * D + 8, embed_dims=D))
+    timeit('sasa.core(split+v3)', lambda: ops.sasa_split(qkvt, qb, cfg['pc_range'], 8, D))
+    timeit('sasa.core(v2)', lambda: ops.sasa(qkvt, qb, qkvt[:, 3 * D:], cfg['pc_range'], 8, ld_qkv=3 * D + 8, ld_tau=3 * D + 8, embed_dims=D))
     heads = layer.sampling._heads(q1.reshape(M, D))
     timeit('sampling.gather', lambda: layer.sampling.sample(qb, heads, feats, metas))
     return res

@@ -185,6 +185,13 @@ int sbev_refine_bbox_fwd(const float* proposal, const float* delta, const float*
 int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bbox, const float* tau, int ld_tau,
                   const uint8_t* dn_mask, const float* pc_range, int B, int Q, int H, int D, float* out, void* stream);
 
+/* Same attention core, tensor-core fast path: the in_proj output pre-split ONCE into bf16 (hi, lo) (sbev_split_bf16
+ * over the whole [B*Q, ld] matrix, ld % 8 == 0); tau stays fp32.  Every warp is an independent worker on
+ * (16 queries, head, quarter of the keys) with its own cp.async double buffer; partials merged per CTA. */
+int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
+                        const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
+                        int B, int Q, int H, int D, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * AdaptiveMixing (models/sparsebev_transformer.py:351-381).
  * (1) dynamic-parameter generation and (3) output projection are GEMMs on the tcgen05 tensor cores

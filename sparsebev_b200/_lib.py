@@ -39,6 +39,7 @@ SIGNATURES = {
     'sbev_refine_bbox_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_sample_points_fwd': [c_vp, c_vp, c_int, c_vp, c_int, c_f32p, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'sbev_sasa_fwd': [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_sasa_split_fwd': [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_mix_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_split_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp],
     'sbev_gemm_bf16_tn': [c_vpp, c_vpp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],

@@ -193,15 +193,21 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
     mma_bf16(d, ah, bh);
 }
 
-// NM = number of 16-row tiles of the in_points dimension (PK = 16*NM >= Pin)
+// NM = number of 16-row tiles of the in_points dimension (PK = 16*NM >= Pin).
+// Persistent CTAs: while item i is being multiplied, the raw fp32 operands of item i + gridDim.x (one contiguous
+// [M | S] block of the params row + the x tile) are already in flight into a shared staging buffer via
+// cp.async.bulk + mbarrier, so the global-load latency of the 40 KB operand set is hidden behind the MMAs.
 template <int NM>
 __global__ void __launch_bounds__(256)
-mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, int G, int Pin,
+mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, int G, int Pin, int num_items,
                __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, float* __restrict__ y_f32) {
     constexpr int PK = 16 * NM;
     constexpr int PS = PK + 8;                       // bf16 row stride of the K=PK operands (S, h^T)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(smem_raw);        // [PK][72]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int per_group = MIX_C * MIX_C + MIX_POUT * Pin;                  // floats: [ M 64x64 | S 128xPin ]
+    float* raw_ms = reinterpret_cast<float*>(smem_raw);                     // staged raw fp32 operands of the current item
+    float* raw_x = raw_ms + per_group;                                     // [Pin][64]
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(raw_x + Pin * MIX_C);   // [PK][72]
     __nv_bfloat16* xl = xh + PK * MX_LD;
     __nv_bfloat16* mh = xl + PK * MX_LD;                                   // M^T [64 c'][72 (c)]
     __nv_bfloat16* ml = mh + MIX_C * MX_LD;
@@ -209,48 +215,28 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
     __nv_bfloat16* sl = sh + MIX_POUT * PS;
     __nv_bfloat16* hh = sl + MIX_POUT * PS;                                // h^T [64 c'][PS (p)]
     __nv_bfloat16* hl = hh + MIX_C * PS;
+    __nv_bfloat16* oh = xh;                                                // epilogue staging [128][72] x2 re-uses the operand arrays
+    __nv_bfloat16* ol = oh + MIX_POUT * MX_LD;
     __shared__ float red[8];
+    __shared__ uint64_t full_bar;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g8 = lane >> 2, t4 = lane & 3;
-    const long long qg = blockIdx.x;
-    const long long per_group = (long long)MIX_C * MIX_C + (long long)MIX_POUT * Pin;
-    const float* pm = params + qg * per_group;
-    const float* ps = pm + MIX_C * MIX_C;
-    const float* px = x + qg * Pin * MIX_C;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar);
+    const uint32_t bytes_ms = (uint32_t)per_group * 4u, bytes_x = (uint32_t)Pin * MIX_C * 4u;
 
-    // ---- stage operands as bf16 (hi, lo)
-    for (int i = tid; i < PK * 16; i += 256) {                  // x: rows p (zero beyond Pin), 4 channels per thread
-        const int p = i >> 4, c = (i & 15) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < Pin) v = ldg4(px + p * MIX_C + c);
-        uint32_t h0, l0, h1, l1;
-        split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
-        *reinterpret_cast<uint2*>(xh + p * MX_LD + c) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(xl + p * MX_LD + c) = make_uint2(l0, l1);
-    }
-    for (int i = tid; i < MIX_C * 16; i += 256) {               // M[c][c'] -> M^T[c'][c]
-        const int c = i >> 4, n = (i & 15) * 4;
-        const float4 v = ldg4(pm + c * MIX_C + n);
-        const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(f[k]);
-            mh[(n + k) * MX_LD + c] = h;
-            ml[(n + k) * MX_LD + c] = __float2bfloat16_rn(f[k] - __bfloat162float(h));
-        }
-    }
-    {
-        const int q4 = Pin >> 2;                                // float4 groups per S row (Pin % 4 == 0)
-        for (int i = tid; i < MIX_POUT * (PK / 4); i += 256) {
-            const int o = i / (PK / 4), pq = i - o * (PK / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pq < q4) v = ldg4(ps + (long long)o * Pin + pq * 4);
-            uint32_t h0, l0, h1, l1;
-            split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
-            *reinterpret_cast<uint2*>(sh + o * PS + pq * 4) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(sl + o * PS + pq * 4) = make_uint2(l0, l1);
-        }
+    auto prefetch = [&](long long item) {             // one thread: arm the barrier, launch the two bulk copies
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_ms + bytes_x) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(raw_ms)), "l"(params + item * per_group), "r"(bytes_ms), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(raw_x)), "l"(x + item * Pin * MIX_C), "r"(bytes_x), "r"(bar) : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((long long)blockIdx.x < num_items) prefetch(blockIdx.x);
     }
     __syncthreads();
 
@@ -259,105 +245,155 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
     const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
     const int b_row = lm_r, b_col = 8 * (lm_id & 1);
 
-    // ---- stage 1: h[p][c'] = sum_c x[p][c] M[c][c'], warp w owns columns c' = 8w..8w+7, all NM row tiles
-    float acc1[NM][4];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) { acc1[m][0] = acc1[m][1] = acc1[m][2] = acc1[m][3] = 0.f; }
-#pragma unroll
-    for (int k0 = 0; k0 < MIX_C; k0 += 16) {
-        uint32_t bh[2], bl[2];
-        ldsm_x2(bh, mh + (8 * warp + b_row) * MX_LD + k0 + b_col);
-        ldsm_x2(bl, ml + (8 * warp + b_row) * MX_LD + k0 + b_col);
-#pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            uint32_t ah[4], al[4];
-            ldsm_x4(ah, xh + (16 * m + a_row) * MX_LD + k0 + a_col);
-            ldsm_x4(al, xl + (16 * m + a_row) * MX_LD + k0 + a_col);
-            mma3(acc1[m], ah, al, bh, bl);
+    uint32_t parity = 0;
+    for (long long qg = blockIdx.x; qg < num_items; qg += gridDim.x, parity ^= 1) {
+        {   // wait for this item's raw operands (bounded spin: a protocol bug traps instead of hanging)
+            uint32_t done = 0;
+            for (uint32_t spins = 0; !done; ++spins) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (!done && spins > (1u << 26)) __trap();
+            }
         }
-    }
-    {   // LayerNorm over the valid Pin x 64 block + ReLU, written as h^T (hi, lo)
+        // ---- split the operands once into bf16 (hi, lo) arrays laid out for ldmatrix
+        for (int i = tid; i < PK * 16; i += 256) {                  // x: rows p (zero beyond Pin), 4 channels per thread
+            const int p = i >> 4, c = (i & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < Pin) v = *reinterpret_cast<const float4*>(raw_x + p * MIX_C + c);
+            uint32_t h0, l0, h1, l1;
+            split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2*>(xh + p * MX_LD + c) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(xl + p * MX_LD + c) = make_uint2(l0, l1);
+        }
+        for (int i = tid; i < MIX_C * 16; i += 256) {               // M[c][c'] -> M^T[c'][c]
+            const int c = i >> 4, n = (i & 15) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(raw_ms + c * MIX_C + n);
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(f[k]);
+                mh[(n + k) * MX_LD + c] = h;
+                ml[(n + k) * MX_LD + c] = __float2bfloat16_rn(f[k] - __bfloat162float(h));
+            }
+        }
+        {
+            const float* raw_s = raw_ms + MIX_C * MIX_C;
+            const int q4 = Pin >> 2;                                // float4 groups per S row (Pin % 4 == 0)
+            for (int i = tid; i < MIX_POUT * (PK / 4); i += 256) {
+                const int o = i / (PK / 4), pq = i - o * (PK / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pq < q4) v = *reinterpret_cast<const float4*>(raw_s + o * Pin + pq * 4);
+                uint32_t h0, l0, h1, l1;
+                split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+                *reinterpret_cast<uint2*>(sh + o * PS + pq * 4) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(sl + o * PS + pq * 4) = make_uint2(l0, l1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && qg + gridDim.x < num_items) {               // staging buffer is free again: fetch the next item now
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            prefetch(qg + gridDim.x);
+        }
+
+        // ---- stage 1: h[p][c'] = sum_c x[p][c] M[c][c'], warp w owns columns c' = 8w..8w+7, all NM row tiles
+        float acc1[NM][4];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { acc1[m][0] = acc1[m][1] = acc1[m][2] = acc1[m][3] = 0.f; }
+#pragma unroll
+        for (int k0 = 0; k0 < MIX_C; k0 += 16) {
+            uint32_t bh[2], bl[2];
+            ldsm_x2(bh, mh + (8 * warp + b_row) * MX_LD + k0 + b_col);
+            ldsm_x2(bl, ml + (8 * warp + b_row) * MX_LD + k0 + b_col);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                uint32_t ah[4], al[4];
+                ldsm_x4(ah, xh + (16 * m + a_row) * MX_LD + k0 + a_col);
+                ldsm_x4(al, xl + (16 * m + a_row) * MX_LD + k0 + a_col);
+                mma3(acc1[m], ah, al, bh, bl);
+            }
+        }
+        {   // LayerNorm over the valid Pin x 64 block + ReLU, written as h^T (hi, lo)
+            float s = 0.f;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                if (16 * m + g8 < Pin) s += acc1[m][0] + acc1[m][1];
+                if (16 * m + g8 + 8 < Pin) s += acc1[m][2] + acc1[m][3];
+            }
+            const float n = (float)(Pin * MIX_C);
+            const float mean = block_sum_256(s, red) / n;
+            float ss = 0.f;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                if (16 * m + g8 < Pin) { const float a = acc1[m][0] - mean, b = acc1[m][1] - mean; ss += a * a + b * b; }
+                if (16 * m + g8 + 8 < Pin) { const float a = acc1[m][2] - mean, b = acc1[m][3] - mean; ss += a * a + b * b; }
+            }
+            const float rstd = rsqrtf(block_sum_256(ss, red) / n + 1e-5f);
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = 16 * m + g8 + 8 * (i >> 1), c = 8 * warp + 2 * t4 + (i & 1);
+                    const float v = (p < Pin) ? fmaxf((acc1[m][i] - mean) * rstd, 0.f) : 0.f;
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    hh[c * PS + p] = h;
+                    hl[c * PS + p] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+        }
+        __syncthreads();
+
+        // ---- stage 2: y[o][c'] = sum_p S[o][p] h[p][c'], warp w owns rows o = 16w..16w+15, all 8 column tiles
+        float acc2[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f; }
+#pragma unroll
+        for (int k0 = 0; k0 < PK; k0 += 16) {
+            uint32_t ah[4], al[4];
+            ldsm_x4(ah, sh + (16 * warp + a_row) * PS + k0 + a_col);
+            ldsm_x4(al, sl + (16 * warp + a_row) * PS + k0 + a_col);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                uint32_t bh[2], bl[2];
+                ldsm_x2(bh, hh + (8 * n + b_row) * PS + k0 + b_col);
+                ldsm_x2(bl, hl + (8 * n + b_row) * PS + k0 + b_col);
+                mma3(acc2[n], ah, al, bh, bl);
+            }
+        }
         float s = 0.f;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            if (16 * m + g8 < Pin) s += acc1[m][0] + acc1[m][1];
-            if (16 * m + g8 + 8 < Pin) s += acc1[m][2] + acc1[m][3];
-        }
-        const float n = (float)(Pin * MIX_C);
-        const float mean = block_sum_256(s, red) / n;
+        for (int n = 0; n < 8; ++n) s += (acc2[n][0] + acc2[n][1]) + (acc2[n][2] + acc2[n][3]);
+        const float cnt = (float)(MIX_POUT * MIX_C);
+        const float mean = block_sum_256(s, red) / cnt;
         float ss = 0.f;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            if (16 * m + g8 < Pin) { const float a = acc1[m][0] - mean, b = acc1[m][1] - mean; ss += a * a + b * b; }
-            if (16 * m + g8 + 8 < Pin) { const float a = acc1[m][2] - mean, b = acc1[m][3] - mean; ss += a * a + b * b; }
-        }
-        const float rstd = rsqrtf(block_sum_256(ss, red) / n + 1e-5f);
+        for (int n = 0; n < 8; ++n)
 #pragma unroll
-        for (int m = 0; m < NM; ++m)
+            for (int i = 0; i < 4; ++i) { const float d = acc2[n][i] - mean; ss += d * d; }
+        const float rstd = rsqrtf(block_sum_256(ss, red) / cnt + 1e-5f);      // (its barriers also order the smem re-use below)
+
+        // ---- epilogue: ReLU(LN) -> (hi, lo) staged in shared memory (operand arrays are dead now) -> 16 B coalesced stores
+        const long long obase = qg * (MIX_POUT * MIX_C);
+        __syncthreads();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int p = 16 * m + g8 + 8 * (i >> 1), c = 8 * warp + 2 * t4 + (i & 1);
-                const float v = (p < Pin) ? fmaxf((acc1[m][i] - mean) * rstd, 0.f) : 0.f;
-                const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                hh[c * PS + p] = h;
-                hl[c * PS + p] = __float2bfloat16_rn(v - __bfloat162float(h));
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int o = 16 * warp + g8 + 8 * hrow, c = 8 * n + 2 * t4;
+                const float v0 = fmaxf((acc2[n][2 * hrow] - mean) * rstd, 0.f), v1 = fmaxf((acc2[n][2 * hrow + 1] - mean) * rstd, 0.f);
+                uint32_t h, l;
+                split2(v0, v1, h, l);
+                *reinterpret_cast<uint32_t*>(oh + o * MX_LD + c) = h;
+                *reinterpret_cast<uint32_t*>(ol + o * MX_LD + c) = l;
+                if (y_f32) *reinterpret_cast<float2*>(y_f32 + obase + o * MIX_C + c) = make_float2(v0, v1);
             }
-    }
-    __syncthreads();
-
-    // ---- stage 2: y[o][c'] = sum_p S[o][p] h[p][c'], warp w owns rows o = 16w..16w+15, all 8 column tiles
-    float acc2[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) { acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f; }
-#pragma unroll
-    for (int k0 = 0; k0 < PK; k0 += 16) {
-        uint32_t ah[4], al[4];
-        ldsm_x4(ah, sh + (16 * warp + a_row) * PS + k0 + a_col);
-        ldsm_x4(al, sl + (16 * warp + a_row) * PS + k0 + a_col);
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            uint32_t bh[2], bl[2];
-            ldsm_x2(bh, hh + (8 * n + b_row) * PS + k0 + b_col);
-            ldsm_x2(bl, hl + (8 * n + b_row) * PS + k0 + b_col);
-            mma3(acc2[n], ah, al, bh, bl);
+        __syncthreads();
+        if (y_hi) {
+            for (int i = tid; i < MIX_POUT * 8; i += 256) {
+                const int o = i >> 3, ch = (i & 7) * 8;
+                *reinterpret_cast<uint4*>(y_hi + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(oh + o * MX_LD + ch);
+                if (y_lo) *reinterpret_cast<uint4*>(y_lo + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(ol + o * MX_LD + ch);
+            }
         }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) s += (acc2[n][0] + acc2[n][1]) + (acc2[n][2] + acc2[n][3]);
-    const float cnt = (float)(MIX_POUT * MIX_C);
-    const float mean = block_sum_256(s, red) / cnt;
-    float ss = 0.f;
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const float d = acc2[n][i] - mean; ss += d * d; }
-    const float rstd = rsqrtf(block_sum_256(ss, red) / cnt + 1e-5f);      // (block_sum's barriers also fence the smem reuse below)
-
-    // ---- epilogue: ReLU(LN) -> (hi, lo) staged in shared memory (operands are dead now) -> 16 B coalesced stores
-    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(smem_raw);       // [128][72]
-    __nv_bfloat16* ol = oh + MIX_POUT * MX_LD;
-    const long long obase = qg * (MIX_POUT * MIX_C);
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-            const int o = 16 * warp + g8 + 8 * hrow, c = 8 * n + 2 * t4;
-            const float v0 = fmaxf((acc2[n][2 * hrow] - mean) * rstd, 0.f), v1 = fmaxf((acc2[n][2 * hrow + 1] - mean) * rstd, 0.f);
-            uint32_t h, l;
-            split2(v0, v1, h, l);
-            *reinterpret_cast<uint32_t*>(oh + o * MX_LD + c) = h;
-            *reinterpret_cast<uint32_t*>(ol + o * MX_LD + c) = l;
-            if (y_f32) *reinterpret_cast<float2*>(y_f32 + obase + o * MIX_C + c) = make_float2(v0, v1);
-        }
-    __syncthreads();
-    if (y_hi) {
-        for (int i = tid; i < MIX_POUT * 8; i += 256) {
-            const int o = i >> 3, ch = (i & 7) * 8;
-            *reinterpret_cast<uint4*>(y_hi + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(oh + o * MX_LD + ch);
-            if (y_lo) *reinterpret_cast<uint4*>(y_lo + obase + o * MIX_C + ch) = *reinterpret_cast<const uint4*>(ol + o * MX_LD + ch);
-        }
+        __syncthreads();                                                    // staging rows read before the next item's split overwrites them
     }
 }
 
@@ -381,13 +417,21 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
     if (impl == 0 && (Pin & 3) == 0) {
         const int NM = (Pin + 15) / 16;
         const int PK = 16 * (NM <= 1 ? 1 : NM <= 2 ? 2 : NM <= 4 ? 4 : 8);
-        size_t smem = 2 * ((size_t)PK * MX_LD + (size_t)MIX_C * MX_LD + (size_t)MIX_POUT * (PK + 8) + (size_t)MIX_C * (PK + 8)) * 2;
+        size_t ops_bytes = 2 * ((size_t)PK * MX_LD + (size_t)MIX_C * MX_LD + (size_t)MIX_POUT * (PK + 8) + (size_t)MIX_C * (PK + 8)) * 2;
         const size_t out_stage = 2 * (size_t)MIX_POUT * MX_LD * 2;
-        if (smem < out_stage) smem = out_stage;
+        if (ops_bytes < out_stage) ops_bytes = out_stage;
+        const size_t raw_bytes = ((size_t)MIX_C * MIX_C + (size_t)MIX_POUT * Pin + (size_t)Pin * MIX_C) * 4;
+        const size_t smem = raw_bytes + ops_bytes;
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, SBEV_ERR_INVALID,
+                     "sbev_mix_fwd: params / x must be 16-byte aligned");
+        static int num_sms = 0;
+        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        const int pgrid = grid < per_sm * num_sms ? grid : per_sm * num_sms;
 #define SBEV_LAUNCH_MMA(R)                                                                                          \
         do {                                                                                                        \
             if (smem > 48 * 1024) cudaFuncSetAttribute(mix_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            mix_mma_kernel<R><<<grid, 256, smem, st>>>(params, x, G, Pin, hi, lo, y_f32);                           \
+            mix_mma_kernel<R><<<pgrid, 256, smem, st>>>(params, x, G, Pin, grid, hi, lo, y_f32);                    \
         } while (0)
         if (PK == 16) SBEV_LAUNCH_MMA(1);
         else if (PK == 32) SBEV_LAUNCH_MMA(2);

@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <mutex>
 
 namespace sbev {
 
@@ -350,6 +351,200 @@ sasa_mma_kernel(const float* __restrict__ qkv, int ld_qkv, const float* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3 (default): every WARP is an independent flash-attention worker on (16 queries, one head, a quarter of the
+// keys): its own double-buffered cp.async pipeline streams 32-key K/V tiles that were pre-split into bf16 (hi, lo)
+// ONCE for the whole layer (sbev_split_bf16 on the in_proj output), straight into ldmatrix-ready shared memory --
+// no block-level barriers, no per-CTA re-conversion.  The four partial (max, sum, O) results of a CTA are merged
+// through shared memory at the end.  456 CTAs x 4 warps at Q = 900 (vs 120 x 4 before).
+constexpr int S3_KT = 32;                                  // keys per tile
+constexpr int S3_ARR = S3_KT * SM_LD;                      // bf16 elements of one [32][40] array
+constexpr int S3_BUF_BYTES = 4 * S3_ARR * 2 + 2 * S3_KT * 4;   // Kh,Kl,Vh,Vl + key centres (x,y)
+
+__global__ void __launch_bounds__(128)
+sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, int ld,
+               const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
+               const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
+               int B, int Q, int H, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char s3_smem[];
+    const int D = H * SA_HD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int q0 = blockIdx.x * 16;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const float scale = 0.17677669529663687f;
+    unsigned char* mybuf = s3_smem + warp * 2 * S3_BUF_BYTES;
+    const long long rowbase = (long long)b * Q;
+
+    // Q fragments straight from global (A operand: a0 (row g, k 2t..), a1 (row g+8), a2 (row g, k 2t+8..), a3 (row g+8, k+8))
+    uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = q0 + g8 + 8 * (i & 1), k = 16 * ks + 2 * t4 + 8 * (i >> 1);
+            uint32_t vh = 0, vl = 0;
+            if (r < Q) {
+                vh = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + (rowbase + r) * ld + h * SA_HD + k));
+                vl = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + (rowbase + r) * ld + h * SA_HD + k));
+            }
+            qh[ks][i] = vh; ql[ks][i] = vl;
+        }
+    float rcx[2], rcy[2], rtau[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int gq = q0 + g8 + 8 * r;
+        const bool ok = gq < Q;
+        rcx[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+        rcy[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        rtau[r] = ok ? __ldg(tau + (rowbase + gq) * ld_tau + h) : 0.f;
+    }
+
+    const int num_tiles = (Q + S3_KT - 1) / S3_KT;
+    auto issue = [&](int tile, int slot) {                         // lane = key: 4 arrays x 4 x 16 B, zero-filled beyond Q
+        unsigned char* buf = mybuf + slot * S3_BUF_BYTES;
+        const int key = tile * S3_KT + lane;
+        const bool ok = key < Q;
+        const long long src_row = (rowbase + (ok ? key : 0)) * ld + h * SA_HD;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf) + lane * SM_LD * 2;
+        const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + src_row + ((a >> 1) ? 2 * D : D);     // 0:Kh 1:Kl 2:Vh 3:Vl
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a * S3_ARR * 2 + c * 16), "l"(src + c * 8), "r"(nbytes) : "memory");
+        }
+        float* kc = reinterpret_cast<float*>(buf + 4 * S3_ARR * 2);
+        kc[lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+        kc[S3_KT + lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int b_row = lm_r, b_col = 8 * (lm_id & 1);
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float oacc[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+
+    int slot = 0;
+    if (warp < num_tiles) issue(warp, 0);
+    for (int tile = warp; tile < num_tiles; tile += 4, slot ^= 1) {
+        if (tile + 4 < num_tiles) { issue(tile + 4, slot ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const unsigned char* buf = mybuf + slot * S3_BUF_BYTES;
+        const __nv_bfloat16* Kh = reinterpret_cast<const __nv_bfloat16*>(buf);
+        const __nv_bfloat16* Kl = Kh + S3_ARR;
+        const __nv_bfloat16* Vh = Kl + S3_ARR;
+        const __nv_bfloat16* Vl = Vh + S3_ARR;
+        const float* kcx = reinterpret_cast<const float*>(buf + 4 * S3_ARR * 2);
+        const float* kcy = kcx + S3_KT;
+        const int k0 = tile * S3_KT;
+
+        float sacc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                uint32_t bh[2], bl[2];
+                sa_ldsm_x2(bh, Kh + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                sa_ldsm_x2(bl, Kl + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                sa_mma3(sacc[n], qh[ks], ql[ks], bh, bl);
+            }
+        float alpha[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float mx = -INFINITY;
+            const int gq = q0 + g8 + 8 * r;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * n + 2 * t4 + e;
+                    const float dx = rcx[r] - kcx[k], dy = rcy[r] - kcy[k];
+                    float v = sacc[n][2 * r + e] * scale + (-sqrtf(dx * dx + dy * dy)) * rtau[r];
+                    if (dn_mask != nullptr && gq < Q && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
+                    if (k0 + k >= Q) v = -INFINITY;
+                    sacc[n][2 * r + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[r], mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            alpha[r] = expf(m_run[r] - m_use);
+            float rs = 0.f;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float pv = expf(sacc[n][2 * r + e] - m_use);
+                    sacc[n][2 * r + e] = pv;
+                    rs += pv;
+                }
+            l_run[r] = l_run[r] * alpha[r] + rs;
+            m_run[r] = m_new;
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { oacc[n][0] *= alpha[0]; oacc[n][1] *= alpha[0]; oacc[n][2] *= alpha[1]; oacc[n][3] *= alpha[1]; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t ph[4], pl[4];
+            sa_split2(sacc[2 * j][0], sacc[2 * j][1], ph[0], pl[0]);
+            sa_split2(sacc[2 * j][2], sacc[2 * j][3], ph[1], pl[1]);
+            sa_split2(sacc[2 * j + 1][0], sacc[2 * j + 1][1], ph[2], pl[2]);
+            sa_split2(sacc[2 * j + 1][2], sacc[2 * j + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                uint32_t bh[2], bl[2];
+                sa_ldsm_x2_trans(bh, Vh + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
+                sa_ldsm_x2_trans(bl, Vl + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
+                sa_mma3(oacc[nd], ph, pl, bh, bl);
+            }
+        }
+        __syncwarp();                                             // all lanes done with this slot before it is refilled
+    }
+
+    // ---- merge the four key-quarter partials of this CTA
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    __syncthreads();                                              // every warp is done with its pipeline buffers
+    float* mo = reinterpret_cast<float*>(s3_smem);                // [4 warps][16 rows][32 + 2]  (O row, m, l)
+    constexpr int MLD = SA_HD + 2;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float* row = mo + (warp * 16 + g8 + 8 * r) * MLD;
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd) { row[8 * nd + 2 * t4] = oacc[nd][2 * r]; row[8 * nd + 2 * t4 + 1] = oacc[nd][2 * r + 1]; }
+        if (t4 == 0) { row[SA_HD] = m_run[r]; row[SA_HD + 1] = l_run[r]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * SA_HD; i += 128) {
+        const int r = i >> 5, d = i & 31;
+        float mmax = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) mmax = fmaxf(mmax, mo[(w * 16 + r) * MLD + SA_HD]);
+        const float muse = (mmax == -INFINITY) ? 0.f : mmax;
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float* row = mo + (w * 16 + r) * MLD;
+            const float f = expf(row[SA_HD] - muse);
+            num += f * row[d];
+            den += f * row[SA_HD + 1];
+        }
+        if (q0 + r < Q) out[(rowbase + q0 + r) * D + h * SA_HD + d] = num / den;
+    }
+}
+
 }  // namespace sbev
 
 using namespace sbev;
@@ -369,4 +564,22 @@ extern "C" int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bb
     else
         sasa_hd32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
     return check_launch("sbev_sasa_fwd");
+}
+
+extern "C" int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
+                                   const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
+                                   int B, int Q, int H, int D, float* out, void* stream) {
+    SBEV_REQUIRE(qkv_hi && qkv_lo && query_bbox && tau && pc_range && out, SBEV_ERR_INVALID, "sbev_sasa_split_fwd: null pointer");
+    SBEV_REQUIRE(B >= 0 && Q >= 0 && H > 0 && ld >= 3 * D && ld_tau >= H, SBEV_ERR_INVALID, "sbev_sasa_split_fwd: bad sizes");
+    SBEV_REQUIRE(D == H * SA_HD, SBEV_ERR_UNSUPPORTED, "sbev_sasa_split_fwd: head dim must be 32 (D=%d, H=%d)", D, H);
+    SBEV_REQUIRE((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0,
+                 SBEV_ERR_INVALID, "sbev_sasa_split_fwd: bf16 operands must be 16-byte aligned with ld % 8 == 0");
+    if (B == 0 || Q == 0) return SBEV_OK;
+    const size_t smem = (size_t)4 * 2 * S3_BUF_BYTES;
+    static std::once_flag once;
+    std::call_once(once, [&] { cudaFuncSetAttribute(sasa_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    dim3 grid((Q + 15) / 16, H, B);
+    sasa_v3_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
+                                                            query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+    return check_launch("sbev_sasa_split_fwd");
 }

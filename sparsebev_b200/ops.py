@@ -281,6 +281,27 @@ def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None, ld_qkv=None,
     return out
 
 
+def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None):
+    """Tensor-core attention core on the concatenated in_proj|gen_tau output `qkvt` [B*Q, 3D+H] (fp32): splits it once
+    into bf16 (hi, lo) and runs the warp-pipelined kernel.  -> [B,Q,D] (heads concatenated, before out_proj)."""
+    lib = _lib.load()
+    qkvt = _chk(qkvt, 'qkvt')
+    qb = _chk(query_bbox, 'query_bbox')
+    B, Q, _ = qb.shape
+    D, H = embed_dims, num_heads
+    ld = qkvt.shape[1]
+    hi, lo = split_bf16(qkvt)
+    m = None
+    if dn_mask is not None:
+        m = _chk(dn_mask.to(torch.uint8).contiguous(), 'dn_mask', torch.uint8)
+    out = torch.empty(B, Q, D, device=qb.device, dtype=torch.float32)
+    with torch.cuda.device(qb.device):
+        _lib.check(lib.sbev_sasa_split_fwd(hi.data_ptr(), lo.data_ptr(), ld, qb.data_ptr(), qkvt.data_ptr() + 3 * D * 4, ld, _p(m),
+                                           _lib.f32_array([float(v) for v in pc_range]), B, Q, H, D, out.data_ptr(), _stream()),
+                   'sbev_sasa_split_fwd')
+    return out
+
+
 def split_bf16(x, need_lo=True):
     """fp32 -> (hi, lo) bf16 with x ~= hi + lo."""
     lib = _lib.load()

@@ -154,6 +154,7 @@ class SparseBEVSelfAttention(BaseModule):
         self.attention = _MHAParams(embed_dims, num_heads, dropout)
         self.gen_tau = nn.Linear(embed_dims, num_heads)
         self._cache_in, self._cache_out = ops.DenseWeight(), ops.DenseWeight()
+        self.core_impl = 'split'
 
     @torch.no_grad()
     def init_weights(self):
@@ -180,8 +181,11 @@ class SparseBEVSelfAttention(BaseModule):
         D, H = self.attention.attn.embed_dim, self.num_heads
         qkvt = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.float32)
         ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt)])
-        o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
-                     ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
+        if self.core_impl == 'split':          # tensor-core path: operands pre-split to bf16 (hi, lo) once per layer
+            o = ops.sasa_split(qkvt, query_bbox, self.pc_range, H, D, dn_mask=pre_attn_mask)
+        else:
+            o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
+                         ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
         return o.reshape(B * Q, D)
 
     def forward_fused(self, query_bbox, query_feat, pre_attn_mask=None, norm=None):
