@@ -547,8 +547,8 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
     if (use_mma) {
         // tensor-core path: pre-split bf16 weights [N][Kpad] streamed by TMA (box 64 k x 128 rows, 128-byte swizzle)
         ChainMaps maps;
-        for (int i = 0; i < CHAIN_MAX_LAYERS; ++i) {
-            const sbev_dense_layer& l = layers[i < n_layers ? i : 0];
+        for (int i = 0; i < n_layers; ++i) {
+            const sbev_dense_layer& l = layers[i];
             SBEV_REQUIRE(l.Kpad >= l.K && (l.Kpad & 63) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: Kpad must be a multiple of 64 >= K", i);
             int rc = make_bf16_map(&maps.hi[i], l.W_hi, l.N, l.Kpad, 128);
             if (rc) return rc;

@@ -276,7 +276,29 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128 B swizzle, zero OOB fill.
+// Encoding a tensor map costs ~1-2 us of host time; the maps are pure functions of (pointer, shape, box), so they are
+// memoised (weights never move; activation buffers are recycled by the caller's allocator).
+struct MapKey {
+    const void* ptr; long long rows, cols; int box_rows;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        h ^= std::hash<long long>()(k.rows * 1000003ll + k.cols) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        return h ^ (size_t)k.box_rows;
+    }
+};
+
 int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, rows, cols, box_rows};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return SBEV_OK; }
+    }
     EncodeTiledFn enc = get_encode_fn();
     SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -287,6 +309,11 @@ int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] box %d", (int)r, rows, cols, box_rows);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (cache.size() > 4096) cache.clear();
+        cache.emplace(key, *out);
+    }
     return SBEV_OK;
 }
 
