@@ -46,43 +46,69 @@ __device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) 
 // Row epilogue shared by the FFMA and the tensor-core chain kernels: one warp finishes one output row held in
 // shared memory (yr[0..N)): + bias -> (+ residual) -> LayerNorm -> ReLU -> (+ residual) -> (refine) -> yr and global.
 __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane) {
+    constexpr int U = 8;                               // columns per lane per batch: their global operands are loaded together
     const int N = L.N;
     const bool live = row < prm.M;
     const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
-    for (int n = lane; n < N; n += 32) {
-        float v = yr[n];
-        if (L.bias) v += __ldg(L.bias + n);
-        if (pre_res && live) v += __ldg(L.residual + (long long)row * N + n);
-        yr[n] = v;
+    const bool has_res = live && L.residual != nullptr;
+    const float* res_row = L.residual ? L.residual + (long long)row * N : nullptr;
+    float s = 0.f;
+    for (int n0 = 0; n0 < N; n0 += 32 * U) {
+        float bv[U], rv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = n0 + lane + 32 * u;
+            bv[u] = (L.bias && n < N) ? __ldg(L.bias + n) : 0.f;
+            rv[u] = (pre_res && has_res && n < N) ? __ldg(res_row + n) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = n0 + lane + 32 * u;
+            if (n < N) { const float v = (yr[n] + bv[u]) + rv[u]; yr[n] = v; s += v; }
+        }
     }
     float mean = 0.f, rstd = 1.f;
     if (L.ln_w != nullptr) {
-        float s = 0.f;
-        for (int n = lane; n < N; n += 32) s += yr[n];
         mean = warp_sum(s) / (float)N;
         float ss = 0.f;
         for (int n = lane; n < N; n += 32) { const float d = yr[n] - mean; ss += d * d; }
         rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
     }
-    for (int n = lane; n < N; n += 32) {
-        float v = yr[n];
-        if (L.ln_w != nullptr) v = (v - mean) * rstd * __ldg(L.ln_w + n) + __ldg(L.ln_b + n);
-        if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
-        if (!pre_res && L.residual != nullptr && live) v += __ldg(L.residual + (long long)row * N + n);
-        if ((L.flags & SBEV_DENSE_REFINE) && live) {
-            // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
-            if (n < 3) {
-                const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
-                v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
-                v = __fdiv_rn(1.f, 1.f + expf(-v));
-            } else if (n >= 8 && prm.aux_T > 1) {
-                float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
-                if (td < 1e-5f) td = 1.0f;
-                v = __fdiv_rn(v, td);
+    const bool refine = (L.flags & SBEV_DENSE_REFINE) && live;
+    for (int n0 = 0; n0 < N; n0 += 32 * U) {
+        float gv[U], ov[U], rv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = n0 + lane + 32 * u;
+            const bool ok = n < N;
+            gv[u] = (L.ln_w && ok) ? __ldg(L.ln_w + n) : 1.f;
+            ov[u] = (L.ln_w && ok) ? __ldg(L.ln_b + n) : 0.f;
+            rv[u] = (!pre_res && has_res && ok) ? __ldg(res_row + n) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = n0 + lane + 32 * u;
+            if (n < N) {
+                float v = yr[n];
+                if (L.ln_w != nullptr) v = (v - mean) * rstd * gv[u] + ov[u];
+                if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
+                v += rv[u];
+                if (refine) {
+                    // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
+                    if (n < 3) {
+                        const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
+                        v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
+                        v = __fdiv_rn(1.f, 1.f + expf(-v));
+                    } else if (n >= 8 && prm.aux_T > 1) {
+                        float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
+                        if (td < 1e-5f) td = 1.0f;
+                        v = __fdiv_rn(v, td);
+                    }
+                }
+                yr[n] = v;
+                if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
             }
         }
-        yr[n] = v;
-        if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
     }
 }
 
@@ -316,7 +342,10 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
             const uint32_t xh_addr = dsmem_u32(xh + lm_r * MC_XLD + 8 * (lm_id & 1));
             const uint32_t xl_addr = dsmem_u32(xl + lm_r * MC_XLD + 8 * (lm_id & 1));
             for (int nb = 0; nb < nblocks; ++nb) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                // four independent accumulator chains (main / cross terms x k-step parity): one chain would serialise every
+                // MMA of the tile behind the ~30-cycle MMA latency, this warp has no other tile to interleave with
+                float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
+                float accC[4] = {0.f, 0.f, 0.f, 0.f}, accD[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const int stage = it % MC_STAGES;
                     chain_mbar_wait(&full_bar[stage], (it / MC_STAGES) & 1);
@@ -331,13 +360,15 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
                         mc_ldsm_x2(bh, xh_addr + xo);
                         mc_ldsm_x2(bl, xl_addr + xo);
-                        mc_mma(acc, al, bh);
-                        mc_mma(acc, ah, bl);
-                        mc_mma(acc, ah, bh);
+                        if (ks & 1) { mc_mma(accB, ah, bh); mc_mma(accD, al, bh); mc_mma(accD, ah, bl); }
+                        else        { mc_mma(accA, ah, bh); mc_mma(accC, al, bh); mc_mma(accC, ah, bl); }
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
                 }
+                float acc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = (accC[i] + accD[i]) + (accA[i] + accB[i]);
                 // D fragment: (feature 16w+g8 [+8], row 2t4 [+1])
                 const int n = nb * 128 + 16 * warp + g8;
                 if (n < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n] = acc[0]; ys[(2 * t4 + 1) * MC_YLD + n] = acc[1]; }

@@ -181,6 +181,43 @@ __device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const __nv_bfloat16* p
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
                  : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+// (count, mean, M2) running statistics and their pairwise merge (Chan et al.): one block reduction gives an
+// accurately centred variance, instead of one reduction for the mean and a second for the squared deviations.
+struct Stat { float n, mean, m2; };
+__device__ __forceinline__ Stat stat_merge(const Stat& a, const Stat& b) {
+    Stat r;
+    r.n = a.n + b.n;
+    if (r.n == 0.f) { r.mean = 0.f; r.m2 = 0.f; return r; }
+    const float d = b.mean - a.mean, fb = b.n / r.n;
+    r.mean = a.mean + d * fb;
+    r.m2 = a.m2 + b.m2 + d * d * a.n * fb;
+    return r;
+}
+__device__ __forceinline__ Stat block_stat_256(Stat s, float* red /* [8*3] */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Stat t;
+        t.n = __shfl_xor_sync(0xffffffffu, s.n, o); t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o); t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
+        s = stat_merge(s, t);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { red[warp * 3] = s.n; red[warp * 3 + 1] = s.mean; red[warp * 3 + 2] = s.m2; }
+    __syncthreads();
+    Stat t;
+    t.n = red[(lane & 7) * 3]; t.mean = red[(lane & 7) * 3 + 1]; t.m2 = red[(lane & 7) * 3 + 2];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        Stat u;
+        u.n = __shfl_xor_sync(0xffffffffu, t.n, o); u.mean = __shfl_xor_sync(0xffffffffu, t.mean, o); u.m2 = __shfl_xor_sync(0xffffffffu, t.m2, o);
+        t = stat_merge(t, u);
+    }
+    return t;
+}
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -209,15 +246,15 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
     float* raw_x = raw_ms + per_group;                                     // [Pin][64]
     __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(raw_x + Pin * MIX_C);   // [PK][72]
     __nv_bfloat16* xl = xh + PK * MX_LD;
-    __nv_bfloat16* mh = xl + PK * MX_LD;                                   // M^T [64 c'][72 (c)]
+    __nv_bfloat16* mh = xl + PK * MX_LD;                                   // M [64 c][72 (c')]  natural layout, read with ldmatrix.trans
     __nv_bfloat16* ml = mh + MIX_C * MX_LD;
     __nv_bfloat16* sh = ml + MIX_C * MX_LD;                                // S [128][PS]
     __nv_bfloat16* sl = sh + MIX_POUT * PS;
-    __nv_bfloat16* hh = sl + MIX_POUT * PS;                                // h^T [64 c'][PS (p)]
-    __nv_bfloat16* hl = hh + MIX_C * PS;
+    __nv_bfloat16* hh = sl + MIX_POUT * PS;                                // h [PK p][72 (c')]  natural layout, read with ldmatrix.trans
+    __nv_bfloat16* hl = hh + PK * MX_LD;
     __nv_bfloat16* oh = xh;                                                // epilogue staging [128][72] x2 re-uses the operand arrays
     __nv_bfloat16* ol = oh + MIX_POUT * MX_LD;
-    __shared__ float red[8];
+    __shared__ float red[24];
     __shared__ uint64_t full_bar;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,7 +280,6 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
     // ldmatrix lane addressing: A (16x16): row = r + 8*(id&1), col = 8*(id>>1); B (8 n x 16 k): row = r, col = 8*(id&1)
     const int lm_r = lane & 7, lm_id = lane >> 3;
     const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
-    const int b_row = lm_r, b_col = 8 * (lm_id & 1);
 
     uint32_t parity = 0;
     for (long long qg = blockIdx.x; qg < num_items; qg += gridDim.x, parity ^= 1) {
@@ -265,16 +301,13 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
             *reinterpret_cast<uint2*>(xh + p * MX_LD + c) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(xl + p * MX_LD + c) = make_uint2(l0, l1);
         }
-        for (int i = tid; i < MIX_C * 16; i += 256) {               // M[c][c'] -> M^T[c'][c]
+        for (int i = tid; i < MIX_C * 16; i += 256) {               // M[c][c'] kept as is (k-major rows), 4 columns per thread
             const int c = i >> 4, n = (i & 15) * 4;
             const float4 v = *reinterpret_cast<const float4*>(raw_ms + c * MIX_C + n);
-            const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(f[k]);
-                mh[(n + k) * MX_LD + c] = h;
-                ml[(n + k) * MX_LD + c] = __float2bfloat16_rn(f[k] - __bfloat162float(h));
-            }
+            uint32_t h0, l0, h1, l1;
+            split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2*>(mh + c * MX_LD + n) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(ml + c * MX_LD + n) = make_uint2(l0, l1);
         }
         {
             const float* raw_s = raw_ms + MIX_C * MIX_C;
@@ -302,8 +335,8 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
 #pragma unroll
         for (int k0 = 0; k0 < MIX_C; k0 += 16) {
             uint32_t bh[2], bl[2];
-            ldsm_x2(bh, mh + (8 * warp + b_row) * MX_LD + k0 + b_col);
-            ldsm_x2(bl, ml + (8 * warp + b_row) * MX_LD + k0 + b_col);
+            ldsm_x2_trans(bh, mh + (k0 + (lane & 15)) * MX_LD + 8 * warp);
+            ldsm_x2_trans(bl, ml + (k0 + (lane & 15)) * MX_LD + 8 * warp);
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
                 uint32_t ah[4], al[4];
@@ -312,31 +345,38 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
                 mma3(acc1[m], ah, al, bh, bl);
             }
         }
-        {   // LayerNorm over the valid Pin x 64 block + ReLU, written as h^T (hi, lo)
-            float s = 0.f;
+        {   // LayerNorm over the valid Pin x 64 block + ReLU, written as h (hi, lo) in natural [p][c'] layout
+            Stat st;
+            {
+                float cnt = 0.f, sum = 0.f;
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                if (16 * m + g8 < Pin) s += acc1[m][0] + acc1[m][1];
-                if (16 * m + g8 + 8 < Pin) s += acc1[m][2] + acc1[m][3];
-            }
-            const float n = (float)(Pin * MIX_C);
-            const float mean = block_sum_256(s, red) / n;
-            float ss = 0.f;
+                for (int m = 0; m < NM; ++m) {
+                    if (16 * m + g8 < Pin) { sum += acc1[m][0] + acc1[m][1]; cnt += 2.f; }
+                    if (16 * m + g8 + 8 < Pin) { sum += acc1[m][2] + acc1[m][3]; cnt += 2.f; }
+                }
+                const float lm = cnt > 0.f ? sum / cnt : 0.f;
+                float m2 = 0.f;
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                if (16 * m + g8 < Pin) { const float a = acc1[m][0] - mean, b = acc1[m][1] - mean; ss += a * a + b * b; }
-                if (16 * m + g8 + 8 < Pin) { const float a = acc1[m][2] - mean, b = acc1[m][3] - mean; ss += a * a + b * b; }
+                for (int m = 0; m < NM; ++m) {
+                    if (16 * m + g8 < Pin) { const float a = acc1[m][0] - lm, b = acc1[m][1] - lm; m2 += a * a + b * b; }
+                    if (16 * m + g8 + 8 < Pin) { const float a = acc1[m][2] - lm, b = acc1[m][3] - lm; m2 += a * a + b * b; }
+                }
+                st.n = cnt; st.mean = lm; st.m2 = m2;
             }
-            const float rstd = rsqrtf(block_sum_256(ss, red) / n + 1e-5f);
+            st = block_stat_256(st, red);
+            const float mean = st.mean, rstd = rsqrtf(st.m2 / (float)(Pin * MIX_C) + 1e-5f);
 #pragma unroll
             for (int m = 0; m < NM; ++m)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int p = 16 * m + g8 + 8 * (i >> 1), c = 8 * warp + 2 * t4 + (i & 1);
-                    const float v = (p < Pin) ? fmaxf((acc1[m][i] - mean) * rstd, 0.f) : 0.f;
-                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                    hh[c * PS + p] = h;
-                    hl[c * PS + p] = __float2bfloat16_rn(v - __bfloat162float(h));
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int p = 16 * m + g8 + 8 * hrow, c = 8 * warp + 2 * t4;
+                    const bool ok = p < Pin;
+                    const float v0 = ok ? fmaxf((acc1[m][2 * hrow] - mean) * rstd, 0.f) : 0.f;
+                    const float v1 = ok ? fmaxf((acc1[m][2 * hrow + 1] - mean) * rstd, 0.f) : 0.f;
+                    uint32_t h, l;
+                    split2(v0, v1, h, l);
+                    *reinterpret_cast<uint32_t*>(hh + p * MX_LD + c) = h;
+                    *reinterpret_cast<uint32_t*>(hl + p * MX_LD + c) = l;
                 }
         }
         __syncthreads();
@@ -353,22 +393,26 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 uint32_t bh[2], bl[2];
-                ldsm_x2(bh, hh + (8 * n + b_row) * PS + k0 + b_col);
-                ldsm_x2(bl, hl + (8 * n + b_row) * PS + k0 + b_col);
+                ldsm_x2_trans(bh, hh + (k0 + (lane & 15)) * MX_LD + 8 * n);
+                ldsm_x2_trans(bl, hl + (k0 + (lane & 15)) * MX_LD + 8 * n);
                 mma3(acc2[n], ah, al, bh, bl);
             }
         }
-        float s = 0.f;
+        Stat st2;
+        {
+            float sum = 0.f;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) s += (acc2[n][0] + acc2[n][1]) + (acc2[n][2] + acc2[n][3]);
-        const float cnt = (float)(MIX_POUT * MIX_C);
-        const float mean = block_sum_256(s, red) / cnt;
-        float ss = 0.f;
+            for (int n = 0; n < 8; ++n) sum += (acc2[n][0] + acc2[n][1]) + (acc2[n][2] + acc2[n][3]);
+            const float lm = sum * (1.f / 32.f);
+            float m2 = 0.f;
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+            for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float d = acc2[n][i] - mean; ss += d * d; }
-        const float rstd = rsqrtf(block_sum_256(ss, red) / cnt + 1e-5f);      // (its barriers also order the smem re-use below)
+                for (int i = 0; i < 4; ++i) { const float d = acc2[n][i] - lm; m2 += d * d; }
+            st2.n = 32.f; st2.mean = lm; st2.m2 = m2;
+        }
+        st2 = block_stat_256(st2, red);                                      // (its barriers also order the smem re-use below)
+        const float mean = st2.mean, rstd = rsqrtf(st2.m2 / (float)(MIX_POUT * MIX_C) + 1e-5f);
 
         // ---- epilogue: ReLU(LN) -> (hi, lo) staged in shared memory (operand arrays are dead now) -> 16 B coalesced stores
         const long long obase = qg * (MIX_POUT * MIX_C);
@@ -414,10 +458,14 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
     __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
     const int grid = BQ * G;
     const int impl = get_option(OPT_MIX_IMPL);   // 1 selects the fp32 FFMA kernel (exact fp32 like the reference)
-    if (impl == 0 && (Pin & 3) == 0) {
+    // tensor-core path needs raw staging + operand arrays in shared memory; very large in_points (> ~96) fall back to FFMA
+    const size_t need_mma = ((size_t)MIX_C * MIX_C + (size_t)MIX_POUT * Pin + (size_t)Pin * MIX_C) * 4 +
+                            2 * ((size_t)2 * 16 * ((Pin + 15) / 16 > 4 ? 8 : (Pin + 15) / 16 > 2 ? 4 : (Pin + 15) / 16 > 1 ? 2 : 1) * MX_LD + (size_t)MIX_C * MX_LD +
+                                 (size_t)MIX_POUT * (16 * ((Pin + 15) / 16 > 4 ? 8 : (Pin + 15) / 16 > 2 ? 4 : (Pin + 15) / 16 > 1 ? 2 : 1) + 8)) * 2;
+    if (impl == 0 && (Pin & 3) == 0 && need_mma <= 220 * 1024) {
         const int NM = (Pin + 15) / 16;
         const int PK = 16 * (NM <= 1 ? 1 : NM <= 2 ? 2 : NM <= 4 ? 4 : 8);
-        size_t ops_bytes = 2 * ((size_t)PK * MX_LD + (size_t)MIX_C * MX_LD + (size_t)MIX_POUT * (PK + 8) + (size_t)MIX_C * (PK + 8)) * 2;
+        size_t ops_bytes = 2 * ((size_t)PK * MX_LD + (size_t)MIX_C * MX_LD + (size_t)MIX_POUT * (PK + 8) + (size_t)PK * MX_LD) * 2;
         const size_t out_stage = 2 * (size_t)MIX_POUT * MX_LD * 2;
         if (ops_bytes < out_stage) ops_bytes = out_stage;
         const size_t raw_bytes = ((size_t)MIX_C * MIX_C + (size_t)MIX_POUT * Pin + (size_t)Pin * MIX_C) * 4;

@@ -353,8 +353,8 @@ sasa_mma_kernel(const float* __restrict__ qkv, int ld_qkv, const float* __restri
 
 
 // ------------------------------------------------------------------------------------------------
-// v3 (default): every WARP is an independent flash-attention worker on (16 queries, one head, a quarter of the
-// keys): its own double-buffered cp.async pipeline streams 32-key K/V tiles that were pre-split into bf16 (hi, lo)
+// v3 (default): every warp is a flash-attention worker on (16 queries, one head, a quarter of the keys); the two
+// query tiles of a CTA that scan the same key quarter share one double-buffered cp.async pipeline that streams 32-key K/V tiles that were pre-split into bf16 (hi, lo)
 // ONCE for the whole layer (sbev_split_bf16 on the in_proj output), straight into ldmatrix-ready shared memory --
 // no block-level barriers, no per-CTA re-conversion.  The four partial (max, sum, O) results of a CTA are merged
 // through shared memory at the end.  456 CTAs x 4 warps at Q = 900 (vs 120 x 4 before).
@@ -362,20 +362,24 @@ constexpr int S3_KT = 32;                                  // keys per tile
 constexpr int S3_ARR = S3_KT * SM_LD;                      // bf16 elements of one [32][40] array
 constexpr int S3_BUF_BYTES = 4 * S3_ARR * 2 + 2 * S3_KT * 4;   // Kh,Kl,Vh,Vl + key centres (x,y)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
 sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, int ld,
                const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
                const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
                int B, int Q, int H, float* __restrict__ out) {
+    // 8 warps = 4 key-quarters x 2 query tiles; the two warps of a key-quarter share one K/V double buffer
+    // (each fills half of it) and synchronise on their own named barrier (64 threads) -- never the whole CTA.
     extern __shared__ __align__(16) unsigned char s3_smem[];
     const int D = H * SA_HD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kq = warp >> 1, mt = warp & 1;
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int q0 = blockIdx.x * 16;
+    const int q0 = blockIdx.x * 32 + 16 * mt;
     const int h = blockIdx.y, b = blockIdx.z;
     const float scale = 0.17677669529663687f;
-    unsigned char* mybuf = s3_smem + warp * 2 * S3_BUF_BYTES;
+    unsigned char* mybuf = s3_smem + kq * 2 * S3_BUF_BYTES;
     const long long rowbase = (long long)b * Q;
+    const int bar_id = 1 + kq;
 
     // Q fragments straight from global (A operand: a0 (row g, k 2t..), a1 (row g+8), a2 (row g, k 2t+8..), a3 (row g+8, k+8))
     uint32_t qh[2][4], ql[2][4];
@@ -402,23 +406,26 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
     }
 
     const int num_tiles = (Q + S3_KT - 1) / S3_KT;
-    auto issue = [&](int tile, int slot) {                         // lane = key: 4 arrays x 4 x 16 B, zero-filled beyond Q
+    // this warp's half of a tile: mt == 0 -> K (hi, lo) + key centres, mt == 1 -> V (hi, lo); lane = key, zero-filled beyond Q
+    auto issue = [&](int tile, int slot) {
         unsigned char* buf = mybuf + slot * S3_BUF_BYTES;
         const int key = tile * S3_KT + lane;
         const bool ok = key < Q;
-        const long long src_row = (rowbase + (ok ? key : 0)) * ld + h * SA_HD;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf) + lane * SM_LD * 2;
+        const long long src_row = (rowbase + (ok ? key : 0)) * ld + h * SA_HD + (mt ? 2 * D : D);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf) + (mt ? 2 * S3_ARR * 2 : 0) + lane * SM_LD * 2;
         const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + src_row + ((a >> 1) ? 2 * D : D);     // 0:Kh 1:Kl 2:Vh 3:Vl
+        for (int a = 0; a < 2; ++a) {
+            const __nv_bfloat16* src = (a ? qkv_lo : qkv_hi) + src_row;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a * S3_ARR * 2 + c * 16), "l"(src + c * 8), "r"(nbytes) : "memory");
         }
-        float* kc = reinterpret_cast<float*>(buf + 4 * S3_ARR * 2);
-        kc[lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
-        kc[S3_KT + lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        if (mt == 0) {
+            float* kc = reinterpret_cast<float*>(buf + 4 * S3_ARR * 2);
+            kc[lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+            kc[S3_KT + lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -430,11 +437,11 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
     for (int n = 0; n < 4; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
 
     int slot = 0;
-    if (warp < num_tiles) issue(warp, 0);
-    for (int tile = warp; tile < num_tiles; tile += 4, slot ^= 1) {
+    if (kq < num_tiles) issue(kq, 0);
+    for (int tile = kq; tile < num_tiles; tile += 4, slot ^= 1) {
         if (tile + 4 < num_tiles) { issue(tile + 4, slot ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both halves of this tile have landed
         const unsigned char* buf = mybuf + slot * S3_BUF_BYTES;
         const __nv_bfloat16* Kh = reinterpret_cast<const __nv_bfloat16*>(buf);
         const __nv_bfloat16* Kl = Kh + S3_ARR;
@@ -507,41 +514,43 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
                 sa_mma3(oacc[nd], ph, pl, bh, bl);
             }
         }
-        __syncwarp();                                             // all lanes done with this slot before it is refilled
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both warps done with this slot before it is refilled
     }
 
-    // ---- merge the four key-quarter partials of this CTA
+    // ---- merge the four key-quarter partials of each query tile
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
     __syncthreads();                                              // every warp is done with its pipeline buffers
-    float* mo = reinterpret_cast<float*>(s3_smem);                // [4 warps][16 rows][32 + 2]  (O row, m, l)
+    float* mo = reinterpret_cast<float*>(s3_smem);                // [2 mt][4 kq][16 rows][32 + 2]  (O row, m, l)
     constexpr int MLD = SA_HD + 2;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        float* row = mo + (warp * 16 + g8 + 8 * r) * MLD;
+        float* row = mo + ((mt * 4 + kq) * 16 + g8 + 8 * r) * MLD;
 #pragma unroll
         for (int nd = 0; nd < 4; ++nd) { row[8 * nd + 2 * t4] = oacc[nd][2 * r]; row[8 * nd + 2 * t4 + 1] = oacc[nd][2 * r + 1]; }
         if (t4 == 0) { row[SA_HD] = m_run[r]; row[SA_HD + 1] = l_run[r]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 16 * SA_HD; i += 128) {
-        const int r = i >> 5, d = i & 31;
+    for (int i = threadIdx.x; i < 32 * SA_HD; i += 256) {
+        const int r32 = i >> 5, d = i & 31;
+        const int m2 = r32 >> 4, r = r32 & 15;
         float mmax = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) mmax = fmaxf(mmax, mo[(w * 16 + r) * MLD + SA_HD]);
+        for (int w = 0; w < 4; ++w) mmax = fmaxf(mmax, mo[((m2 * 4 + w) * 16 + r) * MLD + SA_HD]);
         const float muse = (mmax == -INFINITY) ? 0.f : mmax;
         float num = 0.f, den = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const float* row = mo + (w * 16 + r) * MLD;
+            const float* row = mo + ((m2 * 4 + w) * 16 + r) * MLD;
             const float f = expf(row[SA_HD] - muse);
             num += f * row[d];
             den += f * row[SA_HD + 1];
         }
-        if (q0 + r < Q) out[(rowbase + q0 + r) * D + h * SA_HD + d] = num / den;
+        const int gq = blockIdx.x * 32 + r32;
+        if (gq < Q) out[(rowbase + gq) * D + h * SA_HD + d] = num / den;
     }
 }
 
@@ -578,8 +587,8 @@ extern "C" int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_l
     const size_t smem = (size_t)4 * 2 * S3_BUF_BYTES;
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(sasa_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-    dim3 grid((Q + 15) / 16, H, B);
-    sasa_v3_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
+    dim3 grid((Q + 31) / 32, H, B);
+    sasa_v3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
                                                             query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
     return check_launch("sbev_sasa_split_fwd");
 }
