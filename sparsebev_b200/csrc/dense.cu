@@ -249,6 +249,13 @@ constexpr int MC_XLD = 512 + 8;                        // bf16 row stride of the
 constexpr int MC_YLD = 1024 + 4;                       // fp32 row stride of the layer output (N <= 1024)
 
 struct ChainMaps { CUtensorMap hi[CHAIN_MAX_LAYERS]; CUtensorMap lo[CHAIN_MAX_LAYERS]; };
+constexpr int MC_CLUSTER = 8;                          // CTAs (row groups) per cluster sharing every weight tile by TMA multicast
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void mc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -268,6 +275,11 @@ __device__ __forceinline__ void mc_mma(float (&d)[4], const uint32_t (&a)[4], co
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// CL = cluster size (1 = no cluster).  With CL > 1 the CL CTAs of a cluster own CL different row groups but need the
+// SAME weight tiles: CTA r fetches rows [r*128/CL, (r+1)*128/CL) of each tile and TMA-multicasts them into the
+// shared memory of all CL CTAs, so every weight byte leaves L2 once per cluster instead of once per CTA.  A stage is
+// refilled only after the consumers of ALL CL CTAs released it (each consumer warp arrives on every CTA's barrier).
+template <int CL>
 __global__ void __launch_bounds__(288, 1)
 dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_constant__ ChainMaps maps) {
     extern __shared__ uint8_t mc_smem_raw[];
@@ -282,11 +294,12 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     if (tid == 0) {
         for (int s = 0; s < MC_STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&full_bar[s])), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&empty_bar[s])), "r"(8));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&empty_bar[s])), "r"(8 * CL));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     // stage the input rows as bf16 (hi, lo), zero-padded to the first layer's K rounded up to 64
     {
         const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
@@ -304,6 +317,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         }
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();            // every CTA's mbarriers are initialised before any remote arrive / multicast
 
     if (warp == 8) {
         // ---- producer warp: stream every layer's weight tiles in consumption order
@@ -318,13 +332,25 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         if (it >= MC_STAGES) chain_mbar_wait(&empty_bar[stage], ((it / MC_STAGES) - 1) & 1);
                         uint8_t* dst = wring + stage * 2 * MC_TILE_BYTES;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(&full_bar[stage])), "r"(2 * MC_TILE_BYTES) : "memory");
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                                     ::"r"(dsmem_u32(dst)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                                     ::"r"(dsmem_u32(dst + MC_TILE_BYTES)), "l"(&maps.lo[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
+                        if (CL == 1) {
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                         ::"r"(dsmem_u32(dst)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                         ::"r"(dsmem_u32(dst + MC_TILE_BYTES)), "l"(&maps.lo[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
+                        } else {
+                            constexpr int SL = 128 / CL;                       // tile rows fetched by this CTA
+                            const uint16_t mask = (uint16_t)((1u << CL) - 1);
+                            const uint32_t off = crank * SL * 128;
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                                         ::"r"(dsmem_u32(dst + off)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128 + (int)crank * SL), "h"(mask) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                                         ::"r"(dsmem_u32(dst + MC_TILE_BYTES + off)), "l"(&maps.lo[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128 + (int)crank * SL), "h"(mask) : "memory");
+                        }
                     }
             }
         }
+        __syncwarp();                      // lanes 1..31 wait for the producing lane: the cluster barrier below is warp-aligned
+        if (CL > 1) cluster_sync_all();   // matches the consumers' final cluster barrier: no CTA exits while peers may still touch it
         return;          // the producer warp takes no part in the consumer barriers below (named barrier 1, 256 threads)
     }
     // ---- consumers (warps 0..7)
@@ -364,7 +390,13 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         else        { mc_mma(accA, ah, bh); mc_mma(accC, al, bh); mc_mma(accC, ah, bl); }
                     }
                     __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
+                    if (CL == 1) {
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
+                    } else if (lane < CL) {                  // lane r releases the stage towards CTA r of the cluster
+                        uint32_t remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(dsmem_u32(&empty_bar[stage])), "r"(lane));
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+                    }
                 }
                 float acc[4];
 #pragma unroll
@@ -396,6 +428,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ping ^= 1;
     }
+    if (CL > 1) cluster_sync_all();
 }
 
 // Box decode + offsets -> lidar-frame sample points; softmax over levels.  Thread per point.
@@ -578,18 +611,38 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
     if (use_mma) {
         // tensor-core path: pre-split bf16 weights [N][Kpad] streamed by TMA (box 64 k x 128 rows, 128-byte swizzle)
         ChainMaps maps;
+        const int groups = (M + DENSE_ROWS - 1) / DENSE_ROWS;
+        const bool clustered = get_option(OPT_DENSE_CLUSTER) != 0 && groups >= MC_CLUSTER;
+        const int box_rows = clustered ? 128 / MC_CLUSTER : 128;
         for (int i = 0; i < n_layers; ++i) {
             const sbev_dense_layer& l = layers[i];
             SBEV_REQUIRE(l.Kpad >= l.K && (l.Kpad & 63) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: Kpad must be a multiple of 64 >= K", i);
-            int rc = make_bf16_map(&maps.hi[i], l.W_hi, l.N, l.Kpad, 128);
+            int rc = make_bf16_map(&maps.hi[i], l.W_hi, l.N, l.Kpad, box_rows);
             if (rc) return rc;
-            rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, 128);
+            rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, box_rows);
             if (rc) return rc;
         }
         const size_t smem_mma = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * DENSE_ROWS * MC_XLD * 2 + (size_t)DENSE_ROWS * MC_YLD * 4 + 1024;
         static std::once_flag once_mma;
-        std::call_once(once_mma, [&] { cudaFuncSetAttribute(dense_chain_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma); });
-        dense_chain_mma_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 288, smem_mma, (cudaStream_t)stream>>>(prm, maps);
+        std::call_once(once_mma, [&] {
+            cudaFuncSetAttribute(dense_chain_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            cudaFuncSetAttribute(dense_chain_mma_kernel<MC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+        });
+        if (clustered) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((groups + MC_CLUSTER - 1) / MC_CLUSTER * MC_CLUSTER);
+            cfg.blockDim = dim3(288);
+            cfg.dynamicSmemBytes = smem_mma;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = MC_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<MC_CLUSTER>, prm, maps);
+            if (e != cudaSuccess) { set_error("sbev_dense_chain_fwd(cluster launch): %s", cudaGetErrorString(e)); return SBEV_ERR_CUDA; }
+        } else {
+            dense_chain_mma_kernel<1><<<groups, 288, smem_mma, (cudaStream_t)stream>>>(prm, maps);
+        }
         return check_launch("sbev_dense_chain_fwd(mma)");
     }
     for (int i = 0; i < n_layers; ++i)

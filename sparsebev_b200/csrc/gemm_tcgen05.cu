@@ -123,23 +123,36 @@ struct GemmMapsV2 {
     CUtensorMap c;          // fp32 [split_k][M][N], box {32 cols, 32 rows, 1}, 128-byte swizzle (epilogue TMA stores)
 };
 
-template <int BN, int STAGES, bool X3>
+// ARES (A-resident, for small K): the CTA is pinned to ONE M-tile, loads that tile's whole A operand (all k-blocks, hi and
+// lo) into shared memory once and then only streams B through the ring while it walks its N-tiles -- a third less
+// operand traffic per MMA for the parameter-generation GEMM (K = 256), whose A is the same 900 x 256 query matrix for
+// all 256 N-tiles.  Requires X3, split_k == 1, gridDim.x % m_tiles == 0; ARES_KB = number of resident k-blocks.
+template <int BN, int STAGES, bool X3, int ARES_KB = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_per_split, int m_tiles, int n_tiles, int num_tiles,
                                const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
+    constexpr bool ARES = ARES_KB > 0;
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr int B_BYTES = BN * GEMM_BK * 2;
-    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    constexpr int STAGE_BYTES = ARES ? 2 * B_BYTES : (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    constexpr int ARES_BYTES = ARES_KB * 2 * A_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ares = smem_al;                                  // [ARES_KB][A_hi | A_lo] (only when ARES)
+    uint8_t* smem = smem_al + ARES_BYTES;                     // operand ring
     uint8_t* stg_base = smem + STAGES * STAGE_BYTES;          // epilogue staging: 4 warps x 2 buffers x [32 rows][128 B], swizzled
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2], ares_bar;
+    // ARES tile schedule: M-tile fixed per CTA, N-tiles strided by the number of CTAs that share the M-tile
+    const int ares_m = ARES ? (int)(blockIdx.x % m_tiles) : 0;
+    const int ares_n0 = ARES ? (int)(blockIdx.x / m_tiles) : 0;
+    const int ares_nstep = ARES ? (int)(gridDim.x / m_tiles) : 1;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        mbar_init(&ares_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -158,6 +171,22 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
             }
             int it = 0;
+            if (ARES) {
+                mbar_expect_tx(&ares_bar, ARES_BYTES);
+                for (int kb = 0; kb < ARES_KB; ++kb) {
+                    tma_load_2d(ares + kb * 2 * A_BYTES, &maps.a_hi, &ares_bar, kb * GEMM_BK, ares_m * GEMM_BM);
+                    tma_load_2d(ares + kb * 2 * A_BYTES + A_BYTES, &maps.a_lo, &ares_bar, kb * GEMM_BK, ares_m * GEMM_BM);
+                }
+                for (int nt = ares_n0; nt < n_tiles; nt += ares_nstep)
+                    for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                        const int stage = it % STAGES;
+                        mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                        uint8_t* st = smem + stage * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(st, &maps.b_hi, &full_bar[stage], kb * GEMM_BK, nt * BN);
+                        tma_load_2d(st + B_BYTES, &maps.b_lo, &full_bar[stage], kb * GEMM_BK, nt * BN);
+                    }
+            } else
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile % m_tiles) * GEMM_BM;
                 const int rest = tile / m_tiles;
@@ -182,7 +211,10 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
             int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            if (ARES) { mbar_wait(&ares_bar, 0); tc_fence_after(); }
+            const int my_tiles = ARES ? (n_tiles - ares_n0 + ares_nstep - 1) / ares_nstep
+                                      : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            for (; lt < my_tiles; ++lt) {
                 const int as = lt & 1;
                 mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
@@ -192,13 +224,19 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                     mbar_wait(&full_bar[stage], (it / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_k_sw128(st), b_hi = umma_desc_k_sw128(st + A_BYTES);
+                    uint64_t a_hi, a_lo, b_hi, b_lo;
+                    if (ARES) {
+                        const uint32_t ar = smem_u32(ares + kb * 2 * A_BYTES);
+                        a_hi = umma_desc_k_sw128(ar); a_lo = umma_desc_k_sw128(ar + A_BYTES);
+                        b_hi = umma_desc_k_sw128(st); b_lo = umma_desc_k_sw128(st + B_BYTES);
+                    } else {
+                        a_hi = umma_desc_k_sw128(st); b_hi = umma_desc_k_sw128(st + A_BYTES);
+                        a_lo = umma_desc_k_sw128(st + A_BYTES + B_BYTES); b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
+                    }
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     if (X3) {
-                        const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES + B_BYTES);
-                        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
@@ -212,11 +250,14 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
     } else {
         const int quarter = warp & 3;
         int lt = 0, chunk_ctr = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int m0 = (tile % m_tiles) * GEMM_BM;
+        const int my_tiles = ARES ? (n_tiles - ares_n0 + ares_nstep - 1) / ares_nstep
+                                  : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        for (; lt < my_tiles; ++lt) {
+            const int tile = ARES ? 0 : (int)blockIdx.x + lt * (int)gridDim.x;
+            const int m0 = ARES ? ares_m * GEMM_BM : (tile % m_tiles) * GEMM_BM;
             const int rest = tile / m_tiles;
-            const int n0 = (rest % n_tiles) * BN;
-            const int z = rest / n_tiles;
+            const int n0 = ARES ? (ares_n0 + lt * ares_nstep) * BN : (rest % n_tiles) * BN;
+            const int z = ARES ? 0 : rest / n_tiles;
             const int as = lt & 1;
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
             tc_fence_after();
@@ -354,7 +395,13 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
     const bool x3_pattern = nseg == 3 && A[0] == A[1] && B[0] == B[2];
     if (nseg == 1 || x3_pattern) {
         // ---- v2: persistent, double-buffered TMEM, shared operand tiles for the three bf16x3 products
-        const bool wide = (N % 256 == 0);
+        static int num_sms = 0;
+        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        const int m_tiles_pre = (M + GEMM_BM - 1) / GEMM_BM;
+        // A-resident variant: small K, many N-tiles per M-tile (the parameter-generation GEMM)
+        const bool ares = get_option(OPT_GEMM_IMPL) == 1 && x3_pattern && split_k == 1 && K == 256 && m_tiles_pre <= num_sms &&
+                          (N / 128) >= 2 * (num_sms / m_tiles_pre);
+        const bool wide = !ares && (N % 256 == 0);
         const int BNv = wide ? 256 : 128;
         GemmMapsV2 mp;
         int rc = make_bf16_map(&mp.a_hi, A[0], M, K, GEMM_BM);            if (rc) return rc;
@@ -364,9 +411,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
         rc = make_f32_store_map(&mp.c, C, N, M, split_k);                 if (rc) return rc;
         const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / BNv;
         const int num_tiles = m_tiles * n_tiles * split_k;
-        static int num_sms = 0;
-        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
-        const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+        const int grid = ares ? (num_sms / m_tiles) * m_tiles : (num_tiles < num_sms ? num_tiles : num_sms);
         const int kbs = (K / GEMM_BK) / split_k;
         cudaStream_t st = (cudaStream_t)stream;
 #define SBEV_GEMM_V2(BNN, STG, XX)                                                                                               \
@@ -377,7 +422,13 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \
             gemm_bf16_tn_persistent_kernel<BNN, STG, XX><<<grid, GEMM_THREADS, smem_v2, st>>>(mp, kbs, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
         } while (0)
-        if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
+        if (ares) {
+            constexpr size_t smem_ar = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
+            static std::once_flag once_ar;
+            std::call_once(once_ar, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>,
+                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ar); });
+            gemm_bf16_tn_persistent_kernel<128, 2, true, 4><<<grid, GEMM_THREADS, smem_ar, st>>>(mp, kbs, m_tiles, n_tiles, num_tiles, bias, C, M, N);
+        } else if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
         else            { if (wide) SBEV_GEMM_V2(256, 4, false); else SBEV_GEMM_V2(128, 6, false); }
 #undef SBEV_GEMM_V2
         return check_launch("sbev_gemm_bf16_tn(v2)");

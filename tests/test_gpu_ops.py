@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1, 'dense_impl': 0}
+    defaults = {'gemm_impl': 1, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1, 'dense_impl': 0, 'dense_cluster': 1}
 
     def setter(name, value):
         _lib.set_option(name, value)
@@ -286,11 +286,13 @@ def test_dense_vs_torch(M, K, N, ln, relu, res):
     _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
 
 
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 def test_dense_chain_vs_torch(impl, option):
     """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored.
     impl 0 = tensor-core chain (mma.sync bf16x3, TMA-streamed weights), impl 1 = fp32 FFMA chain."""
-    option('dense_impl', impl)
+    # 0 = tensor-core chain with 8-CTA TMA-multicast clusters (default), 2 = tensor-core chain without clusters, 1 = fp32 FFMA
+    option('dense_impl', 1 if impl == 1 else 0)
+    option('dense_cluster', 0 if impl == 2 else 1)
     atol = 2e-5 if impl == 1 else 1e-4
     ops = _ops()
     torch.manual_seed(1)
@@ -425,8 +427,8 @@ def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
     _close(got, want.float(), rtol=1e-5, atol=1e-4 * np.sqrt(K / 64), what='bf16 gemm (exact products, fp32 accumulate)')
 
 
-@pytest.mark.parametrize('impl', [1])
-@pytest.mark.parametrize('M,N,K,split_k', [(900, 512, 256, 1), (900, 256, 4096, 8), (900, 384, 256, 1)])
+@pytest.mark.parametrize('impl', [0, 1])       # 1 lets small-K / many-N shapes take the A-resident schedule
+@pytest.mark.parametrize('M,N,K,split_k', [(900, 512, 256, 1), (900, 256, 4096, 8), (900, 384, 256, 1), (900, 8192, 256, 1), (130, 5120, 256, 1)])
 def test_gemm_bf16x3_is_fp32_grade(M, N, K, split_k, impl, option):
     option('gemm_impl', impl)
     ops = _ops()
