@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--layout', default='grouped', choices=['grouped', 'nhwc'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='single stream: no concurrent gather || param-GEMM, cls || reg')
     ap.add_argument('--breakdown', action='store_true', help='also write per-stage timings to gpurun_out/breakdown.json')
     ap.add_argument('--cpu-steps', type=int, default=3, help='bounded CPU sample: decoder-layer passes of the oracle')
     ap.add_argument('--skip-cpu', action='store_true')
@@ -187,6 +188,7 @@ def main():
     model = model.to(dev).eval()
     layer = model.decoder.decoder_layer
     layer.mixing.precision = args.precision
+    layer.overlap = not args.no_overlap
 
     # weak scaling: every rank owns its own scene (different seed) -- the reference's only strategy is DP
     feats_host = S.make_feats(args.config, T, batch=1, seed=100 + rank, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')
@@ -376,7 +378,7 @@ def main():
             'dtype': 'f32 (mixing GEMMs: %s on tcgen05, fp32 accumulate)' % args.precision, 'data': 'synthetic',
             'config': {'workload': '%s T=%d Q=%d L=%d, one decoder layer, B=1 per GPU' % (args.config, T, Q, cfg['num_levels']),
                        'l2': 'inputs larger than L2 (feature pyramid %.0f MB per step)' % (feat_bytes / 1e6),
-                       'feat_layout': layer.sampling.feat_layout, 'cuda_graph': graph is not None, 'parallelism': 'dp%d (one scene per GPU)' % world},
+                       'feat_layout': layer.sampling.feat_layout, 'cuda_graph': graph is not None, 'two_stream_overlap': layer.overlap, 'parallelism': 'dp%d (one scene per GPU)' % world},
             'clocks': clk,
             'e2e': {'value': world * 1e3 / e2e_ms, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms, 'steps': e2e_steps,

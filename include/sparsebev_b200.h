@@ -34,11 +34,12 @@ extern "C" {
 int         sbev_abi_version(void);
 const char* sbev_last_error(void);
 /* Kernel-variant selectors for A/B measurements (process-wide; defaults from the environment):
- *   "gemm_impl"      1 = use the A-resident schedule for small-K / many-N GEMMs (default), 0 = always stream A and B
+ *   "gemm_impl"      0 = stream A and B tiles (default), 1 = A-resident schedule for small-K / many-N GEMMs (measured slower)
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
- *   "dense_cluster"  1 = 8-CTA clusters share every weight tile by TMA multicast (default), 0 = every CTA streams its own
+ *   "dense_cluster"  0 = every CTA streams its own weight tiles (default), 1 = 8-CTA clusters share every tile by TMA
+ *                    multicast (correct, measured slower: the clusters run in lock step)
  *   "gather_variant" 1 = two levels' loads in flight at a time, 3 CTAs/SM (default), 0 = all levels in flight, 2 CTAs/SM */
 int         sbev_set_option(const char* name, int value);
 

@@ -302,12 +302,15 @@ def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None):
     return out
 
 
-def split_bf16(x, need_lo=True):
-    """fp32 -> (hi, lo) bf16 with x ~= hi + lo."""
+def split_bf16(x, need_lo=True, out=None):
+    """fp32 -> (hi, lo) bf16 with x ~= hi + lo.  `out` = optional (hi, lo) buffers."""
     lib = _lib.load()
     x = _chk(x, 'x')
-    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    lo = torch.empty_like(hi) if need_lo else None
+    if out is not None:
+        hi, lo = out
+    else:
+        hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if need_lo else None
     with torch.cuda.device(x.device):
         _lib.check(lib.sbev_split_bf16(x.data_ptr(), ctypes.c_int64(x.numel()), hi.data_ptr(), _p(lo), _stream()),
                    'sbev_split_bf16')

@@ -102,6 +102,39 @@ class AdaptiveMixing(nn.Module):
     def init_weights(self):
         nn.init.zeros_(self.parameter_generator.weight)
 
+    def alloc_params(self, M, device):
+        """Buffers of the parameter-generation stage (allocated by the caller BEFORE it forks a side stream)."""
+        n_par = self.n_groups * self.total_parameters
+        return dict(q_hi=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
+                    q_lo=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
+                    params=torch.empty(M, n_par, device=device, dtype=torch.float32))
+
+    def generate_params(self, q2, buf):
+        """Stage 1: dynamic mixing parameters [M, G*(C*C + Pout*Pin)] = query @ W^T + b on tcgen05 (depends on the query only,
+        NOT on the sampled features -> can run concurrently with the gather)."""
+        M, D = q2.shape
+        x3 = self.precision == 'bf16x3'
+        ops.split_bf16(q2, need_lo=x3, out=(buf['q_hi'], buf['q_lo'] if x3 else None))
+        w_hi, w_lo = self._pg.get(self.parameter_generator.weight)
+        a, b = ([buf['q_hi'], buf['q_hi'], buf['q_lo']], [w_hi, w_lo, w_hi]) if x3 else ([buf['q_hi']], [w_hi])
+        ops.gemm_bf16_tn(a, b, M, self.n_groups * self.total_parameters, D, bias=self.parameter_generator.bias, out=buf['params'])
+        return buf['params']
+
+    def mix_and_project(self, params, x, q2, norm=None):
+        """Stages 2+3: per-(query, group) mixing, out_proj (split-K tcgen05) and the fused reduce + residual + LayerNorm."""
+        M, G, P, C = x.shape
+        D = self.query_dim
+        y_hi, y_lo, _ = ops.mix(params, x)
+        o_hi, o_lo = self._op.get(self.out_proj.weight)
+        K2 = self.out_proj.in_features
+        a, b = ([y_hi, y_hi, y_lo], [o_hi, o_lo, o_hi]) if self.precision == 'bf16x3' else ([y_hi], [o_hi])
+        split_k = self.split_k
+        while (K2 // 64) % split_k:
+            split_k //= 2
+        partial = ops.gemm_bf16_tn(a, b, M, D, K2, split_k=split_k)
+        return ops.reduce_ln(partial, bias=self.out_proj.bias, residual=q2,
+                             ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
+
     def forward_fused(self, x, query, norm=None):
         """x [B,Q,G,P,C], query [B,Q,D] -> norm(query + out_proj(mix(x; params(query)))) [B,Q,D]
         (`norm` = the LayerNorm applied right after in the decoder layer, fused into the split-K reduce)."""
@@ -109,28 +142,8 @@ class AdaptiveMixing(nn.Module):
         assert G == self.n_groups and P == self.in_points and C == self.eff_in_dim
         M, D = B * Q, self.query_dim
         q2 = query.reshape(M, D)
-        q_hi, q_lo = ops.split_bf16(q2, need_lo=self.precision == 'bf16x3')
-        w_hi, w_lo = self._pg.get(self.parameter_generator.weight)
-        n_par = self.n_groups * self.total_parameters
-        if self.precision == 'bf16x3':
-            a, b = [q_hi, q_hi, q_lo], [w_hi, w_lo, w_hi]
-        else:
-            a, b = [q_hi], [w_hi]
-        params = ops.gemm_bf16_tn(a, b, M, n_par, D, bias=self.parameter_generator.bias)
-        y_hi, y_lo, _ = ops.mix(params, x.reshape(M, G, P, C))
-        o_hi, o_lo = self._op.get(self.out_proj.weight)
-        K2 = self.out_proj.in_features
-        if self.precision == 'bf16x3':
-            a, b = [y_hi, y_hi, y_lo], [o_hi, o_lo, o_hi]
-        else:
-            a, b = [y_hi], [o_hi]
-        split_k = self.split_k
-        while (K2 // 64) % split_k:
-            split_k //= 2
-        partial = ops.gemm_bf16_tn(a, b, M, D, K2, split_k=split_k)
-        out = ops.reduce_ln(partial, bias=self.out_proj.bias, residual=q2,
-                            ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
-        return out.reshape(B, Q, D)
+        params = self.generate_params(q2, self.alloc_params(M, q2.device))
+        return self.mix_and_project(params, x.reshape(M, G, P, C), q2, norm).reshape(B, Q, D)
 
     def forward(self, x, query):
         return self.forward_fused(x, query, None)
@@ -281,6 +294,14 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self._ffn0, self._ffn1 = _Dense(self.ffn.layers[0][0]), _Dense(self.ffn.layers[1], self.norm3)
         self._cls = [_Dense(cb[3 * i], cb[3 * i + 1]) for i in range(num_cls_fcs)] + [_Dense(cb[3 * num_cls_fcs])]
         self._reg = [_Dense(rb[2 * i]) for i in range(num_reg_fcs)] + [_Dense(rb[2 * num_reg_fcs])]
+        self.overlap = True          # run independent kernels of a layer on a second stream (parallel graph branches)
+        self._streams = {}
+
+    def _side_stream(self, device):
+        key = str(device)
+        if self._streams.get(key) is None:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
 
     @torch.no_grad()
     def init_weights(self):
@@ -297,8 +318,8 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        13 kernel launches: 5 dense chains, SASA core, sample_points, fused gather, bf16 split, 2 tcgen05 GEMMs,
-        mix, split-K reduce + norm2."""
+        15 kernel launches: 6 dense chains, bf16 splits (qkv, q2), SASA core, sample_points, fused gather, 2 tcgen05
+        GEMMs, mix, split-K reduce + norm2; the gather runs concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
         M, dev = B * Q, query_feat.device
         query_bbox = query_bbox.contiguous()
@@ -312,20 +333,41 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         o = self.self_attn.attention_core(query_bbox, q1, attn_mask)
         q2, heads = new(D), new(self.sampling._heads.out_features)
         ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2), self.sampling.heads_layer(heads)])
-        # (3) adaptive spatio-temporal sampling
-        sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
-        # (4) adaptive mixing (+ identity + norm2)
-        q3 = self.mixing.forward_fused(sampled, q2.reshape(B, Q, D), self.norm2).reshape(M, D)
-        # (5) FFN (+ identity + norm3) chained with the classification branch
-        q4, cls_score = new(D), new(self.num_classes)
-        chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
-        chain += [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
-        ops.dense_chain(q3, D, M, chain)
-        # (6) regression branch with the box refinement / velocity rescale as its epilogue
-        bbox_pred = new(self.code_size)
+        # (3) adaptive spatio-temporal sampling  ||  (4a) dynamic-parameter GEMM: independent of each other (the GEMM needs
+        # only q2), complementary resources (gather: LSU / L2 latency, no shared memory; GEMM: tensor cores + TMA) -> two
+        # streams, i.e. two parallel branches when the layer is captured into a CUDA graph.  Buffers are allocated before the
+        # fork so the caching allocator never sees cross-stream frees.
+        main = torch.cuda.current_stream()
+        side = self._side_stream(dev) if self.overlap else None
+        pbuf = self.mixing.alloc_params(M, dev)
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                params = self.mixing.generate_params(q2, pbuf)
+            sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+            main.wait_stream(side)
+        else:
+            params = self.mixing.generate_params(q2, pbuf)
+            sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+        # (4b) adaptive mixing (+ identity + norm2)
+        G, P = self.mixing.n_groups, self.mixing.in_points
+        q3 = self.mixing.mix_and_project(params, sampled.reshape(M, G, P, -1), q2, self.norm2)
+        # (5) FFN (+ identity + norm3); then classification and regression branches side by side
+        q4, cls_score, bbox_pred = new(D), new(self.num_classes), new(self.code_size)
         td = img_metas[0]['time_diff']
-        ops.dense_chain(q4, D, M, [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)],
-                        refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
+        cls_chain = [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
+        reg_chain = [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
+        ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
+        if side is not None:
+            ops.dense_chain(q3, D, M, ffn_chain)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.dense_chain(q4, D, M, reg_chain, refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
+            ops.dense_chain(q4, D, M, cls_chain)
+            main.wait_stream(side)
+        else:
+            ops.dense_chain(q3, D, M, ffn_chain + cls_chain)
+            ops.dense_chain(q4, D, M, reg_chain, refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
         return q4.reshape(B, Q, D), cls_score.reshape(B, Q, self.num_classes), bbox_pred.reshape(B, Q, self.code_size)
 
 
