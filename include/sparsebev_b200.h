@@ -40,7 +40,8 @@ const char* sbev_last_error(void);
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
  *   "dense_cluster"  0 = every CTA streams its own weight tiles (default), 1 = 8-CTA clusters share every tile by TMA
  *                    multicast (correct, measured slower: the clusters run in lock step)
- *   "gather_variant" 1 = two levels' loads in flight at a time, 3 CTAs/SM (default), 0 = all levels in flight, 2 CTAs/SM */
+ *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
+ *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point) */
 int         sbev_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -151,6 +152,8 @@ typedef struct sbev_dense_layer {
     const uint16_t* W_hi;   /* tensor-core path: bf16 (hi, lo) split of W in the nn.Linear layout [N][Kpad], zero padded */
     const uint16_t* W_lo;   /*   (Kpad = K rounded up to 64); NULL selects the fp32 FFMA path, which needs Wt instead   */
     int Kpad;
+    uint16_t* y_hi;         /* optional: bf16 (hi, lo) split of the stored output, [M][ldy] each (feeds the tensor-core   */
+    uint16_t* y_lo;         /*   kernels that follow: attention core, parameter GEMM); both or neither                    */
 } sbev_dense_layer;
 int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
                          const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,

@@ -25,6 +25,7 @@ constexpr int CHAIN_MAX_PASS = 4;                 // N <= 4 * 256
 
 struct ChainLayer {
     const float* Wt; const float* bias; const float* ln_w; const float* ln_b; const float* residual; float* y;
+    __nv_bfloat16* y_hi; __nv_bfloat16* y_lo;     // optional bf16 (hi, lo) split of the stored output, row stride ldy
     int ldw, K, N, flags, ldy, kc;                // kc = weight rows per chunk
 };
 struct ChainParams {
@@ -106,7 +107,14 @@ __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const
                     }
                 }
                 yr[n] = v;
-                if (L.y != nullptr && live) L.y[(long long)row * L.ldy + n] = v;
+                if (live) {
+                    if (L.y != nullptr) L.y[(long long)row * L.ldy + n] = v;
+                    if (L.y_hi != nullptr) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                        L.y_hi[(long long)row * L.ldy + n] = h;
+                        L.y_lo[(long long)row * L.ldy + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+                    }
+                }
             }
         }
     }
@@ -597,6 +605,8 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
         if (l.W_hi == nullptr || l.W_lo == nullptr || l.K > 512 || l.N > 1024) use_mma = false;
         ChainLayer& c = prm.layer[i];
         c.Wt = l.Wt; c.bias = l.bias; c.ln_w = l.ln_w; c.ln_b = l.ln_b; c.residual = l.residual; c.y = l.y;
+        c.y_hi = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_hi)); c.y_lo = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_lo));
+        SBEV_REQUIRE((l.y_hi == nullptr) == (l.y_lo == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: y_hi and y_lo go together");
         c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags; c.ldy = l.ldy;
         int kc = CHAIN_STAGE_FLOATS / l.ldw;
         if (kc >= 4) kc &= ~3;
@@ -661,7 +671,7 @@ extern "C" int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw,
     sbev_dense_layer l;
     l.Wt = Wt; l.ldw = ldw; l.K = K; l.N = N; l.bias = bias; l.ln_w = ln_w; l.ln_b = ln_b; l.residual = residual;
     l.flags = flags & (SBEV_DENSE_RELU | SBEV_DENSE_RES_PRE_LN); l.y = y; l.ldy = N;
-    l.W_hi = nullptr; l.W_lo = nullptr; l.Kpad = 0;
+    l.W_hi = nullptr; l.W_lo = nullptr; l.Kpad = 0; l.y_hi = nullptr; l.y_lo = nullptr;
     return sbev_dense_chain_fwd(x, ldx, M, 1, &l, nullptr, nullptr, 0, 0, stream);
 }
 

@@ -59,20 +59,21 @@ __device__ __forceinline__ int view_from_coord(float z, int N) {
     return (int)roundf(z * (float)(N - 1));     // forward.cu:110 (round-half-away-from-zero)
 }
 
-// Gather all L levels for 4 consecutive channels.  base[l] already points at
+// Gather all L levels for 4*VEC consecutive channels.  base[l] already points at
 // (slice, view, channel lane); pxs[l] = floats between neighbouring pixels (pixel offsets fit 32 bits).
-// LB = levels whose 4*LB loads are in flight together (LB == L: maximum memory-level parallelism;
+// LB = levels whose 4*LB*VEC loads are in flight together (LB == L: maximum memory-level parallelism;
 // smaller LB: fewer live registers -> more resident warps).
-template <int L, int LB>
-__device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], const int (&H)[L],
+template <int L, int LB, int VEC = 1, int VSTRIDE = 4>      // VSTRIDE: floats between the VEC float4 of one lane
+__device__ __forceinline__ void gather_levels_v(const float* const (&base)[L], const int (&H)[L],
                                                 const int (&W)[L], const int (&pxs)[L],
-                                                float u, float v, const float (&wt)[L], bool live) {
+                                                float u, float v, const float (&wt)[L], bool live, float4 (&acc)[VEC]) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc = zero;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = zero;
 #pragma unroll
     for (int l0 = 0; l0 < L; l0 += LB) {
         Tap tp[LB];
-        float4 c1[LB], c2[LB], c3[LB], c4[LB];
+        float4 c1[LB][VEC], c2[LB][VEC], c3[LB][VEC], c4[LB][VEC];
 #pragma unroll
         for (int i = 0; i < LB; ++i) {
             const int l = l0 + i;
@@ -80,10 +81,13 @@ __device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], c
                 tp[i] = make_tap(u, v, H[l], W[l]);
                 const int row = W[l] * pxs[l];
                 const float* p = base[l] + (tp[i].y0 * row + tp[i].x0 * pxs[l]);
-                c1[i] = (live && tp[i].ok1) ? ldg4(p) : zero;
-                c2[i] = (live && tp[i].ok2) ? ldg4(p + pxs[l]) : zero;
-                c3[i] = (live && tp[i].ok3) ? ldg4(p + row) : zero;
-                c4[i] = (live && tp[i].ok4) ? ldg4(p + row + pxs[l]) : zero;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    c1[i][e] = (live && tp[i].ok1) ? ldg4(p + VSTRIDE * e) : zero;
+                    c2[i][e] = (live && tp[i].ok2) ? ldg4(p + pxs[l] + VSTRIDE * e) : zero;
+                    c3[i][e] = (live && tp[i].ok3) ? ldg4(p + row + VSTRIDE * e) : zero;
+                    c4[i][e] = (live && tp[i].ok4) ? ldg4(p + row + pxs[l] + VSTRIDE * e) : zero;
+                }
             }
         }
 #pragma unroll
@@ -91,14 +95,25 @@ __device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], c
             const int l = l0 + i;
             if (l < L && tp[i].inside) {
                 const Tap& t = tp[i];
-                acc.x += (t.w1 * c1[i].x + t.w2 * c2[i].x + t.w3 * c3[i].x + t.w4 * c4[i].x) * wt[l];
-                acc.y += (t.w1 * c1[i].y + t.w2 * c2[i].y + t.w3 * c3[i].y + t.w4 * c4[i].y) * wt[l];
-                acc.z += (t.w1 * c1[i].z + t.w2 * c2[i].z + t.w3 * c3[i].z + t.w4 * c4[i].z) * wt[l];
-                acc.w += (t.w1 * c1[i].w + t.w2 * c2[i].w + t.w3 * c3[i].w + t.w4 * c4[i].w) * wt[l];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    acc[e].x += (t.w1 * c1[i][e].x + t.w2 * c2[i][e].x + t.w3 * c3[i][e].x + t.w4 * c4[i][e].x) * wt[l];
+                    acc[e].y += (t.w1 * c1[i][e].y + t.w2 * c2[i][e].y + t.w3 * c3[i][e].y + t.w4 * c4[i][e].y) * wt[l];
+                    acc[e].z += (t.w1 * c1[i][e].z + t.w2 * c2[i][e].z + t.w3 * c3[i][e].z + t.w4 * c4[i][e].z) * wt[l];
+                    acc[e].w += (t.w1 * c1[i][e].w + t.w2 * c2[i][e].w + t.w3 * c3[i][e].w + t.w4 * c4[i][e].w) * wt[l];
+                }
             }
         }
     }
-    return acc;
+}
+
+template <int L, int LB>
+__device__ __forceinline__ float4 gather_levels(const float* const (&base)[L], const int (&H)[L],
+                                                const int (&W)[L], const int (&pxs)[L],
+                                                float u, float v, const float (&wt)[L], bool live) {
+    float4 acc[1];
+    gather_levels_v<L, LB, 1, 4>(base, H, W, pxs, u, v, wt, live, acc);
+    return acc[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -362,15 +377,19 @@ struct FusedParams {
     float image_h, image_w, eps;
 };
 
-template <int L, int LB, int MINB>
+// LPP = lanes per sample point: 16 (4 channels per lane) or 8 (8 channels per lane; halves the per-point geometry that
+// every lane of a point computes redundantly -- the kernel is issue-bound, not bandwidth-bound, on the realistic rig).
+template <int L, int LB, int MINB, int LPP>
 __global__ void __launch_bounds__(256, MINB)
 sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
-    const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+    constexpr int VEC = 16 / LPP;                     // float4 per lane
+    constexpr int PPB = 256 / LPP;                    // points per block
+    const int lane = threadIdx.x & 31, half = lane / LPP, j = lane % LPP;
     const int T = prm.T, G = prm.G, N = prm.N, Q = prm.Q, P = prm.P;
     // slice (b,t,g) = blockIdx.y (uniform); sample (q,p) inside the slice from blockIdx.x: all 32-bit, no 64-bit div/mod
     const int s = blockIdx.y;
     const int g = s % G, bt = s / G, t = bt % T, b = bt / T;
-    const int idx_raw = blockIdx.x * 16 + (threadIdx.x >> 4);
+    const int idx_raw = blockIdx.x * PPB + (threadIdx.x / LPP);
     const bool live = idx_raw < Q * P;
     const int idx = live ? idx_raw : Q * P - 1;
     const int q = (P == 4) ? (idx >> 2) : (idx / P);
@@ -406,10 +425,10 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
         vn = __fdiv_rn(__fdiv_rn(cy, safe), prm.image_h);
         valid = (dz > prm.eps) && (vn > 0.f) && (vn < 1.f) && (un > 0.f) && (un < 1.f);
     }
-    const unsigned ball = (__ballot_sync(0xffffffffu, valid) >> (16 * half)) & 0xffffu;
+    const unsigned ball = (__ballot_sync(0xffffffffu, valid) >> (LPP * half)) & ((1u << LPP) - 1u);
     const int view = ball ? (__ffs(ball) - 1) : 0;          // argmax of 0/1 flags: first valid, else 0
-    const float u = __shfl_sync(0xffffffffu, un, 16 * half + view);
-    const float v = __shfl_sync(0xffffffffu, vn, 16 * half + view);
+    const float u = __shfl_sync(0xffffffffu, un, LPP * half + view);
+    const float v = __shfl_sync(0xffffffffu, vn, LPP * half + view);
 
     const float* base[L]; int H[L], W[L]; int pxs[L];
 #pragma unroll
@@ -417,10 +436,12 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
         H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = (int)lv.s_px[l];
         base[l] = lv.ptr[l] + ((long long)bt * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
     }
-    const float4 acc = gather_levels<L, LB>(base, H, W, pxs, u, v, wt, live);
+    float4 acc[VEC];
+    gather_levels_v<L, LB, VEC, 4 * LPP>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
     if (live) {
         float* dst = prm.out + ((bq * G + g) * (T * P) + (t * P + p)) * 64 + 4 * j;
-        *reinterpret_cast<float4*>(dst) = acc;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) *reinterpret_cast<float4*>(dst + 4 * LPP * e) = acc[e];
         if (prm.loc_out != nullptr && j == 0) {
             float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
             lo[0] = u; lo[1] = v; lo[2] = __fdiv_rn((float)view, (float)(N - 1));
@@ -561,12 +582,18 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
     for (int l = 0; l < L; ++l)
         SBEV_REQUIRE((long long)lv.H[l] * lv.W[l] * stride_px[l] < (1ll << 31), SBEV_ERR_UNSUPPORTED, "level %d too large for 32-bit pixel offsets", l);
     FusedParams prm{points, velocity, time_diff, lidar2img, scale_w, out, loc_out, B, T, G, N, Q, P, image_h, image_w, eps};
-    const dim3 grid((Q * P + 15) / 16, B * T * G);
-    const int variant = get_option(OPT_GATHER_VARIANT);   // 0 = all levels in flight (default), 1 = two levels at a time, 3 CTAs/SM
+    // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
+    // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views)
+    int variant = get_option(OPT_GATHER_VARIANT);
+    if (variant == 2 && N > 8) variant = 1;
+    const int ppb = variant == 2 ? 32 : 16;
+    const dim3 grid((Q * P + ppb - 1) / ppb, B * T * G);
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
-        if (variant == 1 && LL >= 3) sampling4d_c64_kernel<LL, 2, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);   \
-        else sampling4d_c64_kernel<LL, LL, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);                   \
+        if (variant == 2 && LL >= 2) sampling4d_c64_kernel<LL, 2, 2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);      \
+        else if (variant == 2) sampling4d_c64_kernel<LL, LL, 2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);           \
+        else if (variant == 1 && LL >= 3) sampling4d_c64_kernel<LL, 2, 3, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm); \
+        else sampling4d_c64_kernel<LL, LL, 1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);               \
         break;
     switch (L) { SBEV_LAUNCH_FUSED(1) SBEV_LAUNCH_FUSED(2) SBEV_LAUNCH_FUSED(3) SBEV_LAUNCH_FUSED(4) SBEV_LAUNCH_FUSED(5) }
 #undef SBEV_LAUNCH_FUSED

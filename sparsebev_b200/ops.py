@@ -193,13 +193,14 @@ class DenseWeight:
 
 
 def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None,
-                w_hi=None, w_lo=None, kpad=0):
+                w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None):
     """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path."""
     flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
-    keep = [t for t in (wt, bias, residual, y, w_hi, w_lo) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
+    keep = [t for t in (wt, bias, residual, y, w_hi, w_lo, y_hi, y_lo) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
     return _lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
                            _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
-                           (ldy if ldy is not None else N) if y is not None else 0, _p(w_hi), _p(w_lo), kpad), keep
+                           (ldy if ldy is not None else N) if (y is not None or y_hi is not None) else 0, _p(w_hi), _p(w_lo), kpad,
+                           _p(y_hi), _p(y_lo)), keep
 
 
 def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):
@@ -281,7 +282,7 @@ def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None, ld_qkv=None,
     return out
 
 
-def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None):
+def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None, split=None):
     """Tensor-core attention core on the concatenated in_proj|gen_tau output `qkvt` [B*Q, 3D+H] (fp32): splits it once
     into bf16 (hi, lo) and runs the warp-pipelined kernel.  -> [B,Q,D] (heads concatenated, before out_proj)."""
     lib = _lib.load()
@@ -290,7 +291,7 @@ def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None):
     B, Q, _ = qb.shape
     D, H = embed_dims, num_heads
     ld = qkvt.shape[1]
-    hi, lo = split_bf16(qkvt)
+    hi, lo = split if split is not None else split_bf16(qkvt)
     m = None
     if dn_mask is not None:
         m = _chk(dn_mask.to(torch.uint8).contiguous(), 'dn_mask', torch.uint8)

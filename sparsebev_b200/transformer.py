@@ -49,11 +49,12 @@ class _Dense:
         self.in_features = linear.in_features
         self.out_features = sum(l.out_features for l in self.linears)
 
-    def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None):
+    def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None, y_hi=None, y_lo=None):
         wt, ldw, bias = self.cache.get_with_bias([l.weight for l in self.linears], [l.bias for l in self.linears])
         c = self.cache
         return ops.chain_layer(wt, ldw, self.in_features, self.out_features, bias=bias, ln=self.ln, residual=residual,
-                               relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
+                               relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad,
+                               y_hi=y_hi, y_lo=y_lo)
 
     def __call__(self, x, relu=False, residual=None, res_pre_ln=False, k=None):
         M = x.shape[0]
@@ -109,12 +110,13 @@ class AdaptiveMixing(nn.Module):
                     q_lo=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
                     params=torch.empty(M, n_par, device=device, dtype=torch.float32))
 
-    def generate_params(self, q2, buf):
+    def generate_params(self, q2, buf, presplit=False):
         """Stage 1: dynamic mixing parameters [M, G*(C*C + Pout*Pin)] = query @ W^T + b on tcgen05 (depends on the query only,
         NOT on the sampled features -> can run concurrently with the gather)."""
         M, D = q2.shape
         x3 = self.precision == 'bf16x3'
-        ops.split_bf16(q2, need_lo=x3, out=(buf['q_hi'], buf['q_lo'] if x3 else None))
+        if not presplit:                  # (the decoder layer lets the producing dense chain write q_hi / q_lo directly)
+            ops.split_bf16(q2, need_lo=x3, out=(buf['q_hi'], buf['q_lo'] if x3 else None))
         w_hi, w_lo = self._pg.get(self.parameter_generator.weight)
         a, b = ([buf['q_hi'], buf['q_hi'], buf['q_lo']], [w_hi, w_lo, w_hi]) if x3 else ([buf['q_hi']], [w_hi])
         ops.gemm_bf16_tn(a, b, M, self.n_groups * self.total_parameters, D, bias=self.parameter_generator.bias, out=buf['params'])
@@ -174,31 +176,36 @@ class SparseBEVSelfAttention(BaseModule):
         nn.init.zeros_(self.gen_tau.weight)
         nn.init.uniform_(self.gen_tau.bias, 0.0, 2.0)
 
-    def in_layer(self, y):
-        """in_proj and gen_tau as ONE concatenated Linear: columns [0,3D) = q|k|v, [3D,3D+H) = tau."""
+    def in_layer(self, y, y_hi=None, y_lo=None):
+        """in_proj and gen_tau as ONE concatenated Linear: columns [0,3D) = q|k|v, [3D,3D+H) = tau; optionally also stored
+        as the bf16 (hi, lo) pair the tensor-core attention core consumes."""
         attn = self.attention.attn
         wt, ldw, bias = self._cache_in.get_with_bias([attn.in_proj_weight, self.gen_tau.weight], [attn.in_proj_bias, self.gen_tau.bias])
         c = self._cache_in
-        return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
+        return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad,
+                               y_hi=y_hi, y_lo=y_lo)
 
-    def out_layer(self, residual, norm, y):
+    def out_layer(self, residual, norm, y, y_hi=None, y_lo=None):
         attn = self.attention.attn
         wt, ldw, bias = self._cache_out.get_with_bias([attn.out_proj.weight], [attn.out_proj.bias])
         c = self._cache_out
         return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y,
-                               w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad)
+                               w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad, y_hi=y_hi, y_lo=y_lo)
 
     def attention_core(self, query_bbox, x, pre_attn_mask=None):
         """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj)."""
         B, Q = query_bbox.shape[:2]
         D, H = self.attention.attn.embed_dim, self.num_heads
         qkvt = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.float32)
+        if self.core_impl == 'split':          # tensor-core path: the chain epilogue also emits the bf16 (hi, lo) operands
+            hi = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi)
+            ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt, hi, lo)])
+            o = ops.sasa_split(qkvt, query_bbox, self.pc_range, H, D, dn_mask=pre_attn_mask, split=(hi, lo))
+            return o.reshape(B * Q, D)
         ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt)])
-        if self.core_impl == 'split':          # tensor-core path: operands pre-split to bf16 (hi, lo) once per layer
-            o = ops.sasa_split(qkvt, query_bbox, self.pc_range, H, D, dn_mask=pre_attn_mask)
-        else:
-            o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
-                         ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
+        o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
+                     ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
         return o.reshape(B * Q, D)
 
     def forward_fused(self, query_bbox, query_feat, pre_attn_mask=None, norm=None):
@@ -318,8 +325,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        15 kernel launches: 6 dense chains, bf16 splits (qkv, q2), SASA core, sample_points, fused gather, 2 tcgen05
-        GEMMs, mix, split-K reduce + norm2; the gather runs concurrently with the parameter GEMM, cls with reg."""
+        13 kernel launches: 6 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
+        that follow), SASA core, sample_points, fused gather, 2 tcgen05 GEMMs, mix, split-K reduce + norm2; the gather runs
+        concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
         M, dev = B * Q, query_feat.device
         query_bbox = query_bbox.contiguous()
@@ -332,22 +340,22 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         # (2) scale-adaptive self-attention; out_proj + identity + norm1 chained with the sampling heads
         o = self.self_attn.attention_core(query_bbox, q1, attn_mask)
         q2, heads = new(D), new(self.sampling._heads.out_features)
-        ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2), self.sampling.heads_layer(heads)])
+        pbuf = self.mixing.alloc_params(M, dev)               # q2 also leaves the chain as the bf16 (hi, lo) operand of the param GEMM
+        ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)])
         # (3) adaptive spatio-temporal sampling  ||  (4a) dynamic-parameter GEMM: independent of each other (the GEMM needs
         # only q2), complementary resources (gather: LSU / L2 latency, no shared memory; GEMM: tensor cores + TMA) -> two
         # streams, i.e. two parallel branches when the layer is captured into a CUDA graph.  Buffers are allocated before the
         # fork so the caching allocator never sees cross-stream frees.
         main = torch.cuda.current_stream()
         side = self._side_stream(dev) if self.overlap else None
-        pbuf = self.mixing.alloc_params(M, dev)
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                params = self.mixing.generate_params(q2, pbuf)
+                params = self.mixing.generate_params(q2, pbuf, presplit=True)
             sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
             main.wait_stream(side)
         else:
-            params = self.mixing.generate_params(q2, pbuf)
+            params = self.mixing.generate_params(q2, pbuf, presplit=True)
             sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
         # (4b) adaptive mixing (+ identity + norm2)
         G, P = self.mixing.n_groups, self.mixing.in_points

@@ -225,7 +225,7 @@ def test_fused_sampling_matches_golden_reference(golden_dir):
     _close(pts2, torch.from_numpy(g['points']), rtol=1e-5, atol=1e-5, what='make_sample_points vs reference')
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2])
 @pytest.mark.parametrize('T', [1, 2, 8])
 def test_fused_sampling_loc_bit_exact_vs_oracle_and_layouts(T, variant, option):
     option('gather_variant', variant)
