@@ -25,6 +25,7 @@ import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
 METRIC = 'decoder-layer samples/sec (900q x 6cam x 8f)'
+GATHER_DRAM_TRAFFIC = 131.6e6      # bytes per launch at r50-T8, measured with ncu --set full (profiles/r01_kernels_ncu.md)
 
 
 def parse():
@@ -390,7 +391,9 @@ def main():
             'gpu_launches': launches_per_step * args.steps,
             'launches_per_step': launches_per_step,
             'roofline': {'bound': 'hbm', 'kernel': 'sampling4d_c64_kernel (fused projection + multi-scale gather)',
-                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': GATHER_DRAM_TRAFFIC,
+                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full (profiles/); far below '
+                                         'the algorithmic bytes because neighbouring queries re-sample the same pixels out of L2',
                          'algorithmic_bytes': algo_bytes, 'points': n_points, 'kernel_ms': gather_ms, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'breakdown_ms': breakdown}))

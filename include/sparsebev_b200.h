@@ -41,7 +41,7 @@ const char* sbev_last_error(void);
  *   "dense_cluster"  0 = every CTA streams its own weight tiles (default), 1 = 8-CTA clusters share every tile by TMA
  *                    multicast (correct, measured slower: the clusters run in lock step)
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
- *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point) */
+ *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default) */
 int         sbev_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------

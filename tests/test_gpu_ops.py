@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    defaults = {'gemm_impl': 0, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 1, 'dense_impl': 0, 'dense_cluster': 0}
+    defaults = {'gemm_impl': 0, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 2, 'dense_impl': 0, 'dense_cluster': 0}
 
     def setter(name, value):
         _lib.set_option(name, value)
