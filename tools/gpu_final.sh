@@ -9,8 +9,8 @@ SMI=$!
 timeout 600 python bench.py --steps 50 --warmup 5 --breakdown > gpurun_out/bench.json 2> gpurun_out/bench.err
 kill $SMI
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-timeout 600 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1
-timeout 600 python tools/ref_layer_gpu.py > gpurun_out/ref_layer_gpu.log 2>&1
+timeout 600 python tests/perf/op_bench.py > gpurun_out/op_bench.log 2>&1
+timeout 600 python tests/perf/ref_layer_gpu.py > gpurun_out/ref_layer_gpu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 2 --no-graph --no-overlap --skip-cpu > gpurun_out/bench_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sbev" -s 26 -c 13 -o gpurun_out/prof_layer \

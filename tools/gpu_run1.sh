@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -q --timeout 300 -x --deselect tests/
 echo "pytest ops exit $?" >> gpurun_out/pytest_ops.log
 timeout 900 python -m pytest tests/test_gpu_layer.py -m gpu -q --timeout 300 > gpurun_out/pytest_layer.log 2>&1
 echo "pytest layer exit $?" >> gpurun_out/pytest_layer.log
-timeout 600 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1
+timeout 600 python tests/perf/op_bench.py > gpurun_out/op_bench.log 2>&1
 timeout 900 python bench.py --steps 20 --warmup 3 --breakdown > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph --skip-cpu > gpurun_out/bench_ncu.log 2>&1
