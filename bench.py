@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--layout', default='grouped', choices=['grouped', 'nhwc'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='single stream: no concurrent gather || param-GEMM, cls || reg')
+    ap.add_argument('--no-tma-params', action='store_true', help='mixing: fp32 parameter tensor + converting mix kernel instead of bf16 (hi,lo) + TMA')
     ap.add_argument('--breakdown', action='store_true', help='also write per-stage timings to gpurun_out/breakdown.json')
     ap.add_argument('--cpu-steps', type=int, default=3, help='bounded CPU sample: decoder-layer passes of the oracle')
     ap.add_argument('--skip-cpu', action='store_true')
@@ -190,6 +191,7 @@ def main():
     layer = model.decoder.decoder_layer
     layer.mixing.precision = args.precision
     layer.overlap = not args.no_overlap
+    layer.mixing.tma_params = not args.no_tma_params
 
     # weak scaling: every rank owns its own scene (different seed) -- the reference's only strategy is DP
     feats_host = S.make_feats(args.config, T, batch=1, seed=100 + rank, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')

@@ -220,6 +220,16 @@ int sbev_split_bf16(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void*
 int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const* B, int nseg,
                       const float* bias, int M, int N, int K, int split_k, float* C, void* stream);
 
+/* Same GEMM in bf16x3 mode, but C leaves as a bf16 (hi, lo) pair (C ~= C_hi + C_lo, [M][N] each, N % 256 == 0): the form the
+ * TMA-fed mix kernel consumes, so the dynamic-parameter tensor is written once and never re-converted. */
+int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo,
+                            const float* bias, int M, int N, int K, uint16_t* C_hi, uint16_t* C_lo, void* stream);
+
+/* sbev_mix_fwd with the parameters given as that (hi, lo) pair; in_points must be 32 (M 64x64 and S 128x32 tiles are
+ * pulled by swizzled 2-D TMA loads straight into ldmatrix-ready shared memory, double-buffered across items). */
+int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* params_lo, const float* x, int BQ, int G, int Pin,
+                          int Pout, int C, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, void* stream);
+
 /* out[M,N] = LN(sum_z partial[z] + bias + residual) : split-K reduction fused with the residual
  * and LayerNorm that follow mixing.out_proj (sparsebev_transformer.py:377-379 + norm2 at :171). */
 int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,

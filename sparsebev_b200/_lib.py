@@ -43,6 +43,8 @@ SIGNATURES = {
     'sbev_mix_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_split_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp],
     'sbev_gemm_bf16_tn': [c_vpp, c_vpp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_gemm_bf16_tn_split': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'sbev_mix_presplit_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_reduce_ln_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
 }
 

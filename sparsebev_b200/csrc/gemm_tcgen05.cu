@@ -18,6 +18,7 @@
 // All mbarrier waits are bounded: a protocol bug traps instead of hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -121,13 +122,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
 struct GemmMapsV2 {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap c;          // fp32 [split_k][M][N], box {32 cols, 32 rows, 1}, 128-byte swizzle (epilogue TMA stores)
+    CUtensorMap c_hi, c_lo; // OUT_SPLIT: bf16 [M][N] each, box {64 cols, 32 rows}, 128-byte swizzle
 };
 
 // ARES (A-resident, for small K): the CTA is pinned to ONE M-tile, loads that tile's whole A operand (all k-blocks, hi and
 // lo) into shared memory once and then only streams B through the ring while it walks its N-tiles -- a third less
 // operand traffic per MMA for the parameter-generation GEMM (K = 256), whose A is the same 900 x 256 query matrix for
 // all 256 N-tiles.  Requires X3, split_k == 1, gridDim.x % m_tiles == 0; ARES_KB = number of resident k-blocks.
-template <int BN, int STAGES, bool X3, int ARES_KB = 0>
+// OUT_SPLIT: the epilogue stores C as a bf16 (hi, lo) pair (C ~= hi + lo) instead of fp32 -- the layout the mma.sync mix
+// kernel consumes by TMA, so the 118 MB parameter tensor is never re-converted.
+template <int BN, int STAGES, bool X3, int ARES_KB = 0, bool OUT_SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_per_split, int m_tiles, int n_tiles, int num_tiles,
                                const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
@@ -263,6 +267,43 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
             tc_fence_after();
             const bool add_bias = (bias != nullptr) && (z == 0);
             uint8_t* my_stg = stg_base + (warp - 2) * 2 * 4096;
+            if constexpr (OUT_SPLIT) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 64; ++c) {
+                    float v[64];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64 + 32), v + 32);
+                    // buffers 0 / 1 of this warp hold the hi / lo box; the previous pair of stores must have drained them
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                      // 8 chunks of 8 bf16 (16 B) per 128-byte row
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                            if (add_bias) { a += __ldg(bias + n0 + c * 64 + 8 * j + 2 * e); b += __ldg(bias + n0 + c * 64 + 8 * j + 2 * e + 1); }
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                            const float2 hf = __bfloat1622float2(h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                            hw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        const uint32_t off = lane * 128 + ((j ^ (lane & 7)) << 4);
+                        *reinterpret_cast<uint4*>(my_stg + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(my_stg + 4096 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&maps.c_hi), "r"(smem_u32(my_stg)), "r"(n0 + c * 64), "r"(m0 + quarter * 32) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&maps.c_lo), "r"(smem_u32(my_stg + 4096)), "r"(n0 + c * 64), "r"(m0 + quarter * 32) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 float v[32];
@@ -286,6 +327,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 ++chunk_ctr;
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -355,6 +397,36 @@ int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long c
         if (cache.size() > 4096) cache.clear();
         cache.emplace(key, *out);
     }
+    return SBEV_OK;
+}
+
+// General 2-D bf16 map: [rows][cols] row-major, box {box_cols, box_rows}, swizzle_bytes in {0, 64, 128}.
+int make_bf16_map_ex(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows, int box_cols, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode_fn();
+    SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] box %dx%d", (int)r, rows, cols, box_rows, box_cols);
+    return SBEV_OK;
+}
+
+// bf16 [M][N] output, box = {64 cols, 32 rows}, 128-byte swizzle on the shared-memory side (TMA stores).
+static int make_bf16_store_map(CUtensorMap* out, const void* ptr, long long N, long long M) {
+    EncodeTiledFn enc = get_encode_fn();
+    SBEV_REQUIRE(enc != nullptr, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstride[1] = {(cuuint64_t)N * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SBEV_REQUIRE(r == CUDA_SUCCESS, SBEV_ERR_CUDA, "cuTensorMapEncodeTiled(C bf16) failed (%d)", (int)r);
     return SBEV_OK;
 }
 
@@ -435,4 +507,35 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
     }
     SBEV_REQUIRE(false, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: nseg must be 1, or 3 with the (A0,B0),(A0,B1),(A1,B0) bf16x3 pattern");
     return check_launch("sbev_gemm_bf16_tn");
+}
+
+// Same GEMM (bf16x3 pattern required), but C leaves as a bf16 (hi, lo) pair: C ~= C_hi + C_lo, [M][N] each.
+extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo,
+                                       const float* bias, int M, int N, int K, uint16_t* C_hi, uint16_t* C_lo, void* stream) {
+    SBEV_REQUIRE(A_hi && A_lo && B_hi && B_lo && C_hi && C_lo, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: null pointer");
+    SBEV_REQUIRE(M > 0 && N > 0 && K > 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: bad sizes");
+    SBEV_REQUIRE(K % GEMM_BK == 0 && N % 256 == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn_split: needs K %% 64 == 0 and N %% 256 == 0");
+    const void* ptrs[6] = {A_hi, A_lo, B_hi, B_lo, C_hi, C_lo};
+    for (int i = 0; i < 6; ++i) SBEV_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: operands must be 16-byte aligned");
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: bias must be 16-byte aligned");
+    GemmMapsV2 mp;
+    int rc = make_bf16_map(&mp.a_hi, A_hi, M, K, GEMM_BM);   if (rc) return rc;
+    rc = make_bf16_map(&mp.a_lo, A_lo, M, K, GEMM_BM);       if (rc) return rc;
+    rc = make_bf16_map(&mp.b_hi, B_hi, N, K, 256);           if (rc) return rc;
+    rc = make_bf16_map(&mp.b_lo, B_lo, N, K, 256);           if (rc) return rc;
+    rc = make_bf16_store_map(&mp.c_hi, C_hi, N, M);          if (rc) return rc;
+    rc = make_bf16_store_map(&mp.c_lo, C_lo, N, M);          if (rc) return rc;
+    mp.c = mp.c_hi;
+    static int num_sms = 0;
+    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
+    const int num_tiles = m_tiles * n_tiles;
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    constexpr size_t smem = (size_t)2 * 2 * (GEMM_BM * GEMM_BK * 2 + 256 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
+        mp, K / GEMM_BK, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
+    return check_launch("sbev_gemm_bf16_tn_split");
 }

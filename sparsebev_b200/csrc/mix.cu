@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <mutex>
 
 namespace sbev {
 
@@ -441,6 +442,209 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed version (in_points == 32): the parameter GEMM already stored the dynamic parameters as bf16 (hi, lo)
+// (sbev_gemm_bf16_tn_split), so M [64x64] and S [128x32] of an item arrive by four 2-D TMA loads -- 128-byte / 64-byte
+// swizzled, i.e. directly in the bank-conflict-free layout ldmatrix wants -- into a double-buffered operand set; no
+// conversion pass for the 8192 parameters of an item, only the 32x64 x tile is split on the fly.
+struct MixMaps { CUtensorMap m_hi, m_lo, s_hi, s_lo; };
+
+__global__ void __launch_bounds__(256, 2)
+mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x, int num_items,
+               __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, float* __restrict__ y_f32) {
+    constexpr int Pin = 32, PK = 32;
+    constexpr int SET_BYTES = 4 * 8192;                       // M_hi | M_lo | S_hi | S_lo
+    constexpr int XRAW_BYTES = Pin * MIX_C * 4;               // 8 KB
+    extern __shared__ uint8_t mt_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mt_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sets = base;                                                           // [2][SET_BYTES]
+    float* xraw = reinterpret_cast<float*>(base + 2 * SET_BYTES);                   // [2][Pin*64]
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base + 2 * SET_BYTES + 2 * XRAW_BYTES);   // [32][72]
+    __nv_bfloat16* xl = xh + PK * MX_LD;
+    __nv_bfloat16* hh = xl + PK * MX_LD;                                            // h [32 p][72 (c')]
+    __nv_bfloat16* hl = hh + PK * MX_LD;
+    __shared__ float red[24];
+    __shared__ uint64_t full_bar[2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+
+    auto prefetch = [&](long long item, int slot) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[slot]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sets + slot * SET_BYTES);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(SET_BYTES + XRAW_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(&maps.m_hi), "r"(bar), "r"(0), "r"((int)(item * 128)) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst + 8192), "l"(&maps.m_lo), "r"(bar), "r"(0), "r"((int)(item * 128)) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst + 16384), "l"(&maps.s_hi), "r"(bar), "r"(0), "r"((int)(item * 256 + 128)) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst + 24576), "l"(&maps.s_lo), "r"(bar), "r"(0), "r"((int)(item * 256 + 128)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(xraw + slot * Pin * MIX_C)), "l"(x + item * Pin * MIX_C), "r"(XRAW_BYTES), "r"(bar) : "memory");
+    };
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((long long)blockIdx.x < num_items) prefetch(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
+
+    int n = 0;
+    for (long long qg = blockIdx.x; qg < num_items; qg += gridDim.x, ++n) {
+        const int slot = n & 1;
+        {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[slot]);
+            const uint32_t parity = (n >> 1) & 1;
+            uint32_t done = 0;
+            for (uint32_t spins = 0; !done; ++spins) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (!done && spins > (1u << 26)) __trap();
+            }
+        }
+        const uint32_t mh = (uint32_t)__cvta_generic_to_shared(sets + slot * SET_BYTES);       // M hi: [64 c][128 B], 128B swizzle
+        const uint32_t ml = mh + 8192;
+        const uint32_t sh = mh + 16384;                                                     // S hi: [128 o][64 B], 64B swizzle
+        const uint32_t sl = mh + 24576;
+        {   // x tile -> bf16 (hi, lo), padded rows for ldmatrix
+            const float* rx = xraw + slot * Pin * MIX_C;
+            for (int i = tid; i < Pin * 16; i += 256) {
+                const int p = i >> 4, c = (i & 15) * 4;
+                const float4 v = *reinterpret_cast<const float4*>(rx + p * MIX_C + c);
+                uint32_t h0, l0, h1, l1;
+                split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+                *reinterpret_cast<uint2*>(xh + p * MX_LD + c) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(xl + p * MX_LD + c) = make_uint2(l0, l1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && qg + gridDim.x < num_items) {        // the other operand set and x buffer are free: fetch the next item now
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            prefetch(qg + gridDim.x, slot ^ 1);
+        }
+
+        // ---- stage 1: h[p][c'] = sum_c x[p][c] M[c][c'], warp w owns columns c' = 8w..8w+7
+        float acc1[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) { acc1[m][0] = acc1[m][1] = acc1[m][2] = acc1[m][3] = 0.f; }
+#pragma unroll
+        for (int k0 = 0; k0 < MIX_C; k0 += 16) {
+            uint32_t bh[2], bl[2];
+            const int row = k0 + (lane & 15);                                       // k index = row of M
+            const uint32_t off = (uint32_t)(row * 128 + ((warp ^ (row & 7)) << 4));   // 16-byte chunk `warp` = columns 8w..8w+7
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(bh[0]), "=r"(bh[1]) : "r"(mh + off));
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(bl[0]), "=r"(bl[1]) : "r"(ml + off));
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                uint32_t ah[4], al[4];
+                ldsm_x4(ah, xh + (16 * m + a_row) * MX_LD + k0 + a_col);
+                ldsm_x4(al, xl + (16 * m + a_row) * MX_LD + k0 + a_col);
+                mma3(acc1[m], ah, al, bh, bl);
+            }
+        }
+        {
+            Stat st;
+            {
+                float sum = 0.f;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) sum += (acc1[m][0] + acc1[m][1]) + (acc1[m][2] + acc1[m][3]);
+                const float lm = sum * 0.125f;
+                float m2 = 0.f;
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float d = acc1[m][i] - lm; m2 += d * d; }
+                st.n = 8.f; st.mean = lm; st.m2 = m2;
+            }
+            st = block_stat_256(st, red);
+            const float mean = st.mean, rstd = rsqrtf(st.m2 / (float)(Pin * MIX_C) + 1e-5f);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int p = 16 * m + g8 + 8 * hrow, c = 8 * warp + 2 * t4;
+                    const float v0 = fmaxf((acc1[m][2 * hrow] - mean) * rstd, 0.f), v1 = fmaxf((acc1[m][2 * hrow + 1] - mean) * rstd, 0.f);
+                    uint32_t h, l;
+                    split2(v0, v1, h, l);
+                    *reinterpret_cast<uint32_t*>(hh + p * MX_LD + c) = h;
+                    *reinterpret_cast<uint32_t*>(hl + p * MX_LD + c) = l;
+                }
+        }
+        __syncthreads();
+
+        // ---- stage 2: y[o][c'] = sum_p S[o][p] h[p][c'], warp w owns rows o = 16w..16w+15
+        float acc2[8][4];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) { acc2[nn][0] = acc2[nn][1] = acc2[nn][2] = acc2[nn][3] = 0.f; }
+#pragma unroll
+        for (int k0 = 0; k0 < PK; k0 += 16) {
+            uint32_t ah[4], al[4];
+            const int row = 16 * warp + a_row;
+            const int chunk = (k0 >> 3) + (lm_id >> 1);                              // 16-byte chunk of the 64-byte S row
+            const uint32_t off = (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));   // TMA 64-byte swizzle
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(sh + off));
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(sl + off));
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) {
+                uint32_t bh[2], bl[2];
+                ldsm_x2_trans(bh, hh + (k0 + (lane & 15)) * MX_LD + 8 * nn);
+                ldsm_x2_trans(bl, hl + (k0 + (lane & 15)) * MX_LD + 8 * nn);
+                mma3(acc2[nn], ah, al, bh, bl);
+            }
+        }
+        Stat st2;
+        {
+            float sum = 0.f;
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) sum += (acc2[nn][0] + acc2[nn][1]) + (acc2[nn][2] + acc2[nn][3]);
+            const float lm = sum * (1.f / 32.f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float d = acc2[nn][i] - lm; m2 += d * d; }
+            st2.n = 32.f; st2.mean = lm; st2.m2 = m2;
+        }
+        st2 = block_stat_256(st2, red);                  // its barriers: every warp is past its last read of this operand set
+        const float mean = st2.mean, rstd = rsqrtf(st2.m2 / (float)(MIX_POUT * MIX_C) + 1e-5f);
+
+        // ---- epilogue: ReLU(LN) -> (hi, lo) staged in THIS item's (now dead) operand set, XOR-swizzled 128-byte rows
+        uint8_t* oh = sets + slot * SET_BYTES;            // [128 rows][128 B]
+        uint8_t* ol = oh + 16384;
+        const long long obase = qg * (MIX_POUT * MIX_C);
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int o = 16 * warp + g8 + 8 * hrow, c = 8 * nn + 2 * t4;
+                const float v0 = fmaxf((acc2[nn][2 * hrow] - mean) * rstd, 0.f), v1 = fmaxf((acc2[nn][2 * hrow + 1] - mean) * rstd, 0.f);
+                uint32_t h, l;
+                split2(v0, v1, h, l);
+                const uint32_t off = (uint32_t)(o * 128 + ((nn ^ (o & 7)) << 4) + 4 * t4);     // chunk nn = columns 8nn..8nn+7
+                *reinterpret_cast<uint32_t*>(oh + off) = h;
+                *reinterpret_cast<uint32_t*>(ol + off) = l;
+                if (y_f32) *reinterpret_cast<float2*>(y_f32 + obase + o * MIX_C + c) = make_float2(v0, v1);
+            }
+        __syncthreads();
+        if (y_hi) {
+            for (int i = tid; i < MIX_POUT * 8; i += 256) {
+                const int o = i >> 3, j = i & 7;
+                const uint32_t off = (uint32_t)(o * 128 + ((j ^ (o & 7)) << 4));
+                *reinterpret_cast<uint4*>(y_hi + obase + o * MIX_C + 8 * j) = *reinterpret_cast<const uint4*>(oh + off);
+                if (y_lo) *reinterpret_cast<uint4*>(y_lo + obase + o * MIX_C + 8 * j) = *reinterpret_cast<const uint4*>(ol + off);
+            }
+        }
+        __syncthreads();                                  // staging read out before this set is refilled (two items later)
+    }
+}
+
 }  // namespace sbev
 
 using namespace sbev;
@@ -499,4 +703,32 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
     else SBEV_LAUNCH_MIX(8);
 #undef SBEV_LAUNCH_MIX
     return check_launch("sbev_mix_fwd");
+}
+
+// params given as the bf16 (hi, lo) pair written by sbev_gemm_bf16_tn_split; in_points must be 32.
+extern "C" int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* params_lo, const float* x, int BQ, int G, int Pin,
+                                     int Pout, int C, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, void* stream) {
+    SBEV_REQUIRE(params_hi && params_lo && x && (y_hi || y_f32), SBEV_ERR_INVALID, "sbev_mix_presplit_fwd: null pointer");
+    SBEV_REQUIRE(C == MIX_C && Pout == MIX_POUT && Pin == 32, SBEV_ERR_UNSUPPORTED, "sbev_mix_presplit_fwd: needs C=64, out_points=128, in_points=32");
+    SBEV_REQUIRE(BQ >= 0 && G > 0, SBEV_ERR_INVALID, "sbev_mix_presplit_fwd: bad sizes");
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(params_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(params_lo) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x) & 15) == 0, SBEV_ERR_INVALID, "sbev_mix_presplit_fwd: operands must be 16-byte aligned");
+    if (BQ == 0) return SBEV_OK;
+    const long long items = (long long)BQ * G;
+    SBEV_REQUIRE(items * 256 < (1ll << 31), SBEV_ERR_UNSUPPORTED, "sbev_mix_presplit_fwd: too many items");
+    MixMaps maps;
+    // M view: rows of 64 bf16 (the item's 64x64 block starts at row 128*item); S view: rows of 32 bf16 (block at row 256*item + 128)
+    int rc = make_bf16_map_ex(&maps.m_hi, params_hi, items * 128, 64, 64, 64, 128);   if (rc) return rc;
+    rc = make_bf16_map_ex(&maps.m_lo, params_lo, items * 128, 64, 64, 64, 128);       if (rc) return rc;
+    rc = make_bf16_map_ex(&maps.s_hi, params_hi, items * 256, 32, 128, 32, 64);       if (rc) return rc;
+    rc = make_bf16_map_ex(&maps.s_lo, params_lo, items * 256, 32, 128, 32, 64);       if (rc) return rc;
+    static int num_sms = 0;
+    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const size_t smem = 2 * 32768 + 2 * 8192 + 4 * 32 * MX_LD * 2 + 1024;
+    static std::once_flag once;
+    std::call_once(once, [&] { cudaFuncSetAttribute(mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    const int grid = items < 2 * num_sms ? (int)items : 2 * num_sms;
+    mix_tma_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(maps, x, (int)items, reinterpret_cast<__nv_bfloat16*>(y_hi),
+                                                              reinterpret_cast<__nv_bfloat16*>(y_lo), y_f32);
+    return check_launch("sbev_mix_presplit_fwd");
 }

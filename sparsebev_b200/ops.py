@@ -334,6 +334,36 @@ def gemm_bf16_tn(a_list, b_list, M, N, K, bias=None, split_k=1, out=None):
     return out
 
 
+def gemm_bf16_tn_split(a_hi, a_lo, b_hi, b_lo, M, N, K, bias=None, out=None):
+    """bf16x3 GEMM whose result leaves as a bf16 (hi, lo) pair [M,N] each (C ~= hi + lo)."""
+    lib = _lib.load()
+    for t in (a_hi, a_lo, b_hi, b_lo):
+        _chk(t, 'gemm operand', torch.bfloat16)
+    if out is None:
+        out = (torch.empty(M, N, device=a_hi.device, dtype=torch.bfloat16), torch.empty(M, N, device=a_hi.device, dtype=torch.bfloat16))
+    with torch.cuda.device(a_hi.device):
+        _lib.check(lib.sbev_gemm_bf16_tn_split(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), _p(bias), M, N, K,
+                                               out[0].data_ptr(), out[1].data_ptr(), _stream()), 'sbev_gemm_bf16_tn_split')
+    return out
+
+
+def mix_presplit(params_hi, params_lo, x, want_f32=False, want_split=True):
+    """mix() with the dynamic parameters given as the bf16 (hi, lo) pair of gemm_bf16_tn_split (in_points must be 32)."""
+    lib = _lib.load()
+    _chk(params_hi, 'params_hi', torch.bfloat16)
+    _chk(params_lo, 'params_lo', torch.bfloat16)
+    x = _chk(x, 'x')
+    BQ, G, Pin, C = x.shape
+    n = G * OUT_POINTS * C
+    hi = torch.empty(BQ, n, device=x.device, dtype=torch.bfloat16) if want_split else None
+    lo = torch.empty_like(hi) if want_split else None
+    yf = torch.empty(BQ, n, device=x.device, dtype=torch.float32) if want_f32 else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_mix_presplit_fwd(params_hi.data_ptr(), params_lo.data_ptr(), x.data_ptr(), BQ, G, Pin, OUT_POINTS, C,
+                                             _p(hi), _p(lo), _p(yf), _stream()), 'sbev_mix_presplit_fwd')
+    return hi, lo, yf
+
+
 def mix(params, x, want_f32=False, want_split=True):
     """params [BQ, G*(C*C+Pout*Pin)], x [BQ,G,Pin,C] -> (y_hi, y_lo) bf16 [BQ, G*Pout*C] (and/or fp32 y)."""
     lib = _lib.load()

@@ -97,6 +97,8 @@ class AdaptiveMixing(nn.Module):
         self.act = nn.ReLU(inplace=True)
         self.precision = 'bf16x3'
         self.split_k = 16
+        # parameters leave the GEMM as bf16 (hi, lo) and reach the mix kernel by TMA (needs in_points == 32, bf16x3)
+        self.tma_params = True
         self._pg, self._op = _SplitWeight(), _SplitWeight()
 
     @torch.no_grad()
@@ -106,9 +108,17 @@ class AdaptiveMixing(nn.Module):
     def alloc_params(self, M, device):
         """Buffers of the parameter-generation stage (allocated by the caller BEFORE it forks a side stream)."""
         n_par = self.n_groups * self.total_parameters
-        return dict(q_hi=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
-                    q_lo=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
-                    params=torch.empty(M, n_par, device=device, dtype=torch.float32))
+        buf = dict(q_hi=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16),
+                   q_lo=torch.empty(M, self.query_dim, device=device, dtype=torch.bfloat16))
+        if self._use_tma_params():
+            buf['p_hi'] = torch.empty(M, n_par, device=device, dtype=torch.bfloat16)
+            buf['p_lo'] = torch.empty(M, n_par, device=device, dtype=torch.bfloat16)
+        else:
+            buf['params'] = torch.empty(M, n_par, device=device, dtype=torch.float32)
+        return buf
+
+    def _use_tma_params(self):
+        return self.tma_params and self.precision == 'bf16x3' and self.in_points == 32 and self.eff_in_dim == 64 and self.out_points == 128
 
     def generate_params(self, q2, buf, presplit=False):
         """Stage 1: dynamic mixing parameters [M, G*(C*C + Pout*Pin)] = query @ W^T + b on tcgen05 (depends on the query only,
@@ -118,6 +128,10 @@ class AdaptiveMixing(nn.Module):
         if not presplit:                  # (the decoder layer lets the producing dense chain write q_hi / q_lo directly)
             ops.split_bf16(q2, need_lo=x3, out=(buf['q_hi'], buf['q_lo'] if x3 else None))
         w_hi, w_lo = self._pg.get(self.parameter_generator.weight)
+        if 'p_hi' in buf:
+            ops.gemm_bf16_tn_split(buf['q_hi'], buf['q_lo'], w_hi, w_lo, M, self.n_groups * self.total_parameters, D,
+                                   bias=self.parameter_generator.bias, out=(buf['p_hi'], buf['p_lo']))
+            return buf['p_hi'], buf['p_lo']
         a, b = ([buf['q_hi'], buf['q_hi'], buf['q_lo']], [w_hi, w_lo, w_hi]) if x3 else ([buf['q_hi']], [w_hi])
         ops.gemm_bf16_tn(a, b, M, self.n_groups * self.total_parameters, D, bias=self.parameter_generator.bias, out=buf['params'])
         return buf['params']
@@ -126,7 +140,10 @@ class AdaptiveMixing(nn.Module):
         """Stages 2+3: per-(query, group) mixing, out_proj (split-K tcgen05) and the fused reduce + residual + LayerNorm."""
         M, G, P, C = x.shape
         D = self.query_dim
-        y_hi, y_lo, _ = ops.mix(params, x)
+        if isinstance(params, tuple):
+            y_hi, y_lo, _ = ops.mix_presplit(params[0], params[1], x)
+        else:
+            y_hi, y_lo, _ = ops.mix(params, x)
         o_hi, o_lo = self._op.get(self.out_proj.weight)
         K2 = self.out_proj.in_features
         a, b = ([y_hi, y_hi, y_lo], [o_hi, o_lo, o_hi]) if self.precision == 'bf16x3' else ([y_hi], [o_hi])

@@ -497,3 +497,23 @@ def test_reduce_ln_vs_torch():
     want = torch.nn.functional.layer_norm(part.sum(0) + bias + res, (256,), lw, lb)
     got = ops.reduce_ln(part.to(dev()), bias.to(dev()), res.to(dev()), lw.to(dev()), lb.to(dev()))
     _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
+
+
+def test_gemm_split_output_and_tma_fed_mix():
+    """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path."""
+    ops = _ops()
+    torch.manual_seed(3)
+    M, N, K = 300, 4 * 8192, 256                       # 300 queries x 4 groups x (64*64 + 128*32) parameters
+    a, b = torch.randn(M, K, device=dev()), torch.randn(N, K, device=dev()) * 0.03
+    bias = torch.randn(N, device=dev()) * 0.05
+    ah, al = ops.split_bf16(a)
+    bh, bl = ops.split_bf16(b)
+    want = (a.double() @ b.double().t() + bias.double()).float()
+    ch, cl = ops.gemm_bf16_tn_split(ah, al, bh, bl, M, N, K, bias=bias)
+    err = ((ch.float() + cl.float()) - want).abs().max() / want.abs().max()
+    assert float(err) < 3e-5, 'split-output GEMM relative error %.3e' % float(err)
+    x = hashrand((M, 4, 32, 64), 77, -2, 2).to(dev())
+    hi_ref, lo_ref, y_ref = ops.mix(want, x, want_f32=True)
+    hi, lo, y = ops.mix_presplit(ch, cl, x, want_f32=True)
+    _close(y, y_ref, rtol=1e-4, atol=5e-5, what='TMA-fed mix vs fp32-parameter mix')
+    _close(hi.float() + lo.float(), y_ref, rtol=1e-4, atol=5e-5, what='TMA-fed mix hi+lo')
