@@ -41,6 +41,12 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='single stream: no concurrent gather || param-GEMM, cls || reg')
     ap.add_argument('--no-tma-params', action='store_true', help='mixing: fp32 parameter tensor + converting mix kernel instead of bf16 (hi,lo) + TMA')
+    ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='kernel-variant option passed to sbev_set_option (experiments)')
+    ap.add_argument('--split-k', type=int, default=None, help='split-K slices of the mixing output projection')
+    ap.add_argument('--shard', default='scenes', choices=['scenes', 'frames'],
+                    help='N>1: scenes = one scene per GPU (weak scaling, no collective; default); frames = ONE scene, every GPU holds and samples '
+                         'T/N frames and the sampled rows are exchanged once per layer (strong scaling)')
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='--shard frames: peer stores from the gather kernel, or NCCL all-gather')
     ap.add_argument('--breakdown', action='store_true', help='also write per-stage timings to gpurun_out/breakdown.json')
     ap.add_argument('--cpu-steps', type=int, default=3, help='bounded CPU sample: decoder-layer passes of the oracle')
     ap.add_argument('--skip-cpu', action='store_true')
@@ -161,6 +167,19 @@ def run_reference_arm(args, cfg):
         'gpu_launches': 0}))
 
 
+def _shutdown(graph=None):
+    """Tear the process group down; a watchdog ends the process if NCCL teardown stalls (e.g. a captured graph still
+    holding communicator work) so a finished benchmark can never sit on the GPU box until the caller's timeout."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    threading.Timer(30.0, lambda: os._exit(0)).start()
+    del graph
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------- ours
 def main():
     args = parse()
@@ -192,9 +211,24 @@ def main():
     layer.mixing.precision = args.precision
     layer.overlap = not args.no_overlap
     layer.mixing.tma_params = not args.no_tma_params
+    if args.split_k:
+        layer.mixing.split_k = args.split_k
+    for kv in args.opt:
+        name, value = kv.split('=')
+        _lib.set_option(name, int(value))
 
-    # weak scaling: every rank owns its own scene (different seed) -- the reference's only strategy is DP
-    feats_host = S.make_feats(args.config, T, batch=1, seed=100 + rank, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')
+    frames_mode = args.shard == 'frames' and world > 1
+    if frames_mode:
+        # strong scaling: ONE scene; rank r holds the feature maps of frames [r*T/N, (r+1)*T/N) only
+        from sparsebev_b200 import dist as D
+        shard = D.FrameShard(T, exchange=args.exchange)
+        model.shard_frames(shard)
+        t0, t1 = shard.window
+        feats_host = [f[:, t0 * 6:t1 * 6].contiguous() for f in
+                      S.make_feats(args.config, T, batch=1, seed=100, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')]
+    else:
+        # weak scaling: every rank owns its own scene (different seed) -- the reference's only strategy is DP
+        feats_host = S.make_feats(args.config, T, batch=1, seed=100 + rank, memory_format='nhwc' if args.layout == 'nhwc' else 'nchw')
     metas = S.make_metas(args.config, T, batch=1)
     model.decoder.prepare_metas(metas, 1, dev)
     feats = model.decoder.prepare_feats([f.to(dev) for f in feats_host])
@@ -259,6 +293,20 @@ def main():
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * 1.0 / (ms_per_step * 1e-3)
+    if frames_mode:
+        clk = clocks.stop() if rank == 0 else None
+        if rank == 0:
+            print(json.dumps({
+                'metric': METRIC, 'value': 1.0 / (ms_per_step * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f32 (mixing GEMMs: %s on tcgen05, fp32 accumulate)' % args.precision, 'data': 'synthetic',
+                'config': {'workload': '%s T=%d Q=%d L=%d, one decoder layer, ONE scene (B=1) across %d GPUs' % (args.config, T, Q, cfg['num_levels'], world),
+                           'l2': 'inputs larger than L2 (feature pyramid %.0f MB per GPU per step)' % (feat_bytes / 1e6),
+                           'parallelism': 'frame-sharded: %d frames per GPU, sampled rows exchanged once per layer (%s)' % (T // world, args.exchange),
+                           'cuda_graph': graph is not None, 'two_stream_overlap': layer.overlap},
+                'clocks': clk, 'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step}))
+        _shutdown(graph)
+        return
 
     # ---- e2e: public API call with HOST buffers; every step copies that step's inputs (query tensors, camera
     # metadata AND the feature pyramid) from pinned host memory and reads the results back.  Feature upload of step

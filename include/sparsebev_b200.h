@@ -29,6 +29,7 @@ extern "C" {
 
 #define SBEV_MAX_LEVELS 5          /* c2..c6, reference: MSMVSamplingC23456 */
 #define SBEV_MAX_POINTS 32         /* reference: MAX_POINT, msmv_sampling.cpp:3 / :125 */
+#define SBEV_MAX_PEERS 8           /* GPUs of one NVSwitch node that sbev_sampling4d_scatter_fwd stores to */
 
 /* version / diagnostics */
 int         sbev_abi_version(void);
@@ -38,8 +39,8 @@ const char* sbev_last_error(void);
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
- *   "dense_cluster"  0 = every CTA streams its own weight tiles (default), 1 = 8-CTA clusters share every tile by TMA
- *                    multicast (correct, measured slower: the clusters run in lock step)
+ *   "dense_cluster"  0 = every CTA streams its own weight tiles (default); 2 / 4 / 8 = that many CTAs (row groups) form a
+ *                    cluster and share every weight tile by TMA multicast (8 measured slower: lock step)
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default) */
 int         sbev_set_option(const char* name, int value);
@@ -110,6 +111,37 @@ int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
                         int B, int T, int G, int N, int C, int Q, int P,
                         float image_h, float image_w, float eps,
                         float* out, float* loc_out, void* stream);
+
+/* Frame-window form of sbev_sampling4d_fwd, for the frame-sharded decoder (partitioning B: every GPU keeps
+ * the feature maps of the frames its backbone produced and samples only those).  `feats` hold the Tl frames
+ * [t0, t0+Tl) -- element (b, t, ...) at (b*Tl + (t - t0))*stride_bt[l] + ... -- while time_diff, lidar2img and the
+ * (t,g)->weight-group pairing keep indexing all T frames.  out [B, Q, G, Tl*P, C] (point index (t-t0)*P + p),
+ * loc_out optional [B*Tl*G, Q, P, 3].  t0 = 0, Tl = T is exactly sbev_sampling4d_fwd.  Every sample is computed
+ * independently of the window, so the union of the windows is bit-identical to the unsharded call.
+ */
+int sbev_sampling4d_window_fwd(const float* const* feats, const int* hw, int L,
+                               const int64_t* stride_bt, const int64_t* stride_g,
+                               const int64_t* stride_v, const int64_t* stride_px,
+                               const float* points, const float* velocity, const float* time_diff,
+                               const float* lidar2img, const float* scale_w,
+                               int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                               float image_h, float image_w, float eps,
+                               float* out, float* loc_out, void* stream);
+
+/* Fused gather + all-gather for the frame-sharded decoder: the window's rows are stored straight into n_out FULL-SIZE
+ * buffers [B, Q, G, T*P, C] (point index t*P + p), `outs` = HOST array of n_out DEVICE pointers -- this GPU's buffer
+ * and the peer GPUs' buffers mapped into this process (CUDA IPC / symmetric memory; the stores travel over NVLink).
+ * After every rank has run its window and a cross-GPU barrier, each buffer holds exactly what the unsharded
+ * sbev_sampling4d_fwd writes -- no NCCL call and no re-layout copy in between.  n_out <= SBEV_MAX_PEERS.
+ */
+int sbev_sampling4d_scatter_fwd(const float* const* feats, const int* hw, int L,
+                                const int64_t* stride_bt, const int64_t* stride_g,
+                                const int64_t* stride_v, const int64_t* stride_px,
+                                const float* points, const float* velocity, const float* time_diff,
+                                const float* lidar2img, const float* scale_w,
+                                int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                                float image_h, float image_w, float eps,
+                                float* const* outs, int n_out, float* loc_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small dense building block: y = epilogue(x @ W^T), row-major fp32, with the weight given
@@ -214,7 +246,8 @@ int sbev_split_bf16(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void*
 /* C[M,N] (fp32) = sum_s A_s[M,K] . B_s[N,K]^T over `nseg` operand pairs (bf16, K-major), + bias.
  * tcgen05.mma kind::f16 with fp32 accumulators in TMEM, TMA-staged 128B-swizzled operand tiles.
  * nseg = 1: plain bf16 GEMM; nseg = 3 with (A_hi,B_hi),(A_hi,B_lo),(A_lo,B_hi): fp32-grade "bf16x3".
- *   split_k > 1: partial sums go to `C + z*M*N` for z in [0, split_k) (caller reduces); bias only in z=0.
+ *   split_k > 1: partial sums go to `C + z*M*N` for z in [0, split_k) (caller reduces); bias only in z=0; slice z covers
+ *   k-blocks [z*(K/64)/split_k, (z+1)*(K/64)/split_k) -- split_k need not divide K/64.
  * Requires K % 64 == 0, N % 128 == 0; rows of A beyond M are treated as zero.
  */
 int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const* B, int nseg,

@@ -257,7 +257,6 @@ constexpr int MC_XLD = 512 + 8;                        // bf16 row stride of the
 constexpr int MC_YLD = 1024 + 4;                       // fp32 row stride of the layer output (N <= 1024)
 
 struct ChainMaps { CUtensorMap hi[CHAIN_MAX_LAYERS]; CUtensorMap lo[CHAIN_MAX_LAYERS]; };
-constexpr int MC_CLUSTER = 8;                          // CTAs (row groups) per cluster sharing every weight tile by TMA multicast
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -493,64 +492,71 @@ split_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __res
     }
 }
 
-// out[row] = LN(sum_z partial[z][row] + bias + residual[row]); one warp per row, N <= 1024, N % 4 == 0.
-// All split-K partials of a lane are requested before the first add (nsplit x 16 B loads in flight).
-__global__ void __launch_bounds__(128)
+// out[row] = LN(sum_z partial[z][row] + bias + residual[row]); one 256-thread CTA per row, N <= 1024, N % 4 == 0.
+// Thread t owns the 16-byte column group t % (N/4) of the split-K slices z = t / (N/4), + zpar, ...: every partial of the
+// row is requested at once (the slices were just written by the GEMM and sit in L2), then the slice sums meet in shared
+// memory and the first N/4 threads finish bias + residual + LayerNorm (two-pass variance, like torch).
+__global__ void __launch_bounds__(256)
 reduce_ln_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
                  const float* __restrict__ residual, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                  int M, int N, float* __restrict__ out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + warp;
-    if (row >= M) return;
-    float4 v[8];
-    const int per = (N / 4 + 31) / 32;          // float4 groups per lane (<= 8)
+    __shared__ float4 part[256];
+    __shared__ float red[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = blockIdx.x;
+    const int ng = N >> 2;                       // 16-byte column groups (<= 256)
+    const int zpar = 256 / ng;                   // slices summed side by side (>= 1)
+    const int c = tid % ng, h = tid / ng;
+    const long long zs = (long long)M * N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h < zpar) {
+        const float* p = partial + (long long)row * N + 4 * c;
+        for (int z = h; z < nsplit; z += 8 * zpar) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (z + u * zpar < nsplit) ? ldg4(p + (long long)(z + u * zpar) * zs) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+        }
+    }
+    part[tid] = acc;
+    __syncthreads();
+    const bool owner = tid < ng;
     float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int n = (lane + 32 * i) * 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < per && n < N) {
-            const float* p0 = partial + (long long)row * N + n;
-            const long long zs = (long long)M * N;
-            int z = 0;
-            for (; z + 8 <= nsplit; z += 8) {
-                float4 t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = ldg4(p0 + (z + u) * zs);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
-            }
-            for (; z < nsplit; ++z) { const float4 t = ldg4(p0 + z * zs); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-            if (bias) { const float4 t = ldg4(bias + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-            if (residual) { const float4 t = ldg4(residual + (long long)row * N + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-            s += (a.x + a.y) + (a.z + a.w);
-        }
-        v[i] = a;
+    if (owner) {
+        for (int j = 1; j < zpar; ++j) { const float4 t = part[tid + j * ng]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+        if (bias) { const float4 t = ldg4(bias + 4 * c); acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+        if (residual) { const float4 t = ldg4(residual + (long long)row * N + 4 * c); acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+        s = (acc.x + acc.y) + (acc.z + acc.w);
     }
-    float mean = 0.f, rstd = 1.f;
-    if (ln_w != nullptr) {
-        mean = warp_sum(s) / (float)N;
+    if (ln_w != nullptr) {                       // uniform branch: block reductions over the (<= 8) warps
+        s = warp_sum(s);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        const float mean = tot / (float)N;
+        __syncthreads();
         float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if (i < per && (lane + 32 * i) * 4 < N) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            ss += (a * a + b * b) + (c * c + d * d);
+        if (owner) {
+            const float a = acc.x - mean, b = acc.y - mean, cc = acc.z - mean, d = acc.w - mean;
+            ss = (a * a + b * b) + (cc * cc + d * d);
         }
-        rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
-    }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int n = (lane + 32 * i) * 4;
-        if (i < per && n < N) {
-            float4 a = v[i];
-            if (ln_w != nullptr) {
-                const float4 g = ldg4(ln_w + n), b = ldg4(ln_b + n);
-                a.x = (a.x - mean) * rstd * g.x + b.x; a.y = (a.y - mean) * rstd * g.y + b.y;
-                a.z = (a.z - mean) * rstd * g.z + b.z; a.w = (a.w - mean) * rstd * g.w + b.w;
-            }
-            *reinterpret_cast<float4*>(out + (long long)row * N + n) = a;
+        for (int w = 0; w < 8; ++w) var += red[w];
+        const float rstd = rsqrtf(var / (float)N + 1e-5f);
+        if (owner) {
+            const float4 g = ldg4(ln_w + 4 * c), b = ldg4(ln_b + 4 * c);
+            acc.x = (acc.x - mean) * rstd * g.x + b.x; acc.y = (acc.y - mean) * rstd * g.y + b.y;
+            acc.z = (acc.z - mean) * rstd * g.z + b.z; acc.w = (acc.w - mean) * rstd * g.w + b.w;
         }
     }
+    if (owner) *reinterpret_cast<float4*>(out + (long long)row * N + 4 * c) = acc;
 }
 
 // bbox refinement + velocity rescale (sparsebev_transformer.py:155-160,179-183):
@@ -622,8 +628,10 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
         // tensor-core path: pre-split bf16 weights [N][Kpad] streamed by TMA (box 64 k x 128 rows, 128-byte swizzle)
         ChainMaps maps;
         const int groups = (M + DENSE_ROWS - 1) / DENSE_ROWS;
-        const bool clustered = get_option(OPT_DENSE_CLUSTER) != 0 && groups >= MC_CLUSTER;
-        const int box_rows = clustered ? 128 / MC_CLUSTER : 128;
+        int cl = get_option(OPT_DENSE_CLUSTER);            // 0/1 = no cluster, 2 / 4 / 8 = CTAs per multicast cluster
+        if (cl != 2 && cl != 4 && cl != 8) cl = 1;
+        if (groups < cl) cl = 1;
+        const int box_rows = 128 / cl;
         for (int i = 0; i < n_layers; ++i) {
             const sbev_dense_layer& l = layers[i];
             SBEV_REQUIRE(l.Kpad >= l.K && (l.Kpad & 63) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: Kpad must be a multiple of 64 >= K", i);
@@ -636,19 +644,23 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
         static std::once_flag once_mma;
         std::call_once(once_mma, [&] {
             cudaFuncSetAttribute(dense_chain_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
-            cudaFuncSetAttribute(dense_chain_mma_kernel<MC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            cudaFuncSetAttribute(dense_chain_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            cudaFuncSetAttribute(dense_chain_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            cudaFuncSetAttribute(dense_chain_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
         });
-        if (clustered) {
+        if (cl > 1) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((groups + MC_CLUSTER - 1) / MC_CLUSTER * MC_CLUSTER);
+            cfg.gridDim = dim3((groups + cl - 1) / cl * cl);
             cfg.blockDim = dim3(288);
             cfg.dynamicSmemBytes = smem_mma;
             cfg.stream = (cudaStream_t)stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = MC_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<MC_CLUSTER>, prm, maps);
+            cudaError_t e = cl == 2 ? cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<2>, prm, maps)
+                          : cl == 4 ? cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<4>, prm, maps)
+                                    : cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<8>, prm, maps);
             if (e != cudaSuccess) { set_error("sbev_dense_chain_fwd(cluster launch): %s", cudaGetErrorString(e)); return SBEV_ERR_CUDA; }
         } else {
             dense_chain_mma_kernel<1><<<groups, 288, smem_mma, (cudaStream_t)stream>>>(prm, maps);
@@ -706,7 +718,7 @@ extern "C" int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float*
     SBEV_REQUIRE(N > 0 && N <= 1024 && (N & 3) == 0, SBEV_ERR_UNSUPPORTED, "sbev_reduce_ln_fwd: N must be a multiple of 4 in (0,1024]");
     SBEV_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), SBEV_ERR_INVALID, "sbev_reduce_ln_fwd: ln_w and ln_b go together");
     if (M <= 0) return SBEV_OK;
-    reduce_ln_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
+    reduce_ln_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
     return check_launch("sbev_reduce_ln_fwd");
 }
 

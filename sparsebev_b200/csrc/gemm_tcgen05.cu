@@ -133,7 +133,7 @@ struct GemmMapsV2 {
 // kernel consumes by TMA, so the 118 MB parameter tensor is never re-converted.
 template <int BN, int STAGES, bool X3, int ARES_KB = 0, bool OUT_SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_per_split, int m_tiles, int n_tiles, int num_tiles,
+gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int total_kb, int split_k, int m_tiles, int n_tiles, int num_tiles,
                                const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
     constexpr bool ARES = ARES_KB > 0;
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -182,7 +182,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                     tma_load_2d(ares + kb * 2 * A_BYTES + A_BYTES, &maps.a_lo, &ares_bar, kb * GEMM_BK, ares_m * GEMM_BM);
                 }
                 for (int nt = ares_n0; nt < n_tiles; nt += ares_nstep)
-                    for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                    for (int kb = 0; kb < total_kb; ++kb, ++it) {
                         const int stage = it % STAGES;
                         mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
                         uint8_t* st = smem + stage * STAGE_BYTES;
@@ -195,8 +195,10 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                 const int m0 = (tile % m_tiles) * GEMM_BM;
                 const int rest = tile / m_tiles;
                 const int n0 = (rest % n_tiles) * BN;
-                const int kb0 = (rest / n_tiles) * kb_per_split;
-                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                const int z = rest / n_tiles;                       // split-K slice: k-blocks [z*total/split, (z+1)*total/split)
+                const int kb0 = (int)((long long)z * total_kb / split_k);
+                const int kb_cnt = (int)((long long)(z + 1) * total_kb / split_k) - kb0;
+                for (int kb = 0; kb < kb_cnt; ++kb, ++it) {
                     const int stage = it % STAGES;
                     mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
@@ -223,7 +225,12 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int kb_p
                 mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
+                int kb_cnt = total_kb;
+                if (!ARES) {
+                    const int z = (((int)blockIdx.x + lt * (int)gridDim.x) / m_tiles) / n_tiles;
+                    kb_cnt = (int)((long long)(z + 1) * total_kb / split_k) - (int)((long long)z * total_kb / split_k);
+                }
+                for (int kb = 0; kb < kb_cnt; ++kb, ++it) {
                     const int stage = it % STAGES;
                     mbar_wait(&full_bar[stage], (it / STAGES) & 1);
                     tc_fence_after();
@@ -456,7 +463,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
     SBEV_REQUIRE(M > 0 && N > 0 && K > 0 && split_k >= 1, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: bad sizes");
     SBEV_REQUIRE(K % GEMM_BK == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: K must be a multiple of 64 (got %d)", K);
     SBEV_REQUIRE(N % 128 == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: N must be a multiple of 128 (got %d)", N);
-    SBEV_REQUIRE((K / GEMM_BK) % split_k == 0, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: K/64 must be divisible by split_k");
+    SBEV_REQUIRE(split_k <= K / GEMM_BK, SBEV_ERR_UNSUPPORTED, "sbev_gemm_bf16_tn: split_k must not exceed K/64");
     SBEV_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                  SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: C / bias must be 16-byte aligned");
     for (int sg = 0; sg < nseg; ++sg) {
@@ -484,7 +491,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
         const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / BNv;
         const int num_tiles = m_tiles * n_tiles * split_k;
         const int grid = ares ? (num_sms / m_tiles) * m_tiles : (num_tiles < num_sms ? num_tiles : num_sms);
-        const int kbs = (K / GEMM_BK) / split_k;
+        const int kbs = K / GEMM_BK;
         cudaStream_t st = (cudaStream_t)stream;
 #define SBEV_GEMM_V2(BNN, STG, XX)                                                                                               \
         do {                                                                                                                     \
@@ -492,14 +499,14 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
             static std::once_flag once;                                                                                          \
             std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \
-            gemm_bf16_tn_persistent_kernel<BNN, STG, XX><<<grid, GEMM_THREADS, smem_v2, st>>>(mp, kbs, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
+            gemm_bf16_tn_persistent_kernel<BNN, STG, XX><<<grid, GEMM_THREADS, smem_v2, st>>>(mp, kbs, split_k, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
         } while (0)
         if (ares) {
             constexpr size_t smem_ar = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
             static std::once_flag once_ar;
             std::call_once(once_ar, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>,
                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ar); });
-            gemm_bf16_tn_persistent_kernel<128, 2, true, 4><<<grid, GEMM_THREADS, smem_ar, st>>>(mp, kbs, m_tiles, n_tiles, num_tiles, bias, C, M, N);
+            gemm_bf16_tn_persistent_kernel<128, 2, true, 4><<<grid, GEMM_THREADS, smem_ar, st>>>(mp, kbs, 1, m_tiles, n_tiles, num_tiles, bias, C, M, N);
         } else if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
         else            { if (wide) SBEV_GEMM_V2(256, 4, false); else SBEV_GEMM_V2(128, 6, false); }
 #undef SBEV_GEMM_V2
@@ -536,6 +543,6 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-        mp, K / GEMM_BK, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
+        mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
     return check_launch("sbev_gemm_bf16_tn_split");
 }

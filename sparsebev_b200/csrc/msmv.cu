@@ -371,10 +371,12 @@ struct FusedParams {
     const float* time_diff;  // [B,T]
     const float* lidar2img;  // [B,T*N,16]
     const float* scale_w;    // [B,Q,G,P,L]
-    float* out;              // [B,Q,G,T*P,64]
-    float* loc_out;          // optional [B*T*G,Q,P,3]
+    float* out[SBEV_MAX_PEERS];   // n_out buffers [B,Q,G,To*P,64] that all receive the window's rows (own + peer GPUs)
+    float* loc_out;          // optional [B*Tl*G,Q,P,3]
     int B, T, G, N, Q, P;
     float image_h, image_w, eps;
+    int t0, Tl;              // frame window [t0, t0+Tl) held by feats (t0 = 0, Tl = T: all frames)
+    int o0, To, n_out;       // the out buffers cover frames [o0, o0+To): the window itself, or all T frames (scatter form)
 };
 
 // LPP = lanes per sample point: 16 (4 channels per lane) or 8 (8 channels per lane; halves the per-point geometry that
@@ -387,8 +389,9 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     const int lane = threadIdx.x & 31, half = lane / LPP, j = lane % LPP;
     const int T = prm.T, G = prm.G, N = prm.N, Q = prm.Q, P = prm.P;
     // slice (b,t,g) = blockIdx.y (uniform); sample (q,p) inside the slice from blockIdx.x: all 32-bit, no 64-bit div/mod
-    const int s = blockIdx.y;
-    const int g = s % G, bt = s / G, t = bt % T, b = bt / T;
+    const int s = blockIdx.y, Tl = prm.Tl;
+    const int g = s % G, btl = s / G, tl = btl % Tl, b = btl / Tl;   // btl indexes the LOCAL feature slices
+    const int t = prm.t0 + tl, bt = b * T + t;                       // bt indexes time_diff / lidar2img (all T frames)
     const int idx_raw = blockIdx.x * PPB + (threadIdx.x / LPP);
     const bool live = idx_raw < Q * P;
     const int idx = live ? idx_raw : Q * P - 1;
@@ -434,14 +437,17 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         H[l] = lv.H[l]; W[l] = lv.W[l]; pxs[l] = (int)lv.s_px[l];
-        base[l] = lv.ptr[l] + ((long long)bt * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
+        base[l] = lv.ptr[l] + ((long long)btl * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
     }
     float4 acc[VEC];
     gather_levels_v<L, LB, VEC, 4 * LPP>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
     if (live) {
-        float* dst = prm.out + ((bq * G + g) * (T * P) + (t * P + p)) * 64 + 4 * j;
+        const long long row = ((bq * G + g) * (prm.To * P) + ((t - prm.o0) * P + p)) * 64 + 4 * j;
+        for (int w = 0; w < prm.n_out; ++w) {          // n_out > 1: the same 256 B row also goes to the peers over NVLink
+            float* dst = prm.out[w] + row;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) *reinterpret_cast<float4*>(dst + 4 * LPP * e) = acc[e];
+            for (int e = 0; e < VEC; ++e) *reinterpret_cast<float4*>(dst + 4 * LPP * e) = acc[e];
+        }
         if (prm.loc_out != nullptr && j == 0) {
             float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
             lo[0] = u; lo[1] = v; lo[2] = __fdiv_rn((float)view, (float)(N - 1));
@@ -554,19 +560,21 @@ extern "C" int sbev_msmv_bwd(const float* grad_out, const float* const* feats, c
     return check_launch("sbev_msmv_bwd");
 }
 
-extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
-                                   const int64_t* stride_bt, const int64_t* stride_g,
-                                   const int64_t* stride_v, const int64_t* stride_px,
-                                   const float* points, const float* velocity, const float* time_diff,
-                                   const float* lidar2img, const float* scale_w,
-                                   int B, int T, int G, int N, int C, int Q, int P,
-                                   float image_h, float image_w, float eps,
-                                   float* out, float* loc_out, void* stream) {
+static int launch_sampling4d(const float* const* feats, const int* hw, int L,
+                             const int64_t* stride_bt, const int64_t* stride_g,
+                             const int64_t* stride_v, const int64_t* stride_px,
+                             const float* points, const float* velocity, const float* time_diff,
+                             const float* lidar2img, const float* scale_w,
+                             int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                             float image_h, float image_w, float eps,
+                             float* const* outs, int n_out, bool full_out, float* loc_out, void* stream, const char* who) {
+    SBEV_REQUIRE(t0 >= 0 && Tl >= 0 && t0 + Tl <= T, SBEV_ERR_INVALID, "%s: frame window [%d,%d) outside [0,%d)", who, t0, t0 + Tl, T);
     SBEV_REQUIRE(feats && stride_bt && stride_g && stride_v && stride_px && points && velocity && time_diff &&
-                 lidar2img && scale_w && out, SBEV_ERR_INVALID, "sbev_sampling4d_fwd: null pointer");
-    SBEV_REQUIRE(B >= 0 && T > 0 && G > 0 && N > 0 && Q >= 0 && P > 0, SBEV_ERR_INVALID, "sbev_sampling4d_fwd: bad sizes");
-    SBEV_REQUIRE(C == 64, SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: channels per group must be 64 (got %d)", C);
-    SBEV_REQUIRE(N <= 16, SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: at most 16 views (got %d)", N);
+                 lidar2img && scale_w && outs, SBEV_ERR_INVALID, "%s: null pointer", who);
+    SBEV_REQUIRE(n_out >= 1 && n_out <= SBEV_MAX_PEERS, SBEV_ERR_INVALID, "%s: between 1 and %d output buffers (got %d)", who, SBEV_MAX_PEERS, n_out);
+    SBEV_REQUIRE(B >= 0 && T > 0 && G > 0 && N > 0 && Q >= 0 && P > 0, SBEV_ERR_INVALID, "%s: bad sizes", who);
+    SBEV_REQUIRE(C == 64, SBEV_ERR_UNSUPPORTED, "%s: channels per group must be 64 (got %d)", who, C);
+    SBEV_REQUIRE(N <= 16, SBEV_ERR_UNSUPPORTED, "%s: at most 16 views (got %d)", who, N);
     SBEV_REQUIRE((reinterpret_cast<uintptr_t>(lidar2img) & 15) == 0, SBEV_ERR_INVALID, "lidar2img not 16-byte aligned");
     LevelSet lv;
     int rc = fill_levels(lv, feats, hw, L);
@@ -576,18 +584,28 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
         SBEV_REQUIRE(((stride_bt[l] | stride_g[l] | stride_v[l] | stride_px[l]) & 3) == 0, SBEV_ERR_INVALID,
                      "level %d strides must be multiples of 4 floats", l);
     }
-    const long long total = (long long)B * T * G * Q * P;
+    const long long total = (long long)B * Tl * G * Q * P;
     if (total == 0) return SBEV_OK;
-    SBEV_REQUIRE((long long)B * T * G <= 65535 && (long long)Q * P < (1ll << 30), SBEV_ERR_UNSUPPORTED, "sbev_sampling4d_fwd: too many slices / samples per slice");
+    SBEV_REQUIRE((long long)B * Tl * G <= 65535 && (long long)Q * P < (1ll << 30), SBEV_ERR_UNSUPPORTED, "%s: too many slices / samples per slice", who);
     for (int l = 0; l < L; ++l)
         SBEV_REQUIRE((long long)lv.H[l] * lv.W[l] * stride_px[l] < (1ll << 31), SBEV_ERR_UNSUPPORTED, "level %d too large for 32-bit pixel offsets", l);
-    FusedParams prm{points, velocity, time_diff, lidar2img, scale_w, out, loc_out, B, T, G, N, Q, P, image_h, image_w, eps};
+    FusedParams prm{};
+    prm.points = points; prm.velocity = velocity; prm.time_diff = time_diff; prm.lidar2img = lidar2img; prm.scale_w = scale_w;
+    for (int w = 0; w < n_out; ++w) {
+        SBEV_REQUIRE(outs[w] != nullptr && (reinterpret_cast<uintptr_t>(outs[w]) & 15) == 0, SBEV_ERR_INVALID, "%s: out[%d] null or not 16-byte aligned", who, w);
+        prm.out[w] = outs[w];
+    }
+    prm.loc_out = loc_out;
+    prm.B = B; prm.T = T; prm.G = G; prm.N = N; prm.Q = Q; prm.P = P;
+    prm.image_h = image_h; prm.image_w = image_w; prm.eps = eps;
+    prm.t0 = t0; prm.Tl = Tl; prm.n_out = n_out;
+    prm.o0 = full_out ? 0 : t0; prm.To = full_out ? T : Tl;
     // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
     // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views)
     int variant = get_option(OPT_GATHER_VARIANT);
     if (variant == 2 && N > 8) variant = 1;
     const int ppb = variant == 2 ? 32 : 16;
-    const dim3 grid((Q * P + ppb - 1) / ppb, B * T * G);
+    const dim3 grid((Q * P + ppb - 1) / ppb, B * Tl * G);
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
         if (variant == 2 && LL >= 2) sampling4d_c64_kernel<LL, 2, 2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);      \
@@ -597,5 +615,41 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
         break;
     switch (L) { SBEV_LAUNCH_FUSED(1) SBEV_LAUNCH_FUSED(2) SBEV_LAUNCH_FUSED(3) SBEV_LAUNCH_FUSED(4) SBEV_LAUNCH_FUSED(5) }
 #undef SBEV_LAUNCH_FUSED
-    return check_launch("sbev_sampling4d_fwd");
+    return check_launch(who);
+}
+
+extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
+                                   const int64_t* stride_bt, const int64_t* stride_g,
+                                   const int64_t* stride_v, const int64_t* stride_px,
+                                   const float* points, const float* velocity, const float* time_diff,
+                                   const float* lidar2img, const float* scale_w,
+                                   int B, int T, int G, int N, int C, int Q, int P,
+                                   float image_h, float image_w, float eps,
+                                   float* out, float* loc_out, void* stream) {
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+                             B, T, 0, T, G, N, C, Q, P, image_h, image_w, eps, &out, 1, false, loc_out, stream, "sbev_sampling4d_fwd");
+}
+
+extern "C" int sbev_sampling4d_window_fwd(const float* const* feats, const int* hw, int L,
+                                          const int64_t* stride_bt, const int64_t* stride_g,
+                                          const int64_t* stride_v, const int64_t* stride_px,
+                                          const float* points, const float* velocity, const float* time_diff,
+                                          const float* lidar2img, const float* scale_w,
+                                          int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                                          float image_h, float image_w, float eps,
+                                          float* out, float* loc_out, void* stream) {
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+                             B, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, &out, 1, false, loc_out, stream, "sbev_sampling4d_window_fwd");
+}
+
+extern "C" int sbev_sampling4d_scatter_fwd(const float* const* feats, const int* hw, int L,
+                                           const int64_t* stride_bt, const int64_t* stride_g,
+                                           const int64_t* stride_v, const int64_t* stride_px,
+                                           const float* points, const float* velocity, const float* time_diff,
+                                           const float* lidar2img, const float* scale_w,
+                                           int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                                           float image_h, float image_w, float eps,
+                                           float* const* outs, int n_out, float* loc_out, void* stream) {
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+                             B, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, outs, n_out, true, loc_out, stream, "sbev_sampling4d_scatter_fwd");
 }

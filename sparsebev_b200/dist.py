@@ -64,3 +64,69 @@ def all_gather_frames(local, world=None):
     out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, local.contiguous())
     return out
+
+
+def merge_frame_chunks(chunks):
+    """[W, B, Q, G, Tl*P, C] (rank-major, as all_gather_into_tensor returns it) -> [B, Q, G, W*Tl*P, C].
+
+    Rank r owns frames [r*Tl, (r+1)*Tl), so point index t*P + p of the full tensor is r*(Tl*P) + (t - r*Tl)*P + p."""
+    W, B, Q, G, TP, C = chunks.shape
+    return chunks.permute(1, 2, 3, 0, 4, 5).reshape(B, Q, G, W * TP, C)
+
+
+class FrameShard:
+    """Frame-sharded decoder state of one rank (partitioning B).
+
+    Every rank keeps the feature maps of the frames [t0, t1) its backbone produced, runs the (tiny) query-side
+    stages redundantly, samples ITS frames for all queries, and the sampled rows are exchanged once per layer:
+
+      exchange='p2p'  (default on GPUs): two symmetric-memory buffers [B,Q,G,T*P,C] per rank, mapped into every peer.
+                      The gather kernel stores each 256 B row into all ranks' buffers over NVLink
+                      (sbev_sampling4d_scatter_fwd: compute and all-gather are one kernel), then ONE cross-GPU barrier
+                      on the stream; buffers alternate between layers so a rank never overwrites rows a slower
+                      peer is still mixing (a rank is at most one barrier ahead of any peer).
+      exchange='nccl' local [B,Q,G,Tl*P,C] -> all_gather_into_tensor -> merge_frame_chunks (one re-layout copy).
+                      Also the path the gloo CPU tests drive.
+    """
+
+    def __init__(self, num_frames, rank=None, world=None, group=None, exchange='p2p'):
+        if rank is None or world is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError('FrameShard needs an initialised process group (or explicit rank/world)')
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if exchange not in ('p2p', 'nccl'):
+            raise ValueError('exchange must be "p2p" or "nccl"')
+        self.rank, self.world, self.group, self.exchange = rank, world, group, exchange
+        self.num_frames = num_frames
+        self.window = frame_partition(num_frames, rank, world)
+        self._bufs, self._turn = {}, 0
+
+    # ---- nccl / gloo exchange
+    def all_gather(self, local):
+        """local [B,Q,G,Tl*P,C] -> [B,Q,G,T*P,C]."""
+        if self.world == 1:
+            return local
+        chunks = local.new_empty((self.world * local.shape[0],) + tuple(local.shape[1:]))     # rank-major concatenation
+        dist.all_gather_into_tensor(chunks, local.contiguous(), group=self.group)
+        return merge_frame_chunks(chunks.view((self.world,) + tuple(local.shape)))
+
+    # ---- peer-store exchange
+    def peer_buffers(self, shape, device):
+        """-> (this rank's full-size buffer for the current layer, [device address of that buffer on every rank])."""
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (tuple(shape), str(device))
+        if key not in self._bufs:
+            pair = []
+            for _ in range(2):
+                buf = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                pair.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs]))
+            self._bufs[key] = pair
+        buf, hdl, ptrs = self._bufs[key][self._turn]
+        self._cur = hdl
+        self._turn ^= 1
+        return buf, ptrs
+
+    def peer_barrier(self):
+        """Stream-ordered barrier over all ranks: returns (on the stream) once every rank's rows have landed."""
+        self._cur.barrier(channel=0)

@@ -99,8 +99,14 @@ def msmv_indices(level_hw, sampling_locations, num_views):
 
 
 def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w, image_h, image_w,
-                     num_frames, num_views=6, eps=1e-5, layout='grouped', return_loc=False, out=None):
+                     num_frames, num_views=6, eps=1e-5, layout='grouped', return_loc=False, out=None, frame_window=None,
+                     scatter_ptrs=None):
     """Fused motion-warp + projection + view pick + gather.
+
+    frame_window (t0, t1): the feature maps hold only frames [t0, t1) of the num_frames (frame-sharded decoder); the
+    result is then [B,Q,G,(t1-t0)*P,C].  time_diff / lidar2img always cover all frames.
+    scatter_ptrs: device addresses of full-size [B,Q,G,T*P,C] buffers (this GPU's and its peers', e.g. symmetric memory);
+    the window's rows are stored into every one of them at their frame offset and no tensor is returned.
 
     layout 'grouped': feats L x [B*T*G, N, H, W, C] (the reference's regrouped op layout);
     layout 'nhwc'   : feats L x [B, T*N, H, W, G*C] (un-regrouped, channels-last FPN output).
@@ -115,6 +121,10 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
     sw = _chk(scale_w, 'scale_w')
     B, Q, GP, _ = pts.shape
     T, N, G = num_frames, num_views, GROUPS
+    t0, t1 = frame_window if frame_window is not None else (0, T)
+    Tl = t1 - t0
+    if not (0 <= t0 <= t1 <= T):
+        raise ValueError('frame_window %r outside [0, %d]' % (frame_window, T))
     P = GP // G
     hw, s_bt, s_g, s_v, s_px = [], [], [], [], []
     C = 0
@@ -122,14 +132,14 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
         _chk(f, 'value[%d]' % i)
         if layout == 'grouped':
             BTG, Nf, H, W, C = f.shape
-            if BTG != B * T * G or Nf != N:
-                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,C]' % (i, tuple(f.shape), B * T * G, N))
+            if BTG != B * Tl * G or Nf != N:
+                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,C]' % (i, tuple(f.shape), B * Tl * G, N))
             s_px.append(C); s_v.append(H * W * C); s_g.append(N * H * W * C); s_bt.append(G * N * H * W * C)
         elif layout == 'nhwc':
             Bf, TN, H, W, GC = f.shape
             C = GC // G
-            if Bf != B or TN != T * N:
-                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,G*C]' % (i, tuple(f.shape), B, T * N))
+            if Bf != B or TN != Tl * N:
+                raise RuntimeError('value[%d] has shape %s, expected [%d,%d,H,W,G*C]' % (i, tuple(f.shape), B, Tl * N))
             s_px.append(GC); s_v.append(H * W * GC); s_g.append(C); s_bt.append(N * H * W * GC)
         else:
             raise ValueError('unknown layout %r' % layout)
@@ -138,16 +148,25 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
         raise RuntimeError('scale_w must be [B,Q,G,P,L]=%s, got %s' % ((B, Q, G, P, L), tuple(sw.shape)))
     if tuple(td.shape) != (B, T) or tuple(l2i.shape) != (B, T * N, 4, 4) or tuple(vel.shape) != (B, Q, 2):
         raise RuntimeError('time_diff / lidar2img / velocity shape mismatch')
+    loc = torch.empty(B * Tl * G, Q, P, 3, device=pts.device, dtype=torch.float32) if return_loc else None
+    if scatter_ptrs is not None:
+        with torch.cuda.device(pts.device):
+            _lib.check(lib.sbev_sampling4d_scatter_fwd(
+                _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
+                _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
+                pts.data_ptr(), vel.data_ptr(), td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
+                B, T, t0, Tl, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
+                _lib.ptr_array([int(p) for p in scatter_ptrs]), len(scatter_ptrs), _p(loc), _stream()), 'sbev_sampling4d_scatter_fwd')
+        return (None, loc) if return_loc else None
     if out is None:
-        out = torch.empty(B, Q, G, T * P, C, device=pts.device, dtype=torch.float32)
-    loc = torch.empty(B * T * G, Q, P, 3, device=pts.device, dtype=torch.float32) if return_loc else None
+        out = torch.empty(B, Q, G, Tl * P, C, device=pts.device, dtype=torch.float32)
     with torch.cuda.device(pts.device):
-        _lib.check(lib.sbev_sampling4d_fwd(
+        _lib.check(lib.sbev_sampling4d_window_fwd(
             _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
             _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
             pts.data_ptr(), vel.data_ptr(), td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
-            B, T, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
-            out.data_ptr(), _p(loc), _stream()), 'sbev_sampling4d_fwd')
+            B, T, t0, Tl, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
+            out.data_ptr(), _p(loc), _stream()), 'sbev_sampling4d_window_fwd')
     return (out, loc) if return_loc else out
 
 

@@ -22,6 +22,7 @@ CONFIGS = {
     'r101_1408x512': dict(image_h=512, image_w=1408, levels=[(128, 352), (64, 176), (32, 88), (16, 44), (8, 22)], num_query=900),
     'vov99_1600x640': dict(image_h=640, image_w=1600, levels=[(160, 400), (80, 200), (40, 100), (20, 50), (10, 25)], num_query=1600),
     'tiny': dict(image_h=64, image_w=176, levels=[(8, 22), (4, 11)], num_query=36),
+    'tiny5': dict(image_h=80, image_w=192, levels=[(20, 48), (10, 24), (5, 12), (3, 6), (2, 3)], num_query=40),   # 5 levels like r101 / vov99
 }
 PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 

@@ -96,7 +96,7 @@ class AdaptiveMixing(nn.Module):
         self.out_proj = nn.Linear(self.eff_out_dim * self.out_points * self.n_groups, self.query_dim)
         self.act = nn.ReLU(inplace=True)
         self.precision = 'bf16x3'
-        self.split_k = 16
+        self.split_k = 18            # 8 M-tiles x 18 K-slices = 144 CTAs on 148 SMs
         # parameters leave the GEMM as bf16 (hi, lo) and reach the mix kernel by TMA (needs in_points == 32, bf16x3)
         self.tma_params = True
         self._pg, self._op = _SplitWeight(), _SplitWeight()
@@ -147,9 +147,7 @@ class AdaptiveMixing(nn.Module):
         o_hi, o_lo = self._op.get(self.out_proj.weight)
         K2 = self.out_proj.in_features
         a, b = ([y_hi, y_hi, y_lo], [o_hi, o_lo, o_hi]) if self.precision == 'bf16x3' else ([y_hi], [o_hi])
-        split_k = self.split_k
-        while (K2 // 64) % split_k:
-            split_k //= 2
+        split_k = max(1, min(self.split_k, K2 // 64))
         partial = ops.gemm_bf16_tn(a, b, M, D, K2, split_k=split_k)
         return ops.reduce_ln(partial, bias=self.out_proj.bias, residual=q2,
                              ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
@@ -259,8 +257,9 @@ class SparseBEVSampling(BaseModule):
     def heads_layer(self, y):
         return self._heads.layer(y=y)
 
-    def sample(self, query_bbox, heads_out, mlvl_feats, img_metas):
-        """heads_out [B*Q, G*P*3 + G*P*L] = the concatenated sampling_offset | scale_weights Linear output."""
+    def sample(self, query_bbox, heads_out, mlvl_feats, img_metas, frame_window=None, scatter_ptrs=None):
+        """heads_out [B*Q, G*P*3 + G*P*L] = the concatenated sampling_offset | scale_weights Linear output.
+        frame_window / scatter_ptrs: frame-sharded forms, see ops.sampling4d_fused."""
         B, Q = query_bbox.shape[:2]
         image_h, image_w, _ = img_metas[0]['img_shape'][0]
         G, P, L = self.num_groups, self.num_points, self.num_levels
@@ -270,7 +269,8 @@ class SparseBEVSampling(BaseModule):
         vel = query_bbox[..., 8:10].contiguous()
         return ops.sampling4d_fused(mlvl_feats, pts, vel, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
                                     sw.reshape(B, Q, G, P, L), image_h, image_w, num_frames=self.num_frames,
-                                    num_views=NUM_VIEWS, layout=self.feat_layout)       # [B,Q,G,T*P,C]
+                                    num_views=NUM_VIEWS, layout=self.feat_layout,       # [B,Q,G,T*P,C]
+                                    frame_window=frame_window, scatter_ptrs=scatter_ptrs)
 
     def forward(self, query_bbox, query_feat, mlvl_feats, img_metas):
         B, Q, D = query_feat.shape
@@ -319,6 +319,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self._cls = [_Dense(cb[3 * i], cb[3 * i + 1]) for i in range(num_cls_fcs)] + [_Dense(cb[3 * num_cls_fcs])]
         self._reg = [_Dense(rb[2 * i]) for i in range(num_reg_fcs)] + [_Dense(rb[2 * num_reg_fcs])]
         self.overlap = True          # run independent kernels of a layer on a second stream (parallel graph branches)
+        self.frame_shard = None      # dist.FrameShard: this rank holds / samples only its window of the T frames
         self._streams = {}
 
     def _side_stream(self, device):
@@ -338,6 +339,24 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         return ops.refine_bbox(bbox_proposal, bbox_delta, time_diff)
 
     @torch.no_grad()
+    def _sample(self, query_bbox, heads, mlvl_feats, img_metas):
+        """Sampled features [B,Q,G,T*P,C] of ALL frames.  Unsharded: one fused gather.  Frame-sharded
+        (self.frame_shard = dist.FrameShard): mlvl_feats hold this rank's frames only; the rows of the other frames
+        arrive from the peers (stored by their gather kernels over NVLink, or by one all-gather)."""
+        shard = self.frame_shard
+        if shard is None or shard.world == 1:
+            return self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+        if shard.exchange == 'p2p':
+            B, Q = query_bbox.shape[:2]
+            s = self.sampling
+            buf, ptrs = shard.peer_buffers((B, Q, s.num_groups, s.num_frames * s.num_points, self.embed_dims // s.num_groups),
+                                           query_bbox.device)
+            s.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window, scatter_ptrs=ptrs)
+            shard.peer_barrier()
+            return buf
+        local = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window)
+        return shard.all_gather(local)
+
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
@@ -369,11 +388,11 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 params = self.mixing.generate_params(q2, pbuf, presplit=True)
-            sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas)
             main.wait_stream(side)
         else:
             params = self.mixing.generate_params(q2, pbuf, presplit=True)
-            sampled = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas)
         # (4b) adaptive mixing (+ identity + norm2)
         G, P = self.mixing.n_groups, self.mixing.in_points
         q3 = self.mixing.mix_and_project(params, sampled.reshape(M, G, P, -1), q2, self.norm2)
@@ -466,6 +485,12 @@ class SparseBEVTransformer(BaseModule):
     @torch.no_grad()
     def init_weights(self):
         self.decoder.init_weights()
+
+    def shard_frames(self, shard):
+        """Frame-sharded operation (not in the reference, whose only multi-GPU mode is DDP): `shard` is a dist.FrameShard;
+        afterwards `mlvl_feats` passed to forward hold only this rank's frames, img_metas still describe all of them."""
+        self.decoder.decoder_layer.frame_shard = shard
+        return self
 
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         cls_scores, bbox_preds = self.decoder(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)

@@ -25,6 +25,13 @@ def _worker(rank, world, port, q):
     local = torch.arange(t0, t1, dtype=torch.float32)[:, None].repeat(1, 3)          # [T_local, 3], value = global frame id
     full = D.all_gather_frames(local)
     scenes = D.scene_partition(5, rank, world)
+    # frame-sharded exchange: every rank contributes the rows of its frames, the merged tensor is the unsharded one
+    B, Q, G, T, P, C = 2, 5, 4, 8, 3, 6
+    whole = torch.arange(B * Q * G * T * P * C, dtype=torch.float32).reshape(B, Q, G, T * P, C)
+    shard = D.FrameShard(T, exchange='nccl')
+    assert shard.window == (t0, t1) and (shard.rank, shard.world) == (rank, world)
+    merged = shard.all_gather(whole[:, :, :, t0 * P:t1 * P].contiguous())
+    assert torch.equal(merged, whole)
     q.put((rank, mx, full[:, 0].tolist(), scenes))
     torch.distributed.destroy_process_group()
 
@@ -43,6 +50,16 @@ def test_gloo_world2_partitions_and_timing_reduce():
     assert all(r[1] == 11.0 for r in res)                       # max over ranks
     assert all(r[2] == [0, 1, 2, 3, 4, 5, 6, 7] for r in res)   # frame-major all-gather in rank order
     assert res[0][3] == [0, 1, 2] and res[1][3] == [3, 4]       # scene partition covers everything once
+
+
+def test_merge_frame_chunks_order():
+    from sparsebev_b200 import dist as D
+    W, B, Q, G, Tl, P, C = 4, 1, 3, 4, 2, 4, 2
+    whole = torch.randn(B, Q, G, W * Tl * P, C)
+    chunks = torch.stack([whole[:, :, :, r * Tl * P:(r + 1) * Tl * P] for r in range(W)])
+    assert torch.equal(D.merge_frame_chunks(chunks), whole)
+    one = D.FrameShard(8, rank=0, world=1)
+    assert one.window == (0, 8) and one.all_gather(whole) is whole
 
 
 def test_partitions_single_process():

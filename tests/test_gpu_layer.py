@@ -36,9 +36,9 @@ def _rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize('T,B', [(2, 2), (8, 1)])
-def test_decoder_layer_vs_oracle(T, B):
-    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', T, B)
+@pytest.mark.parametrize('name,T,B', [('tiny', 2, 2), ('tiny', 8, 1), ('tiny5', 3, 1)])
+def test_decoder_layer_vs_oracle(name, T, B):
+    cfg, sd, model, feats, metas, qb, qf = _setup(name, T, B)
     td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
     l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
     taps = {}
@@ -135,3 +135,44 @@ def test_r50_t8_layer_runs_and_is_deterministic():
     ref = ops.msmv_forward(gfeats, loc, w_op)                                                   # [TG,Q,C,P]
     ref = ref.reshape(1, T, G, Q, 64, P).permute(0, 3, 2, 1, 5, 4).reshape(1, Q, G, T * P, 64)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('name,T', [('r101_1408x512', 8), ('vov99_1600x640', 8)])
+def test_five_level_configs_full_size_properties(name, T):
+    """BASELINE configs 4/5 (5 FPN levels; vov99: 1600 queries) at full size: the layer runs finite and deterministic, and the fused
+    gather equals the op-boundary path (sbev_msmv_fwd fed with the fused kernel's own loc) bit for bit -- size-independent
+    properties, since the CPU oracle would need minutes per layer here."""
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import ops, synthetic as S
+    cfg = S.layer_cfg(name, T, num_layers=1)
+    sd = S.make_state_dict(cfg, seed=5)
+    model = sb.SparseBEVTransformer(256, num_frames=T, num_points=4, num_layers=1, num_levels=cfg['num_levels'], pc_range=cfg['pc_range']).cuda().eval()
+    model.load_state_dict({'decoder.decoder_layer.' + k: v for k, v in sd.items()})
+    layer = model.decoder.decoder_layer
+    Q, G, P, Lv = cfg['num_query'], 4, 4, cfg['num_levels']
+    g = torch.Generator(device='cuda').manual_seed(7)
+    feats = [torch.randn(1, T * 6, h, w, 256, device='cuda', generator=g).permute(0, 1, 4, 2, 3) for (h, w) in cfg['levels']]   # NHWC storage: zero-copy
+    metas = S.make_metas(name, T, batch=1)
+    model.decoder.prepare_metas(metas, 1, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats(list(feats))
+    assert layer.sampling.feat_layout == 'nhwc'
+    qb = S.init_query_bbox(Q, seed=2)[None].cuda()
+    qf = torch.randn(1, Q, 256, generator=torch.Generator().manual_seed(3)).cuda()
+    a = layer(qb, qf, gfeats, None, metas)
+    b = layer(qb, qf, gfeats, None, metas)
+    for x, y in zip(a, b):
+        assert torch.isfinite(x).all() and torch.equal(x, y)
+    heads = layer.sampling._heads(qf.reshape(Q, 256))
+    nh = G * P * 3
+    pts, sw = ops.sample_points(qb, heads, heads[:, nh:], cfg['pc_range'], Lv, num_points_total=G * P, ld_off=heads.shape[1], ld_log=heads.shape[1])
+    out, loc = ops.sampling4d_fused(gfeats, pts, qb[..., 8:10].contiguous(), metas[0]['time_diff'], metas[0]['lidar2img'],
+                                    sw.reshape(1, Q, G, P, Lv), cfg['image_h'], cfg['image_w'], num_frames=T, layout='nhwc', return_loc=True)
+    # op-boundary path on ONE frame (regrouping all 8 frames of vov99 would copy 4 GB): frame t's slices are rows t*G..t*G+G-1
+    t = T - 1
+    grouped = [f[:, t * 6:(t + 1) * 6].permute(0, 1, 3, 4, 2).reshape(1, 6, f.shape[3], f.shape[4], G, 64).permute(0, 4, 1, 2, 3, 5)
+               .reshape(G, 6, f.shape[3], f.shape[4], 64).contiguous() for f in feats]
+    i = torch.arange(t * G, (t + 1) * G, device='cuda')
+    w_op = sw.reshape(1, Q, G, P, Lv)[0][:, (i // T)].permute(1, 0, 2, 3).contiguous()          # [G,Q,P,L]
+    ref = ops.msmv_forward(grouped, loc[t * G:(t + 1) * G].contiguous(), w_op)                   # [G,Q,C,P]
+    ref = ref.permute(1, 0, 3, 2)                                                                # [Q,G,P,C]
+    assert torch.equal(out[0, :, :, t * P:(t + 1) * P], ref)

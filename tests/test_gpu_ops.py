@@ -286,13 +286,13 @@ def test_dense_vs_torch(M, K, N, ln, relu, res):
     _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
 
 
-@pytest.mark.parametrize('impl', [0, 1, 2])
+@pytest.mark.parametrize('impl', [0, 1, 2, 4, 8])
 def test_dense_chain_vs_torch(impl, option):
     """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored.
     impl 0 = tensor-core chain (mma.sync bf16x3, TMA-streamed weights), impl 1 = fp32 FFMA chain."""
-    # 0 = tensor-core chain (default), 2 = tensor-core chain with 8-CTA TMA-multicast clusters, 1 = fp32 FFMA
+    # 0 = tensor-core chain (default), 2 / 4 / 8 = tensor-core chain with that many CTAs per TMA-multicast cluster, 1 = fp32 FFMA
     option('dense_impl', 1 if impl == 1 else 0)
-    option('dense_cluster', 1 if impl == 2 else 0)
+    option('dense_cluster', impl if impl >= 2 else 0)
     atol = 2e-5 if impl == 1 else 1e-4
     ops = _ops()
     torch.manual_seed(1)
@@ -412,7 +412,7 @@ def test_sasa_vs_oracle(Q, impl, option):
 # ------------------------------------------------------------------------- tcgen05 GEMM + mixing
 @pytest.mark.parametrize('impl', [0])
 @pytest.mark.parametrize('M,N,K,split_k', [(128, 128, 64, 1), (900, 256, 256, 1), (900, 1024, 256, 1), (300, 256, 2048, 8),
-                                           (1, 128, 128, 2), (900, 384, 512, 2), (2000, 2560, 128, 1)])
+                                           (1, 128, 128, 2), (900, 384, 512, 2), (2000, 2560, 128, 1), (900, 256, 4096, 18), (260, 256, 1024, 5)])
 def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
     option('gemm_impl', impl)            # 1 = persistent double-buffered kernel (default), 0 = one tile per CTA
     ops = _ops()
@@ -489,13 +489,17 @@ def test_mix_stage_vs_oracle(Pin, impl, option):
     assert float((yf.cpu() - want).abs().max() / want.abs().max()) < 2e-5
 
 
-def test_reduce_ln_vs_torch():
+@pytest.mark.parametrize('nsplit,M,N,ln', [(16, 900, 256, True), (18, 900, 256, True), (1, 37, 64, True), (33, 5, 1024, True),
+                                          (3, 130, 96, True), (5, 64, 256, False)])
+def test_reduce_ln_vs_torch(nsplit, M, N, ln):
     ops = _ops()
     torch.manual_seed(0)
-    part, bias, res = torch.randn(16, 900, 256), torch.randn(256), torch.randn(900, 256)
-    lw, lb = torch.randn(256), torch.randn(256)
-    want = torch.nn.functional.layer_norm(part.sum(0) + bias + res, (256,), lw, lb)
-    got = ops.reduce_ln(part.to(dev()), bias.to(dev()), res.to(dev()), lw.to(dev()), lb.to(dev()))
+    part, bias, res = torch.randn(nsplit, M, N), torch.randn(N), torch.randn(M, N)
+    lw, lb = torch.randn(N), torch.randn(N)
+    want = part.sum(0) + bias + res
+    if ln:
+        want = torch.nn.functional.layer_norm(want, (N,), lw, lb)
+    got = ops.reduce_ln(part.to(dev()), bias.to(dev()), res.to(dev()), lw.to(dev()) if ln else None, lb.to(dev()) if ln else None)
     _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
 
 
