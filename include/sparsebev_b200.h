@@ -41,6 +41,8 @@ const char* sbev_last_error(void);
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
  *   "dense_cluster"  0 = every CTA streams its own weight tiles (default); 2 / 4 / 8 = that many CTAs (row groups) form a
  *                    cluster and share every weight tile by TMA multicast (8 measured slower: lock step)
+ *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
+ *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default) */
 int         sbev_set_option(const char* name, int value);
@@ -116,13 +118,15 @@ int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int L,
  * the feature maps of the frames its backbone produced and samples only those).  `feats` hold the Tl frames
  * [t0, t0+Tl) -- element (b, t, ...) at (b*Tl + (t - t0))*stride_bt[l] + ... -- while time_diff, lidar2img and the
  * (t,g)->weight-group pairing keep indexing all T frames.  out [B, Q, G, Tl*P, C] (point index (t-t0)*P + p),
- * loc_out optional [B*Tl*G, Q, P, 3].  t0 = 0, Tl = T is exactly sbev_sampling4d_fwd.  Every sample is computed
+ * loc_out optional [B*Tl*G, Q, P, 3].  The velocity of query (b,q) is read at velocity + (b*Q+q)*ld_vel: 2 for a packed
+ * [B,Q,2] tensor, 10 to read it in place from query_bbox + 8 (no slice copy).  t0 = 0, Tl = T, ld_vel = 2 is exactly
+ * sbev_sampling4d_fwd.  Every sample is computed
  * independently of the window, so the union of the windows is bit-identical to the unsharded call.
  */
 int sbev_sampling4d_window_fwd(const float* const* feats, const int* hw, int L,
                                const int64_t* stride_bt, const int64_t* stride_g,
                                const int64_t* stride_v, const int64_t* stride_px,
-                               const float* points, const float* velocity, const float* time_diff,
+                               const float* points, const float* velocity, int ld_vel, const float* time_diff,
                                const float* lidar2img, const float* scale_w,
                                int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                                float image_h, float image_w, float eps,
@@ -137,7 +141,7 @@ int sbev_sampling4d_window_fwd(const float* const* feats, const int* hw, int L,
 int sbev_sampling4d_scatter_fwd(const float* const* feats, const int* hw, int L,
                                 const int64_t* stride_bt, const int64_t* stride_g,
                                 const int64_t* stride_v, const int64_t* stride_px,
-                                const float* points, const float* velocity, const float* time_diff,
+                                const float* points, const float* velocity, int ld_vel, const float* time_diff,
                                 const float* lidar2img, const float* scale_w,
                                 int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                                 float image_h, float image_w, float eps,

@@ -36,11 +36,11 @@ SIGNATURES = {
                             c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp],
     'sbev_sampling4d_window_fwd': [c_vpp, c_i32p, c_int, c_i64p, c_i64p, c_i64p, c_i64p,
-                                   c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp],
     'sbev_sampling4d_scatter_fwd': [c_vpp, c_i32p, c_int, c_i64p, c_i64p, c_i64p, c_i64p,
-                                    c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vpp, c_int, c_vp, c_vp],
     'sbev_dense_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],

@@ -9,7 +9,7 @@
 namespace sbev {
 
 void set_error(const char* fmt, ...);
-enum { OPT_GEMM_IMPL = 0, OPT_MIX_IMPL = 1, OPT_SASA_IMPL = 2, OPT_GATHER_VARIANT = 3, OPT_DENSE_IMPL = 4, OPT_DENSE_CLUSTER = 5, OPT_COUNT = 6 };
+enum { OPT_GEMM_IMPL = 0, OPT_MIX_IMPL = 1, OPT_SASA_IMPL = 2, OPT_GATHER_VARIANT = 3, OPT_DENSE_IMPL = 4, OPT_DENSE_CLUSTER = 5, OPT_PDL = 6, OPT_COUNT = 7 };
 // 2-D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], 128 B swizzle, zero OOB fill (gemm_tcgen05.cu)
 int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows);
 int make_bf16_map_ex(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows, int box_cols, int swizzle_bytes);
@@ -23,6 +23,29 @@ inline int check_launch(const char* what) {
         return SBEV_ERR_CUDA;
     }
     return SBEV_OK;
+}
+
+// Programmatic dependent launch (PDL).  Every hot-path kernel runs its global-memory-free prologue (barrier init, TMEM
+// allocation, descriptor prefetch, index math), then pdl_wait() -- which returns once the preceding kernel of the stream
+// has completed and flushed -- and immediately pdl_trigger(), so the NEXT kernel of the stream may be scheduled as soon as
+// every CTA of this one is running: its launch latency and prologue hide under this kernel's tail.  No kernel touches
+// global memory before its pdl_wait(), so the usual stream-order semantics are preserved (RAW, WAR and WAW alike).
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch `kernel` with the programmatic-stream-serialization attribute (option "pdl", default on).  ONLY for kernels
+// that call pdl_wait() before their first global access.
+template <typename... P, typename... A>
+inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option(OPT_PDL) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);      // errors are picked up by check_launch()
 }
 
 #define SBEV_REQUIRE(cond, code, ...)            \

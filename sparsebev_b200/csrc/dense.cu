@@ -307,6 +307,8 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    pdl_wait();
+    pdl_trigger();
     // stage the input rows as bf16 (hi, lo), zero-padded to the first layer's K rounded up to 64
     {
         const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
@@ -443,6 +445,8 @@ __global__ void __launch_bounds__(128)
 sample_points_kernel(const float* __restrict__ query_bbox, const float* __restrict__ offset, int ld_off,
                      const float* __restrict__ logits, int ld_log, float r0, float r1, float r2, float r3, float r4, float r5,
                      int BQ, int GP, int L, float* __restrict__ points, float* __restrict__ scale_w) {
+    pdl_wait();
+    pdl_trigger();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)BQ * GP) return;
     const long long bq = idx / GP;
@@ -509,6 +513,8 @@ reduce_ln_kernel(const float* __restrict__ partial, int nsplit, const float* __r
     const int c = tid % ng, h = tid / ng;
     const long long zs = (long long)M * N;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
+    pdl_trigger();
     if (h < zpar) {
         const float* p = partial + (long long)row * N + 4 * c;
         for (int z = h; z < nsplit; z += 8 * zpar) {
@@ -663,7 +669,7 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
                                     : cudaLaunchKernelEx(&cfg, dense_chain_mma_kernel<8>, prm, maps);
             if (e != cudaSuccess) { set_error("sbev_dense_chain_fwd(cluster launch): %s", cudaGetErrorString(e)); return SBEV_ERR_CUDA; }
         } else {
-            dense_chain_mma_kernel<1><<<groups, 288, smem_mma, (cudaStream_t)stream>>>(prm, maps);
+            launch_pdl(dense_chain_mma_kernel<1>, dim3(groups), dim3(288), smem_mma, (cudaStream_t)stream, prm, maps);
         }
         return check_launch("sbev_dense_chain_fwd(mma)");
     }
@@ -695,7 +701,7 @@ extern "C" int sbev_sample_points_fwd(const float* query_bbox, const float* offs
     SBEV_REQUIRE(BQ >= 0 && GP > 0 && L >= 1 && L <= SBEV_MAX_LEVELS && ld_off >= GP * 3 && ld_log >= GP * L, SBEV_ERR_INVALID, "sbev_sample_points_fwd: bad sizes");
     const long long total = (long long)BQ * GP;
     if (total == 0) return SBEV_OK;
-    sample_points_kernel<<<(int)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    launch_pdl(sample_points_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream,
         query_bbox, offset, ld_off, scale_logits, ld_log, pc_range[0], pc_range[1], pc_range[2], pc_range[3], pc_range[4], pc_range[5],
         BQ, GP, L, points, scale_w);
     return check_launch("sbev_sample_points_fwd");
@@ -718,7 +724,7 @@ extern "C" int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float*
     SBEV_REQUIRE(N > 0 && N <= 1024 && (N & 3) == 0, SBEV_ERR_UNSUPPORTED, "sbev_reduce_ln_fwd: N must be a multiple of 4 in (0,1024]");
     SBEV_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), SBEV_ERR_INVALID, "sbev_reduce_ln_fwd: ln_w and ln_b go together");
     if (M <= 0) return SBEV_OK;
-    reduce_ln_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
+    launch_pdl(reduce_ln_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, partial, nsplit, bias, residual, ln_w, ln_b, M, N, out);
     return check_launch("sbev_reduce_ln_fwd");
 }
 

@@ -165,6 +165,8 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait();                 // barriers + TMEM are set up; from here on global memory is read (TMA) and written (epilogue)
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -499,14 +501,14 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
             static std::once_flag once;                                                                                          \
             std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \
-            gemm_bf16_tn_persistent_kernel<BNN, STG, XX><<<grid, GEMM_THREADS, smem_v2, st>>>(mp, kbs, split_k, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
+            launch_pdl(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>, dim3(grid), dim3(GEMM_THREADS), smem_v2, st, mp, kbs, split_k, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
         } while (0)
         if (ares) {
             constexpr size_t smem_ar = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
             static std::once_flag once_ar;
             std::call_once(once_ar, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>,
                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ar); });
-            gemm_bf16_tn_persistent_kernel<128, 2, true, 4><<<grid, GEMM_THREADS, smem_ar, st>>>(mp, kbs, 1, m_tiles, n_tiles, num_tiles, bias, C, M, N);
+            launch_pdl(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>, dim3(grid), dim3(GEMM_THREADS), smem_ar, st, mp, kbs, 1, m_tiles, n_tiles, num_tiles, bias, C, M, N);
         } else if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
         else            { if (wide) SBEV_GEMM_V2(256, 4, false); else SBEV_GEMM_V2(128, 6, false); }
 #undef SBEV_GEMM_V2
@@ -542,7 +544,7 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-    gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-        mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
+    launch_pdl(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>, dim3(grid), dim3(GEMM_THREADS), smem, (cudaStream_t)stream,
+               mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
     return check_launch("sbev_gemm_bf16_tn_split");
 }

@@ -274,8 +274,10 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if ((long long)blockIdx.x < num_items) prefetch(blockIdx.x);
     }
+    pdl_wait();
+    pdl_trigger();
+    if (tid == 0 && (long long)blockIdx.x < num_items) prefetch(blockIdx.x);
     __syncthreads();
 
     // ldmatrix lane addressing: A (16x16): row = r + 8*(id&1), col = 8*(id>>1); B (8 n x 16 k): row = r, col = 8*(id&1)
@@ -489,8 +491,10 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
         for (int s = 0; s < 2; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full_bar[s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if ((long long)blockIdx.x < num_items) prefetch(blockIdx.x, 0);
     }
+    pdl_wait();
+    pdl_trigger();
+    if (tid == 0 && (long long)blockIdx.x < num_items) prefetch(blockIdx.x, 0);
     __syncthreads();
 
     const int lm_r = lane & 7, lm_id = lane >> 3;
@@ -683,7 +687,7 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
 #define SBEV_LAUNCH_MMA(R)                                                                                          \
         do {                                                                                                        \
             if (smem > 48 * 1024) cudaFuncSetAttribute(mix_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            mix_mma_kernel<R><<<pgrid, 256, smem, st>>>(params, x, G, Pin, grid, hi, lo, y_f32);                    \
+            launch_pdl(mix_mma_kernel<R>, dim3(pgrid), dim3(256), smem, st, params, x, G, Pin, grid, hi, lo, y_f32);      \
         } while (0)
         if (PK == 16) SBEV_LAUNCH_MMA(1);
         else if (PK == 32) SBEV_LAUNCH_MMA(2);
@@ -728,7 +732,7 @@ extern "C" int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* 
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     const int grid = items < 2 * num_sms ? (int)items : 2 * num_sms;
-    mix_tma_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(maps, x, (int)items, reinterpret_cast<__nv_bfloat16*>(y_hi),
-                                                              reinterpret_cast<__nv_bfloat16*>(y_lo), y_f32);
+    launch_pdl(mix_tma_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, maps, x, (int)items, reinterpret_cast<__nv_bfloat16*>(y_hi),
+               reinterpret_cast<__nv_bfloat16*>(y_lo), y_f32);
     return check_launch("sbev_mix_presplit_fwd");
 }

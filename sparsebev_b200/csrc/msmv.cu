@@ -367,7 +367,7 @@ msmv_bwd_generic_kernel(LevelSet lv, GradLevelSet glv, int L, const float* __res
 // project the point into one camera; a ballot picks the first valid view.
 struct FusedParams {
     const float* points;     // [B,Q,G*P,3]
-    const float* velocity;   // [B,Q,2]
+    const float* velocity;   // (b,q) -> velocity + (b*Q+q)*ld_vel: [B,Q,2] packed (ld_vel 2) or query_bbox + 8 (ld_vel 10)
     const float* time_diff;  // [B,T]
     const float* lidar2img;  // [B,T*N,16]
     const float* scale_w;    // [B,Q,G,P,L]
@@ -376,6 +376,7 @@ struct FusedParams {
     int B, T, G, N, Q, P;
     float image_h, image_w, eps;
     int t0, Tl;              // frame window [t0, t0+Tl) held by feats (t0 = 0, Tl = T: all frames)
+    int ld_vel;
     int o0, To, n_out;       // the out buffers cover frames [o0, o0+To): the window itself, or all T frames (scatter form)
 };
 
@@ -389,6 +390,8 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     const int lane = threadIdx.x & 31, half = lane / LPP, j = lane % LPP;
     const int T = prm.T, G = prm.G, N = prm.N, Q = prm.Q, P = prm.P;
     // slice (b,t,g) = blockIdx.y (uniform); sample (q,p) inside the slice from blockIdx.x: all 32-bit, no 64-bit div/mod
+    pdl_wait();
+    pdl_trigger();
     const int s = blockIdx.y, Tl = prm.Tl;
     const int g = s % G, btl = s / G, tl = btl % Tl, b = btl / Tl;   // btl indexes the LOCAL feature slices
     const int t = prm.t0 + tl, bt = b * T + t;                       // bt indexes time_diff / lidar2img (all T frames)
@@ -402,8 +405,8 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     // motion warp (sparsebev_transformer.py:286-295): xy -= vel * time_diff[t]; no FMA contraction
     const float* pp = prm.points + (bq * G * P + g * P + p) * 3;
     const float td = __ldg(prm.time_diff + bt);
-    const float px = __fsub_rn(__ldg(pp), __fmul_rn(__ldg(prm.velocity + bq * 2), td));
-    const float py = __fsub_rn(__ldg(pp + 1), __fmul_rn(__ldg(prm.velocity + bq * 2 + 1), td));
+    const float px = __fsub_rn(__ldg(pp), __fmul_rn(__ldg(prm.velocity + bq * prm.ld_vel), td));
+    const float py = __fsub_rn(__ldg(pp + 1), __fmul_rn(__ldg(prm.velocity + bq * prm.ld_vel + 1), td));
     const float pz = __ldg(pp + 2);
 
     // scale weights: the reference pairs loc slice (b,t,g) with weight slice (b,g',t'),
@@ -563,11 +566,12 @@ extern "C" int sbev_msmv_bwd(const float* grad_out, const float* const* feats, c
 static int launch_sampling4d(const float* const* feats, const int* hw, int L,
                              const int64_t* stride_bt, const int64_t* stride_g,
                              const int64_t* stride_v, const int64_t* stride_px,
-                             const float* points, const float* velocity, const float* time_diff,
+                             const float* points, const float* velocity, int ld_vel, const float* time_diff,
                              const float* lidar2img, const float* scale_w,
                              int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                              float image_h, float image_w, float eps,
                              float* const* outs, int n_out, bool full_out, float* loc_out, void* stream, const char* who) {
+    SBEV_REQUIRE(ld_vel >= 2, SBEV_ERR_INVALID, "%s: ld_vel must be >= 2", who);
     SBEV_REQUIRE(t0 >= 0 && Tl >= 0 && t0 + Tl <= T, SBEV_ERR_INVALID, "%s: frame window [%d,%d) outside [0,%d)", who, t0, t0 + Tl, T);
     SBEV_REQUIRE(feats && stride_bt && stride_g && stride_v && stride_px && points && velocity && time_diff &&
                  lidar2img && scale_w && outs, SBEV_ERR_INVALID, "%s: null pointer", who);
@@ -598,7 +602,7 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
     prm.loc_out = loc_out;
     prm.B = B; prm.T = T; prm.G = G; prm.N = N; prm.Q = Q; prm.P = P;
     prm.image_h = image_h; prm.image_w = image_w; prm.eps = eps;
-    prm.t0 = t0; prm.Tl = Tl; prm.n_out = n_out;
+    prm.t0 = t0; prm.Tl = Tl; prm.n_out = n_out; prm.ld_vel = ld_vel;
     prm.o0 = full_out ? 0 : t0; prm.To = full_out ? T : Tl;
     // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
     // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views)
@@ -608,10 +612,10 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
     const dim3 grid((Q * P + ppb - 1) / ppb, B * Tl * G);
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
-        if (variant == 2 && LL >= 2) sampling4d_c64_kernel<LL, 2, 2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);      \
-        else if (variant == 2) sampling4d_c64_kernel<LL, LL, 2, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);           \
-        else if (variant == 1 && LL >= 3) sampling4d_c64_kernel<LL, 2, 3, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm); \
-        else sampling4d_c64_kernel<LL, LL, 1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(lv, prm);               \
+        if (variant == 2 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant == 2) launch_pdl(sampling4d_c64_kernel<LL, LL, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);           \
+        else if (variant == 1 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 3, 16>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm); \
+        else launch_pdl(sampling4d_c64_kernel<LL, LL, 1, 16>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);               \
         break;
     switch (L) { SBEV_LAUNCH_FUSED(1) SBEV_LAUNCH_FUSED(2) SBEV_LAUNCH_FUSED(3) SBEV_LAUNCH_FUSED(4) SBEV_LAUNCH_FUSED(5) }
 #undef SBEV_LAUNCH_FUSED
@@ -626,30 +630,30 @@ extern "C" int sbev_sampling4d_fwd(const float* const* feats, const int* hw, int
                                    int B, int T, int G, int N, int C, int Q, int P,
                                    float image_h, float image_w, float eps,
                                    float* out, float* loc_out, void* stream) {
-    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, 2, time_diff, lidar2img, scale_w,
                              B, T, 0, T, G, N, C, Q, P, image_h, image_w, eps, &out, 1, false, loc_out, stream, "sbev_sampling4d_fwd");
 }
 
 extern "C" int sbev_sampling4d_window_fwd(const float* const* feats, const int* hw, int L,
                                           const int64_t* stride_bt, const int64_t* stride_g,
                                           const int64_t* stride_v, const int64_t* stride_px,
-                                          const float* points, const float* velocity, const float* time_diff,
+                                          const float* points, const float* velocity, int ld_vel, const float* time_diff,
                                           const float* lidar2img, const float* scale_w,
                                           int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                                           float image_h, float image_w, float eps,
                                           float* out, float* loc_out, void* stream) {
-    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, ld_vel, time_diff, lidar2img, scale_w,
                              B, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, &out, 1, false, loc_out, stream, "sbev_sampling4d_window_fwd");
 }
 
 extern "C" int sbev_sampling4d_scatter_fwd(const float* const* feats, const int* hw, int L,
                                            const int64_t* stride_bt, const int64_t* stride_g,
                                            const int64_t* stride_v, const int64_t* stride_px,
-                                           const float* points, const float* velocity, const float* time_diff,
+                                           const float* points, const float* velocity, int ld_vel, const float* time_diff,
                                            const float* lidar2img, const float* scale_w,
                                            int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                                            float image_h, float image_w, float eps,
                                            float* const* outs, int n_out, float* loc_out, void* stream) {
-    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, time_diff, lidar2img, scale_w,
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, ld_vel, time_diff, lidar2img, scale_w,
                              B, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, outs, n_out, true, loc_out, stream, "sbev_sampling4d_scatter_fwd");
 }

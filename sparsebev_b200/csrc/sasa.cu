@@ -380,6 +380,8 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
     unsigned char* mybuf = s3_smem + kq * 2 * S3_BUF_BYTES;
     const long long rowbase = (long long)b * Q;
     const int bar_id = 1 + kq;
+    pdl_wait();
+    pdl_trigger();
 
     // Q fragments straight from global (A operand: a0 (row g, k 2t..), a1 (row g+8), a2 (row g, k 2t+8..), a3 (row g+8, k+8))
     uint32_t qh[2][4], ql[2][4];
@@ -588,7 +590,7 @@ extern "C" int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_l
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(sasa_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     dim3 grid((Q + 31) / 32, H, B);
-    sasa_v3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
-                                                            query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+    launch_pdl(sasa_v3_kernel, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
+               query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
     return check_launch("sbev_sasa_split_fwd");
 }

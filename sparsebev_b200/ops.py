@@ -110,12 +110,16 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
 
     layout 'grouped': feats L x [B*T*G, N, H, W, C] (the reference's regrouped op layout);
     layout 'nhwc'   : feats L x [B, T*N, H, W, G*C] (un-regrouped, channels-last FPN output).
-    points [B,Q,G*P,3], velocity [B,Q,2], time_diff [B,T], lidar2img [B,T*N,4,4], scale_w [B,Q,G,P,L]
+    points [B,Q,G*P,3], velocity [B,Q,2] (or the whole query_bbox [B,Q,10], read in place), time_diff [B,T], lidar2img [B,T*N,4,4], scale_w [B,Q,G,P,L]
     -> [B,Q,G,T*P,C] (+ loc [B*T*G,Q,P,3] when return_loc)."""
     lib = _lib.load()
     L = len(mlvl_feats)
     pts = _chk(points, 'points')
-    vel = _chk(velocity, 'velocity')
+    if velocity.dim() == 3 and velocity.shape[-1] == 10:          # the whole query_bbox [B,Q,10]: read vx, vy in place
+        vel, vel_ptr, ld_vel = _chk(velocity, 'query_bbox'), velocity.data_ptr() + 8 * 4, 10
+    else:
+        vel = _chk(velocity, 'velocity')
+        vel_ptr, ld_vel = vel.data_ptr(), 2
     td = _chk(time_diff, 'time_diff')
     l2i = _chk(lidar2img, 'lidar2img')
     sw = _chk(scale_w, 'scale_w')
@@ -146,7 +150,7 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
         hw += [H, W]
     if tuple(sw.shape) != (B, Q, G, P, L):
         raise RuntimeError('scale_w must be [B,Q,G,P,L]=%s, got %s' % ((B, Q, G, P, L), tuple(sw.shape)))
-    if tuple(td.shape) != (B, T) or tuple(l2i.shape) != (B, T * N, 4, 4) or tuple(vel.shape) != (B, Q, 2):
+    if tuple(td.shape) != (B, T) or tuple(l2i.shape) != (B, T * N, 4, 4) or tuple(vel.shape) != (B, Q, ld_vel):
         raise RuntimeError('time_diff / lidar2img / velocity shape mismatch')
     loc = torch.empty(B * Tl * G, Q, P, 3, device=pts.device, dtype=torch.float32) if return_loc else None
     if scatter_ptrs is not None:
@@ -154,7 +158,7 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
             _lib.check(lib.sbev_sampling4d_scatter_fwd(
                 _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
                 _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
-                pts.data_ptr(), vel.data_ptr(), td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
+                pts.data_ptr(), vel_ptr, ld_vel, td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
                 B, T, t0, Tl, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
                 _lib.ptr_array([int(p) for p in scatter_ptrs]), len(scatter_ptrs), _p(loc), _stream()), 'sbev_sampling4d_scatter_fwd')
         return (None, loc) if return_loc else None
@@ -164,7 +168,7 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
         _lib.check(lib.sbev_sampling4d_window_fwd(
             _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
             _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
-            pts.data_ptr(), vel.data_ptr(), td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
+            pts.data_ptr(), vel_ptr, ld_vel, td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
             B, T, t0, Tl, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
             out.data_ptr(), _p(loc), _stream()), 'sbev_sampling4d_window_fwd')
     return (out, loc) if return_loc else out

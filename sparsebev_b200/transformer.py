@@ -13,7 +13,7 @@ Same class names, constructor kwargs, call signatures, side effects and state-di
     AdaptiveMixing                  :320-387
 
 The nn.Modules only HOLD parameters (so names/shapes match the checkpoint); every forward runs the
-hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- 13 launches per layer, capturable in one
+hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- 12 launches per layer, capturable in one
 CUDA graph (bench.py does).  Forward only: this
 is the eval path (dropout = identity, no activation checkpointing); training the decoder through these
 modules is out of scope (the op-level autograd Functions in `wrapper.py` do have a backward).
@@ -207,18 +207,21 @@ class SparseBEVSelfAttention(BaseModule):
         return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y,
                                w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad, y_hi=y_hi, y_lo=y_lo)
 
-    def attention_core(self, query_bbox, x, pre_attn_mask=None):
-        """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj)."""
+    def attention_core(self, query_bbox, x, pre_attn_mask=None, pre=None):
+        """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj).
+        pre = (x0, ldx0, layers): dense layers chained IN FRONT of the in-projection in the same launch; the last of them
+        must produce x (the decoder layer passes its position encoder here: one launch less)."""
         B, Q = query_bbox.shape[:2]
         D, H = self.attention.attn.embed_dim, self.num_heads
         qkvt = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.float32)
+        x0, ldx0, head = (x, D, []) if pre is None else pre
         if self.core_impl == 'split':          # tensor-core path: the chain epilogue also emits the bf16 (hi, lo) operands
             hi = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.bfloat16)
             lo = torch.empty_like(hi)
-            ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt, hi, lo)])
+            ops.dense_chain(x0, ldx0, B * Q, list(head) + [self.in_layer(qkvt, hi, lo)])
             o = ops.sasa_split(qkvt, query_bbox, self.pc_range, H, D, dn_mask=pre_attn_mask, split=(hi, lo))
             return o.reshape(B * Q, D)
-        ops.dense_chain(x, D, B * Q, [self.in_layer(qkvt)])
+        ops.dense_chain(x0, ldx0, B * Q, list(head) + [self.in_layer(qkvt)])
         o = ops.sasa(qkvt, query_bbox, qkvt[:, 3 * D:], self.pc_range, H, dn_mask=pre_attn_mask,
                      ld_qkv=3 * D + H, ld_tau=3 * D + H, embed_dims=D)
         return o.reshape(B * Q, D)
@@ -266,8 +269,7 @@ class SparseBEVSampling(BaseModule):
         ld = heads_out.shape[1]
         pts, sw = ops.sample_points(query_bbox, heads_out, heads_out[:, G * P * 3:], self.pc_range, L,
                                     num_points_total=G * P, ld_off=ld, ld_log=ld)
-        vel = query_bbox[..., 8:10].contiguous()
-        return ops.sampling4d_fused(mlvl_feats, pts, vel, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
+        return ops.sampling4d_fused(mlvl_feats, pts, query_bbox, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
                                     sw.reshape(B, Q, G, P, L), image_h, image_w, num_frames=self.num_frames,
                                     num_views=NUM_VIEWS, layout=self.feat_layout,       # [B,Q,G,T*P,C]
                                     frame_window=frame_window, scatter_ptrs=scatter_ptrs)
@@ -361,7 +363,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        13 kernel launches: 6 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
+        12 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
         that follow), SASA core, sample_points, fused gather, 2 tcgen05 GEMMs, mix, split-K reduce + norm2; the gather runs
         concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
@@ -371,10 +373,10 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         new = lambda n: torch.empty(M, n, device=dev, dtype=torch.float32)      # noqa: E731
         # (1) position encoder, + query_feat                                     [Linear(3,D) LN ReLU Linear LN ReLU] + residual
         q1 = new(D)
-        ops.dense_chain(query_bbox.reshape(M, -1), query_bbox.shape[-1], M,
-                        [self._pe0.layer(relu=True), self._pe1.layer(relu=True, residual=qf, y=q1)])
-        # (2) scale-adaptive self-attention; out_proj + identity + norm1 chained with the sampling heads
-        o = self.self_attn.attention_core(query_bbox, q1, attn_mask)
+        pos_enc = (query_bbox.reshape(M, -1), query_bbox.shape[-1], [self._pe0.layer(relu=True), self._pe1.layer(relu=True, residual=qf, y=q1)])
+        # (2) scale-adaptive self-attention: in-projection (+ tau) chained behind the position encoder, attention core,
+        #     then out_proj + identity + norm1 chained with the sampling heads
+        o = self.self_attn.attention_core(query_bbox, q1, attn_mask, pre=pos_enc)
         q2, heads = new(D), new(self.sampling._heads.out_features)
         pbuf = self.mixing.alloc_params(M, dev)               # q2 also leaves the chain as the bf16 (hi, lo) operand of the param GEMM
         ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)])
