@@ -46,7 +46,11 @@ __device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) 
 
 // Row epilogue shared by the FFMA and the tensor-core chain kernels: one warp finishes one output row held in
 // shared memory (yr[0..N)): + bias -> (+ residual) -> LayerNorm -> ReLU -> (+ residual) -> (refine) -> yr and global.
-__device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane) {
+// sv / sres (optional): shared-memory copies of the layer's bias | ln_w | ln_b (3 x CHAIN_VEC_LD floats) and of this row's
+// residual, prefetched with cp.async while the layer's GEMM ran -- the epilogue then waits on no global load.
+constexpr int CHAIN_VEC_LD = 1024;
+__device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane,
+                                                   const float* sv = nullptr, const float* sres = nullptr) {
     constexpr int U = 8;                               // columns per lane per batch: their global operands are loaded together
     const int N = L.N;
     const bool live = row < prm.M;
@@ -59,8 +63,8 @@ __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int n = n0 + lane + 32 * u;
-            bv[u] = (L.bias && n < N) ? __ldg(L.bias + n) : 0.f;
-            rv[u] = (pre_res && has_res && n < N) ? __ldg(res_row + n) : 0.f;
+            bv[u] = (L.bias && n < N) ? (sv ? sv[n] : __ldg(L.bias + n)) : 0.f;
+            rv[u] = (pre_res && has_res && n < N) ? (sres ? sres[n] : __ldg(res_row + n)) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -82,9 +86,9 @@ __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const
         for (int u = 0; u < U; ++u) {
             const int n = n0 + lane + 32 * u;
             const bool ok = n < N;
-            gv[u] = (L.ln_w && ok) ? __ldg(L.ln_w + n) : 1.f;
-            ov[u] = (L.ln_w && ok) ? __ldg(L.ln_b + n) : 0.f;
-            rv[u] = (!pre_res && has_res && ok) ? __ldg(res_row + n) : 0.f;
+            gv[u] = (L.ln_w && ok) ? (sv ? sv[CHAIN_VEC_LD + n] : __ldg(L.ln_w + n)) : 1.f;
+            ov[u] = (L.ln_w && ok) ? (sv ? sv[2 * CHAIN_VEC_LD + n] : __ldg(L.ln_b + n)) : 0.f;
+            rv[u] = (!pre_res && has_res && ok) ? (sres ? sres[n] : __ldg(res_row + n)) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -255,6 +259,7 @@ constexpr int MC_STAGES = 4;
 constexpr int MC_TILE_BYTES = 128 * 64 * 2;            // one (hi or lo) 128 x 64 bf16 tile
 constexpr int MC_XLD = 512 + 8;                        // bf16 row stride of the activation operand (K <= 512)
 constexpr int MC_YLD = 1024 + 4;                       // fp32 row stride of the layer output (N <= 1024)
+constexpr int MC_RES_LD = 256;                         // residual rows are staged in shared memory when N <= 256
 
 struct ChainMaps { CUtensorMap hi[CHAIN_MAX_LAYERS]; CUtensorMap lo[CHAIN_MAX_LAYERS]; };
 
@@ -294,6 +299,8 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     uint8_t* wring = smem;                                                             // [STAGES][hi tile | lo tile]
     __nv_bfloat16* xbuf = reinterpret_cast<__nv_bfloat16*>(smem + MC_STAGES * 2 * MC_TILE_BYTES);   // [2 ping-pong][hi,lo][8][MC_XLD]
     float* ys = reinterpret_cast<float*>(xbuf + 2 * 2 * DENSE_ROWS * MC_XLD);          // [8][MC_YLD]
+    float* vecs = ys + DENSE_ROWS * MC_YLD;                                            // [3][CHAIN_VEC_LD]  bias | ln_w | ln_b of the layer
+    float* resb = vecs + 3 * CHAIN_VEC_LD;                                             // [8][MC_RES_LD]     residual rows of the layer
     __shared__ uint64_t full_bar[MC_STAGES], empty_bar[MC_STAGES];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -373,6 +380,23 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         const int kchunks = (L.K + 63) >> 6, nblocks = (L.N + 127) >> 7;
         const __nv_bfloat16* xh = xbuf + ping * 2 * DENSE_ROWS * MC_XLD;
         const __nv_bfloat16* xl = xh + DENSE_ROWS * MC_XLD;
+        // epilogue operands of this layer -> shared memory, asynchronously (LDGSTS), while the GEMM below runs
+        const bool res_staged = L.residual != nullptr && L.N <= MC_RES_LD;
+        {
+            auto cp4 = [](float* dst, const float* src) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsmem_u32(dst)), "l"(src) : "memory");
+            };
+            for (int n = tid; n < L.N; n += 256) {
+                if (L.bias) cp4(vecs + n, L.bias + n);
+                if (L.ln_w) { cp4(vecs + CHAIN_VEC_LD + n, L.ln_w + n); cp4(vecs + 2 * CHAIN_VEC_LD + n, L.ln_b + n); }
+            }
+            if (res_staged)
+                for (int i = tid; i < DENSE_ROWS * L.N; i += 256) {
+                    const int r = i / L.N, n = i - r * L.N;
+                    if (row0 + r < prm.M) cp4(resb + r * MC_RES_LD + n, L.residual + (long long)(row0 + r) * L.N + n);
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         {
             const uint32_t xh_addr = dsmem_u32(xh + lm_r * MC_XLD + 8 * (lm_id & 1));
             const uint32_t xl_addr = dsmem_u32(xl + lm_r * MC_XLD + 8 * (lm_id & 1));
@@ -416,10 +440,11 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                 if (n + 8 < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n + 8] = acc[2]; ys[(2 * t4 + 1) * MC_YLD + n + 8] = acc[3]; }
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         {
             float* yr = ys + warp * MC_YLD;
-            chain_row_epilogue(prm, L, row0 + warp, yr, lane);
+            chain_row_epilogue(prm, L, row0 + warp, yr, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr);
             __syncwarp();
             if (li + 1 < prm.n_layers) {          // next layer's activation operand: bf16 (hi, lo), zero beyond N up to its padded K
                 __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD;
@@ -646,7 +671,8 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
             rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, box_rows);
             if (rc) return rc;
         }
-        const size_t smem_mma = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * DENSE_ROWS * MC_XLD * 2 + (size_t)DENSE_ROWS * MC_YLD * 4 + 1024;
+        const size_t smem_mma = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * DENSE_ROWS * MC_XLD * 2 + (size_t)DENSE_ROWS * MC_YLD * 4 +
+                                (size_t)(3 * CHAIN_VEC_LD + DENSE_ROWS * MC_RES_LD) * 4 + 1024;
         static std::once_flag once_mma;
         std::call_once(once_mma, [&] {
             cudaFuncSetAttribute(dense_chain_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);

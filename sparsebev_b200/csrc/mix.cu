@@ -450,7 +450,7 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
 // (sbev_gemm_bf16_tn_split), so M [64x64] and S [128x32] of an item arrive by four 2-D TMA loads -- 128-byte / 64-byte
 // swizzled, i.e. directly in the bank-conflict-free layout ldmatrix wants -- into a double-buffered operand set; no
 // conversion pass for the 8192 parameters of an item, only the 32x64 x tile is split on the fly.
-struct MixMaps { CUtensorMap m_hi, m_lo, s_hi, s_lo; };
+struct MixMaps { CUtensorMap m_hi, m_lo, s_hi, s_lo, y_hi, y_lo; };   // y_*: [items*128 rows][64 bf16], box 128 rows, 128 B swizzle
 
 __global__ void __launch_bounds__(256, 2)
 mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x, int num_items,
@@ -530,6 +530,7 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
         }
         __syncthreads();
         if (tid == 0 && qg + gridDim.x < num_items) {        // the other operand set and x buffer are free: fetch the next item now
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // ... once the previous item's output tile has left it
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             prefetch(qg + gridDim.x, slot ^ 1);
         }
@@ -636,17 +637,20 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
                 *reinterpret_cast<uint32_t*>(ol + off) = l;
                 if (y_f32) *reinterpret_cast<float2*>(y_f32 + obase + o * MIX_C + c) = make_float2(v0, v1);
             }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staging writes -> visible to the TMA engine
         __syncthreads();
-        if (y_hi) {
-            for (int i = tid; i < MIX_POUT * 8; i += 256) {
-                const int o = i >> 3, j = i & 7;
-                const uint32_t off = (uint32_t)(o * 128 + ((j ^ (o & 7)) << 4));
-                *reinterpret_cast<uint4*>(y_hi + obase + o * MIX_C + 8 * j) = *reinterpret_cast<const uint4*>(oh + off);
-                if (y_lo) *reinterpret_cast<uint4*>(y_lo + obase + o * MIX_C + 8 * j) = *reinterpret_cast<const uint4*>(ol + off);
-            }
+        if (y_hi && tid == 0) {      // the staged tiles are exactly TMA's 128 B-swizzled image of [128 rows][64 bf16]: two tensor stores
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&maps.y_hi), "r"((uint32_t)__cvta_generic_to_shared(oh)), "r"(0), "r"((int)(qg * MIX_POUT)) : "memory");
+            if (y_lo)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(&maps.y_lo), "r"((uint32_t)__cvta_generic_to_shared(ol)), "r"(0), "r"((int)(qg * MIX_POUT)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        __syncthreads();                                  // staging read out before this set is refilled (two items later)
+        // no second barrier: this set is refilled by the prefetch of the NEXT iteration, which first waits (thread 0,
+        // cp.async.bulk.wait_group.read) until the stores above have read it, behind that iteration's own barrier
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory must outlive the last store
 }
 
 }  // namespace sbev
@@ -726,6 +730,14 @@ extern "C" int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* 
     rc = make_bf16_map_ex(&maps.m_lo, params_lo, items * 128, 64, 64, 64, 128);       if (rc) return rc;
     rc = make_bf16_map_ex(&maps.s_hi, params_hi, items * 256, 32, 128, 32, 64);       if (rc) return rc;
     rc = make_bf16_map_ex(&maps.s_lo, params_lo, items * 256, 32, 128, 32, 64);       if (rc) return rc;
+    if (y_hi) {
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(y_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_lo) & 15) == 0, SBEV_ERR_INVALID,
+                     "sbev_mix_presplit_fwd: y_hi / y_lo must be 16-byte aligned");
+        rc = make_bf16_map_ex(&maps.y_hi, y_hi, items * MIX_POUT, 64, MIX_POUT, 64, 128);               if (rc) return rc;
+        rc = make_bf16_map_ex(&maps.y_lo, y_lo ? y_lo : y_hi, items * MIX_POUT, 64, MIX_POUT, 64, 128); if (rc) return rc;
+    } else {
+        maps.y_hi = maps.m_hi; maps.y_lo = maps.m_lo;        // unused
+    }
     static int num_sms = 0;
     if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const size_t smem = 2 * 32768 + 2 * 8192 + 4 * 32 * MX_LD * 2 + 1024;
