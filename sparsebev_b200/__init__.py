@@ -6,5 +6,6 @@ from .sampling import sampling_4d, make_sample_points  # noqa: F401
 from .transformer import (SparseBEVTransformer, SparseBEVTransformerDecoder, SparseBEVTransformerDecoderLayer,  # noqa: F401
                           SparseBEVSelfAttention, SparseBEVSampling, AdaptiveMixing)
 from .head import SparseBEVHead  # noqa: F401
+from .coder import NMSFreeCoder, denormalize_bbox  # noqa: F401
 
 __version__ = '0.1.0'

@@ -13,12 +13,17 @@ import math
 import torch
 import torch.nn as nn
 
+from .coder import NMSFreeCoder
 from .transformer import SparseBEVTransformer
 
 
 class SparseBEVHead(nn.Module):
-    def __init__(self, num_classes=10, in_channels=256, num_query=900, code_size=10, pc_range=None, transformer=None, **kwargs):
+    def __init__(self, num_classes=10, in_channels=256, num_query=900, code_size=10, pc_range=None, transformer=None,
+                 bbox_coder=None, **kwargs):
         super().__init__()
+        ccfg = dict(bbox_coder or {})
+        ccfg.pop('type', None)
+        self.bbox_coder = NMSFreeCoder(**ccfg) if ccfg else None
         self.num_classes, self.embed_dims, self.num_query, self.code_size = num_classes, in_channels, num_query, code_size
         self.pc_range = list(pc_range)
         tcfg = dict(transformer or {})
@@ -57,3 +62,16 @@ class SparseBEVHead(nn.Module):
         bbox_preds[..., 2] = bbox_preds[..., 2] * (pc[5] - pc[2]) + pc[2]
         bbox_preds = torch.cat([bbox_preds[..., 0:2], bbox_preds[..., 3:5], bbox_preds[..., 2:3], bbox_preds[..., 5:10]], dim=-1)
         return {'all_cls_scores': cls_scores, 'all_bbox_preds': bbox_preds, 'enc_cls_scores': None, 'enc_bbox_preds': None}
+
+    @torch.no_grad()
+    def get_bboxes(self, preds_dicts, img_metas=None, rescale=False):
+        """Reference :463-482 without the mmdet3d box class: -> per sample [bboxes [n,9] (bottom-centre z), scores, labels].
+        (The reference wraps `bboxes` into LiDARInstance3DBoxes(bboxes, 9); its legacy-version axis swap is not reproduced.)"""
+        if self.bbox_coder is None:
+            raise RuntimeError('SparseBEVHead was built without bbox_coder=dict(type="NMSFreeCoder", ...)')
+        out = []
+        for preds in self.bbox_coder.decode(preds_dicts):
+            bboxes = preds['bboxes']
+            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+            out.append([bboxes, preds['scores'], preds['labels']])
+        return out

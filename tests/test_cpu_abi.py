@@ -105,3 +105,12 @@ def test_state_dict_keys_match_reference_checkpoint_layout():
     keys = set(k[len('decoder.decoder_layer.'):] for k in model.state_dict())
     assert keys == set(S.make_state_dict(cfg)), keys ^ set(S.make_state_dict(cfg))
     assert model.embed_dims == 256
+
+
+def test_pybind_stand_in_exports_reference_names():
+    from sparsebev_b200 import _msmv_sampling_cuda as ext
+    for name in ('_ms_deform_attn_cuda_c2345_forward', '_ms_deform_attn_cuda_c2345_backward',
+                 '_ms_deform_attn_cuda_c23456_forward', '_ms_deform_attn_cuda_c23456_backward'):
+        assert callable(getattr(ext, name))
+    with pytest.raises(RuntimeError):                       # CPU tensors: refused, never computed on the host
+        ext._ms_deform_attn_cuda_c2345_forward(*[torch.zeros(1, 6, 2, 2, 64)] * 4, torch.zeros(1, 1, 1, 3), torch.zeros(1, 1, 1, 4))

@@ -107,6 +107,16 @@ def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
                           td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
     assert _rel(outs['all_cls_scores'], want['all_cls_scores']) < 1e-3
     assert _rel(outs['all_bbox_preds'], want['all_bbox_preds']) < 1e-3
+    # post-processing on the device tensors: same boxes as decoding the oracle's predictions (top-k ties aside, scores match)
+    head.bbox_coder = sb.NMSFreeCoder(pc_range=cfg['pc_range'], post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_num=20, num_classes=10)
+    dets = head.get_bboxes(outs)
+    ref_dets = sb.NMSFreeCoder(pc_range=cfg['pc_range'], post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_num=20,
+                               num_classes=10).decode({k: v for k, v in want.items() if v is not None})
+    assert len(dets) == B
+    for (bb, sc, lb), r in zip(dets, ref_dets):
+        assert bb.shape[1] == 9 and sc.shape == lb.shape and lb.dtype == torch.int64
+        assert sc.shape == r['scores'].shape and torch.allclose(sc.cpu(), r['scores'], rtol=1e-3, atol=1e-4)
+        assert torch.equal(lb.cpu()[:3], r['labels'][:3])
 
 
 def test_r50_t8_layer_runs_and_is_deterministic():

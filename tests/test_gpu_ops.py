@@ -166,6 +166,24 @@ def test_autograd_function_surface():
         wrapper.msmv_sampling([f.detach().cpu() for f in feats], loc.detach().cpu(), w.detach().cpu())
 
 
+def test_pybind_module_stand_in():
+    """`_msmv_sampling_cuda` surface (msmv_sampling.cpp:362-369): forward value and the 6-/7-element backward list."""
+    from sparsebev_b200 import _msmv_sampling_cuda as ext, ops
+    for hw in ([(6, 8), (3, 4), (2, 2), (1, 2)], [(6, 8), (3, 4), (2, 2), (2, 3), (1, 2)]):
+        feats, loc, w = _rand_case(2, 6, hw, 5, 4, seed=11)
+        feats, loc, w = [f.to(dev()) for f in feats], loc.to(dev()), w.to(dev())
+        fwd = ext._ms_deform_attn_cuda_c2345_forward if len(hw) == 4 else ext._ms_deform_attn_cuda_c23456_forward
+        bwd = ext._ms_deform_attn_cuda_c2345_backward if len(hw) == 4 else ext._ms_deform_attn_cuda_c23456_backward
+        out = fwd(*feats, loc, w)
+        assert torch.equal(out, ops.msmv_forward(feats, loc, w))
+        go = torch.randn_like(out)
+        grads = bwd(go, *feats, loc, w)
+        assert isinstance(grads, list) and len(grads) == len(hw) + 2
+        gf, gl, gw = ops.msmv_backward(go, feats, loc, w)
+        assert torch.allclose(grads[-1], gw) and torch.allclose(grads[-2], gl) and grads[0].shape == feats[0].shape
+        assert float(grads[-2][..., 2].abs().max()) == 0.0          # view coordinate gets no gradient (backward.cu)
+
+
 def test_against_reference_cuda_kernel():
     """O3 of SURVEY 8(c): our op vs the UNMODIFIED reference kernel compiled for sm_100a (oracle/_ref)."""
     ref = _ref_cuda()

@@ -112,3 +112,19 @@ def test_self_attention_matches_torch_mha():
     with torch.no_grad():
         ref = qf + mha(qf.transpose(0, 1), qf.transpose(0, 1), qf.transpose(0, 1), attn_mask=mask)[0].transpose(0, 1)
     np.testing.assert_allclose(ours.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_nms_free_coder_matches_reference_golden(golden_dir):
+    """Post-processing mirror vs the REAL reference NMSFreeCoder (oracle/gen_golden_coder.py): exact."""
+    from sparsebev_b200.coder import NMSFreeCoder
+    g = np.load(os.path.join(golden_dir, 'coder.npz'))
+    cls, box = torch.from_numpy(g['cls']), torch.from_numpy(g['box'])
+    post = [float(v) for v in g['post_center_range']]
+    for tag, kw in [('a', dict(max_num=100, score_threshold=None)), ('b', dict(max_num=37, score_threshold=0.05))]:
+        coder = NMSFreeCoder(pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], post_center_range=post, num_classes=10, **kw)
+        res = coder.decode({'all_cls_scores': cls, 'all_bbox_preds': box})
+        assert len(res) == cls.shape[1]
+        for b, r in enumerate(res):
+            assert np.array_equal(r['labels'].numpy(), g['%s%d_labels' % (tag, b)])
+            assert np.array_equal(r['scores'].numpy(), g['%s%d_scores' % (tag, b)])
+            assert np.array_equal(r['bboxes'].numpy(), g['%s%d_bboxes' % (tag, b)])
