@@ -406,6 +406,29 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (gather_ms * 1e-3) / 1e9
 
+    # ---- second roofline: the tensor-core GEMM of the mixing stage (dynamic-parameter generation), timed alone the same way
+    mixing = layer.mixing
+    pbuf = mixing.alloc_params(Q, dev)
+    mixing.generate_params(x, pbuf, presplit=False)          # fills the bf16 (hi, lo) query operand once
+    for _ in range(3):
+        mixing.generate_params(x, pbuf, presplit=True)
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(n_g):
+        mixing.generate_params(x, pbuf, presplit=True)
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1) / n_g
+    n_par = mixing.n_groups * mixing.total_parameters
+    products = 3 if args.precision == 'bf16x3' else 1
+    gemm_flops = 2.0 * Q * n_par * 256 * products            # tensor-core flops issued (bf16x3 = three bf16 products per fp32-grade one)
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            tensor_peak, tensor_src = float(json.load(f)['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops, burst)'
+    except Exception:
+        tensor_peak, tensor_src = 2250.0, 'fallback (nominal dense bf16)'
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12
+
     clk = clocks.stop() if rank == 0 else None
 
     breakdown = None
@@ -444,7 +467,13 @@ def main():
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': GATHER_DRAM_TRAFFIC,
                          'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full (profiles/); far below '
                                          'the algorithmic bytes because neighbouring queries re-sample the same pixels out of L2',
-                         'algorithmic_bytes': algo_bytes, 'points': n_points, 'kernel_ms': gather_ms, 'peak_source': peak_src},
+                         'algorithmic_bytes': algo_bytes, 'points': n_points, 'kernel_ms': gather_ms, 'peak_source': peak_src,
+                         'dram_achieved': GATHER_DRAM_TRAFFIC / (gather_ms * 1e-3) / 1e9, 'dram_frac': GATHER_DRAM_TRAFFIC / (gather_ms * 1e-3) / 1e9 / peak},
+            'roofline_tensor': {'bound': 'tensor', 'kernel': 'gemm_bf16_tn_persistent_kernel (mixing parameter generation, [%d x 256] x [256 x %d], %s)' % (Q, n_par, args.precision),
+                                'achieved': gemm_tflops, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': gemm_tflops / tensor_peak,
+                                'kernel_ms': gemm_ms, 'flops': gemm_flops, 'fp32_grade_tflops': gemm_tflops / products, 'peak_source': tensor_src,
+                                'note': 'bf16x3 issues three bf16 tensor-core products per fp32-grade product; the kernel is bound by L2->SM operand '
+                                        'traffic (~390 MB per launch), not by the tensor pipe'},
             'cpu_baseline': cpu,
             'breakdown_ms': breakdown}))
     if world > 1:
