@@ -35,7 +35,12 @@ extern "C" {
 int         sbev_abi_version(void);
 const char* sbev_last_error(void);
 /* Kernel-variant selectors for A/B measurements (process-wide; defaults from the environment):
- *   "gemm_impl"      0 = stream A and B tiles (default), 1 = A-resident schedule for small-K / many-N GEMMs (measured slower)
+ *   "gemm_impl"      0 = default: the fp32-output GEMM (sbev_gemm_bf16_tn, bf16x3, N % 256 == 0) runs as CTA pairs -- clusters of 2,
+ *                    tcgen05 cta_group::2, 256 x 256 units, each CTA loads its A rows and half of the B tile (a third less
+ *                    L2->SM operand traffic: 49 -> 39.5 us for the out-projection) -- while the bf16-pair-output GEMM
+ *                    (sbev_gemm_bf16_tn_split, K = 256) stays on single CTAs (pairs measured slower there);
+ *                    2 = CTA pairs for both; 3 = single CTAs for both; 1 = single CTAs + A-resident schedule for
+ *                    small-K / many-N GEMMs (measured slower)
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain

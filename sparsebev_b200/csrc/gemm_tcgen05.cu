@@ -74,6 +74,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA-pair (cta_group::2) flavours: the two CTAs of a cluster act as one 256-row MMA
+__device__ __forceinline__ uint32_t gemm_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void gemm_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_addr_of(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// commit: arrive (once all previously issued MMAs of the pair completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
@@ -131,13 +168,20 @@ struct GemmMapsV2 {
 // all 256 N-tiles.  Requires X3, split_k == 1, gridDim.x % m_tiles == 0; ARES_KB = number of resident k-blocks.
 // OUT_SPLIT: the epilogue stores C as a bf16 (hi, lo) pair (C ~= hi + lo) instead of fp32 -- the layout the mma.sync mix
 // kernel consumes by TMA, so the 118 MB parameter tensor is never re-converted.
-template <int BN, int STAGES, bool X3, int ARES_KB = 0, bool OUT_SPLIT = false>
+// PAIR: the kernel is launched in clusters of two CTAs that act as ONE tcgen05 "CTA pair" (cta_group::2): a work unit is a
+// 256 x BN output tile; CTA r of the pair owns rows [128 r, 128 r + 128) of it (its own TMEM accumulator lanes), loads
+// its 128 rows of A and HALF of the B tile (BN/2 rows) -- the tensor cores of both SMs read both halves -- so each SM
+// pulls a third less operand data through L2 per MMA.  Only the leader (rank 0) issues MMAs; TMA completions of both CTAs
+// count on the leader's "full" barrier, tcgen05.commit multicasts the "empty" / "accumulator full" arrivals to both CTAs,
+// and both epilogues report "accumulator drained" to the leader.
+template <int BN, int STAGES, bool X3, int ARES_KB = 0, bool OUT_SPLIT = false, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int total_kb, int split_k, int m_tiles, int n_tiles, int num_tiles,
                                const float* __restrict__ bias, float* __restrict__ C, int M, int N) {
     constexpr bool ARES = ARES_KB > 0;
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static_assert(!(PAIR && ARES_KB > 0), "the A-resident schedule has no CTA-pair form");
+    constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;      // PAIR: this CTA's half of the B tile
     constexpr int STAGE_BYTES = ARES ? 2 * B_BYTES : (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
     constexpr int ARES_BYTES = ARES_KB * 2 * A_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -153,16 +197,21 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? gemm_cta_rank() : 0u;                       // 0 = leader of the pair
+    const int unit_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // work-unit stream of this CTA (pair)
+    const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;                  // 256-row units per N-tile column
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 8 : 4); }
         mbar_init(&ares_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(&tmem_slot, 2 * BN); else tmem_alloc(&tmem_slot, 2 * BN); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) gemm_cluster_sync();          // both CTAs' barriers exist before any remote arrive / peer-counted TMA
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     pdl_wait();                 // barriers + TMEM are set up; from here on global memory is read (TMA) and written (epilogue)
@@ -193,10 +242,10 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                         tma_load_2d(st + B_BYTES, &maps.b_lo, &full_bar[stage], kb * GEMM_BK, nt * BN);
                     }
             } else
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % m_tiles) * GEMM_BM;
-                const int rest = tile / m_tiles;
-                const int n0 = (rest % n_tiles) * BN;
+            for (int tile = unit_id; tile < num_tiles; tile += unit_step) {
+                const int m0 = ((tile % m_units) * (PAIR ? 2 : 1) + (int)rank) * GEMM_BM;
+                const int rest = tile / m_units;
+                const int n0 = (rest % n_tiles) * BN + (PAIR ? (int)rank * (BN / 2) : 0);      // PAIR: this CTA's half of the B rows
                 const int z = rest / n_tiles;                       // split-K slice: k-blocks [z*total/split, (z+1)*total/split)
                 const int kb0 = (int)((long long)z * total_kb / split_k);
                 const int kb_cnt = (int)((long long)(z + 1) * total_kb / split_k) - kb0;
@@ -204,24 +253,36 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                     const int stage = it % STAGES;
                     mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     const int kc = (kb0 + kb) * GEMM_BK;
-                    tma_load_2d(st, &maps.a_hi, &full_bar[stage], kc, m0);
-                    tma_load_2d(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0);
-                    if (X3) {
-                        tma_load_2d(st + A_BYTES + B_BYTES, &maps.a_lo, &full_bar[stage], kc, m0);
-                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0);
+                    if (PAIR) {
+                        // the leader's barrier counts the bytes of BOTH CTAs' loads of this stage
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        const uint32_t lbar = cluster_addr_of(&full_bar[stage], 0);
+                        tma_load_2d_pair(st, &maps.a_hi, lbar, kc, m0);
+                        tma_load_2d_pair(st + A_BYTES, &maps.b_hi, lbar, kc, n0);
+                        if (X3) {
+                            tma_load_2d_pair(st + A_BYTES + B_BYTES, &maps.a_lo, lbar, kc, m0);
+                            tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, lbar, kc, n0);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(st, &maps.a_hi, &full_bar[stage], kc, m0);
+                        tma_load_2d(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0);
+                        if (X3) {
+                            tma_load_2d(st + A_BYTES + B_BYTES, &maps.a_lo, &full_bar[stage], kc, m0);
+                            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * GEMM_BM : GEMM_BM, BN);
             int it = 0, lt = 0;
             if (ARES) { mbar_wait(&ares_bar, 0); tc_fence_after(); }
             const int my_tiles = ARES ? (n_tiles - ares_n0 + ares_nstep - 1) / ares_nstep
-                                      : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                                      : (num_tiles - unit_id + unit_step - 1) / unit_step;
             for (; lt < my_tiles; ++lt) {
                 const int as = lt & 1;
                 mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
@@ -229,7 +290,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                 const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
                 int kb_cnt = total_kb;
                 if (!ARES) {
-                    const int z = (((int)blockIdx.x + lt * (int)gridDim.x) / m_tiles) / n_tiles;
+                    const int z = ((unit_id + lt * unit_step) / m_units) / n_tiles;
                     kb_cnt = (int)((long long)(z + 1) * total_kb / split_k) - (int)((long long)z * total_kb / split_k);
                 }
                 for (int kb = 0; kb < kb_cnt; ++kb, ++it) {
@@ -246,44 +307,57 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                         a_hi = umma_desc_k_sw128(st); b_hi = umma_desc_k_sw128(st + A_BYTES);
                         a_lo = umma_desc_k_sw128(st + A_BYTES + B_BYTES); b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES);
                     }
+                    auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+                        if (PAIR) umma_bf16_pair(tacc, a, b, idesc, acc); else umma_bf16(tacc, a, b, idesc, acc);
+                    };
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, (kb > 0 || k > 0) ? 1u : 0u);
                     if (X3) {
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) mma(a_hi + 2 * k, b_lo + 2 * k, 1u);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) mma(a_lo + 2 * k, b_hi + 2 * k, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                 }
-                umma_commit(&tmem_full_bar[as]);
+                if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
             }
         }
     } else {
         const int quarter = warp & 3;
         int lt = 0, chunk_ctr = 0;
         const int my_tiles = ARES ? (n_tiles - ares_n0 + ares_nstep - 1) / ares_nstep
-                                  : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                                  : (num_tiles - unit_id + unit_step - 1) / unit_step;
+        const uint32_t leader_empty0 = PAIR ? cluster_addr_of(&tmem_empty_bar[0], 0) : 0u;
+        const uint32_t leader_empty1 = PAIR ? cluster_addr_of(&tmem_empty_bar[1], 0) : 0u;
         for (; lt < my_tiles; ++lt) {
-            const int tile = ARES ? 0 : (int)blockIdx.x + lt * (int)gridDim.x;
-            const int m0 = ARES ? ares_m * GEMM_BM : (tile % m_tiles) * GEMM_BM;
-            const int rest = tile / m_tiles;
+            const int tile = ARES ? 0 : unit_id + lt * unit_step;
+            const int m0 = ARES ? ares_m * GEMM_BM : ((tile % m_units) * (PAIR ? 2 : 1) + (int)rank) * GEMM_BM;
+            const int rest = tile / m_units;
             const int n0 = ARES ? (ares_n0 + lt * ares_nstep) * BN : (rest % n_tiles) * BN;
             const int z = ARES ? 0 : rest / n_tiles;
             const int as = lt & 1;
             mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
             tc_fence_after();
             const bool add_bias = (bias != nullptr) && (z == 0);
-            uint8_t* my_stg = stg_base + (warp - 2) * 2 * 4096;
+            // staging per epilogue warp: 2 x 4 KB (fp32: alternating boxes; bf16 split: one hi / lo pair), or -- CTA-pair bf16
+            // split, whose smaller operand stages leave the room -- two hi / lo pairs so a store drains while the next box is built
+            constexpr int STG_PER_WARP = (OUT_SPLIT && PAIR) ? 4 : 2;
+            uint8_t* stg_warp = stg_base + (warp - 2) * STG_PER_WARP * 4096;
+            uint8_t* my_stg = stg_warp;
             if constexpr (OUT_SPLIT) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     float v[64];
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64), v);
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64 + 32), v + 32);
-                    // buffers 0 / 1 of this warp hold the hi / lo box; the previous pair of stores must have drained them
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    // the stores that last read this hi / lo buffer pair must have drained it
+                    if (PAIR) {
+                        my_stg = stg_warp + (c & 1) * 8192;          // BN / 64 is even: the alternation carries over from tile to tile
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    } else {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {                      // 8 chunks of 8 bf16 (16 B) per 128-byte row
@@ -340,13 +414,17 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+            if (lane == 0) {
+                if (PAIR) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(as ? leader_empty1 : leader_empty0) : "memory");
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // all output tiles written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+    if (PAIR) gemm_cluster_sync();          // no CTA frees TMEM / exits while its peer may still read its shared memory or signal it
+    if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // ------------------------------------------------------------------------------- host side
@@ -458,6 +536,41 @@ static int make_f32_store_map(CUtensorMap* out, const void* ptr, long long N, lo
 
 using namespace sbev;
 
+// Launch in clusters of two CTAs (one tcgen05 CTA pair per cluster), with the PDL attribute when enabled.
+template <typename... P, typename... A>
+static void launch_pair(void (*kernel)(P...), int clusters, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent schedule: no more clusters than can be resident at once (a GPC with a disabled SM leaves a TPC unpaired)
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> resident;
+    int max_clusters = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = resident.find((const void*)kernel);
+        if (it == resident.end()) {
+            cudaLaunchConfig_t probe = cfg;
+            probe.gridDim = dim3(2 * 74);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kernel, &probe) != cudaSuccess || n <= 0) { cudaGetLastError(); n = clusters; }
+            it = resident.emplace((const void*)kernel, n).first;
+        }
+        max_clusters = it->second;
+    }
+    if (clusters > max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+    cfg.numAttrs = get_option(OPT_PDL) ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+constexpr size_t GEMM_PAIR_SMEM = (size_t)3 * 2 * (GEMM_BM * GEMM_BK * 2 + 128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;   // 3 stages x {A, B/2} x {hi, lo}
+constexpr size_t GEMM_PAIR_SPLIT_SMEM = (size_t)2 * 2 * (GEMM_BM * GEMM_BK * 2 + 128 * GEMM_BK * 2) + 4 * 4 * 4096 + 1024;   // 2 stages + double-buffered (hi, lo) staging
+
 extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const* B, int nseg,
                                  const float* bias, int M, int N, int K, int split_k, float* C, void* stream) {
     SBEV_REQUIRE(A && B && C, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn: null pointer");
@@ -484,6 +597,24 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
                           (N / 128) >= 2 * (num_sms / m_tiles_pre);
         const bool wide = !ares && (N % 256 == 0);
         const int BNv = wide ? 256 : 128;
+        if (get_option(OPT_GEMM_IMPL) != 3 && get_option(OPT_GEMM_IMPL) != 1 && x3_pattern && wide && num_sms >= 2) {
+            // ---- CTA-pair (cta_group::2) schedule: 256 x 256 units, each CTA loads its A rows and half of the B tile
+            GemmMapsV2 mp;
+            int rc = make_bf16_map(&mp.a_hi, A[0], M, K, GEMM_BM);   if (rc) return rc;
+            rc = make_bf16_map(&mp.b_hi, B[0], N, K, 128);           if (rc) return rc;
+            rc = make_bf16_map(&mp.a_lo, A[2], M, K, GEMM_BM);       if (rc) return rc;
+            rc = make_bf16_map(&mp.b_lo, B[1], N, K, 128);           if (rc) return rc;
+            rc = make_f32_store_map(&mp.c, C, N, M, split_k);        if (rc) return rc;
+            const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
+            const int num_units = ((m_tiles + 1) / 2) * n_tiles * split_k;
+            const int clusters = num_units < num_sms / 2 ? num_units : num_sms / 2;
+            static std::once_flag once_pair;
+            std::call_once(once_pair, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, false, true>,
+                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SMEM); });
+            launch_pair(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, false, true>, clusters, GEMM_PAIR_SMEM, (cudaStream_t)stream,
+                        mp, K / GEMM_BK, split_k, m_tiles, n_tiles, num_units, bias, C, M, N);
+            return check_launch("sbev_gemm_bf16_tn(pair)");
+        }
         GemmMapsV2 mp;
         int rc = make_bf16_map(&mp.a_hi, A[0], M, K, GEMM_BM);            if (rc) return rc;
         rc = make_bf16_map(&mp.b_hi, B[0], N, K, BNv);                    if (rc) return rc;
@@ -527,17 +658,30 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     const void* ptrs[6] = {A_hi, A_lo, B_hi, B_lo, C_hi, C_lo};
     for (int i = 0; i < 6; ++i) SBEV_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: operands must be 16-byte aligned");
     SBEV_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: bias must be 16-byte aligned");
+    // CTA pairs only when forced: with K = 256 (four k-blocks per unit) the extra cross-SM hop per pipeline stage costs more
+    // than the saved operand traffic (measured 59.7 us vs 55.3 us for the parameter-generation GEMM)
+    const bool pair = get_option(OPT_GEMM_IMPL) == 2;
     GemmMapsV2 mp;
     int rc = make_bf16_map(&mp.a_hi, A_hi, M, K, GEMM_BM);   if (rc) return rc;
     rc = make_bf16_map(&mp.a_lo, A_lo, M, K, GEMM_BM);       if (rc) return rc;
-    rc = make_bf16_map(&mp.b_hi, B_hi, N, K, 256);           if (rc) return rc;
-    rc = make_bf16_map(&mp.b_lo, B_lo, N, K, 256);           if (rc) return rc;
+    rc = make_bf16_map(&mp.b_hi, B_hi, N, K, pair ? 128 : 256);   if (rc) return rc;
+    rc = make_bf16_map(&mp.b_lo, B_lo, N, K, pair ? 128 : 256);   if (rc) return rc;
     rc = make_bf16_store_map(&mp.c_hi, C_hi, N, M);          if (rc) return rc;
     rc = make_bf16_store_map(&mp.c_lo, C_lo, N, M);          if (rc) return rc;
     mp.c = mp.c_hi;
     static int num_sms = 0;
     if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
+    if (pair && num_sms >= 2) {
+        const int num_units = ((m_tiles + 1) / 2) * n_tiles;
+        const int clusters = num_units < num_sms / 2 ? num_units : num_sms / 2;
+        static std::once_flag once_pair;
+        std::call_once(once_pair, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SPLIT_SMEM); });
+        launch_pair(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>, clusters, GEMM_PAIR_SPLIT_SMEM, (cudaStream_t)stream,
+                    mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_units, bias, (float*)nullptr, M, N);
+        return check_launch("sbev_gemm_bf16_tn_split(pair)");
+    }
     const int num_tiles = m_tiles * n_tiles;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
     constexpr size_t smem = (size_t)2 * 2 * (GEMM_BM * GEMM_BK * 2 + 256 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;

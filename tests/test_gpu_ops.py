@@ -445,7 +445,7 @@ def test_gemm_bf16_single_segment(M, N, K, split_k, impl, option):
     _close(got, want.float(), rtol=1e-5, atol=1e-4 * np.sqrt(K / 64), what='bf16 gemm (exact products, fp32 accumulate)')
 
 
-@pytest.mark.parametrize('impl', [0, 1])       # 1 lets small-K / many-N shapes take the A-resident schedule
+@pytest.mark.parametrize('impl', [0, 1, 2, 3])    # 0 / 2: CTA pairs (cta_group::2) when N % 256 == 0; 1: single CTAs, A-resident for small K / many N; 3: single CTAs
 @pytest.mark.parametrize('M,N,K,split_k', [(900, 512, 256, 1), (900, 256, 4096, 8), (900, 384, 256, 1), (900, 8192, 256, 1), (130, 5120, 256, 1)])
 def test_gemm_bf16x3_is_fp32_grade(M, N, K, split_k, impl, option):
     option('gemm_impl', impl)
@@ -521,8 +521,11 @@ def test_reduce_ln_vs_torch(nsplit, M, N, ln):
     _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
 
 
-def test_gemm_split_output_and_tma_fed_mix():
-    """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path."""
+@pytest.mark.parametrize('impl', [0, 2])
+def test_gemm_split_output_and_tma_fed_mix(impl, option):
+    """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path (impl 2: CTA-pair GEMM, 0: single CTAs; M = 300 gives
+    an odd number of 128-row tiles, so the last pair's second CTA is entirely out of range)."""
+    option('gemm_impl', impl)
     ops = _ops()
     torch.manual_seed(3)
     M, N, K = 300, 4 * 8192, 256                       # 300 queries x 4 groups x (64*64 + 128*32) parameters
