@@ -200,6 +200,19 @@ int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbe
                          const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
                          void* stream);
 
+/* The same chain fed by the split-K partials of the preceding GEMM: its input rows are
+ *     x_out[row] = LayerNorm(sum_z partial[z][row] + bias + residual[row])        (ln_w/ln_b NULL: no LayerNorm)
+ * with partial [nsplit][M][K0], K0 = layers[0].K -- i.e. sbev_reduce_ln_fwd fused into the chain's prologue (one launch and
+ * one round trip of the [M, K0] activations less).  x_out [M][K0] is also stored (it is the residual of a later layer:
+ * AdaptiveMixing's out_proj + norm2 feeding the FFN, models/sparsebev_transformer.py:171-175).  Falls back to the two
+ * separate kernels when the tensor-core chain cannot take the layers or K0 is not 128 / 256.
+ */
+int sbev_dense_chain_reduce_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
+                                const float* ln_w, const float* ln_b, float* x_out,
+                                int M, int n_layers, const sbev_dense_layer* layers,
+                                const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                                void* stream);
+
 /* Sampling head epilogue: box decode + offset scaling + yaw rotation + softmax over levels.
  * Replaces make_sample_points (models/sparsebev_sampling.py:8-24), decode_bbox (models/bbox/utils.py:63-77),
  * rotation_3d_in_axis (models/utils.py:49-84) and the softmax at sparsebev_transformer.py:298-299.

@@ -31,6 +31,10 @@ struct ChainLayer {
 struct ChainParams {
     const float* x; int ldx, M, n_layers, act_ld; // act_ld: row stride (floats) of the shared activation buffers
     const float* aux_proposal; const float* aux_time_diff; int aux_Q, aux_T;   // SBEV_DENSE_REFINE epilogue
+    // optional input stage (tensor-core kernel only): the chain's input rows are
+    //   LN(sum_z in_partial[z][row] + in_bias + in_res[row])   (split-K partials of the preceding GEMM, [in_nsplit][M][K0])
+    // computed in the prologue and also stored to in_out [M][K0] (x / ldx are then unused)
+    const float* in_partial; int in_nsplit; const float* in_bias; const float* in_res; const float* in_ln_w; const float* in_ln_b; float* in_out;
     ChainLayer layer[CHAIN_MAX_LAYERS];
 };
 
@@ -316,6 +320,72 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     pdl_wait();
     pdl_trigger();
+    if (prm.in_partial != nullptr) {
+        // input stage: warp w reduces the split-K partials of row row0 + w (K0 = 128 or 256 columns: 1 or 2 float4 per lane),
+        // adds bias + residual, LayerNorms (two-pass, like torch), stores the fp32 row and stages it as bf16 (hi, lo)
+        if (warp < DENSE_ROWS) {
+            const int K0 = prm.layer[0].K, per = K0 >> 7;
+            const int row = row0 + warp;
+            const bool live = row < prm.M;
+            const long long zs = (long long)prm.M * K0;
+            float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+            const float* base = prm.in_partial + (long long)row * K0 + 4 * lane;
+            for (int z = 0; z < prm.in_nsplit; z += 6) {
+                float4 t[2][6];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+                        t[i][u] = (live && i < per && z + u < prm.in_nsplit) ? ldg4(base + 128 * i + (long long)(z + u) * zs) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) { acc[i].x += t[i][u].x; acc[i].y += t[i][u].y; acc[i].z += t[i][u].z; acc[i].w += t[i][u].w; }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < per) {
+                    const int n = 4 * lane + 128 * i;
+                    if (prm.in_bias) { const float4 b = ldg4(prm.in_bias + n); acc[i].x += b.x; acc[i].y += b.y; acc[i].z += b.z; acc[i].w += b.w; }
+                    if (prm.in_res && live) { const float4 r = ldg4(prm.in_res + (long long)row * K0 + n); acc[i].x += r.x; acc[i].y += r.y; acc[i].z += r.z; acc[i].w += r.w; }
+                    sum += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+                }
+            if (prm.in_ln_w != nullptr) {
+                const float mean = warp_sum(sum) / (float)K0;
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (i < per) {
+                        const float a = acc[i].x - mean, b = acc[i].y - mean, c = acc[i].z - mean, d = acc[i].w - mean;
+                        ss += (a * a + b * b) + (c * c + d * d);
+                    }
+                const float rstd = rsqrtf(warp_sum(ss) / (float)K0 + 1e-5f);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (i < per) {
+                        const int n = 4 * lane + 128 * i;
+                        const float4 g = ldg4(prm.in_ln_w + n), b = ldg4(prm.in_ln_b + n);
+                        acc[i].x = (acc[i].x - mean) * rstd * g.x + b.x; acc[i].y = (acc[i].y - mean) * rstd * g.y + b.y;
+                        acc[i].z = (acc[i].z - mean) * rstd * g.z + b.z; acc[i].w = (acc[i].w - mean) * rstd * g.w + b.w;
+                    }
+            }
+            __nv_bfloat16* xh = xbuf + warp * MC_XLD;
+            __nv_bfloat16* xl = xh + DENSE_ROWS * MC_XLD;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < per) {
+                    const int n = 4 * lane + 128 * i;
+                    const float4 v = live ? acc[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && prm.in_out) *reinterpret_cast<float4*>(prm.in_out + (long long)row * K0 + n) = v;
+                    uint32_t h0, l0, h1, l1;
+                    mc_split2(v.x, v.y, h0, l0); mc_split2(v.z, v.w, h1, l1);
+                    *reinterpret_cast<uint2*>(xh + n) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(xl + n) = make_uint2(l0, l1);
+                }
+        }
+        __threadfence_block();             // in_out rows are re-read by this CTA (residual of a later layer)
+    } else
     // stage the input rows as bf16 (hi, lo), zero-padded to the first layer's K rounded up to 64
     {
         const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
@@ -617,15 +687,22 @@ refine_bbox_kernel(const float* __restrict__ proposal, const float* __restrict__
 
 using namespace sbev;
 
-extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
-                                    const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
-                                    void* stream) {
-    SBEV_REQUIRE(x && layers, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
+struct ChainInputReduce { const float* partial; int nsplit; const float* bias; const float* residual; const float* ln_w; const float* ln_b; float* out; };
+
+static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in, int M, int n_layers, const sbev_dense_layer* layers,
+                            const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                            void* stream) {
+    SBEV_REQUIRE((x || in) && layers, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
     SBEV_REQUIRE(n_layers >= 1 && n_layers <= CHAIN_MAX_LAYERS, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_fwd: 1..%d layers", CHAIN_MAX_LAYERS);
     SBEV_REQUIRE(M >= 0 && ldx >= layers[0].K, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: bad sizes");
     ChainParams prm;
     bool use_mma = get_option(OPT_DENSE_IMPL) == 0;
     prm.x = x; prm.ldx = ldx; prm.M = M; prm.n_layers = n_layers;
+    prm.in_partial = nullptr; prm.in_nsplit = 0; prm.in_bias = prm.in_res = prm.in_ln_w = prm.in_ln_b = nullptr; prm.in_out = nullptr;
+    if (in) {
+        prm.in_partial = in->partial; prm.in_nsplit = in->nsplit; prm.in_bias = in->bias; prm.in_res = in->residual;
+        prm.in_ln_w = in->ln_w; prm.in_ln_b = in->ln_b; prm.in_out = in->out;
+    }
     prm.aux_proposal = refine_proposal; prm.aux_time_diff = refine_time_diff; prm.aux_Q = refine_Q > 0 ? refine_Q : 1; prm.aux_T = refine_T;
     int act = 4;
     for (int i = 0; i < n_layers; ++i) {
@@ -699,6 +776,7 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
         }
         return check_launch("sbev_dense_chain_fwd(mma)");
     }
+    SBEV_REQUIRE(in == nullptr, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_reduce_fwd: the fused input stage needs the tensor-core chain");
     for (int i = 0; i < n_layers; ++i)
         SBEV_REQUIRE(layers[i].Wt != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: fp32 weight missing for the FFMA path", i);
     const size_t smem = sizeof(float) * ((size_t)CHAIN_STAGES * CHAIN_STAGE_FLOATS + 2 * (size_t)DENSE_ROWS * prm.act_ld);
@@ -706,6 +784,40 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
     std::call_once(once, [] { cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     dense_chain_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 256, smem, (cudaStream_t)stream>>>(prm);
     return check_launch("sbev_dense_chain_fwd");
+}
+
+extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                                    const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                                    void* stream) {
+    SBEV_REQUIRE(x != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
+    return dense_chain_impl(x, ldx, nullptr, M, n_layers, layers, refine_proposal, refine_time_diff, refine_Q, refine_T, stream);
+}
+
+extern "C" int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
+                                  const float* ln_w, const float* ln_b, int M, int N, float* out, void* stream);
+
+extern "C" int sbev_dense_chain_reduce_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
+                                           const float* ln_w, const float* ln_b, float* x_out,
+                                           int M, int n_layers, const sbev_dense_layer* layers,
+                                           const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                                           void* stream) {
+    SBEV_REQUIRE(partial && x_out && layers && nsplit >= 1, SBEV_ERR_INVALID, "sbev_dense_chain_reduce_fwd: bad arguments");
+    SBEV_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_reduce_fwd: ln_w and ln_b go together");
+    SBEV_REQUIRE(n_layers >= 1 && n_layers <= CHAIN_MAX_LAYERS, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_reduce_fwd: 1..%d layers", CHAIN_MAX_LAYERS);
+    const int K0 = layers[0].K;
+    bool fusable = get_option(OPT_DENSE_IMPL) == 0 && (K0 == 128 || K0 == 256);
+    for (int i = 0; i < n_layers; ++i)
+        if (layers[i].W_hi == nullptr || layers[i].W_lo == nullptr || layers[i].K > 512 || layers[i].N > 1024) fusable = false;
+    const void* al[5] = {partial, bias, residual, ln_w, ln_b};
+    for (int i = 0; i < 5; ++i) SBEV_REQUIRE((reinterpret_cast<uintptr_t>(al[i]) & 15) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_reduce_fwd: operands must be 16-byte aligned");
+    SBEV_REQUIRE((reinterpret_cast<uintptr_t>(x_out) & 15) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_reduce_fwd: x_out must be 16-byte aligned");
+    if (!fusable) {                              // same result in two launches (fp32 FFMA chain, or an input width the fused stage does not cover)
+        int rc = sbev_reduce_ln_fwd(partial, nsplit, bias, residual, ln_w, ln_b, M, K0, x_out, stream);
+        if (rc) return rc;
+        return dense_chain_impl(x_out, K0, nullptr, M, n_layers, layers, refine_proposal, refine_time_diff, refine_Q, refine_T, stream);
+    }
+    const ChainInputReduce in{partial, nsplit, bias, residual, ln_w, ln_b, x_out};
+    return dense_chain_impl(nullptr, K0, &in, M, n_layers, layers, refine_proposal, refine_time_diff, refine_Q, refine_T, stream);
 }
 
 extern "C" int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const float* bias,

@@ -237,6 +237,20 @@ def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, 
                                             refine_Q, refine_T, _stream()), 'sbev_dense_chain_fwd')
 
 
+def dense_chain_reduce(partial, bias, residual, ln_w, ln_b, x_out, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):
+    """dense_chain whose input rows are LN(sum_z partial[z] + bias + residual) (sbev_dense_chain_reduce_fwd): the split-K
+    reduce + norm of the preceding GEMM runs in the chain's prologue.  partial [S,M,K0]; x_out [M,K0] receives the input rows."""
+    lib = _lib.load()
+    partial = _chk(partial, 'partial')
+    S, M, K0 = partial.shape
+    _chk(x_out, 'x_out')
+    arr = (_lib.DenseLayer * len(layers))(*[l[0] for l in layers])
+    with torch.cuda.device(partial.device):
+        _lib.check(lib.sbev_dense_chain_reduce_fwd(partial.data_ptr(), S, _p(bias), _p(residual), _p(ln_w), _p(ln_b), x_out.data_ptr(),
+                                                   M, len(layers), arr, _p(refine_proposal), _p(refine_time_diff), refine_Q, refine_T,
+                                                   _stream()), 'sbev_dense_chain_reduce_fwd')
+
+
 def dense(x, wt, ldw, n_out, bias=None, ln_w=None, ln_b=None, residual=None, relu=False, res_pre_ln=False, out=None, k=None):
     """y[M,N] = epilogue(x[M,K] @ W^T) with W given pre-transposed (see DenseWeight)."""
     lib = _lib.load()

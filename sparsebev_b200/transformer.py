@@ -13,7 +13,7 @@ Same class names, constructor kwargs, call signatures, side effects and state-di
     AdaptiveMixing                  :320-387
 
 The nn.Modules only HOLD parameters (so names/shapes match the checkpoint); every forward runs the
-hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- 12 launches per layer, capturable in one
+hand-written sm_100a kernels in libsparsebev_b200.so through `ops` -- 11 launches per layer, capturable in one
 CUDA graph (bench.py does).  Forward only: this
 is the eval path (dropout = identity, no activation checkpointing); training the decoder through these
 modules is out of scope (the op-level autograd Functions in `wrapper.py` do have a backward).
@@ -136,8 +136,10 @@ class AdaptiveMixing(nn.Module):
         ops.gemm_bf16_tn(a, b, M, self.n_groups * self.total_parameters, D, bias=self.parameter_generator.bias, out=buf['params'])
         return buf['params']
 
-    def mix_and_project(self, params, x, q2, norm=None):
-        """Stages 2+3: per-(query, group) mixing, out_proj (split-K tcgen05) and the fused reduce + residual + LayerNorm."""
+    def mix_and_project(self, params, x, q2, norm=None, defer_reduce=False):
+        """Stages 2+3: per-(query, group) mixing, out_proj (split-K tcgen05) and the fused reduce + residual + LayerNorm.
+        defer_reduce: return the split-K partials and the reduce operands instead (dict for ops.dense_chain_reduce), so the
+        caller's next dense chain performs the reduce + norm in its prologue."""
         M, G, P, C = x.shape
         D = self.query_dim
         if isinstance(params, tuple):
@@ -149,6 +151,9 @@ class AdaptiveMixing(nn.Module):
         a, b = ([y_hi, y_hi, y_lo], [o_hi, o_lo, o_hi]) if self.precision == 'bf16x3' else ([y_hi], [o_hi])
         split_k = max(1, min(self.split_k, K2 // 64))
         partial = ops.gemm_bf16_tn(a, b, M, D, K2, split_k=split_k)
+        if defer_reduce:
+            return dict(partial=partial if partial.dim() == 3 else partial[None], bias=self.out_proj.bias, residual=q2,
+                        ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
         return ops.reduce_ln(partial, bias=self.out_proj.bias, residual=q2,
                              ln_w=None if norm is None else norm.weight, ln_b=None if norm is None else norm.bias)
 
@@ -363,8 +368,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        12 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
-        that follow), SASA core, sample_points, fused gather, 2 tcgen05 GEMMs, mix, split-K reduce + norm2; the gather runs
+        11 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
+        that follow; the FFN chain's prologue performs the mixing stage's split-K reduce + norm2), SASA core, sample_points,
+        fused gather, 2 tcgen05 GEMMs, mix; the gather runs
         concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
         M, dev = B * Q, query_feat.device
@@ -397,22 +403,26 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas)
         # (4b) adaptive mixing (+ identity + norm2)
         G, P = self.mixing.n_groups, self.mixing.in_points
-        q3 = self.mixing.mix_and_project(params, sampled.reshape(M, G, P, -1), q2, self.norm2)
-        # (5) FFN (+ identity + norm3); then classification and regression branches side by side
-        q4, cls_score, bbox_pred = new(D), new(self.num_classes), new(self.code_size)
+        red = self.mixing.mix_and_project(params, sampled.reshape(M, G, P, -1), q2, self.norm2, defer_reduce=True)
+        # (5) FFN (+ identity + norm3), its prologue finishing the mixing stage (split-K reduce + out_proj bias + identity + norm2
+        #     -> q3); then classification and regression branches side by side
+        q3, q4, cls_score, bbox_pred = new(D), new(D), new(self.num_classes), new(self.code_size)
+
+        def ffn(chain):
+            ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, chain)
         td = img_metas[0]['time_diff']
         cls_chain = [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
         reg_chain = [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
         ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
         if side is not None:
-            ops.dense_chain(q3, D, M, ffn_chain)
+            ffn(ffn_chain)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ops.dense_chain(q4, D, M, reg_chain, refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
             ops.dense_chain(q4, D, M, cls_chain)
             main.wait_stream(side)
         else:
-            ops.dense_chain(q3, D, M, ffn_chain + cls_chain)
+            ffn(ffn_chain + cls_chain)
             ops.dense_chain(q4, D, M, reg_chain, refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
         return q4.reshape(B, Q, D), cls_score.reshape(B, Q, self.num_classes), bbox_pred.reshape(B, Q, self.code_size)
 

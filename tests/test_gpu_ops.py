@@ -376,6 +376,40 @@ def test_dense_chain_vs_torch(impl, option):
     _close(y776, w776, rtol=1e-4, atol=atol, what='N=776 layer')
 
 
+@pytest.mark.parametrize('impl,K0,nsplit,ln', [(0, 256, 18, True), (0, 128, 5, True), (0, 256, 1, False), (1, 256, 7, True), (0, 192, 3, True)])
+def test_dense_chain_with_fused_splitk_reduce(impl, K0, nsplit, ln, option):
+    """sbev_dense_chain_reduce_fwd: input rows = LN(sum_z partial + bias + residual), FFN-like chain behind it (impl 1 and
+    K0 = 192 take the documented two-launch fallback)."""
+    option('dense_impl', impl)
+    ops = _ops()
+    torch.manual_seed(5)
+    M = 901
+    part, bias, res = torch.randn(nsplit, M, K0), torch.randn(K0), torch.randn(M, K0)
+    norm_in = torch.nn.LayerNorm(K0)
+    torch.nn.init.normal_(norm_in.weight, 1, 0.1); torch.nn.init.normal_(norm_in.bias, 0, 0.1)
+    lin = [torch.nn.Linear(K0, 512), torch.nn.Linear(512, K0)]
+    norm_out = torch.nn.LayerNorm(K0)
+    with torch.no_grad():
+        x_in = part.sum(0) + bias + res
+        if ln:
+            x_in = norm_in(x_in)
+        want = norm_out(x_in + lin[1](torch.relu(lin[0](x_in))))
+    import copy
+    mods = [copy.deepcopy(m).to(dev()) for m in lin]
+    caches = [ops.DenseWeight() for _ in lin]
+    nin, nout = copy.deepcopy(norm_in).to(dev()), copy.deepcopy(norm_out).to(dev())
+    x_out, y = torch.empty(M, K0, device=dev()), torch.empty(M, K0, device=dev())
+
+    def entry(i, **kw):
+        wt, ldw, b = caches[i].get_with_bias([mods[i].weight], [mods[i].bias])
+        return ops.chain_layer(wt, ldw, mods[i].in_features, mods[i].out_features, bias=b, w_hi=caches[i].w_hi, w_lo=caches[i].w_lo,
+                               kpad=caches[i].kpad, **kw)
+    ops.dense_chain_reduce(part.to(dev()), bias.to(dev()), res.to(dev()), nin.weight if ln else None, nin.bias if ln else None, x_out,
+                           [entry(0, relu=True), entry(1, ln=nout, residual=x_out, res_pre_ln=True, y=y)])
+    _close(x_out, x_in, rtol=1e-4, atol=1e-5, what='fused split-K reduce + LN (chain input)')
+    _close(y, want, rtol=1e-4, atol=2e-5 if impl == 1 else 1e-4, what='chain behind the fused reduce')
+
+
 def test_sample_points_and_refine_vs_oracle():
     ops = _ops()
     pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
