@@ -46,11 +46,17 @@ const char* sbev_last_error(void);
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
  *   "dense_cluster"  0 = every CTA streams its own weight tiles (default); 2 / 4 / 8 = that many CTAs (row groups) form a
  *                    cluster and share every weight tile by TMA multicast (8 measured slower: lock step)
+ *   "dense_nsplit"   0 = off; 2 / 4 = N-split cluster chain: that many CTAs form a cluster that owns 16 / 32 rows and SPLIT
+ *                    every layer's output features (each streams 1/2 / 1/4 of the weights), exchanging the layer outputs
+ *                    through distributed shared memory; chains it cannot express (an inner layer wider than 512 ...) take
+ *                    the "dense_impl" 0 kernel
  *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
  *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default) */
 int         sbev_set_option(const char* name, int value);
+/* current value of an option (the environment / built-in default until sbev_set_option overrides it); -1 = unknown name */
+int         sbev_get_option(const char* name);
 
 /* ---------------------------------------------------------------------------------------------
  * msmv_sampling forward.

@@ -61,7 +61,7 @@ _lib = None
 
 
 def exported_symbols():
-    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error'])
+    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option'])
 
 
 def load():
@@ -74,8 +74,13 @@ def load():
             'sparsebev_b200: %s not found. Build it with `python -m sparsebev_b200.build` '
             '(or `python -c "import __graft_entry__ as g; g.build()"`). There is no CPU / eager fallback.' % SO_PATH)
     lib = ctypes.CDLL(SO_PATH)
+    missing = [n for n in exported_symbols() if not hasattr(lib, n)]
+    if missing:         # a stale build of an older source tree
+        raise RuntimeError('sparsebev_b200: %s lacks %s -- rebuild it (`python sparsebev_b200/build.py -f`)' % (SO_PATH, ', '.join(missing)))
     lib.sbev_abi_version.restype = c_int
     lib.sbev_last_error.restype = ctypes.c_char_p
+    lib.sbev_get_option.argtypes = [ctypes.c_char_p]
+    lib.sbev_get_option.restype = c_int
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -91,6 +96,13 @@ def set_option(name, value):
     rc = load().sbev_set_option(name.encode(), int(value))
     if rc != 0:
         raise RuntimeError('sbev_set_option(%s) failed' % name)
+
+
+def get_option(name):
+    v = load().sbev_get_option(name.encode())
+    if v < 0:
+        raise RuntimeError('sbev_get_option(%s): unknown option' % name)
+    return v
 
 
 def check(rc, what):

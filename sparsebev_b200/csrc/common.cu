@@ -16,10 +16,10 @@ void set_error(const char* fmt, ...) {
 
 // Implementation selectors (A/B testing of kernel variants).  Defaults come from the environment
 // (SBEV_GEMM_IMPL, SBEV_MIX_IMPL, SBEV_SASA_IMPL, SBEV_GATHER_VARIANT), sbev_set_option overrides.
-static const char* kOptNames[OPT_COUNT] = {"gemm_impl", "mix_impl", "sasa_impl", "gather_variant", "dense_impl", "dense_cluster", "pdl"};
-static const char* kOptEnv[OPT_COUNT] = {"SBEV_GEMM_IMPL", "SBEV_MIX_IMPL", "SBEV_SASA_IMPL", "SBEV_GATHER_VARIANT", "SBEV_DENSE_IMPL", "SBEV_DENSE_CLUSTER", "SBEV_PDL"};
-static const int kOptDefault[OPT_COUNT] = {0, 0, 0, 2, 0, 0, 1};
-static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1};
+static const char* kOptNames[OPT_COUNT] = {"gemm_impl", "mix_impl", "sasa_impl", "gather_variant", "dense_impl", "dense_cluster", "pdl", "dense_nsplit"};
+static const char* kOptEnv[OPT_COUNT] = {"SBEV_GEMM_IMPL", "SBEV_MIX_IMPL", "SBEV_SASA_IMPL", "SBEV_GATHER_VARIANT", "SBEV_DENSE_IMPL", "SBEV_DENSE_CLUSTER", "SBEV_PDL", "SBEV_DENSE_NSPLIT"};
+static const int kOptDefault[OPT_COUNT] = {0, 0, 0, 2, 0, 0, 1, 0};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1};
 
 int get_option(int id) {
     if (g_opt[id] < 0) {
@@ -38,6 +38,12 @@ int set_option(const char* name, int value) {
 
 extern "C" int sbev_abi_version(void) { return 1; }
 extern "C" const char* sbev_last_error(void) { return sbev::g_err; }
+extern "C" int sbev_get_option(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < sbev::OPT_COUNT; ++i)
+        if (strcmp(name, sbev::kOptNames[i]) == 0) return sbev::get_option(i);
+    return -1;
+}
 extern "C" int sbev_set_option(const char* name, int value) {
     if (!name || value < 0) { sbev::set_error("sbev_set_option: bad arguments"); return SBEV_ERR_INVALID; }
     return sbev::set_option(name, value);

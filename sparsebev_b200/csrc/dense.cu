@@ -535,6 +535,416 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     if (CL > 1) cluster_sync_all();
 }
 
+// ------------------------------------------------------------------------------------------------
+// N-split cluster chain (option dense_nsplit = 2 | 4).  The kernels above give every CTA 8 rows and make it stream ALL
+// the weights of the chain (3.9 MB per row group and decoder layer, x 113 CTAs = 440 MB of L2->SM traffic): that stream,
+// not the math, is what they wait for.  Here a cluster of CL CTAs owns R = 8*CL rows and splits every layer's OUTPUT
+// FEATURES: CTA r computes the FB = 256/CL-wide feature blocks r, r+CL, ... for all R rows, so it streams 1/CL of the
+// weights and every weight byte leaves L2 once per R rows instead of once per 8.  Rows sit on the MMA N dimension as
+// before (two n8 tiles per warp, so each A = weight fragment is used twice); warp w owns m16 tile w % MB of the block
+// and rows 16*(w / MB) .. +15.
+//   Exchange: a CTA adds bias (+ the pre-LN residual) to its slice, writes it to its own ys[R][N] (fp32) and pushes it
+// with 16-byte st.shared::cluster stores into the ys of its CL-1 peers.  Hand-over is by two cluster-scope mbarriers per
+// CTA, each expecting one arrival per warp of the cluster: ys_full (all slices of the layer have landed; waited with
+// acquire.cluster before the row epilogue) and ys_free (every CTA finished reading the previous layer's ys; waited
+// before the next push, normally long satisfied).  Every CTA then runs the row epilogue (LayerNorm over the full row,
+// ReLU, post-LN residual) for all R rows redundantly -- a few hundred cycles, and it leaves the next layer's bf16
+// (hi, lo) operand in local shared memory without a second exchange -- while global outputs of row r are written by
+// CTA r / 8 only.  A last layer without LayerNorm needs no full rows: each CTA finishes and stores its own feature
+// blocks ("slice mode": in-projection + tau, sampling heads, cls / reg outputs, refine).
+//   The dedicated producer warp never takes part in the hand-over (mbarriers, not barrier.cluster), so weight tiles of
+// the following layers keep streaming while the consumers exchange: the ring is refilled from the moment a stage drains.
+template <int CL>
+struct NsCfg {
+    static constexpr int R = 8 * CL;                 // rows per cluster
+    static constexpr int FB = 256 / CL;              // features per weight block (TMA box rows)
+    static constexpr int MB = FB / 16;               // m16 tiles per block
+    static constexpr int STAGES = CL == 4 ? 6 : 4;
+    static constexpr int TILE_BYTES = FB * 128;      // one (hi or lo) FB x 64 bf16 tile, 128-byte swizzled rows
+    static constexpr int XLD = 512 + 8;              // bf16 row stride of the activation operand (K <= 512)
+    static constexpr int YLD = 512 + 4;              // fp32 row stride of ys (exchanged layers: N <= 512)
+    static constexpr size_t SMEM = (size_t)STAGES * 2 * TILE_BYTES + (size_t)2 * R * XLD * 2 + (size_t)R * YLD * 4 + 1024;
+};
+
+__device__ __forceinline__ void ns_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(dsmem_u32(bar)), "r"(parity) : "memory");
+        if (!done && spins > (1u << 26)) __trap();
+    }
+}
+// one arrival (release, cluster scope) on the copy of `bar` that lives in CTA `rank` of the cluster
+__device__ __forceinline__ void ns_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(dsmem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ uint32_t ns_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    return remote;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(288, 1)
+dense_chain_ns_kernel(const __grid_constant__ ChainParams prm, const __grid_constant__ ChainMaps maps) {
+    using C = NsCfg<CL>;
+    constexpr int R = C::R, FB = C::FB, MB = C::MB, STAGES = C::STAGES, TILE = C::TILE_BYTES, XLD = C::XLD, YLD = C::YLD;
+    extern __shared__ uint8_t ns_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ns_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wring = smem;                                                                  // [STAGES][hi tile | lo tile]
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(smem + STAGES * 2 * TILE);         // [R][XLD]
+    __nv_bfloat16* xl = xh + R * XLD;                                                       // [R][XLD]
+    float* ys = reinterpret_cast<float*>(xl + R * XLD);                                     // [R][YLD]
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], ys_full, ys_free, xin_bar;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int row0 = (blockIdx.x / CL) * R;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&full_bar[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&empty_bar[s])), "r"(8));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&ys_full)), "r"(8 * CL));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&ys_free)), "r"(8 * CL));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&xin_bar)), "r"(8 * CL));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();                 // every CTA's mbarriers exist before any remote arrive / store (no global access yet)
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 8) {
+        // ---- producer warp: this CTA's weight tiles of every layer, in consumption order
+        if (lane == 0) {
+            int it = 0;
+            for (int li = 0; li < prm.n_layers; ++li) {
+                const ChainLayer& L = prm.layer[li];
+                const int kchunks = (L.K + 63) >> 6, nblk = (L.N + FB - 1) / FB;
+                for (int gb = (int)crank; gb < nblk; gb += CL)
+                    for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                        const int stage = it % STAGES;
+                        if (it >= STAGES) chain_mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
+                        uint8_t* dst = wring + stage * 2 * TILE;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(&full_bar[stage])), "r"(2 * TILE) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(dsmem_u32(dst)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(gb * FB) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(dsmem_u32(dst + TILE)), "l"(&maps.lo[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(gb * FB) : "memory");
+                    }
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();             // matches the consumers' final cluster barrier
+        return;
+    }
+
+    // ---- consumers (warps 0..7)
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int lm_r = lane & 7, lm_id = lane >> 3;
+    const int mt = warp % MB, rg = warp / MB;                           // m16 tile of the block, 16-row group
+    const int a_row = 16 * mt + lm_r + 8 * (lm_id & 1);                 // weight-tile row this lane addresses (ldmatrix.x4)
+    const int a_chunk = lm_id >> 1;
+    const int b_row = 16 * rg + 8 * (lm_id >> 1) + lm_r;                // activation row this lane addresses (ldmatrix.x4: two n8 tiles)
+    const uint32_t xh_addr = dsmem_u32(xh + b_row * XLD + 8 * (lm_id & 1));
+    const uint32_t xl_addr = dsmem_u32(xl + b_row * XLD + 8 * (lm_id & 1));
+    const uint32_t ys_u32 = dsmem_u32(ys), xh_u32 = dsmem_u32(xh), xl_u32 = dsmem_u32(xl);
+
+    // ---- input stage
+    if (prm.in_partial != nullptr) {
+        // warp w of CTA r reduces the split-K partials of row 8r + w (K0 = 128 or 256), adds bias + residual, LayerNorms
+        // (two-pass, like torch), stores the fp32 row and pushes it as bf16 (hi, lo) into the operand buffer of every CTA
+        const int K0 = prm.layer[0].K, per = K0 >> 7;
+        const int lr = 8 * (int)crank + warp;
+        const int row = row0 + lr;
+        const bool live = row < prm.M;
+        const long long zs = (long long)prm.M * K0;
+        float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        const float* base = prm.in_partial + (long long)row * K0 + 4 * lane;
+        for (int z = 0; z < prm.in_nsplit; z += 6) {
+            float4 t[2][6];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    t[i][u] = (live && i < per && z + u < prm.in_nsplit) ? ldg4(base + 128 * i + (long long)(z + u) * zs) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int u = 0; u < 6; ++u) { acc[i].x += t[i][u].x; acc[i].y += t[i][u].y; acc[i].z += t[i][u].z; acc[i].w += t[i][u].w; }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (i < per) {
+                const int n = 4 * lane + 128 * i;
+                if (prm.in_bias) { const float4 b = ldg4(prm.in_bias + n); acc[i].x += b.x; acc[i].y += b.y; acc[i].z += b.z; acc[i].w += b.w; }
+                if (prm.in_res && live) { const float4 r = ldg4(prm.in_res + (long long)row * K0 + n); acc[i].x += r.x; acc[i].y += r.y; acc[i].z += r.z; acc[i].w += r.w; }
+                sum += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+            }
+        if (prm.in_ln_w != nullptr) {
+            const float mean = warp_sum(sum) / (float)K0;
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < per) {
+                    const float a = acc[i].x - mean, b = acc[i].y - mean, c = acc[i].z - mean, d = acc[i].w - mean;
+                    ss += (a * a + b * b) + (c * c + d * d);
+                }
+            const float rstd = rsqrtf(warp_sum(ss) / (float)K0 + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < per) {
+                    const int n = 4 * lane + 128 * i;
+                    const float4 g = ldg4(prm.in_ln_w + n), b = ldg4(prm.in_ln_b + n);
+                    acc[i].x = (acc[i].x - mean) * rstd * g.x + b.x; acc[i].y = (acc[i].y - mean) * rstd * g.y + b.y;
+                    acc[i].z = (acc[i].z - mean) * rstd * g.z + b.z; acc[i].w = (acc[i].w - mean) * rstd * g.w + b.w;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (i < per) {
+                const int n = 4 * lane + 128 * i;
+                const float4 v = live ? acc[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && prm.in_out) *reinterpret_cast<float4*>(prm.in_out + (long long)row * K0 + n) = v;
+                uint32_t h0, l0, h1, l1;
+                mc_split2(v.x, v.y, h0, l0); mc_split2(v.z, v.w, h1, l1);
+                const uint32_t off = (uint32_t)((lr * XLD + n) * 2);
+#pragma unroll
+                for (int p = 0; p < CL; ++p) {
+                    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(ns_mapa(xh_u32 + off, p)), "r"(h0), "r"(h1) : "memory");
+                    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(ns_mapa(xl_u32 + off, p)), "r"(l0), "r"(l1) : "memory");
+                }
+            }
+        // the in_out rows are re-read by OTHER CTAs of the cluster (pre-LN residual of a later layer, L2 loads): the
+        // release below orders the global stores too
+        __syncwarp();
+        if (lane < CL) ns_arrive_remote(&xin_bar, lane);
+        ns_wait_cluster(&xin_bar, 0);
+    } else {
+        // every CTA stages all R input rows as bf16 (hi, lo), zero-padded to the first layer's K rounded up to 64
+        const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
+        for (int i = tid; i < R * (K0p / 2); i += 256) {
+            const int r = i / (K0p / 2), k = (i - r * (K0p / 2)) * 2;
+            const bool ok = row0 + r < prm.M;
+            const float a = (ok && k < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k) : 0.f;
+            const float b = (ok && k + 1 < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k + 1) : 0.f;
+            uint32_t h, l;
+            mc_split2(a, b, h, l);
+            *reinterpret_cast<uint32_t*>(xh + r * XLD + k) = h;
+            *reinterpret_cast<uint32_t*>(xl + r * XLD + k) = l;
+        }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    int it = 0, ex = 0;                  // weight tiles consumed; exchanged layers completed
+    for (int li = 0; li < prm.n_layers; ++li) {
+        const ChainLayer& L = prm.layer[li];
+        const int N = L.N;
+        const int kchunks = (L.K + 63) >> 6, nblk = (N + FB - 1) / FB;
+        const bool last = li + 1 == prm.n_layers;
+        const bool exchange = !(last && L.ln_w == nullptr);
+        const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
+        int bi = 0;
+        for (int gb = (int)crank; gb < nblk; gb += CL, ++bi) {
+            // D fragment of n8 tile j: (feature f0 [+8], row r0 + 8j [+1])
+            const int f0 = gb * FB + 16 * mt + g8;
+            const int r0 = 16 * rg + 2 * t4;
+            float pre[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = f0 + 8 * (i >> 1), r = row0 + r0 + 8 * j + (i & 1);
+                    float v = (L.bias != nullptr && f < N) ? __ldg(L.bias + f) : 0.f;
+                    if (pre_res && f < N && r < prm.M) v += __ldcg(L.residual + (long long)r * N + f);
+                    pre[j][i] = v;
+                }
+            float acc[2][2][2][4];       // [k-step parity][main | cross][n8 tile][fragment]: 8 independent accumulator chains
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[a][b][j][i] = 0.f;
+            for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                const int stage = it % STAGES;
+                chain_mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                const uint32_t wh = dsmem_u32(wring + stage * 2 * TILE) + a_row * 128;
+                const uint32_t wl = wh + TILE;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t ah[4], al[4], bh[4], bl[4];
+                    const uint32_t sw = (uint32_t)(((2 * ks + a_chunk) ^ (a_row & 7)) << 4);      // TMA 128-byte swizzle
+                    mc_ldsm_x4(ah, wh + sw);
+                    mc_ldsm_x4(al, wl + sw);
+                    const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
+                    mc_ldsm_x4(bh, xh_addr + xo);
+                    mc_ldsm_x4(bl, xl_addr + xo);
+                    const uint32_t bh0[2] = {bh[0], bh[1]}, bh1[2] = {bh[2], bh[3]}, bl0[2] = {bl[0], bl[1]}, bl1[2] = {bl[2], bl[3]};
+                    mc_mma(acc[ks & 1][0][0], ah, bh0); mc_mma(acc[ks & 1][0][1], ah, bh1);
+                    mc_mma(acc[ks & 1][1][0], al, bh0); mc_mma(acc[ks & 1][1][1], al, bh1);
+                    mc_mma(acc[ks & 1][1][0], ah, bl0); mc_mma(acc[ks & 1][1][1], ah, bl1);
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");
+            }
+            // own slice (+ bias + pre-LN residual) -> local ys; exchanged layers index ys by global feature, slice mode by own block
+            const int c0 = exchange ? f0 : bi * FB + 16 * mt + g8;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = ((acc[0][1][j][i] + acc[1][1][j][i]) + (acc[0][0][j][i] + acc[1][0][j][i])) + pre[j][i];
+                    ys[(r0 + 8 * j + (i & 1)) * YLD + c0 + 8 * (i >> 1)] = v;
+                }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        if (!exchange) {
+            // ---- slice mode: finish and store this CTA's feature blocks (elementwise epilogue)
+            const bool refine = (L.flags & SBEV_DENSE_REFINE) != 0;
+            bi = 0;
+            for (int gb = (int)crank; gb < nblk; gb += CL, ++bi)
+                for (int i = tid; i < R * FB; i += 256) {
+                    const int r = i / FB, fl = i - r * FB;
+                    const int n = gb * FB + fl, row = row0 + r;
+                    if (n >= N || row >= prm.M) continue;
+                    float v = ys[r * YLD + bi * FB + fl];
+                    if (L.flags & SBEV_DENSE_RELU) v = fmaxf(v, 0.f);
+                    if (!pre_res && L.residual != nullptr) v += __ldcg(L.residual + (long long)row * N + n);
+                    if (refine) {
+                        // refine_bbox + velocity rescale (sparsebev_transformer.py:155-160,179-183)
+                        if (n < 3) {
+                            const float x = fminf(fmaxf(__ldg(prm.aux_proposal + (long long)row * N + n), 0.f), 1.f);
+                            v = v + logf(__fdiv_rn(fmaxf(x, 1e-5f), fmaxf(1.f - x, 1e-5f)));
+                            v = __fdiv_rn(1.f, 1.f + expf(-v));
+                        } else if (n >= 8 && prm.aux_T > 1) {
+                            float td = __ldg(prm.aux_time_diff + (row / prm.aux_Q) * prm.aux_T + 1);
+                            if (td < 1e-5f) td = 1.0f;
+                            v = __fdiv_rn(v, td);
+                        }
+                    }
+                    if (L.y != nullptr) L.y[(long long)row * L.ldy + n] = v;
+                    if (L.y_hi != nullptr) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                        L.y_hi[(long long)row * L.ldy + n] = h;
+                        L.y_lo[(long long)row * L.ldy + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+                    }
+                }
+            continue;                    // (slice mode is the last layer)
+        }
+
+        // ---- exchange: push this CTA's feature blocks into every peer's ys
+        if (ex > 0) ns_wait_cluster(&ys_free, (ex - 1) & 1);            // every CTA is done reading the previous layer's ys
+        for (int gb = (int)crank; gb < nblk; gb += CL)
+            for (int i = tid; i < R * (FB / 4); i += 256) {
+                const int r = i / (FB / 4), c = gb * FB + 4 * (i - r * (FB / 4));
+                if (c >= N) continue;
+                const uint32_t off = (uint32_t)((r * YLD + c) * 4);
+                const float4 v = *reinterpret_cast<const float4*>(ys + r * YLD + c);
+#pragma unroll
+                for (int p = 0; p < CL; ++p)
+                    if (p != (int)crank)
+                        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ns_mapa(ys_u32 + off, p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+        // LayerNorm vectors of the first 128-column group are requested before the wait
+        const int per = (N + 127) >> 7;                                 // float4 per lane per row (N <= 512, N % 4 == 0)
+        __syncwarp();
+        if (lane < CL) ns_arrive_remote(&ys_full, lane);
+        ns_wait_cluster(&ys_full, ex & 1);
+
+        // ---- row epilogue on full rows: warp w finishes rows w, w + 8, ...; row r's global outputs belong to CTA r / 8
+        const bool has_ln = L.ln_w != nullptr;
+        const bool post_res = !pre_res && L.residual != nullptr;
+        const int Kn = last ? 0 : ((prm.layer[last ? li : li + 1].K + 63) & ~63);
+#pragma unroll 1
+        for (int j = 0; j < CL; ++j) {
+            const bool owner = j == (int)crank;
+            if (last && !owner) continue;
+            const int r = warp + 8 * j, row = row0 + r;
+            const bool live = row < prm.M;
+            float4 v[4];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = 4 * lane + 128 * i;
+                v[i] = (i < per && n < N) ? *reinterpret_cast<const float4*>(ys + r * YLD + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+            float mean = 0.f, rstd = 1.f;
+            if (has_ln) {
+                mean = warp_sum(s) / (float)N;
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = 4 * lane + 128 * i;
+                    if (i < per && n < N) {
+                        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                        ss += (a * a + b * b) + (c * c + d * d);
+                    }
+                }
+                rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = 4 * lane + 128 * i;
+                if (i < per && n < N) {
+                    float4 o = v[i];
+                    if (has_ln) {
+                        const float4 g = ldg4(L.ln_w + n), b = ldg4(L.ln_b + n);
+                        o.x = (o.x - mean) * rstd * g.x + b.x; o.y = (o.y - mean) * rstd * g.y + b.y;
+                        o.z = (o.z - mean) * rstd * g.z + b.z; o.w = (o.w - mean) * rstd * g.w + b.w;
+                    }
+                    if (L.flags & SBEV_DENSE_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (post_res && live) {
+                        const float4 q = __ldcg(reinterpret_cast<const float4*>(L.residual + (long long)row * N + n));
+                        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                    }
+                    if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (owner && live) {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                        if (L.y != nullptr) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) L.y[(long long)row * L.ldy + n + e] = ov[e];
+                        }
+                        if (L.y_hi != nullptr) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __nv_bfloat16 h = __float2bfloat16_rn(ov[e]);
+                                L.y_hi[(long long)row * L.ldy + n + e] = h;
+                                L.y_lo[(long long)row * L.ldy + n + e] = __float2bfloat16_rn(ov[e] - __bfloat162float(h));
+                            }
+                        }
+                    }
+                    if (!last) {
+                        uint32_t h0, l0, h1, l1;
+                        mc_split2(o.x, o.y, h0, l0); mc_split2(o.z, o.w, h1, l1);
+                        *reinterpret_cast<uint2*>(xh + r * XLD + n) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(xl + r * XLD + n) = make_uint2(l0, l1);
+                    }
+                }
+            }
+            if (!last)                                                  // zero beyond N up to the next layer's padded K
+                for (int k = N + 4 * lane; k < Kn; k += 128) {
+                    *reinterpret_cast<uint2*>(xh + r * XLD + k) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(xl + r * XLD + k) = make_uint2(0u, 0u);
+                }
+        }
+        __syncwarp();
+        if (lane < CL) ns_arrive_remote(&ys_free, lane);                // this warp is done reading ys
+        ++ex;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    cluster_sync_all();                  // no CTA exits while peers may still store into it or arrive on its barriers
+}
+
 // Box decode + offsets -> lidar-frame sample points; softmax over levels.  Thread per point.
 __global__ void __launch_bounds__(128)
 sample_points_kernel(const float* __restrict__ query_bbox, const float* __restrict__ offset, int ld_off,
@@ -739,6 +1149,48 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         int cl = get_option(OPT_DENSE_CLUSTER);            // 0/1 = no cluster, 2 / 4 / 8 = CTAs per multicast cluster
         if (cl != 2 && cl != 4 && cl != 8) cl = 1;
         if (groups < cl) cl = 1;
+        const int ns = get_option(OPT_DENSE_NSPLIT);        // 2 / 4 = N-split cluster chain (dense_chain_ns_kernel)
+        bool ns_ok = ns == 2 || ns == 4;
+        for (int i = 0; i < n_layers && ns_ok; ++i) {
+            const sbev_dense_layer& l = layers[i];
+            const bool slice = i + 1 == n_layers && l.ln_w == nullptr;
+            if (l.K > 512 || l.N > 1024) ns_ok = false;
+            if (!slice) {
+                if (l.N > 512 || (l.N & 3) || (l.flags & SBEV_DENSE_REFINE)) ns_ok = false;
+                if ((reinterpret_cast<uintptr_t>(l.ln_w) | reinterpret_cast<uintptr_t>(l.ln_b) | reinterpret_cast<uintptr_t>(l.residual)) & 15) ns_ok = false;
+            }
+        }
+        if (ns_ok) {
+            const int box = 256 / ns, rows = 8 * ns;
+            for (int i = 0; i < n_layers; ++i) {
+                const sbev_dense_layer& l = layers[i];
+                SBEV_REQUIRE(l.Kpad >= l.K && (l.Kpad & 63) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: Kpad must be a multiple of 64 >= K", i);
+                int rc = make_bf16_map(&maps.hi[i], l.W_hi, l.N, l.Kpad, box);
+                if (rc) return rc;
+                rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, box);
+                if (rc) return rc;
+            }
+            static std::once_flag once_ns;
+            std::call_once(once_ns, [&] {
+                cudaFuncSetAttribute(dense_chain_ns_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<2>::SMEM);
+                cudaFuncSetAttribute(dense_chain_ns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<4>::SMEM);
+            });
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((M + rows - 1) / rows * ns);
+            cfg.blockDim = dim3(288);
+            cfg.dynamicSmemBytes = ns == 2 ? NsCfg<2>::SMEM : NsCfg<4>::SMEM;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = ns; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = get_option(OPT_PDL) ? 2 : 1;
+            cudaError_t e = ns == 2 ? cudaLaunchKernelEx(&cfg, dense_chain_ns_kernel<2>, prm, maps)
+                                    : cudaLaunchKernelEx(&cfg, dense_chain_ns_kernel<4>, prm, maps);
+            if (e != cudaSuccess) { set_error("sbev_dense_chain_fwd(n-split cluster launch): %s", cudaGetErrorString(e)); return SBEV_ERR_CUDA; }
+            return check_launch("sbev_dense_chain_fwd(n-split)");
+        }
         const int box_rows = 128 / cl;
         for (int i = 0; i < n_layers; ++i) {
             const sbev_dense_layer& l = layers[i];

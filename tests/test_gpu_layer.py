@@ -56,6 +56,34 @@ def test_decoder_layer_vs_oracle(name, T, B):
     assert _rel(got_box, want_box) < 2e-4, 'bbox rel err %.3e' % _rel(got_box, want_box)
 
 
+@pytest.mark.parametrize('nsplit', [2, 4])
+def test_decoder_layer_with_nsplit_cluster_chain(nsplit):
+    """Whole layer with the dense chains on the N-split cluster kernel (option dense_nsplit): same parity bar, and
+    agreement with the default chain kernel to fp32 round-off of the bf16x3 products."""
+    from sparsebev_b200 import _lib
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', 4, 2, seed=3)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    grouped = R.regroup_feats(feats, channel_last=True)
+    want_q, want_cls, want_box = R.decoder_layer(qb, qf, grouped, sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics)
+    layer = model.decoder.decoder_layer
+    metas_gpu = copy.deepcopy(metas)
+    model.decoder.prepare_metas(metas_gpu, 2, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    default = _lib.get_option('dense_nsplit')
+    try:
+        _lib.set_option('dense_nsplit', 0)
+        base = [t.clone() for t in layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)]
+        _lib.set_option('dense_nsplit', nsplit)
+        got = layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option('dense_nsplit', default)
+    for g, w, b, what in zip(got, (want_q, want_cls, want_box), base, ('query_feat', 'cls', 'bbox')):
+        assert _rel(g, w) < 2e-4, '%s rel err %.3e' % (what, _rel(g, w))
+        assert _rel(g, b) < 5e-5, '%s vs default chain kernel: %.3e' % (what, _rel(g, b))
+
+
 def test_decoder_stages_vs_oracle():
     """Stage-wise: SASA block, sampling block and mixing block each against the oracle taps."""
     T, B = 4, 1

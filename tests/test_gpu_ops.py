@@ -32,7 +32,8 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    defaults = {'gemm_impl': 0, 'mix_impl': 0, 'sasa_impl': 0, 'gather_variant': 2, 'dense_impl': 0, 'dense_cluster': 0}
+    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit')
+    defaults = {k: _lib.get_option(k) for k in names}
 
     def setter(name, value):
         _lib.set_option(name, value)
@@ -304,13 +305,15 @@ def test_dense_vs_torch(M, K, N, ln, relu, res):
     _close(got, y, rtol=1e-4, atol=2e-5, what='dense')
 
 
-@pytest.mark.parametrize('impl', [0, 1, 2, 4, 8])
+@pytest.mark.parametrize('impl', [0, 1, 2, 4, 8, 12, 14])
 def test_dense_chain_vs_torch(impl, option):
     """5-layer chain (FFN + norm3 -> cls branch) and a 3-layer chain with the refine epilogue, intermediate outputs stored.
     impl 0 = tensor-core chain (mma.sync bf16x3, TMA-streamed weights), impl 1 = fp32 FFMA chain."""
     # 0 = tensor-core chain (default), 2 / 4 / 8 = tensor-core chain with that many CTAs per TMA-multicast cluster, 1 = fp32 FFMA
+    # 12 / 14 = N-split cluster chain (2 / 4 CTAs per cluster split every layer's output features, DSMEM exchange)
     option('dense_impl', 1 if impl == 1 else 0)
-    option('dense_cluster', impl if impl >= 2 else 0)
+    option('dense_cluster', impl if 2 <= impl <= 8 else 0)
+    option('dense_nsplit', impl - 10 if impl >= 10 else 0)
     atol = 2e-5 if impl == 1 else 1e-4
     ops = _ops()
     torch.manual_seed(1)
@@ -376,11 +379,13 @@ def test_dense_chain_vs_torch(impl, option):
     _close(y776, w776, rtol=1e-4, atol=atol, what='N=776 layer')
 
 
-@pytest.mark.parametrize('impl,K0,nsplit,ln', [(0, 256, 18, True), (0, 128, 5, True), (0, 256, 1, False), (1, 256, 7, True), (0, 192, 3, True)])
+@pytest.mark.parametrize('impl,K0,nsplit,ln', [(0, 256, 18, True), (0, 128, 5, True), (0, 256, 1, False), (1, 256, 7, True), (0, 192, 3, True),
+                                               (12, 256, 18, True), (14, 256, 18, True), (14, 128, 5, True), (12, 256, 1, False)])
 def test_dense_chain_with_fused_splitk_reduce(impl, K0, nsplit, ln, option):
     """sbev_dense_chain_reduce_fwd: input rows = LN(sum_z partial + bias + residual), FFN-like chain behind it (impl 1 and
     K0 = 192 take the documented two-launch fallback)."""
-    option('dense_impl', impl)
+    option('dense_impl', impl if impl < 10 else 0)
+    option('dense_nsplit', impl - 10 if impl >= 10 else 0)
     ops = _ops()
     torch.manual_seed(5)
     M = 901
