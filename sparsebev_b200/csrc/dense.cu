@@ -854,7 +854,6 @@ dense_chain_ns_kernel(const __grid_constant__ ChainParams prm, const __grid_cons
                     if (p != (int)crank)
                         asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ns_mapa(ys_u32 + off, p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             }
-        // LayerNorm vectors of the first 128-column group are requested before the wait
         const int per = (N + 127) >> 7;                                 // float4 per lane per row (N <= 512, N % 4 == 0)
         __syncwarp();
         if (lane < CL) ns_arrive_remote(&ys_full, lane);
@@ -864,43 +863,59 @@ dense_chain_ns_kernel(const __grid_constant__ ChainParams prm, const __grid_cons
         const bool has_ln = L.ln_w != nullptr;
         const bool post_res = !pre_res && L.residual != nullptr;
         const int Kn = last ? 0 : ((prm.layer[last ? li : li + 1].K + 63) & ~63);
-#pragma unroll 1
+        // (the CL rows of a warp are processed side by side so that their shuffle reductions overlap)
+        float4 v[CL][4];
+        float mean[CL], rstd[CL];
+        bool act[CL];
+#pragma unroll
         for (int j = 0; j < CL; ++j) {
-            const bool owner = j == (int)crank;
-            if (last && !owner) continue;
-            const int r = warp + 8 * j, row = row0 + r;
-            const bool live = row < prm.M;
-            float4 v[4];
+            act[j] = !last || j == (int)crank;
+            const int r = warp + 8 * j;
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int n = 4 * lane + 128 * i;
-                v[i] = (i < per && n < N) ? *reinterpret_cast<const float4*>(ys + r * YLD + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                v[j][i] = (act[j] && i < per && n < N) ? *reinterpret_cast<const float4*>(ys + r * YLD + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                s += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
             }
-            float mean = 0.f, rstd = 1.f;
-            if (has_ln) {
-                mean = warp_sum(s) / (float)N;
+            mean[j] = s;
+            rstd[j] = 1.f;
+        }
+        if (has_ln) {
+#pragma unroll
+            for (int j = 0; j < CL; ++j) mean[j] = warp_sum(mean[j]) / (float)N;
+#pragma unroll
+            for (int j = 0; j < CL; ++j) {
                 float ss = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int n = 4 * lane + 128 * i;
                     if (i < per && n < N) {
-                        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                        const float a = v[j][i].x - mean[j], b = v[j][i].y - mean[j], c = v[j][i].z - mean[j], d = v[j][i].w - mean[j];
                         ss += (a * a + b * b) + (c * c + d * d);
                     }
                 }
-                rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
+                rstd[j] = ss;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = 4 * lane + 128 * i;
-                if (i < per && n < N) {
-                    float4 o = v[i];
+            for (int j = 0; j < CL; ++j) rstd[j] = rsqrtf(warp_sum(rstd[j]) / (float)N + 1e-5f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = 4 * lane + 128 * i;
+            if (i < per && n < N) {
+                float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_ln) { g = ldg4(L.ln_w + n); b = ldg4(L.ln_b + n); }
+#pragma unroll
+                for (int j = 0; j < CL; ++j) {
+                    if (!act[j]) continue;
+                    const bool owner = j == (int)crank;
+                    const int r = warp + 8 * j, row = row0 + r;
+                    const bool live = row < prm.M;
+                    float4 o = v[j][i];
                     if (has_ln) {
-                        const float4 g = ldg4(L.ln_w + n), b = ldg4(L.ln_b + n);
-                        o.x = (o.x - mean) * rstd * g.x + b.x; o.y = (o.y - mean) * rstd * g.y + b.y;
-                        o.z = (o.z - mean) * rstd * g.z + b.z; o.w = (o.w - mean) * rstd * g.w + b.w;
+                        o.x = (o.x - mean[j]) * rstd[j] * g.x + b.x; o.y = (o.y - mean[j]) * rstd[j] * g.y + b.y;
+                        o.z = (o.z - mean[j]) * rstd[j] * g.z + b.z; o.w = (o.w - mean[j]) * rstd[j] * g.w + b.w;
                     }
                     if (L.flags & SBEV_DENSE_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (post_res && live) {
@@ -931,12 +946,14 @@ dense_chain_ns_kernel(const __grid_constant__ ChainParams prm, const __grid_cons
                     }
                 }
             }
-            if (!last)                                                  // zero beyond N up to the next layer's padded K
-                for (int k = N + 4 * lane; k < Kn; k += 128) {
-                    *reinterpret_cast<uint2*>(xh + r * XLD + k) = make_uint2(0u, 0u);
-                    *reinterpret_cast<uint2*>(xl + r * XLD + k) = make_uint2(0u, 0u);
-                }
         }
+        if (!last)                                                      // zero beyond N up to the next layer's padded K
+#pragma unroll
+            for (int j = 0; j < CL; ++j)
+                for (int k = N + 4 * lane; k < Kn; k += 128) {
+                    *reinterpret_cast<uint2*>(xh + (warp + 8 * j) * XLD + k) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(xl + (warp + 8 * j) * XLD + k) = make_uint2(0u, 0u);
+                }
         __syncwarp();
         if (lane < CL) ns_arrive_remote(&ys_free, lane);                // this warp is done reading ys
         ++ex;
