@@ -296,6 +296,42 @@ int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* params_lo, 
 int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
                        const float* ln_w, const float* ln_b, int M, int N, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backbone convolutions.
+ * Replaces the cuDNN calls (F.conv2d -> norm -> activation) behind the reference's conv wrappers:
+ * models/backbones/eva02/wrappers.py:76-120 (Conv2d), models/backbones/vovnet.py:117-154 (conv3x3 / conv1x1 =
+ * Conv2d + BatchNorm2d + ReLU) and the mmdet ResNet / FPN blocks built by configs/r50_nuimg_704x256.py:31-45, as
+ * called from models/sparsebev.py:46-59 (extract_img_feat, fp16 autocast there; bf16 operands + fp32 accumulate here).
+ *
+ * out[n,ho,wo,co] = act( scale[co] * sum_{kh,kw,ci} x[n, ho*stride+kh-pad, wo*stride+kw-pad, ci] * w[co,kh,kw,ci] + shift[co]
+ *                        + residual[n, ho*res_H/Ho, wo*res_W/Wo, co] )
+ *   x        NHWC bf16 [Nimg][H][W][Cin], Cin % 64 == 0          w  bf16 [Cout][KH][KW][Cin], Cout % 32 == 0
+ *   scale    fp32 [Cout] or NULL (= 1): folded BatchNorm gamma / sqrt(var + eps);  shift fp32 [Cout]: folded beta / conv bias
+ *   residual NHWC bf16 [Nimg][res_H][res_W][Cout] or NULL; res_H x res_W == Ho x Wo is the bottleneck identity, a smaller
+ *            map is read nearest-neighbour (FPN top-down: lateral + upsampled coarser level)
+ *   out      NHWC [Nimg][Ho][Wo][Cout], bf16 (out_f32 == 0) or fp32 (out_f32 != 0); stride 1 or 2, zero padding.
+ * Implicit GEMM on tcgen05 (4-D TMA boxes of 8 x 16 output pixels x 64 channels per tap, weights by 2-D TMA, fp32
+ * accumulators in TMEM).  All operands 16-byte aligned; caller allocates everything. */
+int sbev_conv2d_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int Cin,
+                         const uint16_t* w, int Cout, int KH, int KW, int stride, int pad,
+                         const float* scale, const float* shift,
+                         const uint16_t* residual, int res_H, int res_W, int relu,
+                         void* out, int out_f32, void* stream);
+
+/* ResNet stem: 7x7 stride-2 pad-3 conv of the NCHW fp32 image [Nimg][3][H][W] (what models/sparsebev.py:61-100 hands the
+ * backbone) + folded BN + ReLU -> NHWC bf16 [Nimg][Ho][Wo][64].  w fp32 [7][7][3][64]. */
+int sbev_stem_conv_fwd(const float* img, int Nimg, int H, int W, const float* w, const float* scale, const float* shift,
+                       uint16_t* out, void* stream);
+
+/* 3x3 stride-2 pad-1 max pool, NHWC bf16, C % 8 == 0 -> [Nimg][(H-1)/2+1][(W-1)/2+1][C]. */
+int sbev_maxpool3x3s2_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int C, uint16_t* out, void* stream);
+
+/* out[n,ho,wo,:] = x[n,2ho,2wo,:], fp32 NHWC, C % 4 == 0 (mmdet FPN extra level: F.max_pool2d(x, 1, stride=2)). */
+int sbev_subsample2_nhwc_fwd(const float* x, int Nimg, int H, int W, int C, float* out, void* stream);
+
+/* fp32 -> bf16 (round to nearest even), elementwise. */
+int sbev_cast_bf16(const float* x, int64_t n, uint16_t* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

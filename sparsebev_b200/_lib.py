@@ -55,6 +55,12 @@ SIGNATURES = {
     'sbev_gemm_bf16_tn_split': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'sbev_mix_presplit_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_reduce_ln_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    'sbev_conv2d_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
+                             c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp],
+    'sbev_stem_conv_fwd': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'sbev_maxpool3x3s2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_subsample2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_cast_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp],
 }
 
 _lib = None

@@ -1,0 +1,292 @@
+"""Backbone conv wrappers on the tcgen05 implicit-GEMM convolution.
+
+Mirrors, with the reference's names / constructor arguments / state-dict keys:
+  * `Conv2d`                       /root/reference/models/backbones/eva02/wrappers.py:76-120
+                                   (torch.nn.Conv2d + `norm=` + `activation=` keyword arguments, norm before activation);
+  * `conv3x3`, `conv1x1`           /root/reference/models/backbones/vovnet.py:117-154
+                                   ((name, module) lists of Conv2d + BatchNorm2d + ReLU) and `ConvBNReLUSequence` that runs such a list;
+  * `ResNet`, `FPN`                the mmdet 2.28.2 modules the reference builds from configs/r50_nuimg_704x256.py:31-45
+                                   (third party, absent here: restated from their documented structure; parity of the
+                                   *architecture glue* is therefore unpinned, the convolution arithmetic is pinned against
+                                   torch.nn.functional.conv2d in tests/test_gpu_backbone.py);
+  * `extract_img_feat`             /root/reference/models/sparsebev.py:46-59,124-131 (backbone -> neck -> [B, T*N, C, H, W]).
+
+Everything between the image and the FPN outputs stays NHWC bf16 on the device; the FPN levels leave as fp32 NHWC, which
+is the gather's zero-copy 'nhwc' layout (SparseBEVTransformerDecoder.prepare_feats), so no regroup / permute copy exists
+anywhere between the backbone and the decoder.  Inference only (BatchNorm folded from running statistics).  There is no
+cuDNN / eager fallback: unsupported configurations raise.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def fold_bn(bn, conv_bias=None):
+    """BatchNorm2d (eval) -> per-channel (scale, shift) fp32: y = scale * conv + shift."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def weight_khwc(weight):
+    """nn.Conv2d weight [Cout,Cin,KH,KW] -> [Cout,KH,KW,Cin] (the K-major implicit-GEMM operand), fp32 contiguous."""
+    return weight.detach().float().permute(0, 2, 3, 1).contiguous()
+
+
+class _FusedConv:
+    """Device-side cache of one conv (+ BN) in the kernel's layout; rebuilt when a parameter changes."""
+
+    def __init__(self, conv, bn=None):
+        self.conv, self.bn, self._key, self._val = conv, bn, None, None
+
+    def get(self):
+        ps = [self.conv.weight, self.conv.bias] + ([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var] if self.bn is not None else [])
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in ps if p is not None)
+        if key != self._key:
+            conv, bn = self.conv, self.bn
+            if bn is not None:
+                if bn.training:
+                    raise RuntimeError('sparsebev_b200 backbone: BatchNorm must be in eval mode (inference only)')
+                scale, shift = fold_bn(bn, conv.bias)
+            else:
+                scale = None
+                shift = (conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=conv.weight.device)).contiguous()
+            w = ops.cast_bf16(weight_khwc(conv.weight))
+            self._key, self._val = key, (w, scale, shift)
+        return self._val
+
+    def __call__(self, x, relu=False, residual=None, out_f32=False):
+        conv = self.conv
+        _check_conv(conv)
+        w, scale, shift = self.get()
+        return ops.conv2d_nhwc(x, w, shift, scale, stride=conv.stride[0], pad=conv.padding[0], residual=residual, relu=relu, out_f32=out_f32)
+
+
+def _check_conv(conv):
+    if conv.groups != 1 or conv.dilation != (1, 1) or conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] \
+            or conv.kernel_size[0] != conv.kernel_size[1] or conv.stride[0] not in (1, 2) or conv.padding_mode != 'zeros':
+        raise NotImplementedError('sparsebev_b200 conv kernel: groups=1, dilation=1, square kernel, stride 1|2, zero padding only '
+                                  '(got %r); there is no cuDNN fallback' % (conv,))
+    if conv.in_channels % 64 or conv.out_channels % 32:
+        raise NotImplementedError('sparsebev_b200 conv kernel: in_channels %% 64 == 0 and out_channels %% 32 == 0 required (got %d -> %d)'
+                                  % (conv.in_channels, conv.out_channels))
+
+
+def to_nhwc_bf16(x):
+    """NCHW float tensor -> NHWC bf16 (boundary conversion for NCHW callers)."""
+    return ops.cast_bf16(x.float().permute(0, 2, 3, 1).contiguous())
+
+
+def to_nchw_f32(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+class Conv2d(torch.nn.Conv2d):
+    """Same interface as the reference wrapper (eva02/wrappers.py:76-120): extra keyword arguments `norm` (a
+    normalization layer, applied before the activation) and `activation`.  forward(x: NCHW) -> NCHW runs conv + norm +
+    activation as ONE tcgen05 kernel when norm is None / BatchNorm2d (eval) and activation is None / ReLU."""
+
+    def __init__(self, *args, **kwargs):
+        norm = kwargs.pop('norm', None)
+        activation = kwargs.pop('activation', None)
+        super().__init__(*args, **kwargs)
+        self.norm = norm
+        self.activation = activation
+        self._fused = None
+
+    def _relu(self):
+        act = self.activation
+        if act is None:
+            return False
+        if isinstance(act, nn.ReLU) or act in (torch.relu, torch.nn.functional.relu):
+            return True
+        raise NotImplementedError('sparsebev_b200 Conv2d: activation must be None or ReLU (got %r)' % (act,))
+
+    def forward_nhwc(self, x, residual=None, out_f32=False):
+        if self.norm is not None and not isinstance(self.norm, nn.BatchNorm2d):
+            raise NotImplementedError('sparsebev_b200 Conv2d: norm must be None or BatchNorm2d (got %r)' % (self.norm,))
+        if self._fused is None or self._fused.bn is not self.norm:
+            self._fused = _FusedConv(self, self.norm)
+        return self._fused(x, relu=self._relu(), residual=residual, out_f32=out_f32)
+
+    def forward(self, x):
+        return to_nchw_f32(self.forward_nhwc(to_nhwc_bf16(x), out_f32=True))
+
+
+def conv3x3(in_channels, out_channels, module_name, postfix, stride=1, groups=1, kernel_size=3, padding=1):
+    """3x3 convolution with padding: [(name, module)] exactly as the reference builds it (vovnet.py:117-135)."""
+    return [
+        (f'{module_name}_{postfix}/conv',
+         nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, groups=groups, bias=False)),
+        (f'{module_name}_{postfix}/norm', nn.BatchNorm2d(out_channels)),
+        (f'{module_name}_{postfix}/relu', nn.ReLU(inplace=True)),
+    ]
+
+
+def conv1x1(in_channels, out_channels, module_name, postfix, stride=1, groups=1, kernel_size=1, padding=0):
+    """1x1 convolution: [(name, module)] exactly as the reference builds it (vovnet.py:138-154)."""
+    return [
+        (f'{module_name}_{postfix}/conv',
+         nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, groups=groups, bias=False)),
+        (f'{module_name}_{postfix}/norm', nn.BatchNorm2d(out_channels)),
+        (f'{module_name}_{postfix}/relu', nn.ReLU(inplace=True)),
+    ]
+
+
+class ConvBNReLUSequence(nn.Sequential):
+    """nn.Sequential(OrderedDict(conv3x3(...) + conv1x1(...) + ...)) with the reference's module names; forward_nhwc fuses
+    every (Conv2d, BatchNorm2d, ReLU) triple into one kernel launch."""
+
+    def __init__(self, named_modules):
+        super().__init__(OrderedDict(named_modules))
+        mods = list(self.children())
+        if len(mods) % 3:
+            raise ValueError('expected (conv, norm, relu) triples')
+        self._fused = []
+        for i in range(0, len(mods), 3):
+            c, n, r = mods[i:i + 3]
+            if not (isinstance(c, nn.Conv2d) and isinstance(n, nn.BatchNorm2d) and isinstance(r, nn.ReLU)):
+                raise ValueError('expected (Conv2d, BatchNorm2d, ReLU) triples')
+            self._fused.append(_FusedConv(c, n))
+
+    def forward_nhwc(self, x):
+        for f in self._fused:
+            x = f(x, relu=True)
+        return x
+
+    def forward(self, x):
+        return to_nchw_f32(self.forward_nhwc(to_nhwc_bf16(x)))
+
+
+class Bottleneck(nn.Module):
+    """mmdet / torchvision ResNet bottleneck, style='pytorch' (the stride sits on the 3x3 conv); keys conv1..3, bn1..3, downsample.{0,1}."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self._f1, self._f2, self._f3 = _FusedConv(self.conv1, self.bn1), _FusedConv(self.conv2, self.bn2), _FusedConv(self.conv3, self.bn3)
+        self._fd = _FusedConv(downsample[0], downsample[1]) if downsample is not None else None
+
+    def forward_nhwc(self, x):
+        identity = x if self._fd is None else self._fd(x)
+        out = self._f2(self._f1(x, relu=True), relu=True)
+        return self._f3(out, relu=True, residual=identity)          # relu(bn3(conv3) + identity) in the conv epilogue
+
+
+class ResNet(nn.Module):
+    """ResNet-50 / -101 with mmdet's state-dict keys (conv1, bn1, layer{1..4}.{i}.*) -- the reference's img_backbone
+    (configs/r50_nuimg_704x256.py:31-40: depth=50, num_stages=4, out_indices=(0,1,2,3), style='pytorch', norm_eval)."""
+    arch_settings = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+    def __init__(self, depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style='pytorch', **_ignored):
+        super().__init__()
+        if depth not in self.arch_settings or style != 'pytorch':
+            raise NotImplementedError('ResNet depth 50 / 101, style pytorch')
+        self.out_indices = tuple(out_indices)
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        inplanes = 64
+        self.res_layers = []
+        for i, blocks in enumerate(self.arch_settings[depth][:num_stages]):
+            planes, stride = 64 * 2 ** i, 1 if i == 0 else 2
+            layers = []
+            for b in range(blocks):
+                down = None
+                if b == 0 and (stride != 1 or inplanes != planes * 4):
+                    down = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
+                layers.append(Bottleneck(inplanes, planes, stride if b == 0 else 1, down))
+                inplanes = planes * 4
+            name = 'layer%d' % (i + 1)
+            self.add_module(name, nn.Sequential(*layers))
+            self.res_layers.append(name)
+        self._stem_key, self._stem_val = None, None
+
+    def _stem(self):
+        ps = [self.conv1.weight, self.bn1.weight, self.bn1.bias, self.bn1.running_mean, self.bn1.running_var]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._stem_key:
+            scale, shift = fold_bn(self.bn1)
+            w = self.conv1.weight.detach().float().permute(2, 3, 1, 0).contiguous()        # [7,7,3,64]
+            self._stem_key, self._stem_val = key, (w, scale, shift)
+        return self._stem_val
+
+    @torch.no_grad()
+    def forward_nhwc(self, img):
+        """img NCHW fp32 [N,3,H,W] -> tuple of NHWC bf16 stage outputs (strides 4, 8, 16, 32)."""
+        if self.training:
+            raise RuntimeError('sparsebev_b200 ResNet: inference only (call .eval())')
+        w, scale, shift = self._stem()
+        x = ops.maxpool3x3s2_nhwc(ops.stem_conv(img.float().contiguous(), w, scale, shift))
+        outs = []
+        for i, name in enumerate(self.res_layers):
+            for block in getattr(self, name):
+                x = block.forward_nhwc(x)
+            if i in self.out_indices:
+                outs.append(x)
+        return tuple(outs)
+
+    def forward(self, img):
+        return tuple(to_nchw_f32(o) for o in self.forward_nhwc(img))
+
+
+class _ConvModule(nn.Module):
+    """mmcv ConvModule without norm / activation: keeps the `.conv.weight` / `.conv.bias` key names."""
+
+    def __init__(self, cin, cout, k, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding)
+        self._fused = _FusedConv(self.conv)
+
+
+class FPN(nn.Module):
+    """mmdet FPN (configs/r50_nuimg_704x256.py:41-45: in_channels=[256,512,1024,2048], out_channels=256, num_outs=4; the r101
+    config asks for num_outs=5): lateral 1x1 convs, nearest top-down path, 3x3 output convs, extra levels by stride-2
+    subsampling (F.max_pool2d(x, 1, stride=2)).  The top-down add is the residual operand of the lateral conv's epilogue."""
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False, **_ignored):
+        super().__init__()
+        if add_extra_convs or end_level != -1:
+            raise NotImplementedError('FPN: add_extra_convs / end_level are not used by the reference configs')
+        self.in_channels, self.out_channels, self.num_outs, self.start_level = list(in_channels), out_channels, num_outs, start_level
+        self.lateral_convs = nn.ModuleList(_ConvModule(c, out_channels, 1) for c in self.in_channels[start_level:])
+        self.fpn_convs = nn.ModuleList(_ConvModule(out_channels, out_channels, 3, padding=1) for _ in self.in_channels[start_level:])
+
+    @torch.no_grad()
+    def forward_nhwc(self, inputs):
+        """inputs: NHWC bf16 stage outputs -> list of num_outs NHWC fp32 levels."""
+        feats = list(inputs)[self.start_level:]
+        n = len(feats)
+        lats = [None] * n
+        for i in range(n - 1, -1, -1):                      # top-down: lateral(i) + nearest-upsampled lateral(i+1), one kernel
+            lats[i] = self.lateral_convs[i]._fused(feats[i], residual=lats[i + 1] if i + 1 < n else None)
+        outs = [self.fpn_convs[i]._fused(lats[i], out_f32=True) for i in range(n)]
+        while len(outs) < self.num_outs:
+            outs.append(ops.subsample2_nhwc(outs[-1]))
+        return outs
+
+    def forward(self, inputs):
+        return tuple(o.permute(0, 3, 1, 2) for o in self.forward_nhwc([to_nhwc_bf16(x) for x in inputs]))
+
+
+@torch.no_grad()
+def extract_img_feat(backbone, neck, img):
+    """img [B, T*N, 3, H, W] -> list of [B, T*N, C, H', W'] fp32 whose memory is channels-last, i.e. exactly what
+    SparseBEVTransformerDecoder.prepare_feats consumes without a copy (reference: models/sparsebev.py:46-59,124-131)."""
+    B, TN = img.shape[:2]
+    levels = neck.forward_nhwc(backbone.forward_nhwc(img.reshape(B * TN, *img.shape[2:])))
+    return [f.view(B, TN, *f.shape[1:]).permute(0, 1, 4, 2, 3) for f in levels]

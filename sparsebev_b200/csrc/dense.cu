@@ -128,6 +128,93 @@ __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const
     }
 }
 
+__device__ __forceinline__ void mc_split2(float a, float b, uint32_t& hi, uint32_t& lo);
+// Vectorised form of chain_row_epilogue for the tensor-core chains (profile: the scalar epilogue was ~45 % of the chain
+// kernels' warp-stall samples -- the kernels are bound by the length of each warp's instruction stream, not by weight
+// streaming).  Same arithmetic; a lane owns the 16-byte column groups lane, lane + 32, ...; the row stays in registers
+// between the three passes, every global / shared access is 16 bytes (8 for the bf16 outputs), and the next layer's
+// bf16 (hi, lo) operand row (nh / nl, zero padded up to Kn) is produced in the same pass.  Requires N % 4 == 0,
+// N <= 1024, ldy % 4 == 0, 16-byte aligned operands and no refine epilogue (host sets CHAIN_FLAG_VEC4 when that holds).
+constexpr int CHAIN_FLAG_VEC4 = 1 << 8;
+__device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, const ChainLayer& L, int row, const float* yr, int lane,
+                                                      const float* sv, const float* sres, __nv_bfloat16* nh, __nv_bfloat16* nl, int Kn) {
+    const int N = L.N, ng = N >> 2;
+    const bool live = row < prm.M;
+    const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
+    const bool has_res = live && L.residual != nullptr;
+    const float* res_row = L.residual ? L.residual + (long long)row * N : nullptr;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = lane + 32 * i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < ng) {
+            a = *reinterpret_cast<const float4*>(yr + 4 * g);
+            if (L.bias != nullptr) {
+                const float4 b = sv ? *reinterpret_cast<const float4*>(sv + 4 * g) : ldg4(L.bias + 4 * g);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (pre_res && has_res) {
+                const float4 r = sres ? *reinterpret_cast<const float4*>(sres + 4 * g) : ldg4(res_row + 4 * g);
+                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            }
+            s += (a.x + a.y) + (a.z + a.w);
+        }
+        v[i] = a;
+    }
+    float mean = 0.f, rstd = 1.f;
+    const bool has_ln = L.ln_w != nullptr;
+    if (has_ln) {
+        mean = warp_sum(s) / (float)N;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lane + 32 * i < ng) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+        rstd = rsqrtf(warp_sum(ss) / (float)N + 1e-5f);
+    }
+    const long long yoff = (long long)row * L.ldy;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = lane + 32 * i;
+        if (g < ng) {
+            float4 o = v[i];
+            if (has_ln) {
+                const float4 gm = sv ? *reinterpret_cast<const float4*>(sv + CHAIN_VEC_LD + 4 * g) : ldg4(L.ln_w + 4 * g);
+                const float4 bt = sv ? *reinterpret_cast<const float4*>(sv + 2 * CHAIN_VEC_LD + 4 * g) : ldg4(L.ln_b + 4 * g);
+                o.x = (o.x - mean) * rstd * gm.x + bt.x; o.y = (o.y - mean) * rstd * gm.y + bt.y;
+                o.z = (o.z - mean) * rstd * gm.z + bt.z; o.w = (o.w - mean) * rstd * gm.w + bt.w;
+            }
+            if (L.flags & SBEV_DENSE_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (!pre_res && has_res) {
+                const float4 r = sres ? *reinterpret_cast<const float4*>(sres + 4 * g) : ldg4(res_row + 4 * g);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            uint32_t h0, l0, h1, l1;
+            mc_split2(o.x, o.y, h0, l0); mc_split2(o.z, o.w, h1, l1);
+            if (live) {
+                if (L.y != nullptr) *reinterpret_cast<float4*>(L.y + yoff + 4 * g) = o;
+                if (L.y_hi != nullptr) {
+                    *reinterpret_cast<uint2*>(L.y_hi + yoff + 4 * g) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(L.y_lo + yoff + 4 * g) = make_uint2(l0, l1);
+                }
+            }
+            if (nh != nullptr) {
+                *reinterpret_cast<uint2*>(nh + 4 * g) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(nl + 4 * g) = make_uint2(l0, l1);
+            }
+        }
+    }
+    if (nh != nullptr)
+        for (int k = N + 4 * lane; k < Kn; k += 128) {
+            *reinterpret_cast<uint2*>(nh + k) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(nl + k) = make_uint2(0u, 0u);
+        }
+}
+
 // A chain of up to 6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers (fp32 FFMA version; exact fp32).  One CTA owns 8 full rows from the
 // first layer to the last (activations never leave shared memory, LayerNorm never leaves the CTA); the
 // pre-transposed weights of ALL layers are streamed back-to-back through a 3-stage ring of 32 KB chunks by
@@ -512,7 +599,12 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        {
+        if (L.flags & CHAIN_FLAG_VEC4) {
+            const bool more = li + 1 < prm.n_layers;
+            __nv_bfloat16* nh = more ? xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD : nullptr;
+            chain_row_epilogue_v4(prm, L, row0 + warp, ys + warp * MC_YLD, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr,
+                                  nh, more ? nh + DENSE_ROWS * MC_XLD : nullptr, more ? ((prm.layer[li + 1].K + 63) & ~63) : 0);
+        } else {
             float* yr = ys + warp * MC_YLD;
             chain_row_epilogue(prm, L, row0 + warp, yr, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr);
             __syncwarp();
@@ -1148,7 +1240,15 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         c.Wt = l.Wt; c.bias = l.bias; c.ln_w = l.ln_w; c.ln_b = l.ln_b; c.residual = l.residual; c.y = l.y;
         c.y_hi = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_hi)); c.y_lo = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_lo));
         SBEV_REQUIRE((l.y_hi == nullptr) == (l.y_lo == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: y_hi and y_lo go together");
-        c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags; c.ldy = l.ldy;
+        c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags & 0xff; c.ldy = l.ldy;
+        {
+            const uintptr_t a16 = reinterpret_cast<uintptr_t>(l.bias) | reinterpret_cast<uintptr_t>(l.ln_w) | reinterpret_cast<uintptr_t>(l.ln_b) |
+                                  reinterpret_cast<uintptr_t>(l.residual) | reinterpret_cast<uintptr_t>(l.y);
+            const uintptr_t a8 = reinterpret_cast<uintptr_t>(l.y_hi) | reinterpret_cast<uintptr_t>(l.y_lo);
+            if ((l.N & 3) == 0 && l.N <= 1024 && !(l.flags & SBEV_DENSE_REFINE) && (l.ldy & 3) == 0 && (a16 & 15) == 0 && (a8 & 7) == 0 &&
+                get_option(OPT_DENSE_VEC4))
+                c.flags |= CHAIN_FLAG_VEC4;
+        }
         int kc = CHAIN_STAGE_FLOATS / l.ldw;
         if (kc >= 4) kc &= ~3;
         if (kc > l.K) kc = l.K;

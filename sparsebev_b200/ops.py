@@ -443,3 +443,80 @@ def refine_bbox(proposal, delta, time_diff):
         _lib.check(lib.sbev_refine_bbox_fwd(proposal.data_ptr(), delta.data_ptr(), td.data_ptr(), B, Q, td.shape[1], code,
                                             out.data_ptr(), _stream()), 'sbev_refine_bbox_fwd')
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Backbone convolutions: NHWC bf16 activations, tcgen05 implicit GEMM.
+def cast_bf16(x):
+    """fp32 CUDA tensor -> bf16 tensor of the same shape (our kernel; round to nearest even)."""
+    lib = _lib.load()
+    _chk(x, 'x')
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_cast_bf16(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), 'sbev_cast_bf16')
+    return y
+
+
+def conv_out_size(H, W, k, stride, pad):
+    return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+
+
+def conv2d_nhwc(x, w, shift, scale=None, stride=1, pad=0, residual=None, relu=False, out_f32=False):
+    """x NHWC bf16 [N,H,W,Cin], w bf16 [Cout,KH,KW,Cin], shift / scale fp32 [Cout], residual NHWC bf16 [N,rH,rW,Cout]
+    (same size as the output, or smaller = nearest-upsampled) -> NHWC [N,Ho,Wo,Cout] bf16 | fp32."""
+    lib = _lib.load()
+    _chk(x, 'x', torch.bfloat16); _chk(w, 'weight', torch.bfloat16); _chk(shift, 'shift')
+    if scale is not None:
+        _chk(scale, 'scale')
+    if x.dim() != 4 or w.dim() != 4 or w.shape[3] != x.shape[3]:
+        raise RuntimeError('conv2d_nhwc: x must be [N,H,W,Cin] and weight [Cout,KH,KW,Cin]')
+    N, H, W, Cin = x.shape
+    Cout, KH, KW, _ = w.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    rH = rW = 0
+    if residual is not None:
+        _chk(residual, 'residual', torch.bfloat16)
+        if residual.dim() != 4 or residual.shape[0] != N or residual.shape[3] != Cout:
+            raise RuntimeError('conv2d_nhwc: residual must be [N,rH,rW,Cout]')
+        rH, rW = residual.shape[1], residual.shape[2]
+    out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_conv2d_nhwc_fwd(x.data_ptr(), N, H, W, Cin, w.data_ptr(), Cout, KH, KW, stride, pad,
+                                            _p(scale), shift.data_ptr(), _p(residual), rH, rW, int(relu),
+                                            out.data_ptr(), int(out_f32), _stream()), 'sbev_conv2d_nhwc_fwd')
+    return out
+
+
+def stem_conv(img, w, scale, shift):
+    """img NCHW fp32 [N,3,H,W], w fp32 [7,7,3,64] -> relu(bn(conv7x7/2)) as NHWC bf16 [N,Ho,Wo,64]."""
+    lib = _lib.load()
+    _chk(img, 'img'); _chk(w, 'weight'); _chk(scale, 'scale'); _chk(shift, 'shift')
+    if img.dim() != 4 or img.shape[1] != 3 or tuple(w.shape) != (7, 7, 3, 64):
+        raise RuntimeError('stem_conv: img must be [N,3,H,W] and weight [7,7,3,64]')
+    N, _, H, W = img.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(N, Ho, Wo, 64, device=img.device, dtype=torch.bfloat16)
+    with torch.cuda.device(img.device):
+        _lib.check(lib.sbev_stem_conv_fwd(img.data_ptr(), N, H, W, w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                          out.data_ptr(), _stream()), 'sbev_stem_conv_fwd')
+    return out
+
+
+def maxpool3x3s2_nhwc(x):
+    lib = _lib.load()
+    _chk(x, 'x', torch.bfloat16)
+    N, H, W, C = x.shape
+    out = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_maxpool3x3s2_nhwc_fwd(x.data_ptr(), N, H, W, C, out.data_ptr(), _stream()), 'sbev_maxpool3x3s2_nhwc_fwd')
+    return out
+
+
+def subsample2_nhwc(x):
+    lib = _lib.load()
+    _chk(x, 'x')
+    N, H, W, C = x.shape
+    out = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_subsample2_nhwc_fwd(x.data_ptr(), N, H, W, C, out.data_ptr(), _stream()), 'sbev_subsample2_nhwc_fwd')
+    return out
