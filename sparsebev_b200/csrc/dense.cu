@@ -478,6 +478,17 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
         const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
         __nv_bfloat16* xh = xbuf;
         __nv_bfloat16* xl = xbuf + DENSE_ROWS * MC_XLD;
+        if ((K0 & 63) == 0 && (prm.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.x) & 15) == 0) {
+            const int k4 = K0 >> 2;
+            for (int i = tid; i < DENSE_ROWS * k4; i += 288) {
+                const int r = i / k4, k = (i - r * k4) * 4;
+                const float4 v = (row0 + r < prm.M) ? ldg4(prm.x + (long long)(row0 + r) * prm.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t h0, l0, h1, l1;
+                mc_split2(v.x, v.y, h0, l0); mc_split2(v.z, v.w, h1, l1);
+                *reinterpret_cast<uint2*>(xh + r * MC_XLD + k) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(xl + r * MC_XLD + k) = make_uint2(l0, l1);
+            }
+        } else
         for (int i = tid; i < DENSE_ROWS * (K0p / 2); i += 288) {
             const int r = i / (K0p / 2), k = (i - r * (K0p / 2)) * 2;
             const bool ok = row0 + r < prm.M;
@@ -543,6 +554,21 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
             auto cp4 = [](float* dst, const float* src) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsmem_u32(dst)), "l"(src) : "memory");
             };
+            if (L.flags & CHAIN_FLAG_VEC4) {          // 16-byte copies (N % 4 == 0, aligned operands)
+                auto cp16 = [](float* dst, const float* src) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsmem_u32(dst)), "l"(src) : "memory");
+                };
+                const int n4 = L.N >> 2;
+                for (int g = tid; g < n4; g += 256) {
+                    if (L.bias) cp16(vecs + 4 * g, L.bias + 4 * g);
+                    if (L.ln_w) { cp16(vecs + CHAIN_VEC_LD + 4 * g, L.ln_w + 4 * g); cp16(vecs + 2 * CHAIN_VEC_LD + 4 * g, L.ln_b + 4 * g); }
+                }
+                if (res_staged)
+                    for (int i = tid; i < DENSE_ROWS * n4; i += 256) {
+                        const int r = i / n4, g = i - r * n4;
+                        if (row0 + r < prm.M) cp16(resb + r * MC_RES_LD + 4 * g, L.residual + (long long)(row0 + r) * L.N + 4 * g);
+                    }
+            } else {
             for (int n = tid; n < L.N; n += 256) {
                 if (L.bias) cp4(vecs + n, L.bias + n);
                 if (L.ln_w) { cp4(vecs + CHAIN_VEC_LD + n, L.ln_w + n); cp4(vecs + 2 * CHAIN_VEC_LD + n, L.ln_b + n); }
@@ -552,6 +578,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                     const int r = i / L.N, n = i - r * L.N;
                     if (row0 + r < prm.M) cp4(resb + r * MC_RES_LD + n, L.residual + (long long)(row0 + r) * L.N + n);
                 }
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         {

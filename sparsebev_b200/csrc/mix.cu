@@ -219,6 +219,36 @@ __device__ __forceinline__ Stat block_stat_256(Stat s, float* red /* [8*3] */) {
     }
     return t;
 }
+// Same reduction when every thread contributes the SAME number of elements N0 (mix_tma_kernel: in_points == 32): both sides
+// of every pairwise merge then hold n = N0 * 2^step elements, so  mean = a + d/2,  M2 = M2a + M2b + d^2 * n/2  -- no
+// division, no count to shuffle, no empty-side branch (the general merge was ~25 % of the kernel's instructions).
+template <int N0>
+__device__ __forceinline__ Stat block_stat_256_eq(float mean, float m2, float* red /* [8*2] */) {
+    float n = (float)N0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float bm = __shfl_xor_sync(0xffffffffu, mean, o), b2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const float d = bm - mean;
+        mean += 0.5f * d;
+        m2 = (m2 + b2) + d * d * (0.5f * n);
+        n *= 2.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { red[warp * 2] = mean; red[warp * 2 + 1] = m2; }
+    __syncthreads();
+    mean = red[(lane & 7) * 2]; m2 = red[(lane & 7) * 2 + 1];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const float bm = __shfl_xor_sync(0xffffffffu, mean, o), b2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const float d = bm - mean;
+        mean += 0.5f * d;
+        m2 = (m2 + b2) + d * d * (0.5f * n);
+        n *= 2.f;
+    }
+    Stat r; r.n = n; r.mean = mean; r.m2 = m2;
+    return r;
+}
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -568,7 +598,7 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
                     for (int i = 0; i < 4; ++i) { const float d = acc1[m][i] - lm; m2 += d * d; }
                 st.n = 8.f; st.mean = lm; st.m2 = m2;
             }
-            st = block_stat_256(st, red);
+            st = block_stat_256_eq<8>(st.mean, st.m2, red);
             const float mean = st.mean, rstd = rsqrtf(st.m2 / (float)(Pin * MIX_C) + 1e-5f);
 #pragma unroll
             for (int m = 0; m < 2; ++m)
@@ -617,7 +647,7 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
                 for (int i = 0; i < 4; ++i) { const float d = acc2[nn][i] - lm; m2 += d * d; }
             st2.n = 32.f; st2.mean = lm; st2.m2 = m2;
         }
-        st2 = block_stat_256(st2, red);                  // its barriers: every warp is past its last read of this operand set
+        st2 = block_stat_256_eq<32>(st2.mean, st2.m2, red);                  // its barriers: every warp is past its last read of this operand set
         const float mean = st2.mean, rstd = rsqrtf(st2.m2 / (float)(MIX_POUT * MIX_C) + 1e-5f);
 
         // ---- epilogue: ReLU(LN) -> (hi, lo) staged in THIS item's (now dead) operand set, XOR-swizzled 128-byte rows
