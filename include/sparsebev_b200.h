@@ -53,7 +53,8 @@ const char* sbev_last_error(void);
  *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
  *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
- *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default) */
+ *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default);
+ *                    3 = 2 + the next level pair's lines are prefetched into L2 while the current pair's loads are in flight */
 int         sbev_set_option(const char* name, int value);
 /* current value of an option (the environment / built-in default until sbev_set_option overrides it); -1 = unknown name */
 int         sbev_get_option(const char* name);

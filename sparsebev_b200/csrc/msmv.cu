@@ -63,7 +63,10 @@ __device__ __forceinline__ int view_from_coord(float z, int N) {
 // (slice, view, channel lane); pxs[l] = floats between neighbouring pixels (pixel offsets fit 32 bits).
 // LB = levels whose 4*LB*VEC loads are in flight together (LB == L: maximum memory-level parallelism;
 // smaller LB: fewer live registers -> more resident warps).
-template <int L, int LB, int VEC = 1, int VSTRIDE = 4>      // VSTRIDE: floats between the VEC float4 of one lane
+// PF: while the loads of one level block are in flight, the lines the NEXT block will read are requested into L2
+// (prefetch.global.L2, no destination registers): the kernel is DRAM-latency-bound at 2 CTAs/SM (three dependent round
+// trips per point: geometry, levels 0-1, levels 2-3), and this overlaps the third with the second.
+template <int L, int LB, int VEC = 1, int VSTRIDE = 4, bool PF = false>      // VSTRIDE: floats between the VEC float4 of one lane
 __device__ __forceinline__ void gather_levels_v(const float* const (&base)[L], const int (&H)[L],
                                                 const int (&W)[L], const int (&pxs)[L],
                                                 float u, float v, const float (&wt)[L], bool live, float4 (&acc)[VEC]) {
@@ -87,6 +90,24 @@ __device__ __forceinline__ void gather_levels_v(const float* const (&base)[L], c
                     c2[i][e] = (live && tp[i].ok2) ? ldg4(p + pxs[l] + VSTRIDE * e) : zero;
                     c3[i][e] = (live && tp[i].ok3) ? ldg4(p + row + VSTRIDE * e) : zero;
                     c4[i][e] = (live && tp[i].ok4) ? ldg4(p + row + pxs[l] + VSTRIDE * e) : zero;
+                }
+            }
+        }
+        if (PF && l0 + LB < L) {
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                const int l = l0 + LB + i;
+                if (l < L) {
+                    const Tap t = make_tap(u, v, H[l], W[l]);
+                    const int row = W[l] * pxs[l];
+                    const float* p = base[l] + (t.y0 * row + t.x0 * pxs[l]);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        if (live && t.ok1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + VSTRIDE * e));
+                        if (live && t.ok2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + pxs[l] + VSTRIDE * e));
+                        if (live && t.ok3) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + row + VSTRIDE * e));
+                        if (live && t.ok4) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + row + pxs[l] + VSTRIDE * e));
+                    }
                 }
             }
         }
@@ -382,7 +403,7 @@ struct FusedParams {
 
 // LPP = lanes per sample point: 16 (4 channels per lane) or 8 (8 channels per lane; halves the per-point geometry that
 // every lane of a point computes redundantly -- the kernel is issue-bound, not bandwidth-bound, on the realistic rig).
-template <int L, int LB, int MINB, int LPP>
+template <int L, int LB, int MINB, int LPP, bool PF = false>
 __global__ void __launch_bounds__(256, MINB)
 sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     constexpr int VEC = 16 / LPP;                     // float4 per lane
@@ -443,7 +464,7 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
         base[l] = lv.ptr[l] + ((long long)btl * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
     }
     float4 acc[VEC];
-    gather_levels_v<L, LB, VEC, 4 * LPP>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
+    gather_levels_v<L, LB, VEC, 4 * LPP, PF>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
     if (live) {
         const long long row = ((bq * G + g) * (prm.To * P) + ((t - prm.o0) * P + p)) * 64 + 4 * j;
         for (int w = 0; w < prm.n_out; ++w) {          // n_out > 1: the same 256 B row also goes to the peers over NVLink
@@ -605,15 +626,16 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
     prm.t0 = t0; prm.Tl = Tl; prm.n_out = n_out; prm.ld_vel = ld_vel;
     prm.o0 = full_out ? 0 : t0; prm.To = full_out ? T : Tl;
     // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
-    // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views)
+    // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views); 3 = 2 + L2 prefetch of the next level pair
     int variant = get_option(OPT_GATHER_VARIANT);
-    if (variant == 2 && N > 8) variant = 1;
-    const int ppb = variant == 2 ? 32 : 16;
+    if (variant >= 2 && N > 8) variant = 1;
+    const int ppb = variant >= 2 ? 32 : 16;
     const dim3 grid((Q * P + ppb - 1) / ppb, B * Tl * G);
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
-        if (variant == 2 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
-        else if (variant == 2) launch_pdl(sampling4d_c64_kernel<LL, LL, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);           \
+        if (variant == 3 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant >= 2 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant >= 2) launch_pdl(sampling4d_c64_kernel<LL, LL, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);           \
         else if (variant == 1 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 3, 16>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm); \
         else launch_pdl(sampling4d_c64_kernel<LL, LL, 1, 16>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);               \
         break;
