@@ -50,6 +50,9 @@ const char* sbev_last_error(void);
  *                    every layer's output features (each streams 1/2 / 1/4 of the weights), exchanging the layer outputs
  *                    through distributed shared memory; chains it cannot express (an inner layer wider than 512 ...) take
  *                    the "dense_impl" 0 kernel
+ *   "dense_vec4"     1 = 16-byte vectorised row epilogue / operand staging in the chain kernels (default), 0 = scalar
+ *   "dense_fuse_points" 1 = sbev_dense_chain_points_fwd computes the sample points in the chain's epilogue (default),
+ *                    0 = separate sample_points kernel
  *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
  *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
@@ -206,6 +209,17 @@ typedef struct sbev_dense_layer {
 int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
                          const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
                          void* stream);
+
+/* sbev_dense_chain_fwd whose LAST layer (a plain Linear: no LayerNorm / ReLU / residual, output y required) holds, per row,
+ * GP*3 sampling offsets starting at column off_col and GP*L scale logits starting at column log_col; its epilogue also
+ * turns them into the sample points and the per-level softmax weights of sbev_sample_points_fwd (same arithmetic, same
+ * bits): points [M][GP][3], scale_w [M][GP][L].  Fuses SparseBEVSampling's two Linear heads, make_sample_points and the
+ * softmax (models/sparsebev_transformer.py:279-283,298-299; models/sparsebev_sampling.py:8-24) into the launch that also
+ * applies the attention out-projection + norm1.  Kernel variants without the fused epilogue run the chain, then
+ * sbev_sample_points_fwd. */
+int sbev_dense_chain_points_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                                const float* query_bbox, const float* pc_range, int GP, int L, int off_col, int log_col,
+                                float* points, float* scale_w, void* stream);
 
 /* The same chain fed by the split-K partials of the preceding GEMM: its input rows are
  *     x_out[row] = LayerNorm(sum_z partial[z][row] + bias + residual[row])        (ln_w/ln_b NULL: no LayerNorm)

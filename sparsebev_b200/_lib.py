@@ -27,6 +27,7 @@ class DenseLayer(ctypes.Structure):
 SIGNATURES = {
     'sbev_set_option': [ctypes.c_char_p, c_int],
     'sbev_dense_chain_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
+    'sbev_dense_chain_points_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'sbev_dense_chain_reduce_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,

@@ -35,8 +35,40 @@ struct ChainParams {
     //   LN(sum_z in_partial[z][row] + in_bias + in_res[row])   (split-K partials of the preceding GEMM, [in_nsplit][M][K0])
     // computed in the prologue and also stored to in_out [M][K0] (x / ldx are then unused)
     const float* in_partial; int in_nsplit; const float* in_bias; const float* in_res; const float* in_ln_w; const float* in_ln_b; float* in_out;
+    // optional sample-points epilogue on the last layer (CHAIN_FLAG_POINTS; tensor-core kernel only): its output row
+    // [.. | GP*3 offsets at sp_off_col | GP*L scale logits at sp_log_col | ..] -> sp_points [M][GP][3], sp_scale_w [M][GP][L]
+    const float* sp_bbox; float* sp_points; float* sp_scale_w; float sp_r[6]; int sp_GP, sp_L, sp_off_col, sp_log_col;
     ChainLayer layer[CHAIN_MAX_LAYERS];
 };
+constexpr int CHAIN_FLAG_POINTS = 1 << 9;
+
+// One sample point: box decode + offset scaling + yaw rotation + softmax over the L scale logits
+// (sparsebev_sampling.py:8-24, bbox/utils.py:63-77, models/utils.py:49-84, sparsebev_transformer.py:298-299).
+// Shared by sample_points_kernel and the chain kernel's fused epilogue, so both produce identical bits.
+__device__ __forceinline__ void sample_point_one(const float* bb, const float* op, const float* lp, int L,
+                                                 float r0, float r1, float r2, float r3, float r4, float r5,
+                                                 float* pt, float* w) {
+    // decode_bbox: xyz*(hi-lo)+lo, exp(log-size), atan2(sin, cos)   (separate mul and add as in torch)
+    const float cx = __fadd_rn(__fmul_rn(bb[0], __fsub_rn(r3, r0)), r0);
+    const float cy = __fadd_rn(__fmul_rn(bb[1], __fsub_rn(r4, r1)), r1);
+    const float cz = __fadd_rn(__fmul_rn(bb[2], __fsub_rn(r5, r2)), r2);
+    const float sw = expf(bb[3]), sl = expf(bb[4]), sh = expf(bb[5]);
+    const float yaw = atan2f(bb[6], bb[7]);
+    const float s = sinf(yaw), c = cosf(yaw);
+    const float dx = __fmul_rn(sw, op[0]), dy = __fmul_rn(sl, op[1]), dz = __fmul_rn(sh, op[2]);
+    // rotate counter-clockwise by yaw about z: x' = x*c + y*(-s), y' = x*s + y*c
+    const float rx = __fadd_rn(__fmul_rn(dx, c), __fmul_rn(dy, -s));
+    const float ry = __fadd_rn(__fmul_rn(dx, s), __fmul_rn(dy, c));
+    pt[0] = __fadd_rn(cx, rx);
+    pt[1] = __fadd_rn(cy, ry);
+    pt[2] = __fadd_rn(cz, dz);
+    // softmax over L
+    float mx = -INFINITY;
+    for (int l = 0; l < L; ++l) mx = fmaxf(mx, lp[l]);
+    float e[SBEV_MAX_LEVELS], sum = 0.f;
+    for (int l = 0; l < L; ++l) { e[l] = expf(lp[l] - mx); sum += e[l]; }
+    for (int l = 0; l < L; ++l) w[l] = __fdiv_rn(e[l], sum);
+}
 
 __device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -635,6 +667,13 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
             float* yr = ys + warp * MC_YLD;
             chain_row_epilogue(prm, L, row0 + warp, yr, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr);
             __syncwarp();
+            if ((L.flags & CHAIN_FLAG_POINTS) && row0 + warp < prm.M) {           // lane gp: sample point gp of this query
+                const long long row = row0 + warp;
+                for (int gp = lane; gp < prm.sp_GP; gp += 32)
+                    sample_point_one(prm.sp_bbox + row * 10, yr + prm.sp_off_col + gp * 3, yr + prm.sp_log_col + gp * prm.sp_L, prm.sp_L,
+                                     prm.sp_r[0], prm.sp_r[1], prm.sp_r[2], prm.sp_r[3], prm.sp_r[4], prm.sp_r[5],
+                                     prm.sp_points + (row * prm.sp_GP + gp) * 3, prm.sp_scale_w + (row * prm.sp_GP + gp) * prm.sp_L);
+            }
             if (li + 1 < prm.n_layers) {          // next layer's activation operand: bf16 (hi, lo), zero beyond N up to its padded K
                 __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD;
                 __nv_bfloat16* nl = nh + DENSE_ROWS * MC_XLD;
@@ -1091,30 +1130,9 @@ sample_points_kernel(const float* __restrict__ query_bbox, const float* __restri
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)BQ * GP) return;
     const long long bq = idx / GP;
-    const float* bb = query_bbox + bq * 10;
-    // decode_bbox: xyz*(hi-lo)+lo, exp(log-size), atan2(sin, cos)   (separate mul and add as in torch)
-    const float cx = __fadd_rn(__fmul_rn(__ldg(bb + 0), __fsub_rn(r3, r0)), r0);
-    const float cy = __fadd_rn(__fmul_rn(__ldg(bb + 1), __fsub_rn(r4, r1)), r1);
-    const float cz = __fadd_rn(__fmul_rn(__ldg(bb + 2), __fsub_rn(r5, r2)), r2);
-    const float sw = expf(__ldg(bb + 3)), sl = expf(__ldg(bb + 4)), sh = expf(__ldg(bb + 5));
-    const float yaw = atan2f(__ldg(bb + 6), __ldg(bb + 7));
-    const float s = sinf(yaw), c = cosf(yaw);
     const int gp = (int)(idx - bq * GP);
-    const float* op = offset + bq * ld_off + gp * 3;
-    const float dx = __fmul_rn(sw, __ldg(op)), dy = __fmul_rn(sl, __ldg(op + 1)), dz = __fmul_rn(sh, __ldg(op + 2));
-    // rotate counter-clockwise by yaw about z: x' = x*c + y*(-s), y' = x*s + y*c
-    const float rx = __fadd_rn(__fmul_rn(dx, c), __fmul_rn(dy, -s));
-    const float ry = __fadd_rn(__fmul_rn(dx, s), __fmul_rn(dy, c));
-    points[idx * 3 + 0] = __fadd_rn(cx, rx);
-    points[idx * 3 + 1] = __fadd_rn(cy, ry);
-    points[idx * 3 + 2] = __fadd_rn(cz, dz);
-    // softmax over L
-    const float* lp = logits + bq * ld_log + gp * L;
-    float mx = -INFINITY;
-    for (int l = 0; l < L; ++l) mx = fmaxf(mx, __ldg(lp + l));
-    float e[SBEV_MAX_LEVELS], sum = 0.f;
-    for (int l = 0; l < L; ++l) { e[l] = expf(__ldg(lp + l) - mx); sum += e[l]; }
-    for (int l = 0; l < L; ++l) scale_w[idx * L + l] = __fdiv_rn(e[l], sum);
+    sample_point_one(query_bbox + bq * 10, offset + bq * ld_off + gp * 3, logits + bq * ld_log + gp * L, L, r0, r1, r2, r3, r4, r5,
+                     points + idx * 3, scale_w + idx * L);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1234,10 +1252,13 @@ refine_bbox_kernel(const float* __restrict__ proposal, const float* __restrict__
 using namespace sbev;
 
 struct ChainInputReduce { const float* partial; int nsplit; const float* bias; const float* residual; const float* ln_w; const float* ln_b; float* out; };
+struct ChainPoints { const float* bbox; const float* pc_range; int GP, L, off_col, log_col; float* points; float* scale_w; };
+extern "C" int sbev_sample_points_fwd(const float* query_bbox, const float* offset, int ld_off, const float* scale_logits, int ld_log,
+                                      const float* pc_range, int BQ, int GP, int L, float* points, float* scale_w, void* stream);
 
 static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in, int M, int n_layers, const sbev_dense_layer* layers,
                             const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
-                            void* stream) {
+                            void* stream, const ChainPoints* pts = nullptr) {
     SBEV_REQUIRE((x || in) && layers, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
     SBEV_REQUIRE(n_layers >= 1 && n_layers <= CHAIN_MAX_LAYERS, SBEV_ERR_UNSUPPORTED, "sbev_dense_chain_fwd: 1..%d layers", CHAIN_MAX_LAYERS);
     SBEV_REQUIRE(M >= 0 && ldx >= layers[0].K, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: bad sizes");
@@ -1250,6 +1271,8 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         prm.in_ln_w = in->ln_w; prm.in_ln_b = in->ln_b; prm.in_out = in->out;
     }
     prm.aux_proposal = refine_proposal; prm.aux_time_diff = refine_time_diff; prm.aux_Q = refine_Q > 0 ? refine_Q : 1; prm.aux_T = refine_T;
+    prm.sp_bbox = nullptr; prm.sp_points = prm.sp_scale_w = nullptr; prm.sp_GP = prm.sp_L = prm.sp_off_col = prm.sp_log_col = 0;
+    for (int i = 0; i < 6; ++i) prm.sp_r[i] = 0.f;
     int act = 4;
     for (int i = 0; i < n_layers; ++i) {
         const sbev_dense_layer& l = layers[i];
@@ -1286,6 +1309,33 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
     SBEV_REQUIRE(layers[n_layers - 1].y != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: last layer needs an output pointer");
     prm.act_ld = act + 4;
     if (M == 0) return SBEV_OK;
+    bool fuse_points = false;
+    if (pts != nullptr) {
+        const sbev_dense_layer& ll = layers[n_layers - 1];
+        SBEV_REQUIRE(pts->bbox && pts->pc_range && pts->points && pts->scale_w && pts->GP > 0 && pts->L >= 1 && pts->L <= SBEV_MAX_LEVELS &&
+                     pts->off_col >= 0 && pts->log_col >= 0 && pts->off_col + pts->GP * 3 <= ll.N && pts->log_col + pts->GP * pts->L <= ll.N &&
+                     ll.ln_w == nullptr && !(ll.flags & (SBEV_DENSE_RELU | SBEV_DENSE_REFINE)) && ll.residual == nullptr,
+                     SBEV_ERR_INVALID, "sbev_dense_chain_points_fwd: bad sample-points arguments (plain Linear last layer holding the offsets and logits)");
+        // fused only in the default tensor-core kernel; every other variant runs the chain, then sample_points_kernel
+        bool mma_ok = use_mma && get_option(OPT_DENSE_NSPLIT) == 0 && get_option(OPT_DENSE_CLUSTER) <= 1 && get_option(OPT_DENSE_FUSE_POINTS);
+        for (int i = 0; i < n_layers; ++i)
+            if (layers[i].W_hi == nullptr || layers[i].W_lo == nullptr || layers[i].K > 512 || layers[i].N > 1024) mma_ok = false;
+        if (mma_ok) {
+            fuse_points = true;
+            ChainLayer& c = prm.layer[n_layers - 1];
+            c.flags = (c.flags & ~CHAIN_FLAG_VEC4) | CHAIN_FLAG_POINTS;          // scalar epilogue: the finished row stays in shared memory
+            prm.sp_bbox = pts->bbox; prm.sp_points = pts->points; prm.sp_scale_w = pts->scale_w;
+            for (int i = 0; i < 6; ++i) prm.sp_r[i] = pts->pc_range[i];
+            prm.sp_GP = pts->GP; prm.sp_L = pts->L; prm.sp_off_col = pts->off_col; prm.sp_log_col = pts->log_col;
+        }
+    }
+    if (pts != nullptr && !fuse_points) {
+        int rc = dense_chain_impl(x, ldx, in, M, n_layers, layers, refine_proposal, refine_time_diff, refine_Q, refine_T, stream, nullptr);
+        if (rc) return rc;
+        const sbev_dense_layer& ll = layers[n_layers - 1];
+        return sbev_sample_points_fwd(pts->bbox, ll.y + pts->off_col, ll.ldy, ll.y + pts->log_col, ll.ldy, pts->pc_range, M, pts->GP, pts->L,
+                                      pts->points, pts->scale_w, stream);
+    }
     if (use_mma) {
         // tensor-core path: pre-split bf16 weights [N][Kpad] streamed by TMA (box 64 k x 128 rows, 128-byte swizzle)
         ChainMaps maps;
@@ -1387,6 +1437,14 @@ extern "C" int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers
                                     void* stream) {
     SBEV_REQUIRE(x != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: null pointer");
     return dense_chain_impl(x, ldx, nullptr, M, n_layers, layers, refine_proposal, refine_time_diff, refine_Q, refine_T, stream);
+}
+
+extern "C" int sbev_dense_chain_points_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                                           const float* query_bbox, const float* pc_range, int GP, int L, int off_col, int log_col,
+                                           float* points, float* scale_w, void* stream) {
+    SBEV_REQUIRE(x != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_points_fwd: null pointer");
+    const ChainPoints pts{query_bbox, pc_range, GP, L, off_col, log_col, points, scale_w};
+    return dense_chain_impl(x, ldx, nullptr, M, n_layers, layers, nullptr, nullptr, 0, 0, stream, &pts);
 }
 
 extern "C" int sbev_reduce_ln_fwd(const float* partial, int nsplit, const float* bias, const float* residual,

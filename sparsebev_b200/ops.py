@@ -237,6 +237,23 @@ def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, 
                                             refine_Q, refine_T, _stream()), 'sbev_dense_chain_fwd')
 
 
+def dense_chain_points(x, ldx, M, layers, query_bbox, pc_range, GP, L, off_col, log_col):
+    """dense_chain whose last layer's row holds [GP*3 sampling offsets @ off_col | GP*L scale logits @ log_col]: also returns
+    the sample points [B,Q,GP,3] and softmaxed scale weights [B,Q,GP,L] (sbev_dense_chain_points_fwd, one launch)."""
+    lib = _lib.load()
+    _chk(x, 'x')
+    qb = _chk(query_bbox, 'query_bbox')
+    B, Q, _ = qb.shape
+    pts = torch.empty(B, Q, GP, 3, device=qb.device, dtype=torch.float32)
+    sw = torch.empty(B, Q, GP, L, device=qb.device, dtype=torch.float32)
+    arr = (_lib.DenseLayer * len(layers))(*[l[0] for l in layers])
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_dense_chain_points_fwd(x.data_ptr(), ldx, M, len(layers), arr, qb.data_ptr(),
+                                                   _lib.f32_array([float(v) for v in pc_range]), GP, L, off_col, log_col,
+                                                   pts.data_ptr(), sw.data_ptr(), _stream()), 'sbev_dense_chain_points_fwd')
+    return pts, sw
+
+
 def dense_chain_reduce(partial, bias, residual, ln_w, ln_b, x_out, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):
     """dense_chain whose input rows are LN(sum_z partial[z] + bias + residual) (sbev_dense_chain_reduce_fwd): the split-K
     reduce + norm of the preceding GEMM runs in the chain's prologue.  partial [S,M,K0]; x_out [M,K0] receives the input rows."""

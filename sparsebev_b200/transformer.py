@@ -265,15 +265,25 @@ class SparseBEVSampling(BaseModule):
     def heads_layer(self, y):
         return self._heads.layer(y=y)
 
-    def sample(self, query_bbox, heads_out, mlvl_feats, img_metas, frame_window=None, scatter_ptrs=None):
-        """heads_out [B*Q, G*P*3 + G*P*L] = the concatenated sampling_offset | scale_weights Linear output.
+    def points_args(self):
+        """Arguments of ops.dense_chain_points for a chain that ends in heads_layer: the sample points and scale weights
+        then come out of that launch's epilogue."""
+        G, P, L = self.num_groups, self.num_points, self.num_levels
+        return dict(pc_range=self.pc_range, GP=G * P, L=L, off_col=0, log_col=G * P * 3)
+
+    def sample(self, query_bbox, heads_out, mlvl_feats, img_metas, frame_window=None, scatter_ptrs=None, points=None):
+        """heads_out [B*Q, G*P*3 + G*P*L] = the concatenated sampling_offset | scale_weights Linear output, or
+        points = (pts, scale_w) already produced by ops.dense_chain_points.
         frame_window / scatter_ptrs: frame-sharded forms, see ops.sampling4d_fused."""
         B, Q = query_bbox.shape[:2]
         image_h, image_w, _ = img_metas[0]['img_shape'][0]
         G, P, L = self.num_groups, self.num_points, self.num_levels
-        ld = heads_out.shape[1]
-        pts, sw = ops.sample_points(query_bbox, heads_out, heads_out[:, G * P * 3:], self.pc_range, L,
-                                    num_points_total=G * P, ld_off=ld, ld_log=ld)
+        if points is not None:
+            pts, sw = points
+        else:
+            ld = heads_out.shape[1]
+            pts, sw = ops.sample_points(query_bbox, heads_out, heads_out[:, G * P * 3:], self.pc_range, L,
+                                        num_points_total=G * P, ld_off=ld, ld_log=ld)
         return ops.sampling4d_fused(mlvl_feats, pts, query_bbox, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
                                     sw.reshape(B, Q, G, P, L), image_h, image_w, num_frames=self.num_frames,
                                     num_views=NUM_VIEWS, layout=self.feat_layout,       # [B,Q,G,T*P,C]
@@ -346,31 +356,31 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         return ops.refine_bbox(bbox_proposal, bbox_delta, time_diff)
 
     @torch.no_grad()
-    def _sample(self, query_bbox, heads, mlvl_feats, img_metas):
+    def _sample(self, query_bbox, heads, mlvl_feats, img_metas, points=None):
         """Sampled features [B,Q,G,T*P,C] of ALL frames.  Unsharded: one fused gather.  Frame-sharded
         (self.frame_shard = dist.FrameShard): mlvl_feats hold this rank's frames only; the rows of the other frames
         arrive from the peers (stored by their gather kernels over NVLink, or by one all-gather)."""
         shard = self.frame_shard
         if shard is None or shard.world == 1:
-            return self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas)
+            return self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas, points=points)
         if shard.exchange == 'p2p':
             B, Q = query_bbox.shape[:2]
             s = self.sampling
             buf, ptrs = shard.peer_buffers((B, Q, s.num_groups, s.num_frames * s.num_points, self.embed_dims // s.num_groups),
                                            query_bbox.device)
-            s.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window, scatter_ptrs=ptrs)
+            s.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window, scatter_ptrs=ptrs, points=points)
             shard.peer_barrier()
             return buf
-        local = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window)
+        local = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window, points=points)
         return shard.all_gather(local)
 
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        11 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
-        that follow; the FFN chain's prologue performs the mixing stage's split-K reduce + norm2), SASA core, sample_points,
-        fused gather, 2 tcgen05 GEMMs, mix; the gather runs
+        10 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
+        that follow; one also emits the sample points; the FFN chain's prologue performs the mixing stage's split-K reduce
+        + norm2), SASA core, fused gather, 2 tcgen05 GEMMs, mix; the gather runs
         concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
         M, dev = B * Q, query_feat.device
@@ -385,7 +395,8 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         o = self.self_attn.attention_core(query_bbox, q1, attn_mask, pre=pos_enc)
         q2, heads = new(D), new(self.sampling._heads.out_features)
         pbuf = self.mixing.alloc_params(M, dev)               # q2 also leaves the chain as the bf16 (hi, lo) operand of the param GEMM
-        ops.dense_chain(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)])
+        points = ops.dense_chain_points(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)],
+                                        query_bbox, **self.sampling.points_args())       # sample points + scale weights from the same launch
         # (3) adaptive spatio-temporal sampling  ||  (4a) dynamic-parameter GEMM: independent of each other (the GEMM needs
         # only q2), complementary resources (gather: LSU / L2 latency, no shared memory; GEMM: tensor cores + TMA) -> two
         # streams, i.e. two parallel branches when the layer is captured into a CUDA graph.  Buffers are allocated before the
@@ -396,11 +407,11 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 params = self.mixing.generate_params(q2, pbuf, presplit=True)
-            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas)
+            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas, points)
             main.wait_stream(side)
         else:
             params = self.mixing.generate_params(q2, pbuf, presplit=True)
-            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas)
+            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas, points)
         # (4b) adaptive mixing (+ identity + norm2)
         G, P = self.mixing.n_groups, self.mixing.in_points
         red = self.mixing.mix_and_project(params, sampled.reshape(M, G, P, -1), q2, self.norm2, defer_reduce=True)

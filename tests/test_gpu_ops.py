@@ -415,6 +415,47 @@ def test_dense_chain_with_fused_splitk_reduce(impl, K0, nsplit, ln, option):
     _close(y, want, rtol=1e-4, atol=2e-5 if impl == 1 else 1e-4, what='chain behind the fused reduce')
 
 
+@pytest.mark.parametrize('fuse', [1, 0])
+def test_dense_chain_points_equals_chain_then_sample_points(fuse, option):
+    """sbev_dense_chain_points_fwd: the sample points / scale weights that leave the chain's epilogue are bit-identical to
+    running the chain and then sbev_sample_points_fwd on its output (fuse=0 exercises the documented two-launch form)."""
+    from sparsebev_b200 import _lib
+    ops = _ops()
+    prev = _lib.get_option('dense_fuse_points')
+    _lib.set_option('dense_fuse_points', fuse)
+    try:
+        torch.manual_seed(3)
+        M, D, GP, L = 901, 256, 16, 4
+        x = torch.randn(M, D)
+        lin = [torch.nn.Linear(256, 256), torch.nn.Linear(256, GP * 3 + GP * L)]
+        ln = torch.nn.LayerNorm(256)
+        qb = R.init_query_bbox(961, seed=2)[:M][None].contiguous()
+        import copy
+        mods = [copy.deepcopy(m).to(dev()) for m in lin]
+        lnd = copy.deepcopy(ln).to(dev())
+        caches = [ops.DenseWeight() for _ in lin]
+
+        def entry(i, **kw):
+            wt, ldw, bias = caches[i].get_with_bias([mods[i].weight], [mods[i].bias])
+            return ops.chain_layer(wt, ldw, mods[i].in_features, mods[i].out_features, bias=bias, w_hi=caches[i].w_hi, w_lo=caches[i].w_lo,
+                                   kpad=caches[i].kpad, **kw)
+        xd = x.to(dev())
+        q2, heads = torch.empty(M, 256, device=dev()), torch.empty(M, GP * 3 + GP * L, device=dev())
+        pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+        pts, sw = ops.dense_chain_points(xd, D, M, [entry(0, ln=lnd, residual=xd, res_pre_ln=True, y=q2), entry(1, y=heads)], qb.to(dev()),
+                                         pc, GP, L, 0, GP * 3)
+        q2b, headsb = torch.empty_like(q2), torch.empty_like(heads)
+        ops.dense_chain(xd, D, M, [entry(0, ln=lnd, residual=xd, res_pre_ln=True, y=q2b), entry(1, y=headsb)])
+        pts2, sw2 = ops.sample_points(qb.to(dev()), headsb, headsb[:, GP * 3:], pc, L, num_points_total=GP, ld_off=headsb.shape[1], ld_log=headsb.shape[1])
+        torch.cuda.synchronize()
+        assert torch.equal(heads, headsb) and torch.equal(q2, q2b)
+        assert torch.equal(pts, pts2) and torch.equal(sw, sw2)
+        want_pts = R.make_sample_points(qb, headsb[:, :GP * 3].cpu().reshape(1, M, GP, 3), pc)
+        _close(pts, want_pts, rtol=1e-5, atol=1e-4, what='fused sample points vs oracle')
+    finally:
+        _lib.set_option('dense_fuse_points', prev)
+
+
 def test_sample_points_and_refine_vs_oracle():
     ops = _ops()
     pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
