@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--breakdown', action='store_true', help='also write per-stage timings to gpurun_out/breakdown.json')
     ap.add_argument('--cpu-steps', type=int, default=3, help='bounded CPU sample: decoder-layer passes of the oracle')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-backbone', action='store_true', help='do not time the ResNet-50 + FPN image branch (SURVEY 8 a17) next to the headline metric')
     return ap.parse_args()
 
 
@@ -438,6 +439,10 @@ def main():
         with open(os.path.join(ROOT, 'gpurun_out', 'breakdown.json'), 'w') as f:
             json.dump(breakdown, f, indent=1)
 
+    backbone = None
+    if rank == 0 and world == 1 and not args.skip_backbone:
+        backbone = backbone_record(dev, cfg)
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         best, mean, threads = cpu_layer_timer(cfg, args.cpu_steps)
@@ -475,10 +480,80 @@ def main():
                                 'note': 'bf16x3 issues three bf16 tensor-core products per fp32-grade product; the kernel is bound by L2->SM operand '
                                         'traffic (~390 MB per launch), not by the tensor pipe'},
             'cpu_baseline': cpu,
+            'backbone': backbone,
             'breakdown_ms': breakdown}))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def backbone_record(dev, cfg, images=6):
+    """Secondary record (BASELINE config 4's image branch): ResNet-50 + FPN over the 6 camera images of one new
+    frame (what the reference's online inference runs per sample, models/sparsebev.py:255-321), our tcgen05 implicit-GEMM
+    convolutions (NHWC bf16, fp32 FPN levels in the gather's layout) vs the same modules through stock PyTorch / cuDNN
+    (bf16 autocast, channels_last).  Device-timed with CUDA events after warm-up; random-init weights."""
+    import torch.nn.functional as F
+    from sparsebev_b200 import backbone as BB
+    try:
+        torch.manual_seed(0)
+        net = BB.ResNet(depth=50).to(dev).eval()
+        neck = BB.FPN([256, 512, 1024, 2048], 256, cfg['num_levels']).to(dev).eval()
+        img = torch.randn(1, images, 3, cfg['image_h'], cfg['image_w'], device=dev)
+
+        def timeit(fn, iters=10):
+            for _ in range(3):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+
+        def stock(x):
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                x = net.maxpool(net.relu(net.bn1(net.conv1(x))))
+                outs = []
+                for name in net.res_layers:
+                    for blk in getattr(net, name):
+                        idt = x if blk.downsample is None else blk.downsample(x)
+                        o = blk.relu(blk.bn2(blk.conv2(blk.relu(blk.bn1(blk.conv1(x))))))
+                        x = blk.relu(blk.bn3(blk.conv3(o)) + idt)
+                    outs.append(x)
+                lats = [l.conv(f) for l, f in zip(neck.lateral_convs, outs)]
+                for i in range(len(lats) - 1, 0, -1):
+                    lats[i - 1] = lats[i - 1] + F.interpolate(lats[i], size=lats[i - 1].shape[-2:], mode='nearest')
+                return [c.conv(l).float() for c, l in zip(neck.fpn_convs, lats)]
+        def graphed(fn):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return timeit(g.replay)
+        with torch.no_grad():
+            ours = timeit(lambda: BB.extract_img_feat(net, neck, img))
+            ours_graph = graphed(lambda: BB.extract_img_feat(net, neck, img))
+            flat = img[0].contiguous(memory_format=torch.channels_last)
+            net.to(memory_format=torch.channels_last); neck.to(memory_format=torch.channels_last)
+            ref = timeit(lambda: stock(flat))
+            try:
+                ref_graph = graphed(lambda: stock(flat))
+            except Exception:
+                ref_graph = None
+        return {'workload': 'ResNet-50 + FPN (%d levels), %d images %dx%d' % (cfg['num_levels'], images, cfg['image_w'], cfg['image_h']),
+                'ms': ours_graph, 'images_per_s': images * 1e3 / ours_graph, 'eager_ms': ours,
+                'stock_pytorch_cudnn_bf16_ms': ref_graph, 'stock_pytorch_cudnn_bf16_eager_ms': ref, 'dtype': 'bf16 operands, fp32 accumulate',
+                'note': 'ms = CUDA-graph replay (63 launches of ours: sbev_stem_conv_fwd, sbev_maxpool3x3s2_nhwc_fwd, sbev_conv2d_nhwc_fwd x 61); '
+                        'the stock PyTorch arm runs the same modules through cuDNN under bf16 autocast, channels_last'}
+    except Exception as e:                                    # secondary record: never take the headline line down with it
+        return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
 def stage_breakdown(layer, qb, qf, feats, metas, cfg, iters=20):

@@ -51,8 +51,9 @@ const char* sbev_last_error(void);
  *                    through distributed shared memory; chains it cannot express (an inner layer wider than 512 ...) take
  *                    the "dense_impl" 0 kernel
  *   "dense_vec4"     1 = 16-byte vectorised row epilogue / operand staging in the chain kernels (default), 0 = scalar
- *   "dense_fuse_points" 1 = sbev_dense_chain_points_fwd computes the sample points in the chain's epilogue (default),
- *                    0 = separate sample_points kernel
+ *   "dense_fuse_points" 1 = sbev_dense_chain_points_fwd computes the sample points in the chain's epilogue, 0 = it runs the
+ *                    chain and then sample_points_kernel (default: measured 4 us faster per layer -- the fused epilogue
+ *                    delays the parameter GEMM that waits on the same launch, the separate kernel overlaps with it)
  *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
  *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;

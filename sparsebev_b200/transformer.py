@@ -378,9 +378,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 
-        10 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
-        that follow; one also emits the sample points; the FFN chain's prologue performs the mixing stage's split-K reduce
-        + norm2), SASA core, fused gather, 2 tcgen05 GEMMs, mix; the gather runs
+        11 kernel launches: 5 dense chains (two of them also emit the bf16 (hi, lo) operands of the tensor-core kernels
+        that follow; the FFN chain's prologue performs the mixing stage's split-K reduce + norm2), SASA core, sample_points
+        (or, option dense_fuse_points, the epilogue of the out-projection chain), fused gather, 2 tcgen05 GEMMs, mix; the gather runs
         concurrently with the parameter GEMM, cls with reg."""
         B, Q, D = query_feat.shape
         M, dev = B * Q, query_feat.device
