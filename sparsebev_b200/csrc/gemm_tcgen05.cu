@@ -690,6 +690,20 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
                     mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_units, bias, (float*)nullptr, M, N);
         return check_launch("sbev_gemm_bf16_tn_split(pair)");
     }
+    if (get_option(OPT_GEMM_IMPL) == 4 && K == 4 * GEMM_BK && num_sms >= m_tiles) {
+        // A-resident, 128-wide N tiles: a CTA keeps its M-tile's whole A operand (K = 256: 4 k-blocks x (hi, lo) = 128 KB) in
+        // shared memory and streams only B (2 stages of 32 KB) -- a quarter less L2 -> SM traffic than re-fetching A per tile
+        rc = make_bf16_map(&mp.b_hi, B_hi, N, K, 128);   if (rc) return rc;
+        rc = make_bf16_map(&mp.b_lo, B_lo, N, K, 128);   if (rc) return rc;
+        constexpr size_t smem_ares = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
+        static std::once_flag once_ares;
+        std::call_once(once_ares, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4, true>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ares); });
+        const int grid_ares = (num_sms / m_tiles) * m_tiles;
+        launch_pdl(gemm_bf16_tn_persistent_kernel<128, 2, true, 4, true>, dim3(grid_ares), dim3(GEMM_THREADS), smem_ares, (cudaStream_t)stream,
+                   mp, K / GEMM_BK, 1, m_tiles, N / 128, m_tiles * (N / 128), bias, nullptr, M, N);
+        return check_launch("sbev_gemm_bf16_tn_split(a-resident)");
+    }
     const int num_tiles = m_tiles * n_tiles;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
     constexpr size_t smem = (size_t)2 * 2 * (GEMM_BM * GEMM_BK * 2 + 256 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;

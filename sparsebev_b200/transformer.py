@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 
 try:                                                     # mmcv / mmdet are optional (absent in the build image)
     from mmcv.runner import BaseModule
@@ -395,8 +395,12 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         o = self.self_attn.attention_core(query_bbox, q1, attn_mask, pre=pos_enc)
         q2, heads = new(D), new(self.sampling._heads.out_features)
         pbuf = self.mixing.alloc_params(M, dev)               # q2 also leaves the chain as the bf16 (hi, lo) operand of the param GEMM
-        points = ops.dense_chain_points(o, D, M, [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)],
-                                        query_bbox, **self.sampling.points_args())       # sample points + scale weights from the same launch
+        chain2 = [self.self_attn.out_layer(q1, self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), self.sampling.heads_layer(heads)]
+        if _lib.get_option('dense_fuse_points'):              # sample points + scale weights from the same launch (off by default: measured slower)
+            points = ops.dense_chain_points(o, D, M, chain2, query_bbox, **self.sampling.points_args())
+        else:
+            points = None
+            ops.dense_chain(o, D, M, chain2)
         # (3) adaptive spatio-temporal sampling  ||  (4a) dynamic-parameter GEMM: independent of each other (the GEMM needs
         # only q2), complementary resources (gather: LSU / L2 latency, no shared memory; GEMM: tensor cores + TMA) -> two
         # streams, i.e. two parallel branches when the layer is captured into a CUDA graph.  Buffers are allocated before the

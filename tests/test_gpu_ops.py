@@ -601,9 +601,10 @@ def test_reduce_ln_vs_torch(nsplit, M, N, ln):
     _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
 
 
-@pytest.mark.parametrize('impl', [0, 2])
+@pytest.mark.parametrize('impl', [0, 2, 4])
 def test_gemm_split_output_and_tma_fed_mix(impl, option):
-    """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path (impl 2: CTA-pair GEMM, 0: single CTAs; M = 300 gives
+    """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path (impl 2: CTA-pair GEMM, 0: single CTAs,
+    4: A-resident single CTAs with 128-wide N tiles; M = 300 gives
     an odd number of 128-row tiles, so the last pair's second CTA is entirely out of range)."""
     option('gemm_impl', impl)
     ops = _ops()
