@@ -95,6 +95,21 @@ int sbev_msmv_bwd(const float* grad_out, const float* const* feats, const int* h
                   int Bp, int N, int C, int Q, int P,
                   float* const* grad_feats, float* grad_loc, float* grad_w, void* stream);
 
+/* Deterministic msmv_sampling backward: same contract as sbev_msmv_bwd, but grad_feats is produced
+ * WITHOUT floating-point atomics -- the reference's scatter (one atomicAdd per corner and channel,
+ * msmv_sampling_backward.cu:29-224) is inverted into a per-pixel segmented reduction that sums the contributions of a
+ * pixel in ascending (point, corner) order, so repeated runs are bit-identical.  C must be 64.
+ *   workspace        DEVICE scratch owned by the caller, at least sbev_msmv_bwd_det_workspace(...) bytes, 4-byte aligned;
+ *                    contents are undefined afterwards.  grad_feats need NOT be zeroed (every pixel row is written once).
+ * sbev_msmv_bwd_det_workspace returns the byte count, or -1 for invalid sizes.
+ */
+long long sbev_msmv_bwd_det_workspace(const int* hw, int L, int Bp, int N, int Q, int P);
+int sbev_msmv_bwd_det(const float* grad_out, const float* const* feats, const int* hw, int L,
+                      const float* loc, const float* w,
+                      int Bp, int N, int C, int Q, int P,
+                      float* const* grad_feats, float* grad_loc, float* grad_w,
+                      void* workspace, long long workspace_bytes, void* stream);
+
 /* The integer sample indices the forward kernel derives from `loc` -- for bit-exact index parity
  * tests (same device code path as sbev_msmv_fwd: msmv_sampling_forward.cu:110,123-126,33-36).
  *   view [Bp,Q,P] int32;  y0, x0, inside [Bp,Q,P,L] int32

@@ -32,6 +32,8 @@ SIGNATURES = {
     'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                       c_vpp, c_vp, c_vp, c_vp],
+    'sbev_msmv_bwd_det': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                          c_vpp, c_vp, c_vp, c_vp, ctypes.c_longlong, c_vp],
     'sbev_msmv_indices': [c_i32p, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     'sbev_sampling4d_fwd': [c_vpp, c_i32p, c_int, c_i64p, c_i64p, c_i64p, c_i64p,
                             c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -68,7 +70,7 @@ _lib = None
 
 
 def exported_symbols():
-    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option'])
+    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option', 'sbev_msmv_bwd_det_workspace'])
 
 
 def load():
@@ -88,6 +90,8 @@ def load():
     lib.sbev_last_error.restype = ctypes.c_char_p
     lib.sbev_get_option.argtypes = [ctypes.c_char_p]
     lib.sbev_get_option.restype = c_int
+    lib.sbev_msmv_bwd_det_workspace.argtypes = [c_i32p, c_int, c_int, c_int, c_int, c_int]
+    lib.sbev_msmv_bwd_det_workspace.restype = ctypes.c_longlong
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

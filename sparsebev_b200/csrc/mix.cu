@@ -483,7 +483,7 @@ mix_mma_kernel(const float* __restrict__ params, const float* __restrict__ x, in
 struct MixMaps { CUtensorMap m_hi, m_lo, s_hi, s_lo, y_hi, y_lo; };   // y_*: [items*128 rows][64 bf16], box 128 rows, 128 B swizzle
 
 __global__ void __launch_bounds__(256, 2)
-mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x, int num_items,
+mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x, int num_items, int G, int order,
                __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, float* __restrict__ y_f32) {
     constexpr int Pin = 32, PK = 32;
     constexpr int SET_BYTES = 4 * 8192;                       // M_hi | M_lo | S_hi | S_lo
@@ -524,14 +524,25 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
     }
     pdl_wait();
     pdl_trigger();
-    if (tid == 0 && (long long)blockIdx.x < num_items) prefetch(blockIdx.x, 0);
+    // Work order.  0: items ascending (query-major).  1: group-major, LAST group first -- the parameter GEMM writes its
+    // N-tiles (= groups) in ascending order, so the highest groups' parameters are the ones still resident in L2 when this
+    // kernel starts; and this kernel then finishes with group 0, whose output is what the out-projection's first split-K
+    // slices read.
+    const int BQ = num_items / G;
+    auto item_of = [&](long long i) -> long long {
+        if (!order) return i;
+        const int gi = (int)(i / BQ);
+        return (i - (long long)gi * BQ) * G + (G - 1 - gi);
+    };
+    if (tid == 0 && (long long)blockIdx.x < num_items) prefetch(item_of(blockIdx.x), 0);
     __syncthreads();
 
     const int lm_r = lane & 7, lm_id = lane >> 3;
     const int a_row = lm_r + 8 * (lm_id & 1), a_col = 8 * (lm_id >> 1);
 
     int n = 0;
-    for (long long qg = blockIdx.x; qg < num_items; qg += gridDim.x, ++n) {
+    for (long long it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
+        const long long qg = item_of(it);
         const int slot = n & 1;
         {
             const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[slot]);
@@ -559,10 +570,10 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
             }
         }
         __syncthreads();
-        if (tid == 0 && qg + gridDim.x < num_items) {        // the other operand set and x buffer are free: fetch the next item now
+        if (tid == 0 && it + gridDim.x < num_items) {        // the other operand set and x buffer are free: fetch the next item now
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // ... once the previous item's output tile has left it
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            prefetch(qg + gridDim.x, slot ^ 1);
+            prefetch(item_of(it + gridDim.x), slot ^ 1);
         }
 
         // ---- stage 1: h[p][c'] = sum_c x[p][c] M[c][c'], warp w owns columns c' = 8w..8w+7
@@ -774,7 +785,8 @@ extern "C" int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* 
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     const int grid = items < 2 * num_sms ? (int)items : 2 * num_sms;
-    launch_pdl(mix_tma_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, maps, x, (int)items, reinterpret_cast<__nv_bfloat16*>(y_hi),
+    launch_pdl(mix_tma_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, maps, x, (int)items, G, get_option(OPT_MIX_ORDER),
+               reinterpret_cast<__nv_bfloat16*>(y_hi),
                reinterpret_cast<__nv_bfloat16*>(y_lo), y_f32);
     return check_launch("sbev_mix_presplit_fwd");
 }

@@ -260,7 +260,8 @@ __device__ __forceinline__ void red_add4(float* addr, float4 v) {
 
 struct GradLevelSet { float* ptr[SBEV_MAX_LEVELS]; };
 
-template <int L>
+// SCATTER = false: only grad_loc / grad_w (the deterministic path accumulates grad_feats per pixel, below).
+template <int L, bool SCATTER = true>
 __global__ void __launch_bounds__(256)
 msmv_bwd_c64_kernel(LevelSet lv, GradLevelSet glv, const float* __restrict__ grad_out,
                     const float* __restrict__ loc, const float* __restrict__ wgt,
@@ -309,7 +310,7 @@ msmv_bwd_c64_kernel(LevelSet lv, GradLevelSet glv, const float* __restrict__ gra
                 const float fly = y - floorf(y), flx = x - floorf(x);
                 const float fhy = 1.f - fly, fhx = 1.f - flx;
                 const float4 gv = make_float4(g.x * aw, g.y * aw, g.z * aw, g.w * aw);   // top_grad * attn_weight
-                if (live) {
+                if (SCATTER && live) {
                     if (t.ok1) red_add4(q0, make_float4(t.w1 * gv.x, t.w1 * gv.y, t.w1 * gv.z, t.w1 * gv.w));
                     if (t.ok2) red_add4(q0 + 64, make_float4(t.w2 * gv.x, t.w2 * gv.y, t.w2 * gv.z, t.w2 * gv.w));
                     if (t.ok3) red_add4(q0 + row, make_float4(t.w3 * gv.x, t.w3 * gv.y, t.w3 * gv.z, t.w3 * gv.w));
@@ -379,6 +380,144 @@ msmv_bwd_generic_kernel(LevelSet lv, GradLevelSet glv, int L, const float* __res
             atomicAdd(grad_loc + pi * 3, (float)(W - 1) * (-hy * v1 + hy * v2 - ly * v3 + ly * v4) * gv);
             atomicAdd(grad_loc + pi * 3 + 1, (float)(H - 1) * (-hx * v1 - lx * v2 + hx * v3 + lx * v4) * gv);
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Deterministic grad_feats ("col2im without floating-point atomics").  The scatter of the reference
+// (msmv_sampling_backward.cu:29-224: one atomicAdd per corner and channel) is inverted into a per-pixel gather:
+//   1. bin:    every (point, level, corner) contribution counts into its pixel            (integer atomics: exact)
+//   2. scan:   exclusive prefix sum of the counts -> segment offsets
+//   3. fill:   contribution ids (point*4 + corner) dropped into their pixel's segment      (order within a segment arbitrary)
+//   4. reduce: one half-warp per pixel walks its segment in ASCENDING id order (selection by repeated half-warp min)
+//              and sums  tap * scale_weight * grad_out  in registers; every pixel row -- touched or not -- is written
+//              exactly once by plain 16-byte stores, so grad_feats needs no zero fill either.
+// The summation order is a function of the inputs only: two runs give bit-identical gradients.
+struct PixelSpace { long long base[SBEV_MAX_LEVELS + 1]; };      // first pixel id of every level; base[L] = pixel count
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+msmv_bwd_bin_kernel(LevelSet lv, PixelSpace ps, int L, const float* __restrict__ loc, long long npts, int N, int QP,
+                    int* __restrict__ cnt, const int* __restrict__ off, int* __restrict__ ids) {
+    const long long total = npts * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pi = i / L;
+        const int l = (int)(i - pi * L);
+        const int view = view_from_coord(__ldg(loc + pi * 3 + 2), N);
+        if (view < 0 || view >= N) continue;
+        const int H = lv.H[l], W = lv.W[l];
+        const Tap t = make_tap(__ldg(loc + pi * 3), __ldg(loc + pi * 3 + 1), H, W);
+        if (!t.inside) continue;
+        const long long b = pi / QP;
+        const long long pix = ps.base[l] + (b * N + view) * H * W + (long long)t.y0 * W + t.x0;
+        const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
+        const long long px[4] = {pix, pix + 1, pix + W, pix + W + 1};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (!ok[c]) continue;
+            if (!FILL) atomicAdd(cnt + px[c], 1);
+            else ids[off[px[c]] + atomicSub(cnt + px[c], 1) - 1] = (int)(pi * 4 + c);
+        }
+    }
+}
+
+constexpr int SCAN_ITEMS = 2048;                                 // counts per block (256 threads x 8)
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* total, int* sh /* [9] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; ++w) { const int t = sh[w]; sh[w] = run; run += t; } sh[8] = run; }
+    __syncthreads();
+    const int excl = sh[warp] + inc - v;
+    *total = sh[8];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const int* __restrict__ cnt, long long n, int* __restrict__ bsum) {
+    __shared__ int sh[9];
+    const long long base = (long long)blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+    int s = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (base + e < n) s += cnt[base + e];
+    int total;
+    block_exclusive_scan_256(s, &total, sh);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) scan_bsums_kernel(int* __restrict__ bsum, int nb) {      // ONE block: in-place exclusive scan
+    __shared__ int sh[9];
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 256) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? bsum[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, &total, sh);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__ cnt, long long n, const int* __restrict__ bsum,
+                                                         int* __restrict__ off) {
+    __shared__ int sh[9];
+    const long long base = (long long)blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+    int v[8], s = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[e] = base + e < n ? cnt[base + e] : 0; s += v[e]; }
+    int total;
+    int run = bsum[blockIdx.x] + block_exclusive_scan_256(s, &total, sh);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (base + e < n) off[base + e] = run;
+        run += v[e];
+        if (base + e == n - 1) off[n] = run;                   // grand total closes the last segment
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+msmv_bwd_reduce_kernel(LevelSet lv, GradLevelSet glv, PixelSpace ps, const int* __restrict__ off, const int* __restrict__ ids,
+                       const float* __restrict__ grad_out, const float* __restrict__ loc, const float* __restrict__ wgt, int P) {
+    const int lane = threadIdx.x & 31, j = lane & 15;
+    const unsigned hmask = 0xffffu << (lane & 16);              // the two half-warps of a warp walk different segments
+    const long long total = ps.base[L];
+    const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long hw_stride = ((long long)gridDim.x * blockDim.x) >> 4;
+    for (long long pix = hw_id; pix < total; pix += hw_stride) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < L; ++k) if (pix >= ps.base[k]) l = k;
+        const int H = lv.H[l], W = lv.W[l];
+        const long long local = pix - ps.base[l];
+        const int beg = __ldg(off + pix), n = __ldg(off + pix + 1) - beg;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int mine = (n <= 16 && j < n) ? __ldg(ids + beg + j) : 0x7fffffff;     // short segment: one id per lane
+        int last = -1;
+        for (int k = 0; k < n; ++k) {
+            int m = 0x7fffffff;
+            if (n <= 16) { if (mine > last) m = mine; }
+            else for (int i = j; i < n; i += 16) { const int v = __ldg(ids + beg + i); if (v > last && v < m) m = v; }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(hmask, m, o));
+            last = m;                                                                 // ids are unique: strictly ascending walk
+            const long long pi = m >> 2;
+            const int corner = m & 3;
+            const Tap t = make_tap(__ldg(loc + pi * 3), __ldg(loc + pi * 3 + 1), H, W);
+            const float tw = corner == 0 ? t.w1 : corner == 1 ? t.w2 : corner == 2 ? t.w3 : t.w4;
+            const float aw = __ldg(wgt + pi * L + l);
+            const long long item = pi / P;
+            const int p = (int)(pi - item * P);
+            const float* gp = grad_out + (item * 64 + 4 * j) * P + p;
+            const float4 gv = make_float4(__ldg(gp) * aw, __ldg(gp + P) * aw, __ldg(gp + 2 * P) * aw, __ldg(gp + 3 * P) * aw);
+            acc.x += tw * gv.x; acc.y += tw * gv.y; acc.z += tw * gv.z; acc.w += tw * gv.w;
+        }
+        *reinterpret_cast<float4*>(glv.ptr[l] + local * 64 + 4 * j) = acc;
     }
 }
 
@@ -582,6 +721,78 @@ extern "C" int sbev_msmv_bwd(const float* grad_out, const float* const* feats, c
         msmv_bwd_generic_kernel<<<grid_for(npts * C, 256), 256, 0, st>>>(lv, glv, L, grad_out, loc, w, Bp, N, C, Q, P, grad_loc, grad_w);
     }
     return check_launch("sbev_msmv_bwd");
+}
+
+// Workspace layout of the deterministic backward (ints): cnt[npix] | off[npix + 1] | bsum[blocks] | ids[npts * L * 4]
+static int det_layout(const int* hw, int L, int Bp, int N, int Q, int P, PixelSpace* ps, long long* n_blocks, long long* n_ids) {
+    SBEV_REQUIRE(hw && L >= 1 && L <= SBEV_MAX_LEVELS, SBEV_ERR_INVALID, "sbev_msmv_bwd_det: bad level description");
+    SBEV_REQUIRE(Bp >= 0 && Q >= 0 && N > 0 && P > 0, SBEV_ERR_INVALID, "sbev_msmv_bwd_det: bad sizes");
+    long long base = 0;
+    for (int l = 0; l < L; ++l) {
+        SBEV_REQUIRE(hw[2 * l] > 0 && hw[2 * l + 1] > 0, SBEV_ERR_INVALID, "level %d has non-positive size", l);
+        ps->base[l] = base;
+        base += (long long)Bp * N * hw[2 * l] * hw[2 * l + 1];
+    }
+    for (int l = L; l <= SBEV_MAX_LEVELS; ++l) ps->base[l] = base;
+    *n_blocks = (base + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    *n_ids = (long long)Bp * Q * P * L * 4;
+    SBEV_REQUIRE((long long)Bp * Q * P * 4 < (1ll << 31) && *n_ids < (1ll << 31), SBEV_ERR_UNSUPPORTED, "sbev_msmv_bwd_det: too many sample points");
+    return SBEV_OK;
+}
+
+extern "C" long long sbev_msmv_bwd_det_workspace(const int* hw, int L, int Bp, int N, int Q, int P) {
+    PixelSpace ps; long long nb, ni;
+    if (det_layout(hw, L, Bp, N, Q, P, &ps, &nb, &ni)) return -1;
+    return 4 * (2 * ps.base[L] + 1 + nb + ni) + 64;
+}
+
+extern "C" int sbev_msmv_bwd_det(const float* grad_out, const float* const* feats, const int* hw, int L,
+                                 const float* loc, const float* w, int Bp, int N, int C, int Q, int P,
+                                 float* const* grad_feats, float* grad_loc, float* grad_w,
+                                 void* workspace, long long workspace_bytes, void* stream) {
+    SBEV_REQUIRE(feats && grad_feats, SBEV_ERR_INVALID, "sbev_msmv_bwd_det: null pointer");
+    SBEV_REQUIRE((long long)Bp * Q * P == 0 || (grad_out && loc && w && grad_loc && grad_w), SBEV_ERR_INVALID,
+                 "sbev_msmv_bwd_det: null pointer");          // no sample points: only the (zero) grad_feats are produced
+    SBEV_REQUIRE(C == 64, SBEV_ERR_UNSUPPORTED, "sbev_msmv_bwd_det: needs C = 64 (got %d)", C);
+    SBEV_REQUIRE(P <= SBEV_MAX_POINTS, SBEV_ERR_INVALID, "num_point exceed limits (%d > %d)", P, SBEV_MAX_POINTS);
+    PixelSpace ps; long long nb, ni;
+    int rc = det_layout(hw, L, Bp, N, Q, P, &ps, &nb, &ni);
+    if (rc) return rc;
+    const long long npix = ps.base[L];
+    SBEV_REQUIRE(workspace && workspace_bytes >= 4 * (2 * npix + 1 + nb + ni) + 64 && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0,
+                 SBEV_ERR_INVALID, "sbev_msmv_bwd_det: workspace too small (see sbev_msmv_bwd_det_workspace)");
+    LevelSet lv;
+    rc = fill_levels(lv, feats, hw, L);
+    if (rc) return rc;
+    GradLevelSet glv;
+    for (int l = 0; l < SBEV_MAX_LEVELS; ++l) glv.ptr[l] = nullptr;
+    for (int l = 0; l < L; ++l) {
+        SBEV_REQUIRE(grad_feats[l] != nullptr && (reinterpret_cast<uintptr_t>(grad_feats[l]) & 15) == 0, SBEV_ERR_INVALID,
+                     "grad_feats[%d] is null or not 16-byte aligned", l);
+        glv.ptr[l] = grad_feats[l];
+    }
+    if (npix == 0) return SBEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* cnt = reinterpret_cast<int*>(workspace);
+    int* off = cnt + npix;
+    int* bsum = off + npix + 1;
+    int* ids = bsum + nb;
+    const long long npts = (long long)Bp * Q * P;
+    cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)npix, st);
+    if (npts > 0) msmv_bwd_bin_kernel<false><<<grid_for(npts * L, 256), 256, 0, st>>>(lv, ps, L, loc, npts, N, Q * P, cnt, nullptr, nullptr);
+    scan_block_sums_kernel<<<(unsigned)nb, 256, 0, st>>>(cnt, npix, bsum);
+    scan_bsums_kernel<<<1, 256, 0, st>>>(bsum, (int)nb);
+    scan_apply_kernel<<<(unsigned)nb, 256, 0, st>>>(cnt, npix, bsum, off);
+    if (npts > 0) msmv_bwd_bin_kernel<true><<<grid_for(npts * L, 256), 256, 0, st>>>(lv, ps, L, loc, npts, N, Q * P, cnt, off, ids);
+    const int rgrid = grid_for(npix, 16);
+#define SBEV_LAUNCH_DET(LL)                                                                                                   \
+    case LL:                                                                                                                  \
+        msmv_bwd_reduce_kernel<LL><<<rgrid, 256, 0, st>>>(lv, glv, ps, off, ids, grad_out, loc, w, P);                         \
+        if (npts > 0) msmv_bwd_c64_kernel<LL, false><<<grid_for(npts, 16), 256, 0, st>>>(lv, glv, grad_out, loc, w, Bp, N, Q, P, grad_loc, grad_w); \
+        break;
+    switch (L) { SBEV_LAUNCH_DET(1) SBEV_LAUNCH_DET(2) SBEV_LAUNCH_DET(3) SBEV_LAUNCH_DET(4) SBEV_LAUNCH_DET(5) }
+#undef SBEV_LAUNCH_DET
+    return check_launch("sbev_msmv_bwd_det");
 }
 
 static int launch_sampling4d(const float* const* feats, const int* hw, int L,

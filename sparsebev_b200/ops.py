@@ -64,7 +64,9 @@ def msmv_forward(mlvl_feats, sampling_locations, scale_weights):
     return out
 
 
-def msmv_backward(grad_output, mlvl_feats, sampling_locations, scale_weights):
+def msmv_backward(grad_output, mlvl_feats, sampling_locations, scale_weights, deterministic=False):
+    """deterministic: grad_feats by the per-pixel segmented reduction (sbev_msmv_bwd_det: no floating-point atomics,
+    bit-identical between runs) instead of vector atomics."""
     lib = _lib.load()
     L, fptr, hw = _levels(mlvl_feats)
     loc = _chk(sampling_locations, 'sampling_loc')
@@ -75,6 +77,16 @@ def msmv_backward(grad_output, mlvl_feats, sampling_locations, scale_weights):
     grad_feats = [torch.empty_like(f) for f in mlvl_feats]
     grad_loc = torch.empty_like(loc)
     grad_w = torch.empty_like(w)
+    if deterministic:
+        nbytes = lib.sbev_msmv_bwd_det_workspace(hw, L, Bp, N, Q, P)
+        if nbytes < 0:
+            raise RuntimeError('sbev_msmv_bwd_det_workspace: invalid sizes')
+        work = torch.empty(nbytes // 4 + 1, dtype=torch.int32, device=loc.device)
+        with torch.cuda.device(loc.device):
+            _lib.check(lib.sbev_msmv_bwd_det(go.data_ptr(), fptr, hw, L, loc.data_ptr(), w.data_ptr(), Bp, N, C, Q, P,
+                                             _lib.ptr_array([g.data_ptr() for g in grad_feats]), grad_loc.data_ptr(),
+                                             grad_w.data_ptr(), work.data_ptr(), work.numel() * 4, _stream()), 'sbev_msmv_bwd_det')
+        return grad_feats, grad_loc, grad_w
     with torch.cuda.device(loc.device):
         _lib.check(lib.sbev_msmv_bwd(go.data_ptr(), fptr, hw, L, loc.data_ptr(), w.data_ptr(), Bp, N, C, Q, P,
                                      _lib.ptr_array([g.data_ptr() for g in grad_feats]), grad_loc.data_ptr(),

@@ -41,6 +41,12 @@ def msmv_sampling_pytorch(mlvl_feats, sampling_locations, scale_weights):
     return total.permute(0, 2, 1, 3)
 
 
+def _deterministic(feats):
+    """Deterministic grad_feats (per-pixel segmented reduction instead of atomics) when PyTorch asks for deterministic
+    algorithms (`torch.use_deterministic_algorithms(True)`) and the kernel supports the shape (C = 64)."""
+    return torch.are_deterministic_algorithms_enabled() and feats[0].shape[-1] == 64
+
+
 class _MSMVSamplingBase(torch.autograd.Function):
     NUM_LEVELS = 0
 
@@ -54,8 +60,8 @@ class _MSMVSamplingBase(torch.autograd.Function):
     def _bwd(cls, ctx, grad_output):
         saved = ctx.saved_tensors
         feats, sampling_locations, scale_weights = saved[:cls.NUM_LEVELS], saved[-2], saved[-1]
-        grad_feats, grad_loc, grad_w = ops.msmv_backward(grad_output.contiguous(), list(feats),
-                                                         sampling_locations, scale_weights)
+        grad_feats, grad_loc, grad_w = ops.msmv_backward(grad_output.contiguous(), list(feats), sampling_locations,
+                                                         scale_weights, deterministic=_deterministic(feats))
         return (*grad_feats, grad_loc, grad_w)
 
 
@@ -94,7 +100,8 @@ class _MSMVSamplingAnyLevels(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         sampling_locations, scale_weights, *feats = ctx.saved_tensors
-        grad_feats, grad_loc, grad_w = ops.msmv_backward(grad_output.contiguous(), feats, sampling_locations, scale_weights)
+        grad_feats, grad_loc, grad_w = ops.msmv_backward(grad_output.contiguous(), feats, sampling_locations, scale_weights,
+                                                         deterministic=_deterministic(feats))
         return (grad_loc, grad_w, *grad_feats)
 
 

@@ -71,6 +71,7 @@ def main():
             fb = ref._ms_deform_attn_cuda_c2345_backward if L == 4 else ref._ms_deform_attn_cuda_c23456_backward
             entry['ref_cuda_bwd_ms'] = timeit(lambda: fb(go, *feats, loc, w), iters=10, warm=2)
             entry['ours_bwd_ms'] = timeit(lambda: ops.msmv_backward(go, feats, loc, w), iters=10, warm=2)
+            entry['ours_bwd_deterministic_ms'] = timeit(lambda: ops.msmv_backward(go, feats, loc, w, deterministic=True), iters=10, warm=2)
         res[key] = entry
         print(key, json.dumps(entry), flush=True)
         del feats

@@ -44,6 +44,13 @@ def test_argument_validation_without_gpu():
     assert lib.sbev_gemm_bf16_tn(one, one, 4, None, 128, 128, 64, 1, 16, None) == -1      # nseg > 3
     assert lib.sbev_mix_fwd(16, 16, 1, 4, 32, 64, 64, 16, 16, None, None) == -2           # out_points != 128
     assert lib.sbev_sasa_fwd(16, 384, 16, 16, 8, None, _lib.f32_array([0] * 6), 1, 4, 8, 128, 16, None) == -2   # head dim != 32
+    # deterministic backward: workspace arithmetic and argument checks (cnt[npix] | off[npix+1] | bsum[blocks] | ids[npts*L*4])
+    ws = lib.sbev_msmv_bwd_det_workspace(hw, 1, 2, 6, 10, 4)
+    assert ws == 4 * (2 * 192 + 1 + 1 + 320) + 64
+    assert lib.sbev_msmv_bwd_det_workspace(hw, 9, 2, 6, 10, 4) == -1
+    assert lib.sbev_msmv_bwd_det(16, one, hw, 1, 16, 16, 2, 6, 32, 10, 4, one, 16, 16, 16, ws, None) == -2     # C != 64
+    assert lib.sbev_msmv_bwd_det(16, one, hw, 1, 16, 16, 2, 6, 64, 10, 4, one, 16, 16, 16, 8, None) == -1      # workspace too small
+    assert b'workspace too small' in lib.sbev_last_error()
     # zero-sized problems are a no-op that never touches CUDA
     assert lib.sbev_msmv_fwd(one, hw, 1, 16, 16, 0, 6, 64, 0, 4, 16, None) == 0
 

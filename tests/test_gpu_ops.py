@@ -151,6 +151,82 @@ def test_msmv_bwd_vs_c_oracle(L, P, C):
     assert float(l2[..., 2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('L,P,Q', [(4, 4, 10), (2, 3, 7), (5, 4, 33), (1, 1, 5)])
+def test_msmv_bwd_deterministic_vs_c_oracle(L, P, Q):
+    """sbev_msmv_bwd_det: grad_feats by a per-pixel ordered reduction, no floating-point atomics.
+    Same oracle and tolerances as the atomic backward; grad_feats is allocated uninitialised (torch.empty_like) because the
+    kernel's contract is that every pixel row is written exactly once (no zero fill needed)."""
+    hw = [(7, 9), (4, 6), (3, 3), (2, 2), (1, 2)][:L]
+    feats, loc, w = _rand_case(2, 6, hw, Q, P, seed=70 + L)
+    go = hashrand((2, Q, 64, P), 98, -1, 1)
+    gf, gl, gw = c_oracle.bwd(go, feats, loc, w)
+    args = (go.to(dev()), [f.to(dev()) for f in feats], loc.to(dev()), w.to(dev()))
+    f2, l2, w2 = _ops().msmv_backward(*args, deterministic=True)
+    for a, b in zip(f2, gf):
+        _close(a, b, atol=1e-4, what='deterministic grad feats')
+    _close(l2, gl, atol=1e-3, what='grad loc')
+    _close(w2, gw, atol=1e-4, what='grad w')
+    f3, l3, w3 = _ops().msmv_backward(*args, deterministic=True)
+    assert all(torch.equal(a, b) for a, b in zip(f2, f3)) and torch.equal(l2, l3) and torch.equal(w2, w3)
+
+
+def test_msmv_bwd_deterministic_long_segments_and_full_size():
+    """(a) every point of a query block lands on the same few pixels -> segments far longer than a half-warp (the
+    strided selection path); (b) r50-T1 size: bit-identical between runs, equal to the atomic kernel within fp32
+    summation-order noise, and grad_feats sums to the same total (conservation: sum of taps of a point = its weight)."""
+    ops = _ops()
+    hw = [(5, 6), (3, 3)]
+    feats = [hashrand((1, 2, h, w, 64), 3 + i, -1, 1).to(dev()) for i, (h, w) in enumerate(hw)]
+    loc = torch.zeros(1, 300, 4, 3)
+    loc[..., 0] = 0.41 + 0.001 * torch.arange(4).float()          # all inside the same cell of both levels
+    loc[..., 1] = 0.37
+    loc[:, 150:, :, 2] = 1.0                                      # half of the queries look at view 1
+    w = torch.softmax(hashrand((1, 300, 4, 2), 9, -1, 1), -1)
+    go = hashrand((1, 300, 64, 4), 10, -1, 1)
+    want = c_oracle.bwd(go, [f.cpu() for f in feats], loc, w)[0]
+    got = ops.msmv_backward(go.to(dev()), feats, loc.to(dev()), w.to(dev()), deterministic=True)[0]
+    for a, b in zip(got, want):
+        _close(a, b, rtol=1e-4, atol=2e-3, what='long segments (600 contributions per pixel)')
+    again = ops.msmv_backward(go.to(dev()), feats, loc.to(dev()), w.to(dev()), deterministic=True)[0]
+    assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+    hw = [(64, 176), (32, 88), (16, 44), (8, 22)]
+    torch.manual_seed(1)
+    feats = [torch.randn(4, 6, h, w_, 64, device=dev()) for h, w_ in hw]
+    loc = torch.rand(4, 900, 4, 3, device=dev()) * 1.1 - 0.05
+    loc[..., 2] = torch.randint(0, 6, (4, 900, 4), device=dev()).float() / 5
+    w = torch.softmax(torch.randn(4, 900, 4, 4, device=dev()), -1)
+    go = torch.randn(4, 900, 64, 4, device=dev())
+    d1 = ops.msmv_backward(go, feats, loc, w, deterministic=True)
+    d2 = ops.msmv_backward(go, feats, loc, w, deterministic=True)
+    at = ops.msmv_backward(go, feats, loc, w)
+    for a, b, c in zip(d1[0], d2[0], at[0]):
+        assert torch.equal(a, b), 'deterministic backward differs between two runs'
+        _close(a, c, rtol=1e-4, atol=1e-4, what='deterministic vs atomic grad feats')
+    assert torch.equal(d1[1], at[1]) and torch.equal(d1[2], at[2])          # grad_loc / grad_w: same kernel code
+    empty = ops.msmv_backward(go[:, :0], feats, loc[:, :0], w[:, :0], deterministic=True)
+    assert all(float(g.abs().max()) == 0.0 for g in empty[0])
+
+
+def test_autograd_deterministic_mode():
+    """torch.use_deterministic_algorithms(True) routes the autograd Functions to the deterministic backward."""
+    from sparsebev_b200 import wrapper
+    hw = [(6, 8), (3, 4), (2, 2), (1, 2)]
+    feats, loc, w = _rand_case(2, 6, hw, 50, 4, seed=5)
+    grads = []
+    prev = torch.are_deterministic_algorithms_enabled()
+    try:
+        torch.use_deterministic_algorithms(True)
+        for _ in range(2):
+            f = [x.to(dev()).requires_grad_() for x in feats]
+            out = wrapper.msmv_sampling(f, loc.to(dev()), w.to(dev()))
+            (out * out).sum().backward()
+            grads.append([x.grad.clone() for x in f])
+    finally:
+        torch.use_deterministic_algorithms(prev)
+    assert all(torch.equal(a, b) for a, b in zip(*grads))
+
+
 def test_autograd_function_surface():
     from sparsebev_b200 import wrapper
     hw = [(6, 8), (3, 4), (2, 2), (1, 2)]
