@@ -103,10 +103,15 @@ def load():
 launch_count = 0      # number of successful C-ABI launches (each enqueues exactly one of OUR kernels)
 
 
+options_epoch = 0     # bumped by set_option: captured CUDA graphs bake the kernel variants in and must be re-captured
+
+
 def set_option(name, value):
+    global options_epoch
     rc = load().sbev_set_option(name.encode(), int(value))
     if rc != 0:
         raise RuntimeError('sbev_set_option(%s) failed' % name)
+    options_epoch += 1
 
 
 def get_option(name):

@@ -18,6 +18,8 @@ CUDA graph (bench.py does).  Forward only: this
 is the eval path (dropout = identity, no activation checkpointing); training the decoder through these
 modules is out of scope (the op-level autograd Functions in `wrapper.py` do have a backward).
 """
+import collections
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -337,7 +339,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self._reg = [_Dense(rb[2 * i]) for i in range(num_reg_fcs)] + [_Dense(rb[2 * num_reg_fcs])]
         self.overlap = True          # run independent kernels of a layer on a second stream (parallel graph branches)
         self.frame_shard = None      # dist.FrameShard: this rank holds / samples only its window of the T frames
+        self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
+        self._graphs, self._graph_pool = collections.OrderedDict(), None
 
     def _side_stream(self, device):
         key = str(device)
@@ -374,7 +378,70 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         local = self.sampling.sample(query_bbox, heads, mlvl_feats, img_metas, frame_window=shard.window, points=points)
         return shard.all_gather(local)
 
+    MAX_GRAPHS = 4
+
+    def reset_graphs(self):
+        self._graphs.clear()
+
+    @torch.no_grad()
+    def _forward_graphed(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        """`use_cuda_graph`: the layer's launches (two streams, programmatic dependent launches included) are captured
+        once per input signature and replayed.  The signature is everything the capture bakes in: shapes, the ADDRESSES
+        of the feature maps (a steady-state inference loop gets the same blocks back from the caching allocator every
+        frame; a new address simply captures another graph, the cache keeps the MAX_GRAPHS most recent), image size,
+        parameter versions and the kernel-variant options.  Per call only the small tensors move: query_bbox, query_feat,
+        time_diff, lidar2img (and the mask) are copied into the graph's static inputs -- host (pinned) or device sources
+        alike -- and the three results are returned as copies of the static outputs."""
+        meta = img_metas[0]
+        key = (tuple(query_bbox.shape), tuple(query_feat.shape), tuple((f.data_ptr(), tuple(f.shape)) for f in mlvl_feats),
+               self.sampling.feat_layout, None if attn_mask is None else tuple(attn_mask.shape),
+               tuple(meta['img_shape'][0]), tuple(meta['time_diff'].shape), tuple(meta['lidar2img'].shape),
+               sum(p._version for p in self.parameters()), _lib.options_epoch, self.overlap,
+               self.mixing.precision, self.mixing.tma_params, self.mixing.split_k, self.self_attn.core_impl)
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = mlvl_feats[0].device
+            static = dict(qb=torch.empty(query_bbox.shape, device=dev), qf=torch.empty(query_feat.shape, device=dev),
+                          td=torch.empty(meta['time_diff'].shape, device=dev), l2i=torch.empty(meta['lidar2img'].shape, device=dev),
+                          mask=None if attn_mask is None else torch.empty(attn_mask.shape, device=dev, dtype=attn_mask.dtype))
+            for name, src in (('qb', query_bbox), ('qf', query_feat), ('td', meta['time_diff']), ('l2i', meta['lidar2img']), ('mask', attn_mask)):
+                if src is not None:
+                    static[name].copy_(src, non_blocking=True)
+            smeta = [dict(meta)]
+            smeta[0]['time_diff'], smeta[0]['lidar2img'] = static['td'], static['l2i']
+            # (no reference to the feature tensors is kept: holding them would stop the allocator from handing the same
+            # blocks to the next frame, and a graph whose addresses are never passed again is simply never replayed)
+            run = lambda: self._forward_impl(static['qb'], static['qf'], mlvl_feats, static['mask'], smeta)      # noqa: E731
+            warm = torch.cuda.Stream(device=dev)           # one eager pass off the capture: weight caches, function attributes
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                run()
+            torch.cuda.current_stream().wait_stream(warm)
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()      # one pool for all graphs of this layer: they never run concurrently
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                outs = run()
+            entry = (graph, static, outs)
+            self._graphs[key] = entry
+            while len(self._graphs) > self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+            static = entry[1]
+            for name, src in (('qb', query_bbox), ('qf', query_feat), ('td', meta['time_diff']), ('l2i', meta['lidar2img']), ('mask', attn_mask)):
+                if src is not None:
+                    static[name].copy_(src, non_blocking=True)
+        entry[0].replay()
+        return tuple(o.clone() for o in entry[2])
+
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        if (self.use_cuda_graph and (self.frame_shard is None or self.frame_shard.world == 1)
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_graphed(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
+        return self._forward_impl(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
+
+    def _forward_impl(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         """query_bbox [B,Q,10] (cx,cy,cz,w,h,d,sin,cos,vx,vy normalised), query_feat [B,Q,D]
         -> (query_feat, cls_score [B,Q,num_classes], bbox_pred [B,Q,10])  (reference :162-193).
 

@@ -214,3 +214,42 @@ def test_five_level_configs_full_size_properties(name, T):
     ref = ops.msmv_forward(grouped, loc[t * G:(t + 1) * G].contiguous(), w_op)                   # [G,Q,C,P]
     ref = ref.permute(1, 0, 3, 2)                                                                # [Q,G,P,C]
     assert torch.equal(out[0, :, :, t * P:(t + 1) * P], ref)
+
+
+def test_layer_cuda_graph_mode_equals_eager():
+    """`use_cuda_graph`: the layer replayed as one captured CUDA graph returns exactly what the eager launches return
+    (same kernels, same order) -- for changing query inputs (device or pinned-host sources), for the whole 3-layer decoder
+    built on it, and it re-captures when the feature maps move or a kernel-variant option changes."""
+    from sparsebev_b200 import _lib
+    B, L = 2, 3
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', 4, B, seed=21, num_layers=L)
+    layer = model.decoder.decoder_layer
+    metas_gpu = copy.deepcopy(metas)
+    model.decoder.prepare_metas(metas_gpu, B, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    inputs = [(qb, qf), (qb.flip(1).contiguous(), 0.5 * qf), (qb, qf)]
+    eager = [[t.clone() for t in layer(a.cuda(), b.cuda(), gfeats, None, metas_gpu)] for a, b in inputs]
+    layer.use_cuda_graph = True
+    try:
+        for i, (a, b) in enumerate(inputs):
+            src = (a.pin_memory(), b.pin_memory()) if i == 1 else (a.cuda(), b.cuda())     # host (pinned) sources are accepted too
+            got = layer(src[0], src[1], gfeats, None, metas_gpu)
+            torch.cuda.synchronize()
+            for g, e in zip(got, eager[i]):
+                assert torch.equal(g, e), 'graph replay %d differs from the eager launches' % i
+        assert len(layer._graphs) == 1
+        moved = [f.clone() for f in gfeats]                                  # same values at new addresses -> a second graph
+        got = layer(qb.cuda(), qf.cuda(), moved, None, metas_gpu)
+        assert len(layer._graphs) == 2 and all(torch.equal(g, e) for g, e in zip(got, eager[0]))
+        _lib.set_option('pdl', _lib.get_option('pdl'))                       # any set_option bumps the epoch -> re-capture
+        layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
+        assert len(layer._graphs) == 3
+        # whole decoder (shared-weight layer looped L times, reference :86-99) through the graphed layer
+        layer.use_cuda_graph = False
+        want = model(qb.cuda(), qf.cuda(), [f.cuda() for f in feats], None, copy.deepcopy(metas))
+        layer.use_cuda_graph = True
+        got = model(qb.cuda(), qf.cuda(), [f.cuda() for f in feats], None, copy.deepcopy(metas))
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    finally:
+        layer.use_cuda_graph = False
+        layer.reset_graphs()
