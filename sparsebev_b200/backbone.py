@@ -290,3 +290,11 @@ def extract_img_feat(backbone, neck, img):
     B, TN = img.shape[:2]
     levels = neck.forward_nhwc(backbone.forward_nhwc(img.reshape(B * TN, *img.shape[2:])))
     return [f.view(B, TN, *f.shape[1:]).permute(0, 1, 4, 2, 3) for f in levels]
+
+
+try:                                    # same registry names as mmdet's own modules, when mmdet is importable (absent in the build image)
+    from mmdet.models.builder import BACKBONES, NECKS
+    BACKBONES.register_module(module=ResNet, force=True)
+    NECKS.register_module(module=FPN, force=True)
+except Exception:                       # pragma: no cover
+    pass
