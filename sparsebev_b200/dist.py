@@ -3,7 +3,10 @@
 How the path shards:
   * by SCENE (default; the reference's only strategy is DDP, train.py:90-131): every rank owns whole samples,
     no data-path collective, weak scaling.  `scene_partition` gives each rank its sample indices.
-  * by FRAME (partitioning B): rank r owns frames [r*T/N, (r+1)*T/N) of every scene -- features never cross
+  * by FRAME, features replicated (partitioning A, the north star's wording): rank r's backbone produces frames
+    [r*T/N, (r+1)*T/N); `all_gather_features` (one NCCL all-gather per FPN level per forward) gives every rank the whole
+    pyramid and the decoder runs unsharded (replicated, or scene-/query-parallel on top).
+  * by FRAME, features local (partitioning B): rank r owns frames [r*T/N, (r+1)*T/N) of every scene -- features never cross
     NVLink; each rank gathers its own frames for all queries and ONE all-gather per layer assembles the
     sampled features `[T, B, Q, G, P, C]` (frame-major staging so every rank's chunk is contiguous).
 """
@@ -63,6 +66,35 @@ def all_gather_frames(local, world=None):
     world = world or dist.get_world_size()
     out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, local.contiguous())
+    return out
+
+
+def all_gather_features(mlvl_local, group=None):
+    """Partitioning A of SURVEY.md 8(e) (the north star's "NCCL all-gather of per-camera features"): every rank's
+    backbone produced the FPN levels of ITS frames only, `[B, Tl*N, C, H, W]` per level (frame-major camera axis as in
+    the reference, models/sparsebev.py:124-131; plain NCHW or channels-last memory, e.g. backbone.extract_img_feat);
+    returns the levels of all T = world*Tl frames on every rank, `[B, T*N, C, H, W]`, in the SAME memory format --
+    ready for SparseBEVTransformerDecoder.prepare_feats (channels-last stays zero-copy).  One collective per level per
+    forward (92 MB per frame at r50, 524 MB at vov99); for B == 1 the gathered buffer already is the result (rank order
+    == frame order), for B > 1 one re-layout copy moves the batch axis back in front."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return list(mlvl_local)
+    world = dist.get_world_size(group)
+    if world == 1:
+        return list(mlvl_local)
+    out = []
+    for feat in mlvl_local:
+        nhwc = feat.permute(0, 1, 3, 4, 2)
+        cl = nhwc.is_contiguous() and not feat.is_contiguous()
+        x = nhwc if cl else feat.contiguous()                                # [B, Tl*N, ...] in its memory order
+        B = x.shape[0]
+        buf = x.new_empty((world,) + tuple(x.shape))                          # [W, B, Tl*N, ...]
+        dist.all_gather_into_tensor(buf.view((world * B,) + tuple(x.shape[1:])), x, group=group)
+        if B == 1:
+            full = buf.view((1, world * x.shape[1]) + tuple(x.shape[2:]))
+        else:
+            full = buf.transpose(0, 1).reshape((B, world * x.shape[1]) + tuple(x.shape[2:]))
+        out.append(full.permute(0, 1, 4, 2, 3) if cl else full)
     return out
 
 

@@ -32,6 +32,14 @@ def _worker(rank, world, port, q):
     assert shard.window == (t0, t1) and (shard.rank, shard.world) == (rank, world)
     merged = shard.all_gather(whole[:, :, :, t0 * P:t1 * P].contiguous())
     assert torch.equal(merged, whole)
+    # partitioning A: feature all-gather, NCHW and channels-last memory, B = 1 (no re-layout) and B = 2
+    N, Cc, H, Wd = 6, 4, 3, 5
+    for Bf in (1, 2):
+        pyramid = torch.arange(Bf * T * N * Cc * H * Wd, dtype=torch.float32).reshape(Bf, T * N, Cc, H, Wd)
+        mine = pyramid[:, t0 * N:t1 * N]
+        got = D.all_gather_features([mine.contiguous(), mine.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)])
+        assert torch.equal(got[0], pyramid) and got[0].is_contiguous()
+        assert torch.equal(got[1], pyramid) and got[1].permute(0, 1, 3, 4, 2).is_contiguous()      # stays channels-last
     q.put((rank, mx, full[:, 0].tolist(), scenes))
     torch.distributed.destroy_process_group()
 
@@ -69,3 +77,5 @@ def test_partitions_single_process():
     assert D.max_over_ranks(3.5) == 3.5
     x = torch.ones(2, 4)
     assert D.all_gather_frames(x) is x
+    f = [torch.ones(1, 6, 4, 2, 2)]
+    assert D.all_gather_features(f)[0] is f[0]                    # no process group: identity
