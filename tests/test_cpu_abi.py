@@ -29,6 +29,23 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.sbev_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype in include/sparsebev_b200.h has exactly as many parameters as its ctypes argtypes entry: an
+    argument added on one side only would otherwise corrupt the call silently."""
+    from sparsebev_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'sparsebev_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    text = re.sub(r'//[^\n]*', '', text)
+    protos = re.findall(r'\b(?:int|long long|const char\*)\s+(sbev_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(protos) >= 25
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ('', 'void') else len(args.split(','))
+        if name in _lib.SIGNATURES:
+            assert len(_lib.SIGNATURES[name]) == n, '%s: header has %d parameters, ctypes table %d' % (name, n, len(_lib.SIGNATURES[name]))
+    assert set(_lib.SIGNATURES) <= set(n for n, _ in protos)
+
+
 def test_argument_validation_without_gpu():
     """Validation happens before any CUDA call, so error codes can be checked on a CPU-only box."""
     import ctypes
