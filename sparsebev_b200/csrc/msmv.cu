@@ -480,77 +480,44 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__
     }
 }
 
-// One warp looks at 32 consecutive pixels per step: the (mostly empty) segment table is read coalesced, the rows of
-// untouched pixels are zeroed two per store instruction, and only the touched pixels -- one per half-warp at a time --
-// go through the ordered reduction.
 template <int L>
 __global__ void __launch_bounds__(256)
 msmv_bwd_reduce_kernel(LevelSet lv, GradLevelSet glv, PixelSpace ps, const int* __restrict__ off, const int* __restrict__ ids,
                        const float* __restrict__ grad_out, const float* __restrict__ loc, const float* __restrict__ wgt, int P) {
-    const int lane = threadIdx.x & 31, j = lane & 15, half = lane >> 4;
-    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, j = lane & 15;
     const unsigned hmask = 0xffffu << (lane & 16);              // the two half-warps of a warp walk different segments
     const long long total = ps.base[L];
-    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long warp_stride = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long pix0 = warp_id * 32; pix0 < total; pix0 += warp_stride * 32) {
-        const long long pix = pix0 + lane;                      // lane i inspects pixel pix0 + i
-        int beg = 0, n = 0, l = 0;
-        unsigned long long row = 0;                             // address of the pixel's 64-float grad row (0: beyond the end)
-        if (pix < total) {
-            beg = __ldg(off + pix);
-            n = __ldg(off + pix + 1) - beg;
+    const long long hw_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long hw_stride = ((long long)gridDim.x * blockDim.x) >> 4;
+    for (long long pix = hw_id; pix < total; pix += hw_stride) {
+        int l = 0;
 #pragma unroll
-            for (int k = 1; k < L; ++k) if (pix >= ps.base[k]) l = k;
-            row = reinterpret_cast<unsigned long long>(glv.ptr[l] + (pix - ps.base[l]) * 64);
-        }
-        const unsigned busy = __ballot_sync(full, n > 0);
-#pragma unroll 4
-        for (int r = 0; r < 32; r += 2) {                       // rows r (lanes 0-15) and r + 1 (lanes 16-31)
-            const unsigned long long rp = __shfl_sync(full, row, r + half);
-            if (rp != 0 && !((busy >> (r + half)) & 1u)) *reinterpret_cast<float4*>(reinterpret_cast<float*>(rp) + 4 * j) = zero;
-        }
-        unsigned rest = busy;
-        while (rest) {                                          // warp-uniform: two touched pixels per turn
-            const int b0 = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const int b1 = rest ? __ffs(rest) - 1 : -1;
-            if (rest) rest &= rest - 1;
-            const int src = half ? b1 : b0;
-            const int srcl = src < 0 ? 0 : src;
-            const int sbeg = __shfl_sync(full, beg, srcl);
-            const int sn_raw = __shfl_sync(full, n, srcl);
-            const int sl = __shfl_sync(full, l, srcl);
-            const unsigned long long srow = __shfl_sync(full, row, srcl);
-            const int sn = src < 0 ? 0 : sn_raw;
-            if (sn > 0) {
-                const int H = lv.H[sl], W = lv.W[sl];
-                float4 acc = zero;
-                const int mine = (sn <= 16 && j < sn) ? __ldg(ids + sbeg + j) : 0x7fffffff;    // short segment: one id per lane
-                int last = -1;
-                for (int k = 0; k < sn; ++k) {
-                    int m = 0x7fffffff;
-                    if (sn <= 16) { if (mine > last) m = mine; }
-                    else for (int i = j; i < sn; i += 16) { const int v = __ldg(ids + sbeg + i); if (v > last && v < m) m = v; }
+        for (int k = 1; k < L; ++k) if (pix >= ps.base[k]) l = k;
+        const int H = lv.H[l], W = lv.W[l];
+        const long long local = pix - ps.base[l];
+        const int beg = __ldg(off + pix), n = __ldg(off + pix + 1) - beg;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int mine = (n <= 16 && j < n) ? __ldg(ids + beg + j) : 0x7fffffff;     // short segment: one id per lane
+        int last = -1;
+        for (int k = 0; k < n; ++k) {
+            int m = 0x7fffffff;
+            if (n <= 16) { if (mine > last) m = mine; }
+            else for (int i = j; i < n; i += 16) { const int v = __ldg(ids + beg + i); if (v > last && v < m) m = v; }
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(hmask, m, o));
-                    last = m;                                                             // ids are unique: strictly ascending walk
-                    const long long pi = m >> 2;
-                    const int corner = m & 3;
-                    const Tap t = make_tap(__ldg(loc + pi * 3), __ldg(loc + pi * 3 + 1), H, W);
-                    const float tw = corner == 0 ? t.w1 : corner == 1 ? t.w2 : corner == 2 ? t.w3 : t.w4;
-                    const float aw = __ldg(wgt + pi * L + sl);
-                    const long long item = pi / P;
-                    const int p = (int)(pi - item * P);
-                    const float* gp = grad_out + (item * 64 + 4 * j) * P + p;
-                    const float4 gv = make_float4(__ldg(gp) * aw, __ldg(gp + P) * aw, __ldg(gp + 2 * P) * aw, __ldg(gp + 3 * P) * aw);
-                    acc.x += tw * gv.x; acc.y += tw * gv.y; acc.z += tw * gv.z; acc.w += tw * gv.w;
-                }
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(srow) + 4 * j) = acc;
-            }
-            __syncwarp();
+            for (int o = 8; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(hmask, m, o));
+            last = m;                                                                 // ids are unique: strictly ascending walk
+            const long long pi = m >> 2;
+            const int corner = m & 3;
+            const Tap t = make_tap(__ldg(loc + pi * 3), __ldg(loc + pi * 3 + 1), H, W);
+            const float tw = corner == 0 ? t.w1 : corner == 1 ? t.w2 : corner == 2 ? t.w3 : t.w4;
+            const float aw = __ldg(wgt + pi * L + l);
+            const long long item = pi / P;
+            const int p = (int)(pi - item * P);
+            const float* gp = grad_out + (item * 64 + 4 * j) * P + p;
+            const float4 gv = make_float4(__ldg(gp) * aw, __ldg(gp + P) * aw, __ldg(gp + 2 * P) * aw, __ldg(gp + 3 * P) * aw);
+            acc.x += tw * gv.x; acc.y += tw * gv.y; acc.z += tw * gv.z; acc.w += tw * gv.w;
         }
+        *reinterpret_cast<float4*>(glv.ptr[l] + local * 64 + 4 * j) = acc;
     }
 }
 
@@ -817,7 +784,7 @@ extern "C" int sbev_msmv_bwd_det(const float* grad_out, const float* const* feat
     scan_bsums_kernel<<<1, 256, 0, st>>>(bsum, (int)nb);
     scan_apply_kernel<<<(unsigned)nb, 256, 0, st>>>(cnt, npix, bsum, off);
     if (npts > 0) msmv_bwd_bin_kernel<true><<<grid_for(npts * L, 256), 256, 0, st>>>(lv, ps, L, loc, npts, N, Q * P, cnt, off, ids);
-    const int rgrid = grid_for(npix, 256);
+    const int rgrid = grid_for(npix, 16);
 #define SBEV_LAUNCH_DET(LL)                                                                                                   \
     case LL:                                                                                                                  \
         msmv_bwd_reduce_kernel<LL><<<rgrid, 256, 0, st>>>(lv, glv, ps, off, ids, grad_out, loc, w, P);                         \
