@@ -128,3 +128,23 @@ def test_nms_free_coder_matches_reference_golden(golden_dir):
             assert np.array_equal(r['labels'].numpy(), g['%s%d_labels' % (tag, b)])
             assert np.array_equal(r['scores'].numpy(), g['%s%d_scores' % (tag, b)])
             assert np.array_equal(r['bboxes'].numpy(), g['%s%d_bboxes' % (tag, b)])
+
+
+def test_op_backward_matches_reference_autograd(golden_dir):
+    """Backward of the op: the C restatement of the reference CUDA backward kernel's arithmetic
+    (oracle/msmv_oracle.c) against the gradients autograd derives through the REAL reference's msmv_sampling_pytorch
+    (oracle/gen_golden_bwd.py).  This pins the checker the CUDA backward kernels -- atomic and deterministic -- are compared
+    with on the GPU.  The view-coordinate gradient is excluded: the reference CUDA kernel leaves it at zero."""
+    from oracle import c_oracle
+    g = _load(golden_dir, 'op_bwd.npz')
+    Bp, C, N, Q, P = [int(v) for v in g['shape']]
+    feats_cl = [hashrand((Bp, C, N, int(h), int(w)), int(s), -1.0, 1.0).permute(0, 2, 3, 4, 1).contiguous()
+                for (h, w), s in zip(g['hw'], g['feat_seeds'])]
+    loc, w, go = torch.from_numpy(g['loc']), torch.from_numpy(g['w']), torch.from_numpy(g['grad_out'])
+    np.testing.assert_allclose(c_oracle.fwd(feats_cl, loc, w).numpy(), g['out'], rtol=1e-4, atol=2e-5)
+    gf, gl, gw = c_oracle.bwd(go, feats_cl, loc, w)
+    for i, a in enumerate(gf):
+        np.testing.assert_allclose(a.numpy(), g['grad_feat%d' % i], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gw.numpy(), g['grad_w'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gl[..., :2].numpy(), g['grad_loc_uv'], rtol=1e-4, atol=2e-4)
+    assert float(gl[..., 2].abs().max()) == 0.0
