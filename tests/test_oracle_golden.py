@@ -179,3 +179,47 @@ def test_decoder_restatement_matches_real_reference_decoder(golden_dir):
         np.testing.assert_allclose(box.numpy(), g[tag + '_box'], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(cls_k.numpy(), g[tag + '_cls'], rtol=1e-3, atol=2e-4)
         np.testing.assert_allclose(box_k.numpy(), g[tag + '_box'], rtol=1e-3, atol=2e-4)
+
+
+def test_head_restatement_and_mirror_match_real_reference_head(golden_dir):
+    """SparseBEVHead eval path against the REAL reference head run on the CPU by oracle/gen_golden_head.py
+    (sparsebev_head.py unmodified; mmdet's DETRHead replaced by an arithmetic-free stand-in):
+      * oracle/ref_torch.py::head_forward (query init -> decoder -> metres + reorder) reproduces all_cls_scores / all_bbox_preds;
+      * the product mirror's `_init_layers` lays the learned query boxes out like the reference (grid xy, z = 0, h = 1.5, v = 0);
+      * the product mirror's `get_bboxes` (+ NMSFreeCoder mirror) turns the reference's predictions into the reference's detections."""
+    import pytest
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import synthetic as S
+    g = _load(golden_dir, 'head.npz')
+    T, B, L, Q = [int(v) for v in g['cfg']]
+    cfg = S.layer_cfg('tiny', T, num_layers=L)
+    sd = S.make_state_dict(cfg, seed=21)
+    feats = S.make_feats('tiny', T, batch=B, seed=22)
+    check = np.array([float(feats[0].double().sum()), float(sd['mixing.out_proj.weight'].double().sum())])
+    if not np.allclose(check, g['check'], rtol=0, atol=1e-6):
+        pytest.skip('torch CPU generator stream differs from the one the fixture was generated with')
+    metas = S.make_metas('tiny', T, batch=B)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    with torch.no_grad():
+        out = R.head_forward(torch.from_numpy(g['init_query_bbox']), torch.from_numpy(g['label_enc']), feats, sd, cfg, td, l2i)
+    np.testing.assert_allclose(out['all_cls_scores'].numpy(), g['all_cls_scores'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out['all_bbox_preds'].numpy(), g['all_bbox_preds'], rtol=1e-4, atol=1e-4)
+
+    post = g['post_center_range'].tolist()
+    head = sb.SparseBEVHead(num_classes=10, in_channels=256, num_query=Q, pc_range=cfg['pc_range'],
+                            bbox_coder=dict(type='NMSFreeCoder', pc_range=cfg['pc_range'], post_center_range=post, max_num=20,
+                                            score_threshold=None, num_classes=10),
+                            transformer=dict(type='SparseBEVTransformer', embed_dims=256, num_frames=T, num_points=4, num_layers=L,
+                                             num_levels=cfg['num_levels'], pc_range=cfg['pc_range']))
+    w = head.init_query_bbox.weight.detach().numpy()
+    for cols in ([0, 1], [2], [5], [8, 9]):
+        np.testing.assert_array_equal(w[:, cols], g['init_query_bbox'][:, cols])
+    assert tuple(head.label_enc.weight.shape) == g['label_enc'].shape
+    dets = head.get_bboxes({'all_cls_scores': torch.from_numpy(g['all_cls_scores']).clone(),
+                            'all_bbox_preds': torch.from_numpy(g['all_bbox_preds']).clone()})
+    assert len(dets) == B
+    for b, (boxes, scores, labels) in enumerate(dets):
+        np.testing.assert_allclose(boxes.numpy(), g['det%d_boxes' % b], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(scores.numpy(), g['det%d_scores' % b], rtol=1e-6, atol=1e-7)
+        np.testing.assert_array_equal(labels.numpy(), g['det%d_labels' % b])
