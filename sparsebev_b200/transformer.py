@@ -389,14 +389,14 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         once per input signature and replayed.  The signature is everything the capture bakes in: shapes, the ADDRESSES
         of the feature maps (a steady-state inference loop gets the same blocks back from the caching allocator every
         frame; a new address simply captures another graph, the cache keeps the MAX_GRAPHS most recent), image size,
-        parameter versions and the kernel-variant options.  Per call only the small tensors move: query_bbox, query_feat,
+        parameter addresses + versions and the kernel-variant options.  Per call only the small tensors move: query_bbox, query_feat,
         time_diff, lidar2img (and the mask) are copied into the graph's static inputs -- host (pinned) or device sources
         alike -- and the three results are returned as copies of the static outputs."""
         meta = img_metas[0]
         key = (tuple(query_bbox.shape), tuple(query_feat.shape), tuple((f.data_ptr(), tuple(f.shape)) for f in mlvl_feats),
                self.sampling.feat_layout, None if attn_mask is None else tuple(attn_mask.shape),
                tuple(meta['img_shape'][0]), tuple(meta['time_diff'].shape), tuple(meta['lidar2img'].shape),
-               sum(p._version for p in self.parameters()), _lib.options_epoch, self.overlap,
+               hash(tuple((p.data_ptr(), p._version) for p in self.parameters())), _lib.options_epoch, self.overlap,
                self.mixing.precision, self.mixing.tma_params, self.mixing.split_k, self.self_attn.core_impl)
         entry = self._graphs.get(key)
         if entry is None:
