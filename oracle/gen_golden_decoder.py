@@ -126,7 +126,7 @@ def main():
     ref = import_reference_decoder()
     assert ref.MSMV_CUDA is False
     out = {}
-    for tag, name, T, B, L in (('a', 'tiny', 2, 2, 3), ('b', 'tiny5', 3, 1, 2)):
+    for tag, name, T, B, L in (('a', 'tiny', 2, 2, 3), ('b', 'tiny5', 3, 1, 2), ('c', 'tiny', 2, 2, 2)):
         cfg = S.layer_cfg(name, T, num_layers=L)
         sd = S.make_state_dict(cfg, seed=11)
         model = ref.SparseBEVTransformer(256, num_frames=T, num_points=cfg['num_points'], num_layers=L, num_levels=cfg['num_levels'],
@@ -140,13 +140,18 @@ def main():
         qb = S.init_query_bbox(n, seed=13)[:Q][None].repeat(B, 1, 1).contiguous()
         qb[..., 8:10] = 0.3 * torch.randn(B, Q, 2, generator=torch.Generator().manual_seed(14))
         qf = torch.randn(B, Q, 256, generator=torch.Generator().manual_seed(15))
+        mask = None
+        if tag == 'c':          # query-denoising style attention mask (sparsebev_head.py:190-207: True = this pair may not attend)
+            mask = torch.rand(Q, Q, generator=torch.Generator().manual_seed(16)) < 0.3
+            mask.fill_diagonal_(False)                       # no fully masked row
+            out[tag + '_mask'] = mask.numpy()
         with torch.no_grad():
-            cls, box = model(qb.clone(), qf.clone(), [f.clone() for f in feats], None, copy.deepcopy(metas))
+            cls, box = model(qb.clone(), qf.clone(), [f.clone() for f in feats], mask, copy.deepcopy(metas))
         out.update({tag + '_cfg': np.array([T, B, L]), tag + '_qb': qb.numpy(), tag + '_qf': qf.numpy(),
                     tag + '_cls': cls.numpy(), tag + '_box': box.numpy(),
                     tag + '_check': np.array([float(feats[0].double().sum()), float(sd['mixing.out_proj.weight'].double().sum())])})
         print(tag, name, 'T', T, 'B', B, 'layers', L, 'cls', tuple(cls.shape), 'box', tuple(box.shape), missing)
-    np.savez(os.path.join(OUT, 'decoder.npz'), names=np.array(['tiny', 'tiny5']), **out)
+    np.savez(os.path.join(OUT, 'decoder.npz'), names=np.array(['tiny', 'tiny5', 'tiny']), **out)
     print('wrote', os.path.join(OUT, 'decoder.npz'))
 
 

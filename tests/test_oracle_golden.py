@@ -154,12 +154,12 @@ def test_decoder_restatement_matches_real_reference_decoder(golden_dir):
     """oracle/ref_torch.py::decoder against the REAL reference decoder (sparsebev_transformer.py executed unmodified on the
     CPU by oracle/gen_golden_decoder.py with only mmcv's MultiheadAttention / FFN / BaseModule and mmdet's registry stubbed):
     multi-layer outputs incl. box refinement, velocity rescale, metadata handling and the feature regroup.  Two cases:
-    2 levels / T=2 / B=2 / 3 layers and 5 levels / T=3 / B=1 / 2 layers.  Also run with the CUDA-kernel sampling semantics
+    2 levels / T=2 / B=2 / 3 layers, 5 levels / T=3 / B=1 / 2 layers, and a query-denoising style attention mask (2 layers).  Also run with the CUDA-kernel sampling semantics
     (rounded view, 2-D bilinear), which is what the GPU tests compare the CUDA decoder with."""
     import pytest
     from sparsebev_b200 import synthetic as S
     g = _load(golden_dir, 'decoder.npz')
-    for tag, name in zip(('a', 'b'), g['names']):
+    for tag, name in zip(('a', 'b', 'c'), g['names']):
         name = str(name)
         T, B, L = [int(v) for v in g[tag + '_cfg']]
         cfg = S.layer_cfg(name, T, num_layers=L)
@@ -172,9 +172,10 @@ def test_decoder_restatement_matches_real_reference_decoder(golden_dir):
         td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
         l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
         qb, qf = torch.from_numpy(g[tag + '_qb']), torch.from_numpy(g[tag + '_qf'])
+        mask = torch.from_numpy(g[tag + '_mask']) if (tag + '_mask') in g else None      # case c: query-denoising attention mask
         with torch.no_grad():
-            cls, box = R.decoder(qb, qf, feats, sd, cfg, td, l2i)                       # grid_sample path, like the reference on CPU
-            cls_k, box_k = R.decoder(qb, qf, feats, sd, cfg, td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
+            cls, box = R.decoder(qb, qf, feats, sd, cfg, td, l2i, pre_attn_mask=mask)   # grid_sample path, like the reference on CPU
+            cls_k, box_k = R.decoder(qb, qf, feats, sd, cfg, td, l2i, pre_attn_mask=mask, channel_last=True, op=R.msmv_sampling_kernel_semantics)
         np.testing.assert_allclose(cls.numpy(), g[tag + '_cls'], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(box.numpy(), g[tag + '_box'], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(cls_k.numpy(), g[tag + '_cls'], rtol=1e-3, atol=2e-4)
