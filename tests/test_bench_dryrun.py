@@ -111,3 +111,52 @@ def test_bench_refuses_to_run_without_cuda(monkeypatch):
     monkeypatch.setattr(sys, 'argv', ['bench.py', '--config', 'tiny', '--frames', '2', '--steps', '1', '--warmup', '1'])
     with pytest.raises(AssertionError, match='needs a GPU'):
         bench.main()
+
+
+def test_layer_graph_cache_policy_dry_run(monkeypatch):
+    """Host policy of the layer's CUDA-graph mode without a GPU (capture / replay are shims; the numerical equality of graph
+    and eager launches is a GPU test): one capture per input signature, replays reuse it, a moved feature map or a bumped
+    parameter version captures again, the cache keeps MAX_GRAPHS entries, outputs are copies of the static outputs."""
+    import sparsebev_b200 as sb
+    from sparsebev_b200 import synthetic as S, transformer as TR
+    captures = {'n': 0, 'replays': 0}
+
+    class G(_Graph):
+        def replay(self):
+            captures['replays'] += 1
+    fake_cuda = types.SimpleNamespace(Stream=lambda *a, **k: _Stream(), current_stream=lambda *a: _Stream(), stream=lambda s: contextlib.nullcontext(),
+                                      CUDAGraph=G, graph=lambda g, **k: contextlib.nullcontext(), graph_pool_handle=lambda: 0,
+                                      is_current_stream_capturing=lambda: False)
+    monkeypatch.setattr(TR.torch, 'cuda', fake_cuda)
+    cfg = S.layer_cfg('tiny', 2, num_layers=1)
+    model = sb.SparseBEVTransformer(256, num_frames=2, num_points=4, num_layers=1, num_levels=2, pc_range=cfg['pc_range']).eval()
+    layer = model.decoder.decoder_layer
+
+    def impl(qb, qf, feats, mask, metas):
+        captures['n'] += 1
+        return qf * 2, qb[..., :10] + 1, qb + metas[0]['time_diff'].sum()
+    monkeypatch.setattr(layer, '_forward_impl', impl)
+    layer.use_cuda_graph = True
+    feats = [torch.zeros(1, 12, 256, 8, 22), torch.zeros(1, 12, 256, 4, 11)]
+    metas = [dict(img_shape=[(64, 176, 3)], time_diff=torch.ones(1, 2), lidar2img=torch.zeros(1, 12, 4, 4))]
+    qb, qf = torch.rand(1, 36, 10), torch.rand(1, 36, 256)
+    a = layer(qb, qf, feats, None, metas)
+    assert captures['n'] == 2 and captures['replays'] == 1 and len(layer._graphs) == 1          # warm-up pass + capture pass
+    static = next(iter(layer._graphs.values()))[1]
+    assert torch.equal(static['qb'], qb) and torch.equal(static['td'], metas[0]['time_diff'])
+    assert a[0].data_ptr() != next(iter(layer._graphs.values()))[2][0].data_ptr()                 # outputs are copies
+    layer(qb * 0.5, qf, feats, None, metas)
+    assert captures['n'] == 2 and captures['replays'] == 2 and torch.equal(static['qb'], qb * 0.5)
+    keep = [[f.clone() for f in feats]]                                                          # (kept alive: distinct addresses)
+    layer(qb, qf, keep[-1], None, metas)                                                         # moved features
+    assert len(layer._graphs) == 2
+    with torch.no_grad():
+        layer.norm1.weight.add_(1.0)                                                             # parameter version bump
+    layer(qb, qf, feats, None, metas)
+    assert len(layer._graphs) == 3
+    for _ in range(4):
+        keep.append([f.clone() for f in feats])
+        layer(qb, qf, keep[-1], None, metas)
+    assert len(layer._graphs) == layer.MAX_GRAPHS
+    layer.reset_graphs()
+    assert len(layer._graphs) == 0
