@@ -24,13 +24,17 @@ It restates, in plain fp32 PyTorch that runs on the CPU, the algorithm of the re
     decoder / transformer               models/sparsebev_transformer.py:32-38, 56-101
     head_forward                        models/sparsebev_head.py:69-117, 216-220 (eval path)
 
-Pinning status (see tests/golden/ and oracle/gen_golden.py): the functions whose reference
-files import in this container (`bbox/utils.py`, `utils.py`, `csrc/wrapper.py`,
-`sparsebev_sampling.py`, and the `AdaptiveMixing` class body) are pinned against the REAL
-reference through committed golden vectors.  The decoder-layer glue that needs mmcv 1.6.0
-(`MultiheadAttention`, `FFN`) cannot be imported here (mmcv is not installed, no network):
-for those the restatement follows mmcv-full 1.6.0's documented semantics and is
-"parity unpinned" beyond the `torch.nn.MultiheadAttention` it wraps.
+Pinning status (see tests/golden/ and the oracle/gen_golden*.py generators): every function above is
+pinned against the REAL reference through committed golden vectors --
+  * op, geometry, sampling_4d, AdaptiveMixing: the reference files that import in this container
+    (`bbox/utils.py`, `utils.py`, `csrc/wrapper.py`, `sparsebev_sampling.py`, the `AdaptiveMixing` class
+    body), gen_golden.py; the op's gradients through autograd of `msmv_sampling_pytorch`, gen_golden_bwd.py;
+  * decoder_layer / decoder (incl. the query-denoising attention mask) and head_forward: the reference's
+    `sparsebev_transformer.py` / `sparsebev_head.py` executed UNMODIFIED on the CPU with only the absent
+    third-party names stubbed (gen_golden_decoder.py, gen_golden_head.py).
+What stays "parity unpinned": mmcv-full 1.6.0's `MultiheadAttention` / `FFN` wrappers themselves (mmcv is
+not installed, no network) -- stubbed in those generators from their documented semantics
+(identity + nn.MultiheadAttention, identity + Linear-ReLU-Linear), which is also what this file restates.
 
 Weights are passed as a flat dict keyed exactly like the reference checkpoint, relative to
 `...transformer.decoder.decoder_layer.` (checkpoint row).
