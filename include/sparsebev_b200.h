@@ -178,6 +178,42 @@ int sbev_sampling4d_scatter_fwd(const float* const* feats, const int* hw, int L,
                                 float image_h, float image_w, float eps,
                                 float* const* outs, int n_out, float* loc_out, void* stream);
 
+/* Owner form of the fused gather, for the query- AND frame-sharded decoder (B must be 1): this GPU holds the
+ * feature maps of frames [t0, t0+Tl) and samples them for ALL Q queries, but query q is mixed by rank q / q_per_rank only,
+ * so each 256 B row is stored exactly once -- into outs[q / q_per_rank], that rank's [q_per_rank, G, T*P, C] buffer (peer
+ * memory over NVLink, or this GPU's own), at row (q % q_per_rank).  After every rank has run its window and a
+ * sbev_peer_exchange barrier, rank r holds the rows sbev_sampling4d_fwd would have written for its queries: the all-to-all
+ * of the sampled features (models/sparsebev_sampling.py:112-128 regroups them per query) is fused into the gather's stores.
+ * `outs` = HOST array of n_ranks DEVICE pointers, n_ranks * q_per_rank >= Q, n_ranks <= SBEV_MAX_PEERS. */
+int sbev_sampling4d_owner_fwd(const float* const* feats, const int* hw, int L,
+                              const int64_t* stride_bt, const int64_t* stride_g,
+                              const int64_t* stride_v, const int64_t* stride_px,
+                              const float* points, const float* velocity, int ld_vel, const float* time_diff,
+                              const float* lidar2img, const float* scale_w,
+                              int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                              float image_h, float image_w, float eps,
+                              float* const* outs, int n_ranks, int q_per_rank, void* stream);
+
+/* Cross-GPU exchange + barrier in ONE kernel (no counterpart in the reference, whose only multi-GPU mode is DDP; this is
+ * what the sharded decoder layer moves between ranks -- sample points / scale weights, refined boxes, query features).
+ * Segment s: `bytes` (multiple of 4) are copied from `src` (this rank's freshly produced rows, inside its own buffer) to
+ * dst[w] for every rank w != rank -- the same rows inside rank w's buffer (same address modulo 16), mapped into this process
+ * (CUDA IPC / torch symmetric memory; stores travel over NVLink).  Then an all-ranks barrier: flags[w] is rank w's array of SBEV_MAX_PEERS
+ * uint32 words (zero before the first call); the kernel stores its epoch into word [rank] of every peer's array
+ * (st.release.sys) and waits until all words of its own array reached it (ld.acquire.sys).  When the kernel completes, every
+ * peer's segments of the same exchange have landed in this rank's buffers, and every peer has completed all stream work it
+ * enqueued before ITS call.  nseg = 0 is a pure barrier (used after sbev_sampling4d_owner_fwd).
+ *   ctl   DEVICE, 3 uint32 owned by this rank, zero-initialised: epoch, arrival counter, status.  status becomes 1 when a
+ *         wait gave up after ~4 s (a peer died); later calls then return without waiting.  Every rank must issue the same
+ *         sequence of exchanges.  Plain kernel launch: capturable in a CUDA graph, never synchronises the host. */
+typedef struct sbev_peer_segment {
+    const void* src;
+    void* dst[SBEV_MAX_PEERS];
+    int64_t bytes;
+} sbev_peer_segment;
+int sbev_peer_exchange(const sbev_peer_segment* segs, int nseg, int n_peers, int rank,
+                       uint32_t* const* flags, uint32_t* ctl, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Small dense building block: y = epilogue(x @ W^T), row-major fp32, with the weight given
  * PRE-TRANSPOSED as Wt[K][ldw] (= W^T, zero-padded to ldw >= N, ldw % 4 == 0; the host mirror caches
@@ -287,6 +323,13 @@ int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bbox, const f
 int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
                         const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
                         int B, int Q, int H, int D, float* out, void* stream);
+
+/* sbev_sasa_split_fwd for the QUERIES [q_begin, q_end) only (keys / values are always all Q rows): the query-sharded decoder
+ * runs the attention of its own queries.  Only rows [q_begin, q_end) of out [B,Q,D] are written; they are bit-identical to
+ * the same rows of the full call (a query's result does not depend on which other queries share its tile). */
+int sbev_sasa_split_range_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
+                              const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
+                              int B, int Q, int H, int D, int q_begin, int q_end, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * AdaptiveMixing (models/sparsebev_transformer.py:351-381).

@@ -23,6 +23,14 @@ class DenseLayer(ctypes.Structure):
                 ('residual', c_vp), ('flags', c_int), ('y', c_vp), ('ldy', c_int), ('W_hi', c_vp), ('W_lo', c_vp), ('Kpad', c_int), ('y_hi', c_vp), ('y_lo', c_vp)]
 
 
+MAX_PEERS = 8
+
+
+class PeerSegment(ctypes.Structure):
+    """struct sbev_peer_segment (include/sparsebev_b200.h)"""
+    _fields_ = [('src', c_vp), ('dst', c_vp * MAX_PEERS), ('bytes', ctypes.c_int64)]
+
+
 # name -> argtypes; every function returns int (SBEV_OK = 0)
 SIGNATURES = {
     'sbev_set_option': [ctypes.c_char_p, c_int],
@@ -47,6 +55,12 @@ SIGNATURES = {
                                     c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vpp, c_int, c_vp, c_vp],
+    'sbev_sampling4d_owner_fwd': [c_vpp, c_i32p, c_int, c_i64p, c_i64p, c_i64p, c_i64p,
+                                  c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vpp, c_int, c_int, c_vp],
+    'sbev_peer_exchange': [ctypes.POINTER(PeerSegment), c_int, c_int, c_int, c_vpp, c_vp, c_vp],
+    'sbev_sasa_split_range_fwd': [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_dense_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_refine_bbox_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_sample_points_fwd': [c_vp, c_vp, c_int, c_vp, c_int, c_f32p, c_int, c_int, c_int, c_vp, c_vp, c_vp],

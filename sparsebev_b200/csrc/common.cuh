@@ -48,6 +48,41 @@ inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
     cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);      // errors are picked up by check_launch()
 }
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute opt-ins are per device, not per process: a process that drives
+// cuda:0 and then cuda:1 must set them on both).  `first_use()` is true once for every device ordinal; a race between
+// two host threads only repeats an idempotent call.
+struct DeviceOnce {
+    unsigned long long mask[4] = {0, 0, 0, 0};          // 256 device ordinals
+    bool first_use() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        unsigned long long& m = mask[(dev >> 6) & 3];
+        if (m & bit) return false;
+        m |= bit;
+        return true;
+    }
+};
+#define SBEV_PER_DEVICE_ONCE(...)                      \
+    do {                                               \
+        static ::sbev::DeviceOnce once_per_device_;    \
+        if (once_per_device_.first_use()) { __VA_ARGS__; } \
+    } while (0)
+
+// SM count of the CURRENT device (cached per device ordinal).
+inline int device_num_sms() {
+    static int cache[256] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = cache[dev & 255];
+    if (n == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n = v > 0 ? v : 148;
+    }
+    return n;
+}
+
 #define SBEV_REQUIRE(cond, code, ...)            \
     do {                                         \
         if (!(cond)) {                           \

@@ -354,10 +354,8 @@ static int make_act_map(CUtensorMap* out, const void* x, int N, int H, int W, in
 template <int BN, int STAGES>
 static int launch_conv(const ConvParams& prm, const ConvMaps& maps, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (CONV_A_BYTES + BN * 128) + 1024;
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-    static int sms = 0;
-    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = device_num_sms();
     const int tiles = prm.m_tiles * prm.n_tiles;
     launch_pdl(conv_igemm_kernel<BN, STAGES>, dim3(tiles < sms ? tiles : sms), dim3(CONV_THREADS), smem, st, prm, maps);
     return check_launch("sbev_conv2d_nhwc_fwd");
@@ -418,8 +416,7 @@ extern "C" int sbev_stem_conv_fwd(const float* img, int Nimg, int H, int W, cons
     if (Nimg == 0) return SBEV_OK;
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
     const size_t smem = (size_t)(147 * 64 + 3 * STEM_PH * STEM_PW) * sizeof(float);
-    static std::once_flag once;
-    std::call_once(once, [&] { cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = Nimg * ((Wo + STEM_TW - 1) / STEM_TW) * ((Ho + STEM_TH - 1) / STEM_TH);
     launch_pdl(stem_conv7x7_kernel, dim3(tiles), dim3(256), smem, (cudaStream_t)stream, img, w, scale, shift, Nimg, H, W, Ho, Wo,
                reinterpret_cast<__nv_bfloat16*>(out));

@@ -1364,11 +1364,8 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
                 rc = make_bf16_map(&maps.lo[i], l.W_lo, l.N, l.Kpad, box);
                 if (rc) return rc;
             }
-            static std::once_flag once_ns;
-            std::call_once(once_ns, [&] {
-                cudaFuncSetAttribute(dense_chain_ns_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<2>::SMEM);
-                cudaFuncSetAttribute(dense_chain_ns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<4>::SMEM);
-            });
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(dense_chain_ns_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<2>::SMEM);
+                cudaFuncSetAttribute(dense_chain_ns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NsCfg<4>::SMEM));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((M + rows - 1) / rows * ns);
             cfg.blockDim = dim3(288);
@@ -1396,13 +1393,10 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         }
         const size_t smem_mma = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * DENSE_ROWS * MC_XLD * 2 + (size_t)DENSE_ROWS * MC_YLD * 4 +
                                 (size_t)(3 * CHAIN_VEC_LD + DENSE_ROWS * MC_RES_LD) * 4 + 1024;
-        static std::once_flag once_mma;
-        std::call_once(once_mma, [&] {
-            cudaFuncSetAttribute(dense_chain_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+        SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(dense_chain_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
             cudaFuncSetAttribute(dense_chain_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
             cudaFuncSetAttribute(dense_chain_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
-            cudaFuncSetAttribute(dense_chain_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
-        });
+            cudaFuncSetAttribute(dense_chain_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
         if (cl > 1) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((groups + cl - 1) / cl * cl);
@@ -1426,8 +1420,7 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
     for (int i = 0; i < n_layers; ++i)
         SBEV_REQUIRE(layers[i].Wt != nullptr, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: fp32 weight missing for the FFMA path", i);
     const size_t smem = sizeof(float) * ((size_t)CHAIN_STAGES * CHAIN_STAGE_FLOATS + 2 * (size_t)DENSE_ROWS * prm.act_ld);
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dense_chain_kernel<<<(M + DENSE_ROWS - 1) / DENSE_ROWS, 256, smem, (cudaStream_t)stream>>>(prm);
     return check_launch("sbev_dense_chain_fwd");
 }

@@ -597,8 +597,7 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
     const bool x3_pattern = nseg == 3 && A[0] == A[1] && B[0] == B[2];
     if (nseg == 1 || x3_pattern) {
         // ---- v2: persistent, double-buffered TMEM, shared operand tiles for the three bf16x3 products
-        static int num_sms = 0;
-        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        const int num_sms = device_num_sms();
         const int m_tiles_pre = (M + GEMM_BM - 1) / GEMM_BM;
         // A-resident variant: small K, many N-tiles per M-tile (the parameter-generation GEMM)
         const bool ares = get_option(OPT_GEMM_IMPL) == 1 && x3_pattern && split_k == 1 && K == 256 && m_tiles_pre <= num_sms &&
@@ -616,9 +615,8 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
             const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
             const int num_units = ((m_tiles + 1) / 2) * n_tiles * split_k;
             const int clusters = num_units < num_sms / 2 ? num_units : num_sms / 2;
-            static std::once_flag once_pair;
-            std::call_once(once_pair, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, false, true>,
-                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SMEM); });
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, false, true>,
+                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SMEM));
             launch_pair(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, false, true>, clusters, GEMM_PAIR_SMEM, (cudaStream_t)stream,
                         mp, K / GEMM_BK, split_k, m_tiles, n_tiles, num_units, bias, C, M, N);
             return check_launch("sbev_gemm_bf16_tn(pair)");
@@ -637,16 +635,14 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
 #define SBEV_GEMM_V2(BNN, STG, XX)                                                                                               \
         do {                                                                                                                     \
             constexpr size_t smem_v2 = (size_t)STG * (XX ? 2 : 1) * (GEMM_BM * GEMM_BK * 2 + BNN * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;          \
-            static std::once_flag once;                                                                                          \
-            std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
-                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2); });       \
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>,                         \
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));       \
             launch_pdl(gemm_bf16_tn_persistent_kernel<BNN, STG, XX>, dim3(grid), dim3(GEMM_THREADS), smem_v2, st, mp, kbs, split_k, m_tiles, n_tiles, num_tiles, bias, C, M, N); \
         } while (0)
         if (ares) {
             constexpr size_t smem_ar = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
-            static std::once_flag once_ar;
-            std::call_once(once_ar, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>,
-                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ar); });
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>,
+                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ar));
             launch_pdl(gemm_bf16_tn_persistent_kernel<128, 2, true, 4>, dim3(grid), dim3(GEMM_THREADS), smem_ar, st, mp, kbs, 1, m_tiles, n_tiles, num_tiles, bias, C, M, N);
         } else if (x3_pattern) { if (wide) SBEV_GEMM_V2(256, 2, true); else SBEV_GEMM_V2(128, 3, true); }
         else            { if (wide) SBEV_GEMM_V2(256, 4, false); else SBEV_GEMM_V2(128, 6, false); }
@@ -677,15 +673,13 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     rc = make_bf16_store_map(&mp.c_hi, C_hi, N, M);          if (rc) return rc;
     rc = make_bf16_store_map(&mp.c_lo, C_lo, N, M);          if (rc) return rc;
     mp.c = mp.c_hi;
-    static int num_sms = 0;
-    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int num_sms = device_num_sms();
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
     if (pair && num_sms >= 2) {
         const int num_units = ((m_tiles + 1) / 2) * n_tiles;
         const int clusters = num_units < num_sms / 2 ? num_units : num_sms / 2;
-        static std::once_flag once_pair;
-        std::call_once(once_pair, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>,
-                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SPLIT_SMEM); });
+        SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SPLIT_SMEM));
         launch_pair(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>, clusters, GEMM_PAIR_SPLIT_SMEM, (cudaStream_t)stream,
                     mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_units, bias, (float*)nullptr, M, N);
         return check_launch("sbev_gemm_bf16_tn_split(pair)");
@@ -696,9 +690,8 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
         rc = make_bf16_map(&mp.b_hi, B_hi, N, K, 128);   if (rc) return rc;
         rc = make_bf16_map(&mp.b_lo, B_lo, N, K, 128);   if (rc) return rc;
         constexpr size_t smem_ares = (size_t)4 * 2 * (GEMM_BM * GEMM_BK * 2) + (size_t)2 * 2 * (128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
-        static std::once_flag once_ares;
-        std::call_once(once_ares, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4, true>,
-                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ares); });
+        SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<128, 2, true, 4, true>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ares));
         const int grid_ares = (num_sms / m_tiles) * m_tiles;
         launch_pdl(gemm_bf16_tn_persistent_kernel<128, 2, true, 4, true>, dim3(grid_ares), dim3(GEMM_THREADS), smem_ares, (cudaStream_t)stream,
                    mp, K / GEMM_BK, 1, m_tiles, N / 128, m_tiles * (N / 128), bias, nullptr, M, N);
@@ -707,9 +700,8 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     const int num_tiles = m_tiles * n_tiles;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
     constexpr size_t smem = (size_t)2 * 2 * (GEMM_BM * GEMM_BK * 2 + 256 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true>, dim3(grid), dim3(GEMM_THREADS), smem, (cudaStream_t)stream,
                mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_tiles, bias, nullptr, M, N);
     return check_launch("sbev_gemm_bf16_tn_split");

@@ -725,8 +725,7 @@ extern "C" int sbev_mix_fwd(const float* params, const float* x, int BQ, int G, 
         const size_t smem = raw_bytes + ops_bytes;
         SBEV_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, SBEV_ERR_INVALID,
                      "sbev_mix_fwd: params / x must be 16-byte aligned");
-        static int num_sms = 0;
-        if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        const int num_sms = device_num_sms();
         const int per_sm = smem <= 110 * 1024 ? 2 : 1;
         const int pgrid = grid < per_sm * num_sms ? grid : per_sm * num_sms;
 #define SBEV_LAUNCH_MMA(R)                                                                                          \
@@ -779,11 +778,9 @@ extern "C" int sbev_mix_presplit_fwd(const uint16_t* params_hi, const uint16_t* 
     } else {
         maps.y_hi = maps.m_hi; maps.y_lo = maps.m_lo;        // unused
     }
-    static int num_sms = 0;
-    if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int num_sms = device_num_sms();
     const size_t smem = 2 * 32768 + 2 * 8192 + 4 * 32 * MX_LD * 2 + 1024;
-    static std::once_flag once;
-    std::call_once(once, [&] { cudaFuncSetAttribute(mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = items < 2 * num_sms ? (int)items : 2 * num_sms;
     launch_pdl(mix_tma_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, maps, x, (int)items, G, get_option(OPT_MIX_ORDER),
                reinterpret_cast<__nv_bfloat16*>(y_hi),

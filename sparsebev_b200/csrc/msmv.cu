@@ -538,6 +538,7 @@ struct FusedParams {
     int t0, Tl;              // frame window [t0, t0+Tl) held by feats (t0 = 0, Tl = T: all frames)
     int ld_vel;
     int o0, To, n_out;       // the out buffers cover frames [o0, o0+To): the window itself, or all T frames (scatter form)
+    int q_per_rank;          // > 0 (owner form, B == 1): query q's rows go ONLY to out[q / q_per_rank], a [q_per_rank,G,T*P,64] buffer
 };
 
 // LPP = lanes per sample point: 16 (4 channels per lane) or 8 (8 channels per lane; halves the per-point geometry that
@@ -605,11 +606,18 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     float4 acc[VEC];
     gather_levels_v<L, LB, VEC, 4 * LPP, PF>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
     if (live) {
+        if (prm.q_per_rank > 0) {                      // owner form: the row goes to the one rank that mixes query q
+            const int ow = q / prm.q_per_rank;
+            float* dst = prm.out[ow] + ((((long long)(q - ow * prm.q_per_rank) * G + g) * (T * P) + (t * P + p)) * 64 + 4 * j);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) *reinterpret_cast<float4*>(dst + 4 * LPP * e) = acc[e];
+        } else {
         const long long row = ((bq * G + g) * (prm.To * P) + ((t - prm.o0) * P + p)) * 64 + 4 * j;
         for (int w = 0; w < prm.n_out; ++w) {          // n_out > 1: the same 256 B row also goes to the peers over NVLink
             float* dst = prm.out[w] + row;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) *reinterpret_cast<float4*>(dst + 4 * LPP * e) = acc[e];
+        }
         }
         if (prm.loc_out != nullptr && j == 0) {
             float* lo = prm.loc_out + (((long long)s * Q + q) * P + p) * 3;
@@ -802,7 +810,8 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
                              const float* lidar2img, const float* scale_w,
                              int B, int T, int t0, int Tl, int G, int N, int C, int Q, int P,
                              float image_h, float image_w, float eps,
-                             float* const* outs, int n_out, bool full_out, float* loc_out, void* stream, const char* who) {
+                             float* const* outs, int n_out, bool full_out, float* loc_out, void* stream, const char* who,
+                             int q_per_rank = 0) {
     SBEV_REQUIRE(ld_vel >= 2, SBEV_ERR_INVALID, "%s: ld_vel must be >= 2", who);
     SBEV_REQUIRE(t0 >= 0 && Tl >= 0 && t0 + Tl <= T, SBEV_ERR_INVALID, "%s: frame window [%d,%d) outside [0,%d)", who, t0, t0 + Tl, T);
     SBEV_REQUIRE(feats && stride_bt && stride_g && stride_v && stride_px && points && velocity && time_diff &&
@@ -836,6 +845,11 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
     prm.image_h = image_h; prm.image_w = image_w; prm.eps = eps;
     prm.t0 = t0; prm.Tl = Tl; prm.n_out = n_out; prm.ld_vel = ld_vel;
     prm.o0 = full_out ? 0 : t0; prm.To = full_out ? T : Tl;
+    prm.q_per_rank = q_per_rank;
+    if (q_per_rank > 0) {
+        SBEV_REQUIRE(B == 1, SBEV_ERR_UNSUPPORTED, "%s: the owner form needs B == 1 (got %d)", who, B);
+        SBEV_REQUIRE((long long)q_per_rank * n_out >= Q, SBEV_ERR_INVALID, "%s: %d ranks x %d queries do not cover Q = %d", who, n_out, q_per_rank, Q);
+    }
     // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
     // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views); 3 = 2 + L2 prefetch of the next level pair
     int variant = get_option(OPT_GATHER_VARIANT);
@@ -889,4 +903,17 @@ extern "C" int sbev_sampling4d_scatter_fwd(const float* const* feats, const int*
                                            float* const* outs, int n_out, float* loc_out, void* stream) {
     return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, ld_vel, time_diff, lidar2img, scale_w,
                              B, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, outs, n_out, true, loc_out, stream, "sbev_sampling4d_scatter_fwd");
+}
+
+extern "C" int sbev_sampling4d_owner_fwd(const float* const* feats, const int* hw, int L,
+                                         const int64_t* stride_bt, const int64_t* stride_g,
+                                         const int64_t* stride_v, const int64_t* stride_px,
+                                         const float* points, const float* velocity, int ld_vel, const float* time_diff,
+                                         const float* lidar2img, const float* scale_w,
+                                         int T, int t0, int Tl, int G, int N, int C, int Q, int P,
+                                         float image_h, float image_w, float eps,
+                                         float* const* outs, int n_ranks, int q_per_rank, void* stream) {
+    SBEV_REQUIRE(q_per_rank > 0, SBEV_ERR_INVALID, "sbev_sampling4d_owner_fwd: q_per_rank must be positive");
+    return launch_sampling4d(feats, hw, L, stride_bt, stride_g, stride_v, stride_px, points, velocity, ld_vel, time_diff, lidar2img, scale_w,
+                             1, T, t0, Tl, G, N, C, Q, P, image_h, image_w, eps, outs, n_ranks, true, nullptr, stream, "sbev_sampling4d_owner_fwd", q_per_rank);
 }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256, 2)
 sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, int ld,
                const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
                const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
-               int B, int Q, int H, float* __restrict__ out) {
+               int B, int Q, int H, int qa, int qb, float* __restrict__ out) {
     // 8 warps = 4 key-quarters x 2 query tiles; the two warps of a key-quarter share one K/V double buffer
     // (each fills half of it) and synchronise on their own named barrier (64 threads) -- never the whole CTA.
     extern __shared__ __align__(16) unsigned char s3_smem[];
@@ -381,7 +381,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kq = warp >> 1, mt = warp & 1;
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int q0 = blockIdx.x * 32 + 16 * mt;
+    const int q0 = qa + blockIdx.x * 32 + 16 * mt;      // queries [qa, qb) of this launch; keys are always all Q
     const int h = blockIdx.y, b = blockIdx.z;
     const float scale = 0.17677669529663687f;
     unsigned char* mybuf = s3_smem + kq * 2 * S3_BUF_BYTES;
@@ -398,7 +398,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
         for (int i = 0; i < 4; ++i) {
             const int r = q0 + g8 + 8 * (i & 1), k = 16 * ks + 2 * t4 + 8 * (i >> 1);
             uint32_t vh = 0, vl = 0;
-            if (r < Q) {
+            if (r < qb) {
                 vh = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + (rowbase + r) * ld + h * SA_HD + k));
                 vl = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + (rowbase + r) * ld + h * SA_HD + k));
             }
@@ -408,7 +408,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int gq = q0 + g8 + 8 * r;
-        const bool ok = gq < Q;
+        const bool ok = gq < qb;
         rcx[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
         rcy[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
         rtau[r] = ok ? __ldg(tau + (rowbase + gq) * ld_tau + h) : 0.f;
@@ -484,7 +484,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
                     const int k = 8 * n + 2 * t4 + e;
                     const float dx = rcx[r] - kcx[k], dy = rcy[r] - kcy[k];
                     float v = sacc[n][2 * r + e] * scale + (-sa_sqrt(dx * dx + dy * dy)) * rtau[r];
-                    if (HAS_MASK && gq < Q && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
+                    if (HAS_MASK && gq < qb && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
                     if (k0 + k >= Q) v = -INFINITY;
                     sacc[n][2 * r + e] = v;
                     mx = fmaxf(mx, v);
@@ -558,8 +558,8 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
             num += f * row[d];
             den += f * row[SA_HD + 1];
         }
-        const int gq = blockIdx.x * 32 + r32;
-        if (gq < Q) out[(rowbase + gq) * D + h * SA_HD + d] = num / den;
+        const int gq = qa + blockIdx.x * 32 + r32;
+        if (gq < qb) out[(rowbase + gq) * D + h * SA_HD + d] = num / den;
     }
 }
 
@@ -584,27 +584,31 @@ extern "C" int sbev_sasa_fwd(const float* qkv, int ld_qkv, const float* query_bb
     return check_launch("sbev_sasa_fwd");
 }
 
-extern "C" int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
-                                   const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
-                                   int B, int Q, int H, int D, float* out, void* stream) {
+extern "C" int sbev_sasa_split_range_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
+                                         const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
+                                         int B, int Q, int H, int D, int q_begin, int q_end, float* out, void* stream) {
+    SBEV_REQUIRE(q_begin >= 0 && q_begin <= q_end && q_end <= Q, SBEV_ERR_INVALID, "sbev_sasa_split_range_fwd: query range [%d,%d) outside [0,%d]", q_begin, q_end, Q);
     SBEV_REQUIRE(qkv_hi && qkv_lo && query_bbox && tau && pc_range && out, SBEV_ERR_INVALID, "sbev_sasa_split_fwd: null pointer");
     SBEV_REQUIRE(B >= 0 && Q >= 0 && H > 0 && ld >= 3 * D && ld_tau >= H, SBEV_ERR_INVALID, "sbev_sasa_split_fwd: bad sizes");
     SBEV_REQUIRE(D == H * SA_HD, SBEV_ERR_UNSUPPORTED, "sbev_sasa_split_fwd: head dim must be 32 (D=%d, H=%d)", D, H);
     SBEV_REQUIRE((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0,
                  SBEV_ERR_INVALID, "sbev_sasa_split_fwd: bf16 operands must be 16-byte aligned with ld % 8 == 0");
-    if (B == 0 || Q == 0) return SBEV_OK;
+    if (B == 0 || q_end == q_begin) return SBEV_OK;
     const size_t smem = (size_t)4 * 2 * S3_BUF_BYTES;
-    static std::once_flag once;
-    std::call_once(once, [&] {
-        cudaFuncSetAttribute(sasa_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sasa_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
-    dim3 grid((Q + 31) / 32, H, B);
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(sasa_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sasa_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((q_end - q_begin + 31) / 32, H, B);
     if (dn_mask != nullptr)
         launch_pdl(sasa_v3_kernel<true>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
-                   query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+                   query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, q_begin, q_end, out);
     else
         launch_pdl(sasa_v3_kernel<false>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
-                   query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, out);
+                   query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, q_begin, q_end, out);
     return check_launch("sbev_sasa_split_fwd");
+}
+
+extern "C" int sbev_sasa_split_fwd(const uint16_t* qkv_hi, const uint16_t* qkv_lo, int ld, const float* query_bbox,
+                                   const float* tau, int ld_tau, const uint8_t* dn_mask, const float* pc_range,
+                                   int B, int Q, int H, int D, float* out, void* stream) {
+    return sbev_sasa_split_range_fwd(qkv_hi, qkv_lo, ld, query_bbox, tau, ld_tau, dn_mask, pc_range, B, Q, H, D, 0, Q, out, stream);
 }

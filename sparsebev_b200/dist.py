@@ -162,3 +162,113 @@ class FrameShard:
     def peer_barrier(self):
         """Stream-ordered barrier over all ranks: returns (on the stream) once every rank's rows have landed."""
         self._cur.barrier(channel=0)
+
+
+def query_partition(num_query, rank, world):
+    """-> (q_per_rank, q0, q1): rank r owns queries [r*q_per_rank, min((r+1)*q_per_rank, Q)), q_per_rank = ceil(Q / world)
+    (the last ranks may own fewer -- or none, when Q < world)."""
+    qpr = -(-num_query // world)
+    q0 = min(rank * qpr, num_query)
+    return qpr, q0, min(q0 + qpr, num_query)
+
+
+class QueryShard:
+    """Query- AND frame-sharded decoder state of one rank: ONE scene (B = 1) across `world` GPUs, strong scaling
+    (frames local as in partitioning B, every query-side stage sharded over queries).
+
+    Rank r keeps the feature maps of frames [t0, t1) (what its backbone produced; the pyramid never crosses NVLink) and
+    OWNS queries [q0, q1).  Per decoder layer:
+      * position encoder + attention in-projection run for all Q rows on every rank (K / V of every query are needed);
+      * attention core, out-projection, sampling heads, sample points: own queries only;
+      * exchange 1 (sbev_peer_exchange): every rank's sample points + scale weights -> all ranks (0.4 MB at Q = 900);
+      * gather: own frames, ALL queries; each 256 B row is stored straight into the buffer of the rank that owns the
+        query (sbev_sampling4d_owner_fwd: the all-to-all of sampled rows is the gather's store), then a barrier;
+      * parameter GEMM, mixing, out-projection, FFN, cls / reg branches, box refinement: own queries only;
+      * exchange 2: refined boxes, query features, class scores of the own queries -> all ranks (1 MB at Q = 900).
+    Every exchange is one kernel of ours that stores into the peers' symmetric memory over NVLink and ends in an
+    all-ranks barrier on flag words in that memory; no NCCL on the data path.  All buffers are written at most once
+    between two barriers and read only after the barrier that follows the write, so nothing is double-buffered except
+    the layer outputs (a layer reads the previous layer's output buffers while it fills the other set).
+    """
+
+    FLAG_WORDS = 64            # 256 B at the start of the arena: SBEV_MAX_PEERS flag words + padding
+
+    def __init__(self, num_frames, rank=None, world=None, group=None):
+        if rank is None or world is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError('QueryShard needs an initialised process group (or explicit rank/world)')
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world > 8:
+            raise ValueError('QueryShard supports at most 8 ranks (one NVSwitch node)')
+        self.rank, self.world, self.group = rank, world, group
+        self.num_frames = num_frames
+        self.window = frame_partition(num_frames, rank, world)
+        self._arenas = {}
+        self._parity = 0
+        self.exchanges = 0         # exchanges enqueued (host-side count; every rank must issue the same sequence)
+        self.bytes_sent = 0        # payload bytes this rank stored into peers through sbev_peer_exchange (host-side count)
+
+    def partition(self, num_query):
+        return query_partition(num_query, self.rank, self.world)
+
+    @staticmethod
+    def layout(fields):
+        """fields [(name, shape)] -> ({name: (offset_in_floats, shape)}, total_floats); every field starts on a 256-byte boundary."""
+        off, table = QueryShard.FLAG_WORDS, {}
+        for name, shape in fields:
+            n = 1
+            for s in shape:
+                n *= int(s)
+            table[name] = (off, tuple(int(s) for s in shape))
+            off += (n + 63) // 64 * 64
+        return table, off
+
+    def arena(self, fields, device):
+        """One symmetric-memory allocation per distinct field list: local tensor views + every rank's base address."""
+        key = (tuple((n, tuple(s)) for n, s in fields), str(device))
+        ar = self._arenas.get(key)
+        if ar is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            table, total = self.layout(fields)
+            buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            buf.zero_()
+            ctl = torch.zeros(4, dtype=torch.int32, device=device)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)          # every rank's flag words are zero before anyone signals
+            views = {n: buf[o:o + _numel(s)].view(s) for n, (o, s) in table.items()}
+            ar = dict(buf=buf, hdl=hdl, ptrs=[int(p) for p in hdl.buffer_ptrs], table=table, views=views, ctl=ctl, device=device)
+            self._arenas[key] = ar
+        return ar
+
+    def peer_ptrs(self, ar, name):
+        off = ar['table'][name][0]
+        return [p + 4 * off for p in ar['ptrs']]
+
+    def exchange(self, ar, rows):
+        """rows = [(field, r0, r1)]: rows [r0, r1) of every field (leading dimension) go to all peers; then the barrier."""
+        from . import ops
+        segs = []
+        for name, r0, r1 in rows:
+            off, shape = ar['table'][name]
+            per = _numel(shape[1:])
+            start, nbytes = 4 * (off + r0 * per), 4 * max(0, r1 - r0) * per
+            segs.append((ar['ptrs'][self.rank] + start, [p + start for p in ar['ptrs']], nbytes))
+            self.bytes_sent += nbytes * (self.world - 1)
+        self.exchanges += 1
+        ops.peer_exchange(segs, self.world, self.rank, ar['ptrs'], ar['ctl'].data_ptr(), ar['device'])
+
+    def flip(self):
+        self._parity ^= 1
+        return self._parity
+
+    def status(self, ar):
+        """0 = healthy; 1 = an exchange gave up waiting for a peer (synchronises the stream)."""
+        return int(ar['ctl'][2].item())
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n

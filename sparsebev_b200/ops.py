@@ -112,13 +112,15 @@ def msmv_indices(level_hw, sampling_locations, num_views):
 
 def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w, image_h, image_w,
                      num_frames, num_views=6, eps=1e-5, layout='grouped', return_loc=False, out=None, frame_window=None,
-                     scatter_ptrs=None):
+                     scatter_ptrs=None, owner_ptrs=None, q_per_rank=0):
     """Fused motion-warp + projection + view pick + gather.
 
     frame_window (t0, t1): the feature maps hold only frames [t0, t1) of the num_frames (frame-sharded decoder); the
     result is then [B,Q,G,(t1-t0)*P,C].  time_diff / lidar2img always cover all frames.
     scatter_ptrs: device addresses of full-size [B,Q,G,T*P,C] buffers (this GPU's and its peers', e.g. symmetric memory);
     the window's rows are stored into every one of them at their frame offset and no tensor is returned.
+    owner_ptrs + q_per_rank (B == 1): device addresses of every rank's [q_per_rank,G,T*P,C] buffer; query q's rows are stored
+    only into owner_ptrs[q // q_per_rank] (query- and frame-sharded decoder); no tensor is returned.
 
     layout 'grouped': feats L x [B*T*G, N, H, W, C] (the reference's regrouped op layout);
     layout 'nhwc'   : feats L x [B, T*N, H, W, G*C] (un-regrouped, channels-last FPN output).
@@ -165,6 +167,17 @@ def sampling4d_fused(mlvl_feats, points, velocity, time_diff, lidar2img, scale_w
     if tuple(td.shape) != (B, T) or tuple(l2i.shape) != (B, T * N, 4, 4) or tuple(vel.shape) != (B, Q, ld_vel):
         raise RuntimeError('time_diff / lidar2img / velocity shape mismatch')
     loc = torch.empty(B * Tl * G, Q, P, 3, device=pts.device, dtype=torch.float32) if return_loc else None
+    if owner_ptrs is not None:
+        if B != 1 or return_loc:
+            raise RuntimeError('the owner form of the gather needs B == 1 and cannot return loc')
+        with torch.cuda.device(pts.device):
+            _lib.check(lib.sbev_sampling4d_owner_fwd(
+                _lib.ptr_array([f.data_ptr() for f in mlvl_feats]), _lib.i32_array(hw), L,
+                _lib.i64_array(s_bt), _lib.i64_array(s_g), _lib.i64_array(s_v), _lib.i64_array(s_px),
+                pts.data_ptr(), vel_ptr, ld_vel, td.data_ptr(), l2i.data_ptr(), sw.data_ptr(),
+                T, t0, Tl, G, N, C, Q, P, float(image_h), float(image_w), float(eps),
+                _lib.ptr_array([int(p) for p in owner_ptrs]), len(owner_ptrs), int(q_per_rank), _stream()), 'sbev_sampling4d_owner_fwd')
+        return None
     if scatter_ptrs is not None:
         with torch.cuda.device(pts.device):
             _lib.check(lib.sbev_sampling4d_scatter_fwd(
@@ -300,7 +313,7 @@ def dense(x, wt, ldw, n_out, bias=None, ln_w=None, ln_b=None, residual=None, rel
     return out
 
 
-def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels, num_points_total=None, ld_off=None, ld_log=None):
+def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels, num_points_total=None, ld_off=None, ld_log=None, out=None):
     """query_bbox [B,Q,10]; offset rows of GP*3 floats, scale_logits rows of GP*L floats (either plain [B,Q,GP*3] /
     [B,Q,GP*L] tensors, or column blocks of a wider matrix given with explicit row strides ld_off / ld_log)
     -> points [B,Q,GP,3], scale_w [B,Q,GP,L] (GP = G*P, group-major)."""
@@ -315,8 +328,14 @@ def sample_points(query_bbox, offset, scale_logits, pc_range, num_levels, num_po
         ld_off, ld_log = GP * 3, GP * L
     else:
         off, lg, GP = offset, scale_logits, num_points_total
-    pts = torch.empty(B, Q, GP, 3, device=qb.device, dtype=torch.float32)
-    sw = torch.empty(B, Q, GP, L, device=qb.device, dtype=torch.float32)
+    if out is not None:                  # caller-provided (e.g. rows of a symmetric-memory buffer)
+        pts, sw = out
+        if pts.numel() != B * Q * GP * 3 or sw.numel() != B * Q * GP * L:
+            raise RuntimeError('sample_points: out buffers have the wrong size')
+        _chk(pts, 'points'); _chk(sw, 'scale_w')
+    else:
+        pts = torch.empty(B, Q, GP, 3, device=qb.device, dtype=torch.float32)
+        sw = torch.empty(B, Q, GP, L, device=qb.device, dtype=torch.float32)
     with torch.cuda.device(qb.device):
         _lib.check(lib.sbev_sample_points_fwd(qb.data_ptr(), off.data_ptr(), ld_off, lg.data_ptr(), ld_log,
                                               _lib.f32_array([float(v) for v in pc_range]), B * Q, GP, L,
@@ -348,9 +367,10 @@ def sasa(qkv, query_bbox, tau, pc_range, num_heads=8, dn_mask=None, ld_qkv=None,
     return out
 
 
-def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None, split=None):
+def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None, split=None, q_range=None, out=None):
     """Tensor-core attention core on the concatenated in_proj|gen_tau output `qkvt` [B*Q, 3D+H] (fp32): splits it once
-    into bf16 (hi, lo) and runs the warp-pipelined kernel.  -> [B,Q,D] (heads concatenated, before out_proj)."""
+    into bf16 (hi, lo) and runs the warp-pipelined kernel.  -> [B,Q,D] (heads concatenated, before out_proj).
+    q_range (qa, qb): only those queries attend (to all Q keys) and only their rows of the result are written."""
     lib = _lib.load()
     qkvt = _chk(qkvt, 'qkvt')
     qb = _chk(query_bbox, 'query_bbox')
@@ -361,11 +381,13 @@ def sasa_split(qkvt, query_bbox, pc_range, num_heads, embed_dims, dn_mask=None, 
     m = None
     if dn_mask is not None:
         m = _chk(dn_mask.to(torch.uint8).contiguous(), 'dn_mask', torch.uint8)
-    out = torch.empty(B, Q, D, device=qb.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, Q, D, device=qb.device, dtype=torch.float32)
+    qa, qe = (0, Q) if q_range is None else q_range
     with torch.cuda.device(qb.device):
-        _lib.check(lib.sbev_sasa_split_fwd(hi.data_ptr(), lo.data_ptr(), ld, qb.data_ptr(), qkvt.data_ptr() + 3 * D * 4, ld, _p(m),
-                                           _lib.f32_array([float(v) for v in pc_range]), B, Q, H, D, out.data_ptr(), _stream()),
-                   'sbev_sasa_split_fwd')
+        _lib.check(lib.sbev_sasa_split_range_fwd(hi.data_ptr(), lo.data_ptr(), ld, qb.data_ptr(), qkvt.data_ptr() + 3 * D * 4, ld, _p(m),
+                                                 _lib.f32_array([float(v) for v in pc_range]), B, Q, H, D, int(qa), int(qe), out.data_ptr(), _stream()),
+                   'sbev_sasa_split_range_fwd')
     return out
 
 
@@ -472,6 +494,21 @@ def refine_bbox(proposal, delta, time_diff):
         _lib.check(lib.sbev_refine_bbox_fwd(proposal.data_ptr(), delta.data_ptr(), td.data_ptr(), B, Q, td.shape[1], code,
                                             out.data_ptr(), _stream()), 'sbev_refine_bbox_fwd')
     return out
+
+
+def peer_exchange(segments, n_peers, rank, flag_ptrs, ctl_ptr, device):
+    """One kernel: copy `segments` = [(src_ptr, [dst_ptr per rank], nbytes), ...] to every peer, then an all-ranks barrier
+    (sbev_peer_exchange).  No segments = pure barrier."""
+    lib = _lib.load()
+    arr = (_lib.PeerSegment * max(1, len(segments)))()
+    for i, (src, dsts, nbytes) in enumerate(segments):
+        arr[i].src = src
+        for w, d in enumerate(dsts):
+            arr[i].dst[w] = d
+        arr[i].bytes = nbytes
+    with torch.cuda.device(device):
+        _lib.check(lib.sbev_peer_exchange(arr, len(segments), n_peers, rank, _lib.ptr_array([int(p) for p in flag_ptrs]), ctl_ptr, _stream()),
+                   'sbev_peer_exchange')
 
 
 # ------------------------------------------------------------------------------------------------

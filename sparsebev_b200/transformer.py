@@ -339,6 +339,8 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self._reg = [_Dense(rb[2 * i]) for i in range(num_reg_fcs)] + [_Dense(rb[2 * num_reg_fcs])]
         self.overlap = True          # run independent kernels of a layer on a second stream (parallel graph branches)
         self.frame_shard = None      # dist.FrameShard: this rank holds / samples only its window of the T frames
+        self.query_shard = None      # dist.QueryShard: ONE scene across ranks -- frames local, every query-side stage sharded over queries
+        self.qshard_split_k = None   # split-K slices of the out-projection in query-sharded mode (None: chosen from the local row count)
         self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
         self._graphs, self._graph_pool = collections.OrderedDict(), None
@@ -435,7 +437,110 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         entry[0].replay()
         return tuple(o.clone() for o in entry[2])
 
+    @torch.no_grad()
+    def _forward_qshard(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        """Query- and frame-sharded layer (dist.QueryShard; B must be 1): same inputs and outputs as _forward_impl on
+        EVERY rank (full query_bbox / query_feat in, full query_feat / cls / bbox out), `mlvl_feats` holding this rank's
+        frames only.  Stages are the same kernels as the unsharded layer run on the rank's own rows [q0, q1); rows of the
+        results are bit-identical to the unsharded layer when the out-projection uses the same split-K count."""
+        sh = self.query_shard
+        B, Q, D = query_feat.shape
+        if B != 1:
+            raise RuntimeError('query-sharded decoder layer: batch must be 1 (got %d)' % B)
+        dev = query_feat.device
+        smp, mixing = self.sampling, self.mixing
+        G, P, L, T = smp.num_groups, smp.num_points, smp.num_levels, smp.num_frames
+        GP, C = G * P, D // G
+        qpr, q0, q1 = sh.partition(Q)
+        Ml = q1 - q0
+        ar = sh.arena([('points', (Q, GP, 3)), ('scale_w', (Q, GP, L)), ('sampled', (qpr, G, T * P, C)),
+                       ('feat0', (Q, D)), ('feat1', (Q, D)), ('cls0', (Q, self.num_classes)), ('cls1', (Q, self.num_classes)),
+                       ('box0', (Q, self.code_size)), ('box1', (Q, self.code_size))], dev)
+        v = ar['views']
+        par = sh.flip()
+        out_feat, out_cls, out_box = v['feat%d' % par], v['cls%d' % par], v['box%d' % par]
+        query_bbox = query_bbox.contiguous()
+        qb2 = query_bbox.reshape(Q, -1)
+        qf = query_feat.reshape(Q, D).contiguous()
+        new = lambda m, n: torch.empty(m, n, device=dev, dtype=torch.float32)      # noqa: E731
+        sl = slice(q0, q1)
+        # (1) position encoder + in-projection for ALL rows (every query's K / V is needed by every rank)
+        q1_all = new(Q, D)
+        pos_enc = (qb2, qb2.shape[-1], [self._pe0.layer(relu=True), self._pe1.layer(relu=True, residual=qf, y=q1_all)])
+        attn = self.self_attn
+        H = attn.num_heads
+        qkvt = new(Q, 3 * D + H)
+        hi = torch.empty(Q, 3 * D + H, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        ops.dense_chain(pos_enc[0], pos_enc[1], Q, list(pos_enc[2]) + [attn.in_layer(qkvt, hi, lo)])
+        # (2) attention core of the own queries, out-projection + norm1 + sampling heads, sample points -> exchange 1
+        o = new(Q, D)
+        pbuf = mixing.alloc_params(max(Ml, 1), dev)
+        q2, heads = new(max(Ml, 1), D), new(max(Ml, 1), smp._heads.out_features)
+        if Ml > 0:
+            ops.sasa_split(qkvt, query_bbox, attn.pc_range, H, D, dn_mask=attn_mask, split=(hi, lo), q_range=(q0, q1), out=o.view(1, Q, D))
+            ops.dense_chain(o[sl], D, Ml, [attn.out_layer(q1_all[sl], self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), smp.heads_layer(heads)])
+            ld = heads.shape[1]
+            ops.sample_points(query_bbox[:, sl], heads, heads[:, GP * 3:], smp.pc_range, L, num_points_total=GP, ld_off=ld, ld_log=ld,
+                              out=(v['points'][sl], v['scale_w'][sl]))
+        sh.exchange(ar, [('points', q0, q1), ('scale_w', q0, q1)])
+        # (3) gather: own frames, all queries, rows stored to the owning rank  ||  (4a) parameter GEMM of the own queries
+        image_h, image_w, _ = img_metas[0]['img_shape'][0]
+        meta = img_metas[0]
+
+        def gather():
+            ops.sampling4d_fused(mlvl_feats, v['points'].view(1, Q, GP, 3), query_bbox, meta['time_diff'], meta['lidar2img'],
+                                 v['scale_w'].view(1, Q, G, P, L), image_h, image_w, num_frames=T, num_views=NUM_VIEWS,
+                                 layout=smp.feat_layout, frame_window=sh.window, owner_ptrs=sh.peer_ptrs(ar, 'sampled'), q_per_rank=qpr)
+            sh.exchange(ar, [])
+        main = torch.cuda.current_stream()
+        side = self._side_stream(dev) if self.overlap else None
+        params = None
+        if side is not None and Ml > 0:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                params = mixing.generate_params(q2, pbuf, presplit=True)
+            gather()
+            main.wait_stream(side)
+        else:
+            if Ml > 0:
+                params = mixing.generate_params(q2, pbuf, presplit=True)
+            gather()
+        # (4b) mixing, (5) FFN, cls / reg + refine: own queries, results into this rank's rows of the output buffers -> exchange 2
+        if Ml > 0:
+            keep_split = mixing.split_k
+            if self.qshard_split_k is not None:
+                mixing.split_k = self.qshard_split_k
+            else:                    # fill ~72 CTA-pair units (148 SMs): the unsharded layer has ceil(900/256) = 4 row units x 18 slices
+                mixing.split_k = max(keep_split, min(128, (72 + (Ml + 255) // 256 - 1) // ((Ml + 255) // 256)))
+            try:
+                red = mixing.mix_and_project(params, v['sampled'][:Ml], q2, self.norm2, defer_reduce=True)
+            finally:
+                mixing.split_k = keep_split
+            q3 = new(Ml, D)
+            td = meta['time_diff']
+            q4, cls_score, bbox_pred = out_feat[sl], out_cls[sl], out_box[sl]
+            cls_chain = [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
+            reg_chain = [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
+            ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
+            refine = dict(refine_proposal=qb2[sl], refine_time_diff=td, refine_Q=Ml, refine_T=td.shape[1])
+            if side is not None:
+                ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.dense_chain(q4, D, Ml, reg_chain, **refine)
+                ops.dense_chain(q4, D, Ml, cls_chain)
+                main.wait_stream(side)
+            else:
+                ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain + cls_chain)
+                ops.dense_chain(q4, D, Ml, reg_chain, **refine)
+        sh.exchange(ar, [('feat%d' % par, q0, q1), ('cls%d' % par, q0, q1), ('box%d' % par, q0, q1)])
+        # (the symmetric output buffers are reused two layers later: hand out copies of the small results)
+        return out_feat.view(1, Q, D), out_cls.view(1, Q, self.num_classes).clone(), out_box.view(1, Q, self.code_size).clone()
+
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        if self.query_shard is not None and self.query_shard.world > 1:
+            return self._forward_qshard(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
         if (self.use_cuda_graph and (self.frame_shard is None or self.frame_shard.world == 1)
                 and not torch.cuda.is_current_stream_capturing()):
             return self._forward_graphed(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
@@ -584,6 +689,13 @@ class SparseBEVTransformer(BaseModule):
         """Frame-sharded operation (not in the reference, whose only multi-GPU mode is DDP): `shard` is a dist.FrameShard;
         afterwards `mlvl_feats` passed to forward hold only this rank's frames, img_metas still describe all of them."""
         self.decoder.decoder_layer.frame_shard = shard
+        return self
+
+    def shard_queries(self, shard):
+        """Query- and frame-sharded operation (strong scaling of ONE scene; not in the reference): `shard` is a
+        dist.QueryShard (None switches it off).  `mlvl_feats` passed to forward then hold only this rank's frames, every
+        rank passes the same queries / img_metas and every rank gets the full result."""
+        self.decoder.decoder_layer.query_shard = shard
         return self
 
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):

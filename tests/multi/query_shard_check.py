@@ -1,0 +1,76 @@
+"""2+-rank GPU check of the query- and frame-sharded decoder (launched by tests/test_gpu_multi.py under torchrun).
+
+Every rank builds the SAME synthetic scene and runs the unsharded decoder on all frames; then the sharded decoder
+(dist.QueryShard: this rank's frame window of the feature maps, this rank's queries) -- first with the unsharded layer's
+split-K count, where every row must be BIT-IDENTICAL (each stage is the same kernel on a subset of independent rows), then
+with the split-K count the sharded layer picks for its smaller row count (fp32 summation order of the out-projection
+changes: <= 2e-5 of the output scale).  Prints `QUERY_SHARD_OK rank=<r> ...` per rank; any mismatch raises.
+"""
+import copy
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import sparsebev_b200 as sb                    # noqa: E402
+from sparsebev_b200 import dist as D           # noqa: E402
+from sparsebev_b200 import synthetic as S      # noqa: E402
+
+
+def main():
+    config = sys.argv[1] if len(sys.argv) > 1 else 'tiny'
+    T = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    layers = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    D.init('nccl', dev)
+    cfg = S.layer_cfg(config, T, num_layers=layers)
+    sd = S.make_state_dict(cfg, seed=0)
+    model = sb.SparseBEVTransformer(embed_dims=256, num_frames=T, num_points=4, num_layers=layers, num_levels=cfg['num_levels'],
+                                    pc_range=cfg['pc_range']).to(dev).eval()
+    model.load_state_dict({'decoder.decoder_layer.' + k: v for k, v in sd.items()})
+    layer = model.decoder.decoder_layer
+    Q = cfg['num_query']
+    feats = S.make_feats(config, T, batch=1, seed=1)
+    metas = S.make_metas(config, T, batch=1)
+    qb = S.init_query_bbox(Q, seed=2)[None].to(dev)
+    qf = torch.randn(1, Q, 256, generator=torch.Generator().manual_seed(3)).to(dev)
+    with torch.no_grad():
+        want = model(qb, qf, [f.to(dev) for f in feats], None, copy.deepcopy(metas))
+        shard = D.QueryShard(T)
+        t0, t1 = shard.window
+        assert (t0, t1) == D.frame_partition(T, rank, world)
+        model.shard_queries(shard)
+        local_feats = [f[:, t0 * 6:t1 * 6].contiguous().to(dev) for f in feats]
+        for name, split in (('same split-K', layer.mixing.split_k), ('own split-K', None)):
+            layer.qshard_split_k = split
+            for rep in range(3):          # repeated forwards also exercise buffer reuse across layers and forwards
+                got = model(qb, qf, [f.clone() for f in local_feats], None, copy.deepcopy(metas))
+                torch.cuda.synchronize()
+                for g, w in zip(got, want):
+                    if split is not None:
+                        if not torch.equal(g, w):
+                            raise AssertionError('rank %d %s rep %d: max |diff| %.3e' % (rank, name, rep, float((g - w).abs().max())))
+                    else:
+                        err = float((g - w).abs().max() / w.abs().max())
+                        if not err < 2e-5:
+                            raise AssertionError('rank %d %s rep %d: rel-to-max %.3e' % (rank, name, rep, err))
+            ar = next(iter(shard._arenas.values()))
+            assert shard.status(ar) == 0, 'an exchange timed out'
+            print('QUERY_SHARD_OK rank=%d world=%d mode=%s window=[%d,%d) queries=[%d,%d) config=%s exchanges=%d' %
+                  ((rank, world, name.replace(' ', '_'), t0, t1) + shard.partition(Q)[1:] + (config, shard.exchanges)), flush=True)
+        model.shard_queries(None)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    try:
+        main()
+    except BaseException:
+        import traceback
+        print('QUERY_SHARD_FAILED rank=%s\n%s' % (os.environ.get('RANK'), traceback.format_exc()), flush=True)
+        os._exit(1)                    # do not hang the peers in a collective teardown

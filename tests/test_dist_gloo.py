@@ -79,3 +79,41 @@ def test_partitions_single_process():
     assert D.all_gather_frames(x) is x
     f = [torch.ones(1, 6, 4, 2, 2)]
     assert D.all_gather_features(f)[0] is f[0]                    # no process group: identity
+
+
+def test_query_shard_partition_layout_and_segments(monkeypatch):
+    """Host logic of the query- and frame-sharded decoder (no GPU, no process group: explicit rank / world): the query
+    partition covers every query once (ragged tail included), arena fields start on 256-byte boundaries behind the flag
+    words, and an exchange hands sbev_peer_exchange the own rows at the SAME offset of every rank's buffer."""
+    from sparsebev_b200 import dist as D, ops
+    for Q, world in ((900, 8), (900, 4), (900, 2), (1600, 8), (36, 8), (5, 8), (40, 3)):
+        seen = []
+        for r in range(world):
+            qpr, q0, q1 = D.query_partition(Q, r, world)
+            assert qpr * world >= Q and 0 <= q0 <= q1 <= Q and q1 - q0 <= qpr
+            seen += list(range(q0, q1))
+            if q1 > q0:
+                assert q0 // qpr == r and (q1 - 1) // qpr == r          # the gather's owner rule: q // q_per_rank
+        assert seen == list(range(Q))
+    fields = [('points', (900, 16, 3)), ('scale_w', (900, 16, 4)), ('sampled', (113, 4, 32, 64)), ('box0', (900, 10))]
+    table, total = D.QueryShard.layout(fields)
+    prev_end = D.QueryShard.FLAG_WORDS
+    for name, shape in fields:
+        off, shp = table[name]
+        assert shp == shape and off % 64 == 0 and off >= prev_end
+        prev_end = off + D._numel(shape)
+    assert total >= prev_end
+    sh = D.QueryShard(8, rank=3, world=8)
+    assert sh.window == (3, 4) and sh.partition(900) == (113, 339, 452)
+    calls = []
+    monkeypatch.setattr(ops, 'peer_exchange', lambda segs, n, r, flags, ctl, dev: calls.append((segs, n, r, flags)))
+    bases = [1 << 40 | (w << 32) for w in range(8)]
+    ar = dict(ptrs=bases, table=table, ctl=torch.zeros(4, dtype=torch.int32), device='cpu')
+    sh.exchange(ar, [('points', 339, 452), ('box0', 339, 452)])
+    sh.exchange(ar, [])
+    (segs, n, r, flags), (segs2, _, _, _) = calls
+    assert (n, r, flags) == (8, 3, bases) and segs2 == [] and sh.exchanges == 2
+    for (src, dsts, nbytes), (name, per) in zip(segs, (('points', 48), ('box0', 10))):
+        start = 4 * (table[name][0] + 339 * per)
+        assert src == bases[3] + start and dsts == [b + start for b in bases] and nbytes == 4 * 113 * per
+    assert sh.bytes_sent == 7 * 4 * 113 * (48 + 10)

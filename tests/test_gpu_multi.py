@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, *args, port=29731):
+def _run(nproc, *args, port=29731, script='frame_shard_check.py'):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc),
-           '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'multi', 'frame_shard_check.py')] + list(args)
+           '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'multi', script)] + list(args)
     return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
 
 
@@ -26,3 +26,14 @@ def test_frame_sharded_decoder_is_bit_identical(config, T):
     assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-1500:]
     for ex in ('p2p', 'nccl'):
         assert r.stdout.count('exchange=%s' % ex) == world, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize('config,T,world', [('tiny', 8, 2), ('r50_704x256', 8, 2), ('tiny', 8, 4), ('r50_704x256', 8, 4), ('r50_704x256', 8, 8)])
+def test_query_sharded_decoder_matches_unsharded(config, T, world):
+    """ONE scene across `world` GPUs (frames + queries sharded, NVLink peer exchanges): bit-identical to the unsharded
+    decoder with the same split-K, <= 2e-5 with the sharded layer's own split-K.  Self-skips below `world` GPUs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs >= %d GPUs' % world)
+    r = _run(world, config, str(T), port=29741 + world, script='query_shard_check.py')
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-1500:]
+    assert r.stdout.count('QUERY_SHARD_OK') == 2 * world, r.stdout[-3000:]
