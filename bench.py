@@ -42,7 +42,8 @@ def parse():
     ap.add_argument('--config', default='r50_704x256')
     ap.add_argument('--frames', type=int, default=8)
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
-    ap.add_argument('--layout', default='grouped', choices=['grouped', 'nhwc'])
+    ap.add_argument('--layout', default='nhwc', choices=['grouped', 'nhwc'],
+                    help='nhwc (default): channels-last FPN output consumed zero-copy, as our backbone emits it; grouped: the reference\'s regrouped op layout')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='single stream: no concurrent gather || param-GEMM, cls || reg')
     ap.add_argument('--no-tma-params', action='store_true', help='mixing: fp32 parameter tensor + converting mix kernel instead of bf16 (hi,lo) + TMA')
@@ -58,6 +59,9 @@ def parse():
     ap.add_argument('--skip-backbone', action='store_true', help='do not time the ResNet-50 + FPN image branch (SURVEY 8 a17) next to the headline metric')
     ap.add_argument('--skip-gpu-baseline', action='store_true', help='do not time the reference CUDA op / stock-PyTorch layer (oracle/_ref) next to the headline')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--emulate-world', type=int, default=0, metavar='N', help='development: ONE GPU plays rank --emulate-rank of an N-GPU `--shard queries` run '
+                    '(no peers; rank-local kernel sequence only, for ncu) -- the line is marked "emulated" and is not a benchmark result')
+    ap.add_argument('--emulate-rank', type=int, default=0)
     return ap.parse_args()
 
 
@@ -173,17 +177,28 @@ def committed_dram_traffic(key):
         return None
 
 
-def event_ms(fn, iters=20, warm=3):
+def event_ms(fn, iters=20, warm=3, prefill_ms=0.0):
+    """Device time per call of `fn` (CUDA events on the launch stream, after warm-up, synchronised on both sides).
+    prefill_ms > 0: a spin kernel first occupies the stream for about that long while the host enqueues all `iters` calls,
+    so the events bracket back-to-back DEVICE execution -- without it a kernel shorter than the host's ~20 us per Python
+    launch is timed at the host's launch rate, not its own (every kernel of a T = 1 workload is that short)."""
     for _ in range(warm):
         fn()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if prefill_ms > 0:
+        torch.cuda._sleep(int(prefill_ms * 1.9e6))
     a.record()
     for _ in range(iters):
         fn()
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / iters
+
+
+def kernel_ms(fn, iters=20, warm=3):
+    """event_ms with the launch queue pre-filled (0.06 ms of spin per enqueued call covers the slowest Python front-end)."""
+    return event_ms(fn, iters=iters, warm=warm, prefill_ms=0.06 * iters + 0.2)
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
@@ -295,6 +310,9 @@ class Bench:
             _lib.set_option(name, int(value))
         self.layer = layer
         self.mode = 'single' if self.world == 1 else args.shard
+        if args.emulate_world > 1:
+            assert self.world == 1, '--emulate-world is a single-process development mode'
+            self.mode = 'queries'
         self.fmt = 'nhwc' if args.layout == 'nhwc' else 'nchw'
         self.qb_host = S.init_query_bbox(Q, seed=2)[None].contiguous().pin_memory()
         self.qf_host = torch.randn(1, Q, 256, generator=torch.Generator().manual_seed(3)).pin_memory()
@@ -340,7 +358,10 @@ class Bench:
 
     def setup_sharding(self):
         from sparsebev_b200 import dist as D
-        if self.mode == 'queries':
+        if self.mode == 'queries' and self.args.emulate_world > 1:
+            self.shard = D.QueryShard(self.T, rank=self.args.emulate_rank, world=self.args.emulate_world, emulate=True)
+            self.model.shard_queries(self.shard)
+        elif self.mode == 'queries':
             self.shard = D.QueryShard(self.T)
             self.model.shard_queries(self.shard)
         elif self.mode == 'frames':
@@ -538,7 +559,7 @@ class Bench:
         def gather(return_loc=False):
             return ops.sampling4d_fused(self.feats, pts, self.qb, meta['time_diff'], meta['lidar2img'], sw5, cfg['image_h'], cfg['image_w'],
                                         num_frames=T, layout=layer.sampling.feat_layout, out=out_buf, frame_window=window, return_loc=return_loc)
-        gather_ms = event_ms(gather)
+        gather_ms = kernel_ms(gather)
         algo_bytes, n_points = gather_algorithmic_bytes(cfg, frames=Tl)
         _, loc = gather(return_loc=True)
         comp_bytes, live = gather_compulsory_bytes(ops, loc, cfg['levels'])
@@ -563,7 +584,7 @@ class Bench:
         roof_u = None
         if True:
             gfeats = self.grouped_feats()
-            op_ms = event_ms(lambda: ops.msmv_forward(gfeats, uloc, uw))
+            op_ms = kernel_ms(lambda: ops.msmv_forward(gfeats, uloc, uw))
             ub, ulive = gather_compulsory_bytes(ops, uloc, cfg['levels'])
             roof_u = {'bound': 'hbm', 'kernel': 'msmv_fwd_c64_kernel (op boundary, msmv_sampling), uniform locations + views',
                       'achieved': ub / (op_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': ub / (op_ms * 1e-3) / 1e9 / peak,
@@ -576,7 +597,7 @@ class Bench:
         xm = x[:M].contiguous()
         pbuf = mixing.alloc_params(M, dev)
         mixing.generate_params(xm, pbuf, presplit=False)
-        gemm_ms = event_ms(lambda: mixing.generate_params(xm, pbuf, presplit=True))
+        gemm_ms = kernel_ms(lambda: mixing.generate_params(xm, pbuf, presplit=True))
         n_par = mixing.n_groups * mixing.total_parameters
         products = 3 if a.precision == 'bf16x3' else 1
         flops = 2.0 * M * n_par * 256 * products
@@ -619,19 +640,19 @@ class Bench:
             logits = torch.randn(1, Q, G * P * L, generator=torch.Generator().manual_seed(8)).to(dev)
             pts, sw = ops.sample_points(self.qb, off, logits, cfg['pc_range'], L)
             td = (torch.arange(T, dtype=torch.float32)[None] * 0.5).to(dev)
-            fused = lambda rl=False: ops.sampling4d_fused(feats, pts, self.qb, td, l2i[None].contiguous().to(dev), sw.reshape(1, Q, G, P, L),   # noqa: E731
-                                                          cfg['image_h'], cfg['image_w'], num_frames=T, return_loc=rl)
+            l2i_d, sw5 = l2i[None].contiguous().to(dev), sw.reshape(1, Q, G, P, L)
+            fused = lambda rl=False: ops.sampling4d_fused(feats, pts, self.qb, td, l2i_d, sw5, cfg['image_h'], cfg['image_w'], num_frames=T, return_loc=rl)   # noqa: E731
             _, rloc = fused(True)
             g = torch.Generator(device='cpu').manual_seed(5)
             uloc = torch.rand(Bp, Q, P, 3, generator=g)
             uloc[..., 2] = torch.randint(0, 6, (Bp, Q, P), generator=g).float() / 5
             w = torch.softmax(torch.randn(Bp, Q, P, L, generator=g), -1).to(dev)
             for dist_name, loc in (('realistic', rloc.contiguous()), ('uniform', uloc.to(dev))):
-                ours = event_ms(lambda: ops.msmv_forward(feats, loc, w), iters=30, warm=5)
-                theirs = event_ms(lambda: fwd(*feats, loc, w), iters=30, warm=5)
+                ours = kernel_ms(lambda: ops.msmv_forward(feats, loc, w), iters=30, warm=5)
+                theirs = kernel_ms(lambda: fwd(*feats, loc, w), iters=30, warm=5)
                 e = {'ref_cuda_op_ms': theirs, 'ours_op_ms': ours, 'speedup': theirs / ours, 'points': Bp * Q * P}
                 if dist_name == 'realistic':
-                    e['ours_fused_ms'] = event_ms(fused, iters=30, warm=5)
+                    e['ours_fused_ms'] = kernel_ms(fused, iters=30, warm=5)
                     e['note'] = 'ours_fused_ms also does the motion warp + projection + view pick the reference runs as ~40 extra torch kernels'
                 out['op']['T%d_%s' % (T, dist_name)] = e
             if T != self.T:
@@ -678,6 +699,11 @@ def main():
     T, Q = b.T, b.Q
 
     extra = {}
+    emulating = args.emulate_world > 1
+    if emulating:
+        extra['emulated'] = {'world': args.emulate_world, 'rank': args.emulate_rank,
+                             'note': 'DEVELOPMENT: one GPU plays one rank of the sharded run without peers; not a benchmark result'}
+        world = args.emulate_world          # (shapes only: this process is alone)
     if mode == 'queries':
         sh = b.shard
         qpr, q0, q1 = sh.partition(Q)
@@ -690,7 +716,7 @@ def main():
             'outputs_bytes_per_rank': (q1 - q0) * (256 + 10 + 10) * 4 * (world - 1),
             'queries_per_rank': qpr, 'frames_per_rank': T // world, 'timeout_status': sh.status(ar)}
         try:
-            extra['exchange']['barrier_us'] = 1e3 * event_ms(lambda: sh.exchange(ar, []), iters=50, warm=5)
+            extra['exchange']['barrier_us'] = 1e3 * kernel_ms(lambda: sh.exchange(ar, []), iters=50, warm=5)
         except Exception as exc:                          # pragma: no cover
             extra['exchange']['barrier_us'] = repr(exc)[:200]
 
@@ -720,7 +746,7 @@ def main():
             feats_full = b.model.decoder.prepare_feats([f.to(b.dev) for f in full])
             del full
             dp_ms = b.max_over_ranks(event_ms(lambda: layer(b.qb, b.qf, feats_full, None, b.metas), iters=max(5, min(args.steps, 30))))
-            extra['dp_replicas'] = {'value': world * 1e3 / dp_ms, 'unit': 'samples/s', 'ms_per_step': dp_ms, 'scaling': 'weak',
+            extra['dp_replicas'] = {'value': b.world * 1e3 / dp_ms, 'unit': 'samples/s', 'ms_per_step': dp_ms, 'scaling': 'weak',
                                     'note': 'one independent scene per GPU (the reference\'s DDP), eager launches, no data-path collective'}
             del feats_full
             b.model.shard_queries(b.shard)
@@ -735,6 +761,9 @@ def main():
             json.dump(breakdown, f, indent=1)
 
     gpu_base = None
+    if emulating:
+        args.skip_gpu_baseline = args.skip_backbone = args.skip_cpu = True
+        world = 1
     if rank == 0 and world == 1 and not args.skip_gpu_baseline:
         try:
             gpu_base = b.gpu_baseline()
@@ -752,13 +781,15 @@ def main():
                'sample': '%d decoder-layer passes (mean %.0f ms, best %.0f ms) of the reference native-PyTorch path '
                          '(oracle/ref_torch.py), same workload; %d of %d host threads (auto-tuned)' % (args.cpu_steps, mean * 1e3, best * 1e3, threads, os.cpu_count() or 1)}
 
+    if emulating:
+        world = args.emulate_world
     if rank == 0:
         par = {'single': 'one GPU', 'scenes': 'dp%d: one independent scene per GPU, no collective' % world,
                'frames': 'ONE scene, %d frames per GPU, query-side stages replicated, sampled rows exchanged once per layer (%s)' % (T // world, args.exchange),
                'queries': 'ONE scene: %d frames + %d queries per GPU; gather on own frames for all queries with rows stored to the owning GPU, '
                           'every other stage on own queries; 3 NVLink exchanges per layer' % (T // world, -(-Q // world))}[mode]
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': b.world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if mode in ('single', 'scenes') else 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': make_config(args, cfg),
@@ -776,7 +807,7 @@ def main():
             'breakdown_ms': breakdown}
         line.update(extra)
         print(json.dumps(line))
-    if world > 1:
+    if b.world > 1:
         _shutdown(b.graph)
 
 

@@ -56,6 +56,9 @@ const char* sbev_last_error(void);
  *                    delays the parameter GEMM that waits on the same launch, the separate kernel overlaps with it)
  *   "pdl"            1 = hot-path kernels are launched with programmatic stream serialization (default): each kernel runs its
  *                    global-memory-free prologue while its predecessor drains, then griddepcontrol.wait; 0 = plain launches
+ *   "legacy_rotation" 0 = v1.0.0 box convention (default); 1 = the sample-point rotation of checkpoints whose `version` is 'v0.17.1'
+ *                    (models/utils.py:66-71: rotation_3d_in_axis turns the other way; toggled like the reference's global
+ *                    VERSION.name, val.py:128-129) -- affects sbev_sample_points_fwd and sbev_dense_chain_points_fwd
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default);
  *                    3 = 2 + the next level pair's lines are prefetched into L2 while the current pair's loads are in flight */

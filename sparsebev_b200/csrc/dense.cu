@@ -37,7 +37,7 @@ struct ChainParams {
     const float* in_partial; int in_nsplit; const float* in_bias; const float* in_res; const float* in_ln_w; const float* in_ln_b; float* in_out;
     // optional sample-points epilogue on the last layer (CHAIN_FLAG_POINTS; tensor-core kernel only): its output row
     // [.. | GP*3 offsets at sp_off_col | GP*L scale logits at sp_log_col | ..] -> sp_points [M][GP][3], sp_scale_w [M][GP][L]
-    const float* sp_bbox; float* sp_points; float* sp_scale_w; float sp_r[6]; int sp_GP, sp_L, sp_off_col, sp_log_col;
+    const float* sp_bbox; float* sp_points; float* sp_scale_w; float sp_r[6]; int sp_GP, sp_L, sp_off_col, sp_log_col; float sp_ssign;
     ChainLayer layer[CHAIN_MAX_LAYERS];
 };
 constexpr int CHAIN_FLAG_POINTS = 1 << 9;
@@ -47,14 +47,15 @@ constexpr int CHAIN_FLAG_POINTS = 1 << 9;
 // Shared by sample_points_kernel and the chain kernel's fused epilogue, so both produce identical bits.
 __device__ __forceinline__ void sample_point_one(const float* bb, const float* op, const float* lp, int L,
                                                  float r0, float r1, float r2, float r3, float r4, float r5,
-                                                 float* pt, float* w) {
+                                                 float* pt, float* w, float ssign = 1.f) {
     // decode_bbox: xyz*(hi-lo)+lo, exp(log-size), atan2(sin, cos)   (separate mul and add as in torch)
     const float cx = __fadd_rn(__fmul_rn(bb[0], __fsub_rn(r3, r0)), r0);
     const float cy = __fadd_rn(__fmul_rn(bb[1], __fsub_rn(r4, r1)), r1);
     const float cz = __fadd_rn(__fmul_rn(bb[2], __fsub_rn(r5, r2)), r2);
     const float sw = expf(bb[3]), sl = expf(bb[4]), sh = expf(bb[5]);
     const float yaw = atan2f(bb[6], bb[7]);
-    const float s = sinf(yaw), c = cosf(yaw);
+    // ssign = -1: the legacy 'v0.17.1' checkpoint convention rotates the other way (models/utils.py:66-71)
+    const float s = ssign * sinf(yaw), c = cosf(yaw);
     const float dx = __fmul_rn(sw, op[0]), dy = __fmul_rn(sl, op[1]), dz = __fmul_rn(sh, op[2]);
     // rotate counter-clockwise by yaw about z: x' = x*c + y*(-s), y' = x*s + y*c
     const float rx = __fadd_rn(__fmul_rn(dx, c), __fmul_rn(dy, -s));
@@ -672,7 +673,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                 for (int gp = lane; gp < prm.sp_GP; gp += 32)
                     sample_point_one(prm.sp_bbox + row * 10, yr + prm.sp_off_col + gp * 3, yr + prm.sp_log_col + gp * prm.sp_L, prm.sp_L,
                                      prm.sp_r[0], prm.sp_r[1], prm.sp_r[2], prm.sp_r[3], prm.sp_r[4], prm.sp_r[5],
-                                     prm.sp_points + (row * prm.sp_GP + gp) * 3, prm.sp_scale_w + (row * prm.sp_GP + gp) * prm.sp_L);
+                                     prm.sp_points + (row * prm.sp_GP + gp) * 3, prm.sp_scale_w + (row * prm.sp_GP + gp) * prm.sp_L, prm.sp_ssign);
             }
             if (li + 1 < prm.n_layers) {          // next layer's activation operand: bf16 (hi, lo), zero beyond N up to its padded K
                 __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD;
@@ -1124,7 +1125,7 @@ dense_chain_ns_kernel(const __grid_constant__ ChainParams prm, const __grid_cons
 __global__ void __launch_bounds__(128)
 sample_points_kernel(const float* __restrict__ query_bbox, const float* __restrict__ offset, int ld_off,
                      const float* __restrict__ logits, int ld_log, float r0, float r1, float r2, float r3, float r4, float r5,
-                     int BQ, int GP, int L, float* __restrict__ points, float* __restrict__ scale_w) {
+                     int BQ, int GP, int L, float* __restrict__ points, float* __restrict__ scale_w, float ssign) {
     pdl_wait();
     pdl_trigger();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1132,7 +1133,7 @@ sample_points_kernel(const float* __restrict__ query_bbox, const float* __restri
     const long long bq = idx / GP;
     const int gp = (int)(idx - bq * GP);
     sample_point_one(query_bbox + bq * 10, offset + bq * ld_off + gp * 3, logits + bq * ld_log + gp * L, L, r0, r1, r2, r3, r4, r5,
-                     points + idx * 3, scale_w + idx * L);
+                     points + idx * 3, scale_w + idx * L, ssign);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1273,6 +1274,7 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
     prm.aux_proposal = refine_proposal; prm.aux_time_diff = refine_time_diff; prm.aux_Q = refine_Q > 0 ? refine_Q : 1; prm.aux_T = refine_T;
     prm.sp_bbox = nullptr; prm.sp_points = prm.sp_scale_w = nullptr; prm.sp_GP = prm.sp_L = prm.sp_off_col = prm.sp_log_col = 0;
     for (int i = 0; i < 6; ++i) prm.sp_r[i] = 0.f;
+    prm.sp_ssign = get_option(OPT_LEGACY_ROTATION) ? -1.f : 1.f;
     int act = 4;
     for (int i = 0; i < n_layers; ++i) {
         const sbev_dense_layer& l = layers[i];
@@ -1488,7 +1490,7 @@ extern "C" int sbev_sample_points_fwd(const float* query_bbox, const float* offs
     if (total == 0) return SBEV_OK;
     launch_pdl(sample_points_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream,
         query_bbox, offset, ld_off, scale_logits, ld_log, pc_range[0], pc_range[1], pc_range[2], pc_range[3], pc_range[4], pc_range[5],
-        BQ, GP, L, points, scale_w);
+        BQ, GP, L, points, scale_w, get_option(OPT_LEGACY_ROTATION) ? -1.f : 1.f);
     return check_launch("sbev_sample_points_fwd");
 }
 

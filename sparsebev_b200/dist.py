@@ -193,7 +193,12 @@ class QueryShard:
 
     FLAG_WORDS = 64            # 256 B at the start of the arena: SBEV_MAX_PEERS flag words + padding
 
-    def __init__(self, num_frames, rank=None, world=None, group=None):
+    def __init__(self, num_frames, rank=None, world=None, group=None, emulate=False):
+        """emulate=True (development / profiling on ONE GPU): this process plays rank `rank` of `world` without peers -- the
+        arena is ordinary device memory, every "peer" buffer aliases it and the exchanges degenerate to the local part of
+        the kernel, so the rank-local kernel sequence of an N-GPU run can be profiled (ncu) on a single GPU.  Results are
+        NOT the sharded decoder's (rows of the other ranks never arrive)."""
+        self.emulate = bool(emulate)
         if rank is None or world is None:
             if not (dist.is_available() and dist.is_initialized()):
                 raise RuntimeError('QueryShard needs an initialised process group (or explicit rank/world)')
@@ -227,6 +232,13 @@ class QueryShard:
         """One symmetric-memory allocation per distinct field list: local tensor views + every rank's base address."""
         key = (tuple((n, tuple(s)) for n, s in fields), str(device))
         ar = self._arenas.get(key)
+        if ar is None and self.emulate:
+            table, total = self.layout(fields)
+            buf = torch.zeros(total, dtype=torch.float32, device=device)
+            views = {n: buf[o:o + _numel(s)].view(s) for n, (o, s) in table.items()}
+            ar = dict(buf=buf, hdl=None, ptrs=[buf.data_ptr()] * self.world, table=table, views=views,
+                      ctl=torch.zeros(4, dtype=torch.int32, device=device), device=device)
+            self._arenas[key] = ar
         if ar is None:
             import torch.distributed._symmetric_memory as symm_mem
             table, total = self.layout(fields)
@@ -256,6 +268,9 @@ class QueryShard:
             segs.append((ar['ptrs'][self.rank] + start, [p + start for p in ar['ptrs']], nbytes))
             self.bytes_sent += nbytes * (self.world - 1)
         self.exchanges += 1
+        if self.emulate:             # no peers: the kernel's local part only (arrival counter + epoch), nothing to copy or wait for
+            ops.peer_exchange([], 1, 0, ar['ptrs'][:1], ar['ctl'].data_ptr(), ar['device'])
+            return
         ops.peer_exchange(segs, self.world, self.rank, ar['ptrs'], ar['ctl'].data_ptr(), ar['device'])
 
     def flip(self):

@@ -66,12 +66,18 @@ class SparseBEVHead(nn.Module):
     @torch.no_grad()
     def get_bboxes(self, preds_dicts, img_metas=None, rescale=False):
         """Reference :463-482 without the mmdet3d box class: -> per sample [bboxes [n,9] (bottom-centre z), scores, labels].
-        (The reference wraps `bboxes` into LiDARInstance3DBoxes(bboxes, 9); its legacy-version axis swap is not reproduced.)"""
+        (The reference wraps `bboxes` into LiDARInstance3DBoxes(bboxes, 9).)  With utils.VERSION.name == 'v0.17.1' the
+        legacy-checkpoint convention of :472-476 applies: w / l swapped, yaw -> -yaw - pi/2."""
+        from .utils import VERSION
         if self.bbox_coder is None:
             raise RuntimeError('SparseBEVHead was built without bbox_coder=dict(type="NMSFreeCoder", ...)')
         out = []
         for preds in self.bbox_coder.decode(preds_dicts):
             bboxes = preds['bboxes']
             bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+            if VERSION.legacy:
+                w, l = bboxes[:, 3].clone(), bboxes[:, 4].clone()
+                bboxes[:, 3], bboxes[:, 4] = l, w
+                bboxes[:, 6] = -bboxes[:, 6] - math.pi / 2
             out.append([bboxes, preds['scores'], preds['labels']])
         return out

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .utils import DUMP
 
 try:                                                     # mmcv / mmdet are optional (absent in the build image)
     from mmcv.runner import BaseModule
@@ -40,6 +41,39 @@ except Exception:                                        # pragma: no cover
     TRANSFORMER = None
 
 NUM_VIEWS = 6     # hard-coded in the reference (sparsebev_transformer.py:61,75)
+
+
+def decode_bbox(bboxes, pc_range=None):
+    """Torch mirror of models/bbox/utils.py:63-77 (used by the DUMP export only; the kernels decode in registers)."""
+    xyz = bboxes[..., 0:3].clone()
+    wlh = bboxes[..., 3:6].exp()
+    rot = torch.atan2(bboxes[..., 6:7], bboxes[..., 7:8])
+    if pc_range is not None:
+        for i in range(3):
+            xyz[..., i] = xyz[..., i] * (pc_range[3 + i] - pc_range[i]) + pc_range[i]
+    if bboxes.shape[-1] > 8:
+        return torch.cat([xyz, wlh, rot, bboxes[..., 8:10].clone()], dim=-1)
+    return torch.cat([xyz, wlh, rot], dim=-1)
+
+
+def projected_sample_points(points, velocity, time_diff, lidar2img, image_h, image_w, eps=1e-5, num_views=NUM_VIEWS):
+    """Slow export path of what the fused gather keeps in registers: all T x N projections of the (motion-warped) sample
+    points, in the form models/sparsebev_sampling.py:82-86 dumps for viz_sample_points.py.
+    points [B,Q,GP,3], velocity [B,Q,2], time_diff [B,T], lidar2img [B,T*N,4,4]
+    -> (cam [B,T,N,Q,GP,3] = (u / image_w, v / image_h, max(depth, eps)), valid_mask [B,T,N,Q,GP] float)."""
+    B, Q, GP, _ = points.shape
+    T = time_diff.shape[1]
+    p = points[:, :, None].expand(B, Q, T, GP, 3)
+    xy = p[..., 0:2] - (velocity[:, :, None, :] * time_diff[:, None, :, None])[:, :, :, None, :]       # sparsebev_transformer.py:286-295
+    ph = torch.cat([xy, p[..., 2:3], torch.ones_like(p[..., :1])], dim=-1)                             # [B,Q,T,GP,4]
+    l2i = lidar2img.reshape(B, T, num_views, 4, 4)
+    cam = torch.einsum('btnij,bqtpj->btnqpi', l2i, ph)                                                  # [B,T,N,Q,GP,4]
+    homo = cam[..., 2:3]
+    homo_nonzero = torch.maximum(homo, torch.zeros_like(homo) + eps)
+    uv = cam[..., 0:2] / homo_nonzero
+    uv = torch.stack([uv[..., 0] / image_w, uv[..., 1] / image_h], dim=-1)
+    valid = ((homo > eps) & (uv[..., 1:2] > 0.0) & (uv[..., 1:2] < 1.0) & (uv[..., 0:1] > 0.0) & (uv[..., 0:1] < 1.0)).squeeze(-1).float()
+    return torch.cat([uv, homo_nonzero], dim=-1), valid
 
 
 class _Dense:
@@ -226,6 +260,8 @@ class SparseBEVSelfAttention(BaseModule):
             hi = torch.empty(B * Q, 3 * D + H, device=x.device, dtype=torch.bfloat16)
             lo = torch.empty_like(hi)
             ops.dense_chain(x0, ldx0, B * Q, list(head) + [self.in_layer(qkvt, hi, lo)])
+            if DUMP.enabled:               # reference :218-219
+                torch.save(qkvt[:, 3 * D:3 * D + H].reshape(B, Q, H).cpu(), '{}/sasa_tau_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
             o = ops.sasa_split(qkvt, query_bbox, self.pc_range, H, D, dn_mask=pre_attn_mask, split=(hi, lo))
             return o.reshape(B * Q, D)
         ops.dense_chain(x0, ldx0, B * Q, list(head) + [self.in_layer(qkvt)])
@@ -286,6 +322,11 @@ class SparseBEVSampling(BaseModule):
             ld = heads_out.shape[1]
             pts, sw = ops.sample_points(query_bbox, heads_out, heads_out[:, G * P * 3:], self.pc_range, L,
                                         num_points_total=G * P, ld_off=ld, ld_log=ld)
+        if DUMP.enabled:                   # reference models/sparsebev_sampling.py:82-86 (slow export path, a few torch ops)
+            cam, valid = projected_sample_points(pts, query_bbox[..., 8:10], img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
+                                                 image_h, image_w, num_views=NUM_VIEWS)
+            torch.save(cam.cpu(), '{}/sample_points_cam_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
+            torch.save(valid.cpu(), '{}/sample_points_cam_valid_mask_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
         return ops.sampling4d_fused(mlvl_feats, pts, query_bbox, img_metas[0]['time_diff'], img_metas[0]['lidar2img'],
                                     sw.reshape(B, Q, G, P, L), image_h, image_w, num_frames=self.num_frames,
                                     num_views=NUM_VIEWS, layout=self.feat_layout,       # [B,Q,G,T*P,C]
@@ -448,6 +489,14 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         if B != 1:
             raise RuntimeError('query-sharded decoder layer: batch must be 1 (got %d)' % B)
         dev = query_feat.device
+        probe = getattr(self, '_probe', None)          # bench.py --breakdown: [(stage, event)] recorded on the main stream
+
+        def mark(name):
+            if probe is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                probe.append((name, ev))
+        mark('start')
         smp, mixing = self.sampling, self.mixing
         G, P, L, T = smp.num_groups, smp.num_points, smp.num_levels, smp.num_frames
         GP, C = G * P, D // G
@@ -473,17 +522,22 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         hi = torch.empty(Q, 3 * D + H, device=dev, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
         ops.dense_chain(pos_enc[0], pos_enc[1], Q, list(pos_enc[2]) + [attn.in_layer(qkvt, hi, lo)])
+        mark('pos_enc+in_proj (all rows)')
         # (2) attention core of the own queries, out-projection + norm1 + sampling heads, sample points -> exchange 1
         o = new(Q, D)
         pbuf = mixing.alloc_params(max(Ml, 1), dev)
         q2, heads = new(max(Ml, 1), D), new(max(Ml, 1), smp._heads.out_features)
         if Ml > 0:
             ops.sasa_split(qkvt, query_bbox, attn.pc_range, H, D, dn_mask=attn_mask, split=(hi, lo), q_range=(q0, q1), out=o.view(1, Q, D))
+            mark('attention core (own queries)')
             ops.dense_chain(o[sl], D, Ml, [attn.out_layer(q1_all[sl], self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), smp.heads_layer(heads)])
+            mark('out_proj+norm1+heads')
             ld = heads.shape[1]
             ops.sample_points(query_bbox[:, sl], heads, heads[:, GP * 3:], smp.pc_range, L, num_points_total=GP, ld_off=ld, ld_log=ld,
                               out=(v['points'][sl], v['scale_w'][sl]))
+            mark('sample_points')
         sh.exchange(ar, [('points', q0, q1), ('scale_w', q0, q1)])
+        mark('exchange 1 (points)')
         # (3) gather: own frames, all queries, rows stored to the owning rank  ||  (4a) parameter GEMM of the own queries
         image_h, image_w, _ = img_metas[0]['img_shape'][0]
         meta = img_metas[0]
@@ -492,7 +546,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             ops.sampling4d_fused(mlvl_feats, v['points'].view(1, Q, GP, 3), query_bbox, meta['time_diff'], meta['lidar2img'],
                                  v['scale_w'].view(1, Q, G, P, L), image_h, image_w, num_frames=T, num_views=NUM_VIEWS,
                                  layout=smp.feat_layout, frame_window=sh.window, owner_ptrs=sh.peer_ptrs(ar, 'sampled'), q_per_rank=qpr)
+            mark('gather (own frames, rows to owners)')
             sh.exchange(ar, [])
+            mark('barrier')
         main = torch.cuda.current_stream()
         side = self._side_stream(dev) if self.overlap else None
         params = None
@@ -517,6 +573,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
                 red = mixing.mix_and_project(params, v['sampled'][:Ml], q2, self.norm2, defer_reduce=True)
             finally:
                 mixing.split_k = keep_split
+            mark('wait param GEMM + mix + out_proj GEMM')
             q3 = new(Ml, D)
             td = meta['time_diff']
             q4, cls_score, bbox_pred = out_feat[sl], out_cls[sl], out_box[sl]
@@ -529,16 +586,23 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     ops.dense_chain(q4, D, Ml, reg_chain, **refine)
+                mark('reduce+norm2+FFN')
                 ops.dense_chain(q4, D, Ml, cls_chain)
                 main.wait_stream(side)
             else:
                 ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain + cls_chain)
                 ops.dense_chain(q4, D, Ml, reg_chain, **refine)
+            mark('cls || reg+refine')
         sh.exchange(ar, [('feat%d' % par, q0, q1), ('cls%d' % par, q0, q1), ('box%d' % par, q0, q1)])
+        mark('exchange 2 (outputs)')
         # (the symmetric output buffers are reused two layers later: hand out copies of the small results)
         return out_feat.view(1, Q, D), out_cls.view(1, Q, self.num_classes).clone(), out_box.view(1, Q, self.code_size).clone()
 
     def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        if DUMP.enabled:                   # export path: plain launches of the unsharded layer (files are written between kernels)
+            if (self.query_shard is not None and self.query_shard.world > 1) or (self.frame_shard is not None and self.frame_shard.world > 1):
+                raise RuntimeError('DUMP export needs the unsharded decoder layer')
+            return self._forward_impl(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
         if self.query_shard is not None and self.query_shard.world > 1:
             return self._forward_qshard(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
         if (self.use_cuda_graph and (self.frame_shard is None or self.frame_shard.world == 1)
@@ -611,6 +675,10 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         else:
             ffn(ffn_chain + cls_chain)
             ops.dense_chain(q4, D, M, reg_chain, refine_proposal=query_bbox, refine_time_diff=td, refine_Q=Q, refine_T=td.shape[1])
+        if DUMP.enabled:                   # reference :185-191
+            torch.save(decode_bbox(query_bbox, self.pc_range).cpu(), '{}/query_bbox_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
+            torch.save(decode_bbox(bbox_pred.reshape(B, Q, -1), self.pc_range).cpu(), '{}/bbox_pred_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
+            torch.save(torch.sigmoid(cls_score.reshape(B, Q, -1)).cpu(), '{}/cls_score_stage{}.pth'.format(DUMP.out_dir, DUMP.stage_count))
         return q4.reshape(B, Q, D), cls_score.reshape(B, Q, self.num_classes), bbox_pred.reshape(B, Q, self.code_size)
 
 
@@ -663,7 +731,8 @@ class SparseBEVTransformerDecoder(BaseModule):
         self.prepare_metas(img_metas, query_bbox.shape[0], query_bbox.device)
         self.prepare_feats(mlvl_feats)
         cls_scores, bbox_preds = [], []
-        for _ in range(self.num_layers):
+        for i in range(self.num_layers):
+            DUMP.stage_count = i
             query_feat, cls_score, bbox_pred = self.decoder_layer(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
             query_bbox = bbox_pred.clone().detach()
             cls_scores.append(cls_score)

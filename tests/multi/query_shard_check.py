@@ -4,7 +4,7 @@ Every rank builds the SAME synthetic scene and runs the unsharded decoder on all
 (dist.QueryShard: this rank's frame window of the feature maps, this rank's queries) -- first with the unsharded layer's
 split-K count, where every row must be BIT-IDENTICAL (each stage is the same kernel on a subset of independent rows), then
 with the split-K count the sharded layer picks for its smaller row count (fp32 summation order of the out-projection
-changes: <= 2e-5 of the output scale).  Prints `QUERY_SHARD_OK rank=<r> ...` per rank; any mismatch raises.
+changes: <= 5e-5 of the output scale, the whole-layer parity bar).  Prints `QUERY_SHARD_OK rank=<r> ...` per rank; any mismatch raises.
 """
 import copy
 import os
@@ -56,7 +56,7 @@ def main():
                             raise AssertionError('rank %d %s rep %d: max |diff| %.3e' % (rank, name, rep, float((g - w).abs().max())))
                     else:
                         err = float((g - w).abs().max() / w.abs().max())
-                        if not err < 2e-5:
+                        if not err < 5e-5:
                             raise AssertionError('rank %d %s rep %d: rel-to-max %.3e' % (rank, name, rep, err))
             ar = next(iter(shard._arenas.values()))
             assert shard.status(ar) == 0, 'an exchange timed out'

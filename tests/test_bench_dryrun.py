@@ -45,7 +45,7 @@ class _TorchProxy(types.ModuleType):
             is_available=lambda: True, set_device=lambda i: None, synchronize=lambda *a: None,
             Stream=lambda *a, **k: _Stream(), Event=_Event, current_stream=lambda *a: _Stream(),
             stream=lambda s: contextlib.nullcontext(), CUDAGraph=_Graph, graph=lambda g, **k: contextlib.nullcontext(),
-            graph_pool_handle=lambda: 0, is_current_stream_capturing=lambda: False, empty_cache=lambda: None)
+            graph_pool_handle=lambda: 0, is_current_stream_capturing=lambda: False, empty_cache=lambda: None, _sleep=lambda n: None)
         self.__dict__['cuda'] = cuda
 
     def device(self, *a, **k):

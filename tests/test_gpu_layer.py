@@ -51,9 +51,9 @@ def test_decoder_layer_vs_oracle(name, T, B):
     gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
     got_q, got_cls, got_box = layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
     assert torch.equal(metas_gpu[0]['time_diff'].cpu(), td)
-    assert _rel(got_q, want_q) < 2e-4, 'query_feat rel err %.3e' % _rel(got_q, want_q)
-    assert _rel(got_cls, want_cls) < 2e-4, 'cls rel err %.3e' % _rel(got_cls, want_cls)
-    assert _rel(got_box, want_box) < 2e-4, 'bbox rel err %.3e' % _rel(got_box, want_box)
+    assert _rel(got_q, want_q) < 5e-5, 'query_feat rel err %.3e' % _rel(got_q, want_q)
+    assert _rel(got_cls, want_cls) < 5e-5, 'cls rel err %.3e' % _rel(got_cls, want_cls)
+    assert _rel(got_box, want_box) < 5e-5, 'bbox rel err %.3e' % _rel(got_box, want_box)
 
 
 @pytest.mark.parametrize('nsplit', [2, 4])
@@ -80,7 +80,7 @@ def test_decoder_layer_with_nsplit_cluster_chain(nsplit):
     finally:
         _lib.set_option('dense_nsplit', default)
     for g, w, b, what in zip(got, (want_q, want_cls, want_box), base, ('query_feat', 'cls', 'bbox')):
-        assert _rel(g, w) < 2e-4, '%s rel err %.3e' % (what, _rel(g, w))
+        assert _rel(g, w) < 5e-5, '%s rel err %.3e' % (what, _rel(g, w))
         assert _rel(g, b) < 5e-5, '%s vs default chain kernel: %.3e' % (what, _rel(g, b))
 
 
@@ -118,7 +118,7 @@ def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
     want_cls, want_box = R.decoder(qb, qf, feats, sd, cfg, td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
     got_cls, got_box = model(qb.cuda(), qf.cuda(), [f.cuda() for f in feats], None, copy.deepcopy(metas))
     assert got_cls.shape == (L, B, cfg['num_query'], 10) and got_box.shape == (L, B, cfg['num_query'], 10)
-    assert _rel(got_cls, want_cls) < 1e-3 and _rel(got_box, want_box) < 1e-3, (_rel(got_cls, want_cls), _rel(got_box, want_box))
+    assert _rel(got_cls, want_cls) < 2e-4 and _rel(got_box, want_box) < 2e-4, (_rel(got_cls, want_cls), _rel(got_box, want_box))   # 3 chained layers
     # channels-last features take the zero-copy 'nhwc' path and must agree exactly with the regrouped path
     nhwc = [f.cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f in feats]
     ptrs = [f.data_ptr() for f in nhwc]
@@ -133,8 +133,8 @@ def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
     outs = head([f.cuda() for f in feats], copy.deepcopy(metas))
     want = R.head_forward(head.init_query_bbox.weight.detach().cpu(), head.label_enc.weight.detach().cpu(), feats, sd, cfg,
                           td, l2i, channel_last=True, op=R.msmv_sampling_kernel_semantics)
-    assert _rel(outs['all_cls_scores'], want['all_cls_scores']) < 1e-3
-    assert _rel(outs['all_bbox_preds'], want['all_bbox_preds']) < 1e-3
+    assert _rel(outs['all_cls_scores'], want['all_cls_scores']) < 2e-4
+    assert _rel(outs['all_bbox_preds'], want['all_bbox_preds']) < 2e-4
     # post-processing on the device tensors: same boxes as decoding the oracle's predictions (top-k ties aside, scores match)
     head.bbox_coder = sb.NMSFreeCoder(pc_range=cfg['pc_range'], post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_num=20, num_classes=10)
     dets = head.get_bboxes(outs)
@@ -145,6 +145,66 @@ def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
         assert bb.shape[1] == 9 and sc.shape == lb.shape and lb.dtype == torch.int64
         assert sc.shape == r['scores'].shape and torch.allclose(sc.cpu(), r['scores'], rtol=1e-3, atol=1e-4)
         assert torch.equal(lb.cpu()[:3], r['labels'][:3])
+
+
+# Whole-layer bars: every tensor-core stage is bf16x3 (fp32-grade), smoke measures ~2e-5 on the tiny layer; 5e-5 of the
+# output scale leaves 2.5x head-room and is 4x tighter than round 1's 2e-4.
+LAYER_BAR = 5e-5
+
+
+@pytest.mark.parametrize('name,T', [('r50_704x256', 8), ('r50_704x256', 1), ('r101_1408x512', 2), ('vov99_1600x640', 2)])
+def test_full_size_layer_vs_oracle(name, T):
+    """The BENCH workload itself (r50 704x256, 900 queries, T = 8: BASELINE config 3's per-layer shape; T = 1: config 2)
+    and the 5-level configs 4 / 5 at full resolution and query count (two frames: the CPU oracle holds the pyramid twice)
+    held to the CPU oracle's restatement of SparseBEVTransformerDecoderLayer.forward
+    (/root/reference/models/sparsebev_transformer.py:162-193), incl. the 900 = 7 x 128 + 4 row tail of every GEMM tile."""
+    cfg, sd, model, feats, metas, qb, qf = _setup(name, T, 1, seed=1, num_layers=1)
+    td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
+    l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
+    taps = {}
+    with torch.no_grad():
+        want = R.decoder_layer(qb, qf, R.regroup_feats(feats, channel_last=True), sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics, taps=taps)
+    layer = model.decoder.decoder_layer
+    metas_gpu = copy.deepcopy(metas)
+    model.decoder.prepare_metas(metas_gpu, 1, torch.device('cuda'))
+    gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
+    got = layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
+    for g, w, what in zip(got, want, ('query_feat', 'cls', 'bbox')):
+        assert g.shape == w.shape and torch.isfinite(g).all()
+        assert _rel(g, w) < LAYER_BAR, '%s %s T=%d: rel-to-max %.3e' % (name, what, T, _rel(g, w))
+    # the two big intermediate tensors of the bench workload against the oracle's taps
+    sampled = layer.sampling(qb.cuda(), taps['after_sasa'].cuda(), gfeats, metas_gpu)
+    assert _rel(sampled, taps['sampled']) < 2e-5, 'sampled features rel-to-max %.3e' % _rel(sampled, taps['sampled'])
+    mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), taps['after_sasa'].cuda(), layer.norm2)
+    assert _rel(mixed, taps['mixed']) < LAYER_BAR, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])
+
+
+def test_mix_presplit_m900_vs_oracle():
+    """The production mix path (tcgen05 parameter GEMM emitting bf16 (hi, lo) -> TMA-fed mix kernel) at M = 900 rows
+    directly against the oracle's fp32 restatement of AdaptiveMixing's middle stage
+    (/root/reference/models/sparsebev_transformer.py:358-375), not against our own fp32-parameter kernel."""
+    from sparsebev_b200 import ops
+    M, G, Pin, C, D = 900, 4, 32, 64, 256
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(M, D, generator=g)
+    W = torch.randn(G * (C * C + 128 * Pin), D, generator=g) * 0.02
+    b = torch.randn(G * (C * C + 128 * Pin), generator=g) * 0.05
+    x = torch.randn(M, G, Pin, C, generator=g)
+    params = (q.double() @ W.double().t() + b.double()).float().reshape(M, G, -1)
+    m = params[..., :C * C].reshape(M, G, C, C)
+    sm = params[..., C * C:].reshape(M, G, 128, Pin)
+    h = torch.relu(torch.nn.functional.layer_norm(x @ m, (Pin, C)))
+    want = torch.relu(torch.nn.functional.layer_norm(sm @ h, (128, C))).reshape(M, -1)
+    qh, ql = ops.split_bf16(q.cuda())
+    wh, wl = ops.split_bf16(W.cuda())
+    ph, pl = ops.gemm_bf16_tn_split(qh, ql, wh, wl, M, W.shape[0], D, bias=b.cuda())
+    hi, lo, y = ops.mix_presplit(ph, pl, x.cuda(), want_f32=True)
+    for got, what in ((y, 'fp32 output'), (hi.float() + lo.float(), 'bf16 hi+lo output')):
+        err = (got.cpu() - want).abs()
+        assert float(err.max() / want.abs().max()) < 2e-5, '%s: max-abs / max-ref %.3e' % (what, float(err.max() / want.abs().max()))
+        assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=5e-5), '%s: worst abs err %.3e' % (what, float(err.max()))
+    tail = slice(896, 900)                       # the 4 valid rows of the eighth 128-row GEMM tile
+    assert torch.allclose(y[tail].cpu(), want[tail], rtol=1e-4, atol=5e-5)
 
 
 def test_r50_t8_layer_runs_and_is_deterministic():
