@@ -186,15 +186,40 @@ class Bottleneck(nn.Module):
         return self._f3(out, relu=True, residual=identity)          # relu(bn3(conv3) + identity) in the conv epilogue
 
 
+def _reject_unsupported(who, kwargs, training_only=(), checked=None):
+    """mmdet config kwargs the inference mirrors do not implement: the ones that only matter for TRAINING (or for how
+    weights get initialised -- the caller loads a checkpoint) are accepted and dropped; anything that would change the
+    network the config describes raises instead of silently building a different model."""
+    import warnings
+    checked = checked or {}
+    for k, v in kwargs.items():
+        if k in training_only:
+            if k in ('init_cfg', 'pretrained') and v is not None:
+                warnings.warn('%s: %s=%r is not applied by the inference mirror -- load the weights with load_state_dict' % (who, k, v))
+            continue
+        if k in checked:
+            if not checked[k](v):
+                raise NotImplementedError('%s: %s=%r is not implemented by the sparsebev_b200 mirror' % (who, k, v))
+            continue
+        raise NotImplementedError('%s: unsupported argument %s=%r (it would change the architecture or is unknown to the mirror)' % (who, k, v))
+
+
 class ResNet(nn.Module):
     """ResNet-50 / -101 with mmdet's state-dict keys (conv1, bn1, layer{1..4}.{i}.*) -- the reference's img_backbone
     (configs/r50_nuimg_704x256.py:31-40: depth=50, num_stages=4, out_indices=(0,1,2,3), style='pytorch', norm_eval)."""
     arch_settings = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
 
-    def __init__(self, depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style='pytorch', **_ignored):
+    def __init__(self, depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style='pytorch', **kwargs):
         super().__init__()
         if depth not in self.arch_settings or style != 'pytorch':
             raise NotImplementedError('ResNet depth 50 / 101, style pytorch')
+        _reject_unsupported('ResNet', kwargs, training_only=('frozen_stages', 'norm_eval', 'with_cp', 'zero_init_residual', 'init_cfg', 'pretrained'),
+                            checked={'norm_cfg': lambda v: v is None or str(v.get('type', 'BN')).startswith('BN'),
+                                     'dcn': lambda v: v is None, 'stage_with_dcn': lambda v: not any(v), 'plugins': lambda v: v is None,
+                                     'deep_stem': lambda v: not v, 'avg_down': lambda v: not v, 'in_channels': lambda v: v == 3,
+                                     'base_channels': lambda v: v == 64, 'strides': lambda v: tuple(v) == (1, 2, 2, 2),
+                                     'dilations': lambda v: all(d == 1 for d in v), 'conv_cfg': lambda v: v is None,
+                                     'stem_channels': lambda v: v in (None, 64)})
         self.out_indices = tuple(out_indices)
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
@@ -258,10 +283,14 @@ class FPN(nn.Module):
     config asks for num_outs=5): lateral 1x1 convs, nearest top-down path, 3x3 output convs, extra levels by stride-2
     subsampling (F.max_pool2d(x, 1, stride=2)).  The top-down add is the residual operand of the lateral conv's epilogue."""
 
-    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False, **_ignored):
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False, **kwargs):
         super().__init__()
         if add_extra_convs or end_level != -1:
             raise NotImplementedError('FPN: add_extra_convs / end_level are not used by the reference configs')
+        _reject_unsupported('FPN', kwargs, training_only=('init_cfg',),
+                            checked={'relu_before_extra_convs': lambda v: not v, 'no_norm_on_lateral': lambda v: True, 'conv_cfg': lambda v: v is None,
+                                     'norm_cfg': lambda v: v is None, 'act_cfg': lambda v: v is None,
+                                     'upsample_cfg': lambda v: v is None or (v.get('mode', 'nearest') == 'nearest' and 'scale_factor' not in v)})
         self.in_channels, self.out_channels, self.num_outs, self.start_level = list(in_channels), out_channels, num_outs, start_level
         self.lateral_convs = nn.ModuleList(_ConvModule(c, out_channels, 1) for c in self.in_channels[start_level:])
         self.fpn_convs = nn.ModuleList(_ConvModule(out_channels, out_channels, 3, padding=1) for _ in self.in_channels[start_level:])
@@ -292,9 +321,20 @@ def extract_img_feat(backbone, neck, img):
     return [f.view(B, TN, *f.shape[1:]).permute(0, 1, 4, 2, 3) for f in levels]
 
 
-try:                                    # same registry names as mmdet's own modules, when mmdet is importable (absent in the build image)
+def enable(force=False):
+    """Register the inference-only mirrors with mmdet's registries (when mmdet is importable): always under the distinct names
+    `ResNetB200` / `FPNB200`; with force=True ALSO under mmdet's own names `ResNet` / `FPN`, replacing mmdet's classes for
+    every model built afterwards in this process -- an explicit opt-in, because the mirrors cannot train and reject the
+    architecture-changing kwargs they do not implement (see _reject_unsupported)."""
     from mmdet.models.builder import BACKBONES, NECKS
-    BACKBONES.register_module(module=ResNet, force=True)
-    NECKS.register_module(module=FPN, force=True)
-except Exception:                       # pragma: no cover
+    BACKBONES.register_module(name='ResNetB200', module=ResNet, force=True)
+    NECKS.register_module(name='FPNB200', module=FPN, force=True)
+    if force:
+        BACKBONES.register_module(module=ResNet, force=True)
+        NECKS.register_module(module=FPN, force=True)
+
+
+try:                                    # distinct names only: importing this module never shadows mmdet's own ResNet / FPN
+    enable(force=False)
+except Exception:                       # pragma: no cover  (mmdet absent in the build image)
     pass

@@ -66,7 +66,9 @@ __device__ __forceinline__ int view_from_coord(float z, int N) {
 // PF: while the loads of one level block are in flight, the lines the NEXT block will read are requested into L2
 // (prefetch.global.L2, no destination registers): the kernel is DRAM-latency-bound at 2 CTAs/SM (three dependent round
 // trips per point: geometry, levels 0-1, levels 2-3), and this overlaps the third with the second.
-template <int L, int LB, int VEC = 1, int VSTRIDE = 4, bool PF = false>      // VSTRIDE: floats between the VEC float4 of one lane
+// SKIP: a level block none of the warp's points falls inside (dead points: no camera sees them) is skipped as a whole --
+// warp-uniform branch, so the ~30 % of taps that load nothing also issue nothing.
+template <int L, int LB, int VEC = 1, int VSTRIDE = 4, bool PF = false, bool SKIP = false>      // VSTRIDE: floats between the VEC float4 of one lane
 __device__ __forceinline__ void gather_levels_v(const float* const (&base)[L], const int (&H)[L],
                                                 const int (&W)[L], const int (&pxs)[L],
                                                 float u, float v, const float (&wt)[L], bool live, float4 (&acc)[VEC]) {
@@ -77,11 +79,18 @@ __device__ __forceinline__ void gather_levels_v(const float* const (&base)[L], c
     for (int l0 = 0; l0 < L; l0 += LB) {
         Tap tp[LB];
         float4 c1[LB][VEC], c2[LB][VEC], c3[LB][VEC], c4[LB][VEC];
+        if (SKIP) {
+            bool any_in = false;
+#pragma unroll
+            for (int i = 0; i < LB; ++i)
+                if (l0 + i < L) { tp[i] = make_tap(u, v, H[l0 + i], W[l0 + i]); any_in |= live && tp[i].inside; }
+            if (!__any_sync(0xffffffffu, any_in)) continue;
+        }
 #pragma unroll
         for (int i = 0; i < LB; ++i) {
             const int l = l0 + i;
             if (l < L) {
-                tp[i] = make_tap(u, v, H[l], W[l]);
+                if (!SKIP) tp[i] = make_tap(u, v, H[l], W[l]);
                 const int row = W[l] * pxs[l];
                 const float* p = base[l] + (tp[i].y0 * row + tp[i].x0 * pxs[l]);
 #pragma unroll
@@ -543,7 +552,7 @@ struct FusedParams {
 
 // LPP = lanes per sample point: 16 (4 channels per lane) or 8 (8 channels per lane; halves the per-point geometry that
 // every lane of a point computes redundantly -- the kernel is issue-bound, not bandwidth-bound, on the realistic rig).
-template <int L, int LB, int MINB, int LPP, bool PF = false>
+template <int L, int LB, int MINB, int LPP, bool PF = false, bool SKIP = false>
 __global__ void __launch_bounds__(256, MINB)
 sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
     constexpr int VEC = 16 / LPP;                     // float4 per lane
@@ -604,7 +613,7 @@ sampling4d_c64_kernel(LevelSet lv, FusedParams prm) {
         base[l] = lv.ptr[l] + ((long long)btl * lv.s_bt[l] + (long long)g * lv.s_g[l] + (long long)view * lv.s_v[l] + 4 * j);
     }
     float4 acc[VEC];
-    gather_levels_v<L, LB, VEC, 4 * LPP, PF>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
+    gather_levels_v<L, LB, VEC, 4 * LPP, PF, SKIP>(base, H, W, pxs, u, v, wt, live, acc);     // lane j: channels 4j..4j+3 (+ 4*LPP per extra vector)
     if (live) {
         if (prm.q_per_rank > 0) {                      // owner form: the row goes to the one rank that mixes query q
             const int ow = q / prm.q_per_rank;
@@ -851,14 +860,18 @@ static int launch_sampling4d(const float* const* feats, const int* hw, int L,
         SBEV_REQUIRE((long long)q_per_rank * n_out >= Q, SBEV_ERR_INVALID, "%s: %d ranks x %d queries do not cover Q = %d", who, n_out, q_per_rank, Q);
     }
     // 0 = 16 lanes/point, all levels in flight (2 CTAs/SM); 1 = 16 lanes/point, two levels at a time (3 CTAs/SM);
-    // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views); 3 = 2 + L2 prefetch of the next level pair
+    // 2 = 8 lanes/point (8 channels per lane), two levels at a time (needs N <= 8 views); 3 = 2 + L2 prefetch of the next level pair;
+    // 4 = 2 + warp-uniform skip of level blocks without a live tap; 5 = 4 at 3 CTAs/SM; 6 = 4 with one level at a time, 4 CTAs/SM
     int variant = get_option(OPT_GATHER_VARIANT);
     if (variant >= 2 && N > 8) variant = 1;
     const int ppb = variant >= 2 ? 32 : 16;
     const dim3 grid((Q * P + ppb - 1) / ppb, B * Tl * G);
 #define SBEV_LAUNCH_FUSED(LL)                                                                                     \
     case LL:                                                                                                      \
-        if (variant == 3 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        if (variant == 6) launch_pdl(sampling4d_c64_kernel<LL, 1, 4, 8, false, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant == 5 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 3, 8, false, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant == 4 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8, false, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
+        else if (variant == 3 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8, true>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
         else if (variant >= 2 && LL >= 2) launch_pdl(sampling4d_c64_kernel<LL, 2, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);      \
         else if (variant >= 2) launch_pdl(sampling4d_c64_kernel<LL, LL, 2, 8>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm);           \
         else if (variant == 1 && LL >= 3) launch_pdl(sampling4d_c64_kernel<LL, 2, 3, 16>, grid, dim3(256), 0, (cudaStream_t)stream, lv, prm); \

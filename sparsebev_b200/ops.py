@@ -435,16 +435,23 @@ def gemm_bf16_tn_split(a_hi, a_lo, b_hi, b_lo, M, N, K, bias=None, out=None):
     return out
 
 
-def mix_presplit(params_hi, params_lo, x, want_f32=False, want_split=True):
-    """mix() with the dynamic parameters given as the bf16 (hi, lo) pair of gemm_bf16_tn_split (in_points must be 32)."""
+def mix_presplit(params_hi, params_lo, x, want_f32=False, want_split=True, out=None):
+    """mix() with the dynamic parameters given as the bf16 (hi, lo) pair of gemm_bf16_tn_split (in_points must be 32).
+    out = optional (hi, lo) bf16 buffers [BQ, G*Pout*C] to write into."""
     lib = _lib.load()
     _chk(params_hi, 'params_hi', torch.bfloat16)
     _chk(params_lo, 'params_lo', torch.bfloat16)
     x = _chk(x, 'x')
     BQ, G, Pin, C = x.shape
     n = G * OUT_POINTS * C
-    hi = torch.empty(BQ, n, device=x.device, dtype=torch.bfloat16) if want_split else None
-    lo = torch.empty_like(hi) if want_split else None
+    if out is not None:
+        hi, lo = out
+        _chk(hi, 'y_hi', torch.bfloat16); _chk(lo, 'y_lo', torch.bfloat16)
+        if hi.numel() != BQ * n or lo.numel() != BQ * n:
+            raise RuntimeError('mix_presplit: out buffers must hold [BQ, G*Pout*C]')
+    else:
+        hi = torch.empty(BQ, n, device=x.device, dtype=torch.bfloat16) if want_split else None
+        lo = torch.empty_like(hi) if want_split else None
     yf = torch.empty(BQ, n, device=x.device, dtype=torch.float32) if want_f32 else None
     with torch.cuda.device(x.device):
         _lib.check(lib.sbev_mix_presplit_fwd(params_hi.data_ptr(), params_lo.data_ptr(), x.data_ptr(), BQ, G, Pin, OUT_POINTS, C,

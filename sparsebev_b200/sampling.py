@@ -12,8 +12,23 @@ from .wrapper import msmv_sampling, msmv_sampling_pytorch  # noqa: F401  (re-exp
 NUM_VIEWS = 6     # reference hard-codes N = 6 (sparsebev_sampling.py:45)
 
 
+def _forward_only(what, *tensors):
+    """These two functions launch the forward kernels directly (no autograd Function): used in a training graph they would
+    silently cut the gradient to the sampling offsets, the scale weights and every backbone / FPN feature while the loss
+    still back-propagates through mixing, FFN and the heads.  Fail loudly instead; the differentiable drop-in is level 1
+    of INTEGRATION.md (`sparsebev_b200.wrapper.msmv_sampling` under the reference's own sampling_4d)."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            ts = t if isinstance(t, (list, tuple)) else [t]
+            if any(torch.is_tensor(x) and x.requires_grad for x in ts):
+                raise RuntimeError('sparsebev_b200.sampling.%s is forward-only (no backward kernel for the fused front-end): call it under '
+                                   'torch.no_grad(), or keep the reference\'s %s and swap only models.csrc.wrapper for '
+                                   'sparsebev_b200.wrapper, whose msmv_sampling has a backward (INTEGRATION.md, level 1)' % (what, what))
+
+
 def make_sample_points(query_bbox, offset, pc_range):
     """query_bbox [B,Q,10], offset [B,Q,GP,3] -> [B,Q,GP,3] lidar-frame points."""
+    _forward_only('make_sample_points', query_bbox, offset)
     B, Q, GP, _ = offset.shape
     logits = torch.zeros(B, Q, GP, device=offset.device, dtype=torch.float32)     # 1 level of logits, result unused
     pts, _ = ops.sample_points(query_bbox.contiguous().float(), offset.reshape(B, Q, GP * 3).contiguous().float(),
@@ -29,6 +44,7 @@ def sampling_4d(sample_points, mlvl_feats, scale_weights, lidar2img, image_h, im
     The fused kernel wants the un-warped points + velocity; to keep THIS signature (warped points per
     frame) we hand it per-frame points through a zero velocity: points of frame t are read from
     sample_points[:, :, t]."""
+    _forward_only('sampling_4d', sample_points, mlvl_feats, scale_weights)
     B, Q, T, G, P, _ = sample_points.shape
     L = scale_weights.shape[-1]
     zero_v = torch.zeros(B, Q, 2, device=sample_points.device, dtype=torch.float32)

