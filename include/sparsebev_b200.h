@@ -50,6 +50,8 @@ const char* sbev_last_error(void);
  *                    every layer's output features (each streams 1/2 / 1/4 of the weights), exchanging the layer outputs
  *                    through distributed shared memory; chains it cannot express (an inner layer wider than 512 ...) take
  *                    the "dense_impl" 0 kernel
+ *   "dense_pack"     1 = chains stream the pre-tiled weight copy (sbev_dense_layer.W_pack) with one bulk copy per stage when the caller
+ *                    provides it (default); 0 = always the tensor-map path
  *   "dense_vec4"     1 = 16-byte vectorised row epilogue / operand staging in the chain kernels (default), 0 = scalar
  *   "dense_fuse_points" 1 = sbev_dense_chain_points_fwd computes the sample points in the chain's epilogue, 0 = it runs the
  *                    chain and then sample_points_kernel (default: measured 4 us faster per layer -- the fused epilogue
@@ -260,6 +262,10 @@ typedef struct sbev_dense_layer {
     int Kpad;
     uint16_t* y_hi;         /* optional: bf16 (hi, lo) split of the stored output, [M][ldy] each (feeds the tensor-core   */
     uint16_t* y_lo;         /*   kernels that follow: attention core, parameter GEMM); both or neither                    */
+    const uint16_t* W_pack; /* optional: the same (hi, lo) weights PRE-TILED in streaming order -- [ceil(N/128)][Kpad/64][hi|lo][128 rows][64 k]
+                               bf16, rows zero-padded to a multiple of 128, each 128-byte row stored with its 16-byte chunks XOR-swizzled
+                               by (row & 7) (the layout ldmatrix reads, = TMA's 128-byte swizzle).  Every pipeline stage is then ONE contiguous
+                               32 KB cp.async.bulk instead of two tensor-map box loads of 128 separate 128-byte rows.  128-byte aligned. */
 } sbev_dense_layer;
 int sbev_dense_chain_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
                          const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,

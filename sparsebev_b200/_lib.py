@@ -20,7 +20,7 @@ c_vpp = ctypes.POINTER(c_vp)
 class DenseLayer(ctypes.Structure):
     """struct sbev_dense_layer (include/sparsebev_b200.h)"""
     _fields_ = [('Wt', c_vp), ('ldw', c_int), ('K', c_int), ('N', c_int), ('bias', c_vp), ('ln_w', c_vp), ('ln_b', c_vp),
-                ('residual', c_vp), ('flags', c_int), ('y', c_vp), ('ldy', c_int), ('W_hi', c_vp), ('W_lo', c_vp), ('Kpad', c_int), ('y_hi', c_vp), ('y_lo', c_vp)]
+                ('residual', c_vp), ('flags', c_int), ('y', c_vp), ('ldy', c_int), ('W_hi', c_vp), ('W_lo', c_vp), ('Kpad', c_int), ('y_hi', c_vp), ('y_lo', c_vp), ('W_pack', c_vp)]
 
 
 MAX_PEERS = 8

@@ -27,6 +27,7 @@ struct ChainLayer {
     const float* Wt; const float* bias; const float* ln_w; const float* ln_b; const float* residual; float* y;
     __nv_bfloat16* y_hi; __nv_bfloat16* y_lo;     // optional bf16 (hi, lo) split of the stored output, row stride ldy
     int ldw, K, N, flags, ldy, kc;                // kc = weight rows per chunk
+    const uint8_t* wpack;                         // optional pre-tiled (hi | lo) weight stream: 32 KB per (128-feature block, 64-k chunk), see the header
 };
 struct ChainParams {
     const float* x; int ldx, M, n_layers, act_ld; // act_ld: row stride (floats) of the shared activation buffers
@@ -549,7 +550,11 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         if (it >= MC_STAGES) chain_mbar_wait(&empty_bar[stage], ((it / MC_STAGES) - 1) & 1);
                         uint8_t* dst = wring + stage * 2 * MC_TILE_BYTES;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(&full_bar[stage])), "r"(2 * MC_TILE_BYTES) : "memory");
-                        if (CL == 1) {
+                        if (CL == 1 && L.wpack != nullptr) {          // pre-tiled stream: the whole stage is one contiguous 32 KB bulk copy
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(dsmem_u32(dst)), "l"(L.wpack + (size_t)(nb * kchunks + kc) * (2 * MC_TILE_BYTES)), "r"(2 * MC_TILE_BYTES),
+                                           "r"(dsmem_u32(&full_bar[stage])) : "memory");
+                        } else if (CL == 1) {
                             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                                          ::"r"(dsmem_u32(dst)), "l"(&maps.hi[li]), "r"(dsmem_u32(&full_bar[stage])), "r"(kc * 64), "r"(nb * 128) : "memory");
                             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -1293,6 +1298,8 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         c.y_hi = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_hi)); c.y_lo = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_lo));
         SBEV_REQUIRE((l.y_hi == nullptr) == (l.y_lo == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: y_hi and y_lo go together");
         c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags & 0xff; c.ldy = l.ldy;
+        c.wpack = get_option(OPT_DENSE_PACK) ? reinterpret_cast<const uint8_t*>(l.W_pack) : nullptr;
+        SBEV_REQUIRE((reinterpret_cast<uintptr_t>(l.W_pack) & 127) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: W_pack not 128-byte aligned", i);
         {
             const uintptr_t a16 = reinterpret_cast<uintptr_t>(l.bias) | reinterpret_cast<uintptr_t>(l.ln_w) | reinterpret_cast<uintptr_t>(l.ln_b) |
                                   reinterpret_cast<uintptr_t>(l.residual) | reinterpret_cast<uintptr_t>(l.y);

@@ -74,32 +74,31 @@ peer_exchange_kernel(const __grid_constant__ PeerParams prm) {
             }
         }
     }
-    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        // one system-scope fence per CTA: cumulative over the whole CTA's stores (ordered before it by the barrier above),
+        // so they are performed at the peers before the arrival below -- and hence before the last CTA's flag stores
         __threadfence_system();
         s_last = atomicAdd(prm.ctl + 1, 1u) == gridDim.x - 1;
+        __threadfence();                                 // acquire side of the arrival chain for the last CTA
     }
     __syncthreads();
     if (!s_last) return;
-    // ---- last CTA: signal every peer, then wait for every peer
+    // ---- last CTA: signal every peer (release), then wait for every peer (acquire)
     const uint32_t epoch = prm.ctl[0] + 1;
     const bool dead = prm.ctl[2] != 0;
     __syncthreads();
     if (tid == 0) { prm.ctl[0] = epoch; prm.ctl[1] = 0; }
     if (tid < prm.n_peers && tid != prm.rank) {
-        __threadfence_system();
         st_release_sys(prm.flags[tid] + prm.rank, epoch);
         if (!dead) {
             const uint32_t* mine = prm.flags[prm.rank] + tid;
             const unsigned long long t0 = global_ns();
             while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-                __nanosleep(64);
                 if (global_ns() - t0 > 4000000000ull) { prm.ctl[2] = 1; break; }
             }
         }
     }
-    __threadfence_system();
 }
 
 }  // namespace sbev

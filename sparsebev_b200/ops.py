@@ -211,6 +211,7 @@ class DenseWeight:
         self.ldw = 0
         self.n = 0
         self.w_hi = self.w_lo = None
+        self.w_pack = None
         self.kpad = 0
 
     def get(self, weight, *more_weights):
@@ -235,20 +236,40 @@ class DenseWeight:
             wpad = torch.zeros(N, kpad, device=weights[0].device, dtype=torch.float32)
             wpad[:, :K] = torch.cat([w.detach() for w in weights], dim=0)
             self.w_hi, self.w_lo = split_bf16(wpad) if wpad.is_cuda else (None, None)
+            self.w_pack = pack_weight_tiles(self.w_hi, self.w_lo) if wpad.is_cuda else None
             self.kpad = kpad
             self.wt, self.ldw, self.n, self.key = wt, ldw, N, key
         return self.wt, self.ldw, self.bias
 
 
+def pack_weight_tiles(w_hi, w_lo):
+    """bf16 (hi, lo) weights [N][Kpad] (Kpad % 64 == 0) -> the pre-tiled streaming copy of sbev_dense_layer.W_pack:
+    [ceil(N/128)][Kpad/64][hi|lo][128][64] bf16, rows zero-padded to a multiple of 128, 16-byte chunks of every 128-byte
+    row XOR-swizzled by (row & 7).  Built once per weight version; every pipeline stage of the chain kernels becomes one
+    contiguous 32 KB bulk copy."""
+    N, Kp = w_hi.shape
+    nb, kc = (N + 127) // 128, Kp // 64
+    r = torch.arange(128, device=w_hi.device)
+    src_chunk = torch.arange(8, device=w_hi.device)[None, :] ^ (r[:, None] & 7)          # stored position p of row r holds chunk p ^ (r & 7)
+
+    def one(w):
+        wp = torch.zeros(nb * 128, Kp, device=w.device, dtype=w.dtype)
+        wp[:N] = w
+        t = wp.view(nb, 128, kc, 8, 8).permute(0, 2, 1, 3, 4)                            # [nb, kc, row, chunk, elem]
+        return t[:, :, r[:, None], src_chunk, :]                                         # [nb, kc, row, position, elem]
+    return torch.stack([one(w_hi), one(w_lo)], dim=2).contiguous()                       # [nb, kc, 2, 128, 8, 8]
+
+
 def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None,
-                w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None):
-    """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path."""
+                w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None, w_pack=None):
+    """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path; w_pack
+    (pack_weight_tiles) its bulk-copy weight stream."""
     flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
-    keep = [t for t in (wt, bias, residual, y, w_hi, w_lo, y_hi, y_lo) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
+    keep = [t for t in (wt, bias, residual, y, w_hi, w_lo, y_hi, y_lo, w_pack) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
     return _lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
                            _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
                            (ldy if ldy is not None else N) if (y is not None or y_hi is not None) else 0, _p(w_hi), _p(w_lo), kpad,
-                           _p(y_hi), _p(y_lo)), keep
+                           _p(y_hi), _p(y_lo), _p(w_pack)), keep
 
 
 def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):

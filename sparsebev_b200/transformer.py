@@ -90,7 +90,7 @@ class _Dense:
         c = self.cache
         return ops.chain_layer(wt, ldw, self.in_features, self.out_features, bias=bias, ln=self.ln, residual=residual,
                                relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad,
-                               y_hi=y_hi, y_lo=y_lo)
+                               y_hi=y_hi, y_lo=y_lo, w_pack=c.w_pack)
 
     def __call__(self, x, relu=False, residual=None, res_pre_ln=False, k=None):
         M = x.shape[0]
@@ -239,14 +239,14 @@ class SparseBEVSelfAttention(BaseModule):
         wt, ldw, bias = self._cache_in.get_with_bias([attn.in_proj_weight, self.gen_tau.weight], [attn.in_proj_bias, self.gen_tau.bias])
         c = self._cache_in
         return ops.chain_layer(wt, ldw, attn.embed_dim, 3 * attn.embed_dim + self.num_heads, bias=bias, y=y, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad,
-                               y_hi=y_hi, y_lo=y_lo)
+                               y_hi=y_hi, y_lo=y_lo, w_pack=c.w_pack)
 
     def out_layer(self, residual, norm, y, y_hi=None, y_lo=None):
         attn = self.attention.attn
         wt, ldw, bias = self._cache_out.get_with_bias([attn.out_proj.weight], [attn.out_proj.bias])
         c = self._cache_out
         return ops.chain_layer(wt, ldw, attn.embed_dim, attn.embed_dim, bias=bias, ln=norm, residual=residual, res_pre_ln=True, y=y,
-                               w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad, y_hi=y_hi, y_lo=y_lo)
+                               w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad, y_hi=y_hi, y_lo=y_lo, w_pack=c.w_pack)
 
     def attention_core(self, query_bbox, x, pre_attn_mask=None, pre=None):
         """x [B*Q, D] -> softmax(qk^T/sqrt(d) - tau*dist) v, heads concatenated [B*Q, D] (before out_proj).

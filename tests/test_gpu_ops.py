@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit')
+    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit', 'dense_pack', 'legacy_rotation')
     defaults = {k: _lib.get_option(k) for k in names}
 
     def setter(name, value):
@@ -491,6 +491,42 @@ def test_dense_chain_with_fused_splitk_reduce(impl, K0, nsplit, ln, option):
     _close(y, want, rtol=1e-4, atol=2e-5 if impl == 1 else 1e-4, what='chain behind the fused reduce')
 
 
+def test_dense_chain_packed_weight_stream_is_bit_identical(option):
+    """sbev_dense_layer.W_pack (pre-tiled, pre-swizzled weights streamed by one 32 KB bulk copy per stage) puts exactly the
+    bytes into shared memory that the tensor-map path does: outputs are bit-identical, ragged N (10, 776) and K (3) included."""
+    ops = _ops()
+    torch.manual_seed(7)
+    M = 333
+    lin = [torch.nn.Linear(3, 256), torch.nn.Linear(256, 256), torch.nn.Linear(256, 776)]
+    lin2 = [torch.nn.Linear(256, 512), torch.nn.Linear(512, 256), torch.nn.Linear(256, 10)]
+    for chain, K0 in ((lin, 3), (lin2, 256)):
+        mods = [m.to(dev()) for m in chain]
+        caches = [ops.DenseWeight() for _ in mods]
+        x = torch.randn(M, K0).to(dev())
+        outs = {}
+        for pack in (1, 0):
+            option('dense_pack', pack)
+            ys = [torch.empty(M, m.out_features, device=dev()) for m in mods]
+            entries = []
+            for i, m in enumerate(mods):
+                wt, ldw, bias = caches[i].get_with_bias([m.weight], [m.bias])
+                assert caches[i].w_pack is not None and caches[i].w_pack.shape[:3] == ((m.out_features + 127) // 128, caches[i].kpad // 64, 2)
+                entries.append(ops.chain_layer(wt, ldw, m.in_features, m.out_features, bias=bias, relu=i + 1 < len(mods), y=ys[i],
+                                               w_hi=caches[i].w_hi, w_lo=caches[i].w_lo, kpad=caches[i].kpad, w_pack=caches[i].w_pack))
+            ops.dense_chain(x, K0, M, entries)
+            torch.cuda.synchronize()
+            outs[pack] = ys
+        for a, b in zip(outs[1], outs[0]):
+            assert torch.equal(a, b)
+        with torch.no_grad():
+            h = x
+            for i, m in enumerate(mods):
+                h = m(h)
+                if i + 1 < len(mods):
+                    h = torch.relu(h)
+        _close(outs[1][-1], h.cpu(), rtol=1e-4, atol=1e-4, what='packed-stream chain vs torch')
+
+
 @pytest.mark.parametrize('fuse', [1, 0])
 def test_dense_chain_points_equals_chain_then_sample_points(fuse, option):
     """sbev_dense_chain_points_fwd: the sample points / scale weights that leave the chain's epilogue are bit-identical to
@@ -549,6 +585,28 @@ def test_sample_points_and_refine_vs_oracle():
     t[t < 1e-5] = 1.0
     want = torch.cat([want[..., :8], want[..., 8:] / t[:, 1:2, None]], -1)
     _close(ops.refine_bbox(qb.to(dev()), delta.to(dev()), td.to(dev())), want, rtol=1e-5, atol=1e-6, what='refine_bbox')
+
+
+def test_sample_points_legacy_rotation(option):
+    """Option "legacy_rotation" (checkpoints with version 'v0.17.1', /root/reference/models/utils.py:66-71): rot_mat_T =
+    [[c, -s, 0], [s, c, 0], [0, 0, 1]] instead of [[c, s, 0], [-s, c, 0], [0, 0, 1]], i.e. the offsets are rotated by -yaw."""
+    ops = _ops()
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    qb = R.init_query_bbox(900, seed=2)[None].contiguous()
+    off = hashrand((1, 900, 16, 3), 2, -0.5, 0.5)
+    logits = hashrand((1, 900, 16, 4), 3, -3, 3)
+    dec = R.decode_bbox(qb, pc)
+    delta = dec[..., None, 3:6] * off
+    yaw = dec[..., 6]
+    c, s_ = torch.cos(yaw)[..., None], torch.sin(yaw)[..., None]
+    want = torch.stack([delta[..., 0] * c + delta[..., 1] * s_, -delta[..., 0] * s_ + delta[..., 1] * c, delta[..., 2]], -1) + dec[..., None, 0:3]
+    option('legacy_rotation', 1)
+    pts, _ = ops.sample_points(qb.to(dev()), off.reshape(1, 900, 48).to(dev()), logits.reshape(1, 900, 64).to(dev()), pc, 4)
+    _close(pts, want, rtol=1e-5, atol=2e-5, what='sample points, legacy v0.17.1 rotation')
+    option('legacy_rotation', 0)
+    pts0, _ = ops.sample_points(qb.to(dev()), off.reshape(1, 900, 48).to(dev()), logits.reshape(1, 900, 64).to(dev()), pc, 4)
+    _close(pts0, R.make_sample_points(qb, off, pc), rtol=1e-5, atol=2e-5, what='sample points, v1.0.0 rotation')
+    assert float((pts.cpu() - pts0.cpu()).abs().max()) > 0.1
 
 
 @pytest.mark.parametrize('impl', [0, 1])
