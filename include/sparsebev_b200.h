@@ -50,6 +50,8 @@ const char* sbev_last_error(void);
  *                    every layer's output features (each streams 1/2 / 1/4 of the weights), exchanging the layer outputs
  *                    through distributed shared memory; chains it cannot express (an inner layer wider than 512 ...) take
  *                    the "dense_impl" 0 kernel
+ *   "sasa_kq"        key splits per CTA of the attention core: 0 = automatic (8 when the launch is below one wave, i.e. a query shard;
+ *                    else 4), 4 / 8 = forced.  The result of a query depends on the split (partial softmax merge order): <= 1e-6 relative
  *   "dense_pack"     1 = chains stream the pre-tiled weight copy (sbev_dense_layer.W_pack) with one bulk copy per stage when the caller
  *                    provides it (default); 0 = always the tensor-map path
  *   "dense_vec4"     1 = 16-byte vectorised row epilogue / operand staging in the chain kernels (default), 0 = scalar

@@ -627,6 +627,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                 // MMA of the tile behind the ~30-cycle MMA latency, this warp has no other tile to interleave with
                 float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
                 float accC[4] = {0.f, 0.f, 0.f, 0.f}, accD[4] = {0.f, 0.f, 0.f, 0.f};
+                float accE[4] = {0.f, 0.f, 0.f, 0.f}, accF[4] = {0.f, 0.f, 0.f, 0.f};      // six chains: no MMA of a k-step waits for another
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const int stage = it % MC_STAGES;
                     chain_mbar_wait(&full_bar[stage], (it / MC_STAGES) & 1);
@@ -641,8 +642,8 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
                         mc_ldsm_x2(bh, xh_addr + xo);
                         mc_ldsm_x2(bl, xl_addr + xo);
-                        if (ks & 1) { mc_mma(accB, ah, bh); mc_mma(accD, al, bh); mc_mma(accD, ah, bl); }
-                        else        { mc_mma(accA, ah, bh); mc_mma(accC, al, bh); mc_mma(accC, ah, bl); }
+                        if (ks & 1) { mc_mma(accB, ah, bh); mc_mma(accD, al, bh); mc_mma(accF, ah, bl); }
+                        else        { mc_mma(accA, ah, bh); mc_mma(accC, al, bh); mc_mma(accE, ah, bl); }
                     }
                     __syncwarp();
                     if (CL == 1) {
@@ -655,7 +656,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                 }
                 float acc[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = (accC[i] + accD[i]) + (accA[i] + accB[i]);
+                for (int i = 0; i < 4; ++i) acc[i] = ((accC[i] + accD[i]) + (accE[i] + accF[i])) + (accA[i] + accB[i]);
                 // D fragment: (feature 16w+g8 [+8], row 2t4 [+1])
                 const int n = nb * 128 + 16 * warp + g8;
                 if (n < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n] = acc[0]; ys[(2 * t4 + 1) * MC_YLD + n] = acc[1]; }
@@ -1480,7 +1481,7 @@ extern "C" int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw,
                               const float* ln_w, const float* ln_b, const float* residual,
                               int M, int K, int N, int flags, float* y, void* stream) {
     SBEV_REQUIRE(y != nullptr, SBEV_ERR_INVALID, "sbev_dense_fwd: null pointer");
-    sbev_dense_layer l;
+    sbev_dense_layer l{};
     l.Wt = Wt; l.ldw = ldw; l.K = K; l.N = N; l.bias = bias; l.ln_w = ln_w; l.ln_b = ln_b; l.residual = residual;
     l.flags = flags & (SBEV_DENSE_RELU | SBEV_DENSE_RES_PRE_LN); l.y = y; l.ldy = N;
     l.W_hi = nullptr; l.W_lo = nullptr; l.Kpad = 0; l.y_hi = nullptr; l.y_lo = nullptr;

@@ -604,7 +604,8 @@ extern "C" int sbev_gemm_bf16_tn(const uint16_t* const* A, const uint16_t* const
                           (N / 128) >= 2 * (num_sms / m_tiles_pre);
         const bool wide = !ares && (N % 256 == 0);
         const int BNv = wide ? 256 : 128;
-        if (get_option(OPT_GEMM_IMPL) != 3 && get_option(OPT_GEMM_IMPL) != 1 && x3_pattern && wide && num_sms >= 2) {
+        // (a single row tile -- a query shard of <= 128 rows -- would leave half of every 256-row pair unit empty: single CTAs)
+        if (get_option(OPT_GEMM_IMPL) != 3 && get_option(OPT_GEMM_IMPL) != 1 && x3_pattern && wide && num_sms >= 2 && m_tiles_pre > 1) {
             // ---- CTA-pair (cta_group::2) schedule: 256 x 256 units, each CTA loads its A rows and half of the B tile
             GemmMapsV2 mp;
             int rc = make_bf16_map(&mp.a_hi, A[0], M, K, GEMM_BM);   if (rc) return rc;

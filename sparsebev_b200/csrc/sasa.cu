@@ -368,13 +368,15 @@ constexpr int S3_BUF_BYTES = 4 * S3_ARR * 2 + 2 * S3_KT * 4;   // Kh,Kl,Vh,Vl + 
 __device__ __forceinline__ float sa_sqrt(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sa_exp(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f)); return y; }
 
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 2)
+// KQ = key splits per CTA (4: 256 threads, two CTAs per SM -- the full-size layer; 8: 512 threads, half as many key tiles per
+// warp -- when only a shard of the queries attends and the grid is far below one wave, latency per warp is what counts)
+template <bool HAS_MASK, int KQ>
+__global__ void __launch_bounds__(64 * KQ, KQ == 4 ? 2 : 1)
 sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, int ld,
                const float* __restrict__ query_bbox, const float* __restrict__ tau, int ld_tau,
                const uint8_t* __restrict__ dn_mask, float x_lo, float x_hi, float y_lo, float y_hi,
                int B, int Q, int H, int qa, int qb, float* __restrict__ out) {
-    // 8 warps = 4 key-quarters x 2 query tiles; the two warps of a key-quarter share one K/V double buffer
+    // 2*KQ warps = KQ key splits x 2 query tiles; the two warps of a key-quarter share one K/V double buffer
     // (each fills half of it) and synchronise on their own named barrier (64 threads) -- never the whole CTA.
     extern __shared__ __align__(16) unsigned char s3_smem[];
     const int D = H * SA_HD;
@@ -447,8 +449,8 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
 
     int slot = 0;
     if (kq < num_tiles) issue(kq, 0);
-    for (int tile = kq; tile < num_tiles; tile += 4, slot ^= 1) {
-        if (tile + 4 < num_tiles) { issue(tile + 4, slot ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    for (int tile = kq; tile < num_tiles; tile += KQ, slot ^= 1) {
+        if (tile + KQ < num_tiles) { issue(tile + KQ, slot ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both halves of this tile have landed
         const unsigned char* buf = mybuf + slot * S3_BUF_BYTES;
@@ -533,27 +535,27 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
     __syncthreads();                                              // every warp is done with its pipeline buffers
-    float* mo = reinterpret_cast<float*>(s3_smem);                // [2 mt][4 kq][16 rows][32 + 2]  (O row, m, l)
+    float* mo = reinterpret_cast<float*>(s3_smem);                // [2 mt][KQ][16 rows][32 + 2]  (O row, m, l)
     constexpr int MLD = SA_HD + 2;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        float* row = mo + ((mt * 4 + kq) * 16 + g8 + 8 * r) * MLD;
+        float* row = mo + ((mt * KQ + kq) * 16 + g8 + 8 * r) * MLD;
 #pragma unroll
         for (int nd = 0; nd < 4; ++nd) { row[8 * nd + 2 * t4] = oacc[nd][2 * r]; row[8 * nd + 2 * t4 + 1] = oacc[nd][2 * r + 1]; }
         if (t4 == 0) { row[SA_HD] = m_run[r]; row[SA_HD + 1] = l_run[r]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * SA_HD; i += 256) {
+    for (int i = threadIdx.x; i < 32 * SA_HD; i += 64 * KQ) {
         const int r32 = i >> 5, d = i & 31;
         const int m2 = r32 >> 4, r = r32 & 15;
         float mmax = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) mmax = fmaxf(mmax, mo[((m2 * 4 + w) * 16 + r) * MLD + SA_HD]);
+        for (int w = 0; w < KQ; ++w) mmax = fmaxf(mmax, mo[((m2 * KQ + w) * 16 + r) * MLD + SA_HD]);
         const float muse = (mmax == -INFINITY) ? 0.f : mmax;
         float num = 0.f, den = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const float* row = mo + ((m2 * 4 + w) * 16 + r) * MLD;
+        for (int w = 0; w < KQ; ++w) {
+            const float* row = mo + ((m2 * KQ + w) * 16 + r) * MLD;
             const float f = sa_exp(row[SA_HD] - muse);
             num += f * row[d];
             den += f * row[SA_HD + 1];
@@ -594,15 +596,25 @@ extern "C" int sbev_sasa_split_range_fwd(const uint16_t* qkv_hi, const uint16_t*
     SBEV_REQUIRE((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0,
                  SBEV_ERR_INVALID, "sbev_sasa_split_fwd: bf16 operands must be 16-byte aligned with ld % 8 == 0");
     if (B == 0 || q_end == q_begin) return SBEV_OK;
-    const size_t smem = (size_t)4 * 2 * S3_BUF_BYTES;
-    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(sasa_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sasa_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // key splits per CTA: 8 (512 threads) when the grid would not fill the GPU with 4 (a query shard), option "sasa_kq" overrides
+    int kq = get_option(OPT_SASA_KQ);
+    if (kq != 4 && kq != 8) kq = ((long long)((q_end - q_begin + 31) / 32) * H * B <= device_num_sms()) ? 8 : 4;
+    const size_t smem = (size_t)kq * 2 * S3_BUF_BYTES;
+    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(sasa_v3_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 2 * S3_BUF_BYTES));
+        cudaFuncSetAttribute(sasa_v3_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 2 * S3_BUF_BYTES));
+        cudaFuncSetAttribute(sasa_v3_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 2 * S3_BUF_BYTES));
+        cudaFuncSetAttribute(sasa_v3_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 2 * S3_BUF_BYTES)));
     dim3 grid((q_end - q_begin + 31) / 32, H, B);
+#define SBEV_SASA_LAUNCH(MASK, KQV)                                                                                                      \
+    launch_pdl(sasa_v3_kernel<MASK, KQV>, grid, dim3(64 * KQV), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), \
+               reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld, query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1],  \
+               pc_range[4], B, Q, H, q_begin, q_end, out)
+    if (kq == 8) { if (dn_mask != nullptr) SBEV_SASA_LAUNCH(true, 8); else SBEV_SASA_LAUNCH(false, 8); return check_launch("sbev_sasa_split_fwd"); }
     if (dn_mask != nullptr)
-        launch_pdl(sasa_v3_kernel<true>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
+        launch_pdl(sasa_v3_kernel<true, 4>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
                    query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, q_begin, q_end, out);
     else
-        launch_pdl(sasa_v3_kernel<false>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
+        launch_pdl(sasa_v3_kernel<false, 4>, grid, dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(qkv_hi), reinterpret_cast<const __nv_bfloat16*>(qkv_lo), ld,
                    query_bbox, tau, ld_tau, dn_mask, pc_range[0], pc_range[3], pc_range[1], pc_range[4], B, Q, H, q_begin, q_end, out);
     return check_launch("sbev_sasa_split_fwd");
 }

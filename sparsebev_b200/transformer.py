@@ -584,11 +584,15 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             gather()
         # (4b) mixing, (5) FFN, cls / reg + refine: own queries, results into this rank's rows of the output buffers -> exchange 2
         if Ml > 0:
+            # split-K of the out-projection by local row count (tests/perf/kernel_sweep.py on the B200: the GEMM wants ~148 CTAs
+            # of work, the reduce in front of the FFN chain wants few partials): 18 / 36 slices reduced in the FFN chain's
+            # prologue as in the unsharded layer, 72 / 128 slices by the one-CTA-per-row reduce kernel
             keep_split = mixing.split_k
             if self.qshard_split_k is not None:
                 mixing.split_k = self.qshard_split_k
-            else:                    # fill ~72 CTA-pair units (148 SMs): the unsharded layer has ceil(900/256) = 4 row units x 18 slices
-                mixing.split_k = max(keep_split, min(128, (72 + (Ml + 255) // 256 - 1) // ((Ml + 255) // 256)))
+            else:
+                mixing.split_k = 128 if Ml <= 128 else 72 if Ml <= 256 else 36 if Ml <= 512 else keep_split
+            separate_reduce = mixing.split_k > 36
             try:
                 red = mixing.mix_and_project(params, v['sampled'][:Ml], q2, self.norm2, defer_reduce=True)
             finally:
@@ -601,8 +605,14 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             reg_chain = [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
             ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
             refine = dict(refine_proposal=qb2[sl], refine_time_diff=td, refine_Q=Ml, refine_T=td.shape[1])
+            if separate_reduce:
+                q3r = ops.reduce_ln(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'])
+                ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3r, res_pre_ln=True, y=q4)]
             if side is not None:
-                ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain)
+                if separate_reduce:
+                    ops.dense_chain(q3r, D, Ml, ffn_chain)
+                else:
+                    ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     ops.dense_chain(q4, D, Ml, reg_chain, **refine)
@@ -610,7 +620,10 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
                 ops.dense_chain(q4, D, Ml, cls_chain)
                 main.wait_stream(side)
             else:
-                ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain + cls_chain)
+                if separate_reduce:
+                    ops.dense_chain(q3r, D, Ml, ffn_chain + cls_chain)
+                else:
+                    ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, ffn_chain + cls_chain)
                 ops.dense_chain(q4, D, Ml, reg_chain, **refine)
             mark('cls || reg+refine')
         sh.exchange(ar, [('feat%d' % par, q0, q1), ('cls%d' % par, q0, q1), ('box%d' % par, q0, q1)])

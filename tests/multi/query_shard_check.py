@@ -45,8 +45,10 @@ def main():
         assert (t0, t1) == D.frame_partition(T, rank, world)
         model.shard_queries(shard)
         local_feats = [f[:, t0 * 6:t1 * 6].contiguous().to(dev) for f in feats]
+        from sparsebev_b200 import _lib
         for name, split in (('same split-K', layer.mixing.split_k), ('own split-K', None)):
             layer.qshard_split_k = split
+            _lib.set_option('sasa_kq', 4 if split is not None else 0)      # bit-identity needs the unsharded layer's key-split count too
             for rep in range(3):          # repeated forwards also exercise buffer reuse across layers and forwards
                 got = model(qb, qf, [f.clone() for f in local_feats], None, copy.deepcopy(metas))
                 torch.cuda.synchronize()

@@ -178,19 +178,41 @@ def _rows_within(got, want, bar, fragile, what):
     return int(bad.sum())
 
 
+def _smooth_feats(cfg, T, seed):
+    """FPN-like SMOOTH feature maps: unit-variance noise generated at 1/8 resolution and bilinearly upsampled.  The default
+    synthetic maps are i.i.d. noise per pixel -- maximally rough: a sample point that moves by 1e-6 of its coordinate (the
+    fp32-grade round-off of the sampling-offset Linear: tensor-core bf16x3 vs the oracle's fp32, max 2.3e-6 relative measured,
+    tests/perf/parity_stages.py) changes the bilinear tap by ~2e-4 of the feature scale, which then IS the whole-layer error
+    (measured 1.7e-4 at r50-T8, 3.8e-4 at vov99; the gather itself is exact to 2e-7 on identical points).  Backbone features
+    are smooth at the pixel scale; on such maps the layer-level bar measures the kernels, not the roughness of the test data."""
+    g = torch.Generator().manual_seed(seed)
+    feats = []
+    for (h, w) in cfg['levels']:
+        low = torch.randn(T * 6, 256, h // 8 + 2, w // 8 + 2, generator=g)
+        f = torch.nn.functional.interpolate(low, size=(h, w), mode='bilinear', align_corners=True)
+        feats.append((f / f.std())[None].contiguous())
+    return feats
+
+
 @pytest.mark.parametrize('name,T', [('r50_704x256', 8), ('r50_704x256', 1), ('r101_1408x512', 2), ('vov99_1600x640', 2)])
 def test_full_size_layer_vs_oracle(name, T):
     """The BENCH workload itself (r50 704x256, 900 queries, T = 8: BASELINE config 3's per-layer shape; T = 1: config 2)
     and the 5-level configs 4 / 5 at full resolution and query count (two frames: the CPU oracle holds the pyramid twice)
     held to the CPU oracle's restatement of SparseBEVTransformerDecoderLayer.forward
     (/root/reference/models/sparsebev_transformer.py:162-193), incl. the 900 = 7 x 128 + 4 row tail of every GEMM tile.
-    Bar: every query row within 5e-5 of the output scale; the documented exception is _fragile_queries."""
-    cfg, sd, model, feats, metas, qb, qf = _setup(name, T, 1, seed=1, num_layers=1)
+      * whole layer on smooth feature maps (_smooth_feats): every query row within 5e-5 of the output scale, except rows
+        with a sample point on a camera's validity border (_fragile_queries);
+      * every stage fed with the ORACLE's inputs (errors cannot compound): 2e-5, the gather on identical points 1e-6."""
+    from sparsebev_b200 import ops
+    cfg, sd, model, _, metas, qb, qf = _setup(name, T, 1, seed=1, num_layers=1)
+    feats = _smooth_feats(cfg, T, seed=7)
     td = R.time_diff_from_timestamps([m['img_timestamp'] for m in metas])
     l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas]).astype(np.float32))
     taps = {}
     with torch.no_grad():
         want = R.decoder_layer(qb, qf, R.regroup_feats(feats, channel_last=True), sd, cfg, td, l2i, op=R.msmv_sampling_kernel_semantics, taps=taps)
+        pos = qf + R.position_encoder(qb[..., :3], sd)
+        ffn_want = R._ln(R.ffn(taps['mixed'], sd), sd['norm3.weight'], sd['norm3.bias'])
     fragile = _fragile_queries(taps['points'], l2i, cfg['image_h'], cfg['image_w'])
     assert float(fragile.float().mean()) < 0.25
     layer = model.decoder.decoder_layer
@@ -202,12 +224,29 @@ def test_full_size_layer_vs_oracle(name, T):
     for g, w, what in zip(got, want, ('query_feat', 'cls', 'bbox')):
         assert g.shape == w.shape and torch.isfinite(g).all()
         flips = max(flips, _rows_within(g, w, LAYER_BAR, fragile, '%s %s T=%d' % (name, what, T)))
-    # the two big intermediate tensors of the bench workload against the oracle's taps
-    sampled = layer.sampling(qb.cuda(), taps['after_sasa'].cuda(), gfeats, metas_gpu)
+    # ---- stage by stage on the oracle's inputs
+    Q, D, G, P, L = cfg['num_query'], 256, 4, 4, cfg['num_levels']
+    qbc = qb.cuda()
+    sasa = layer.self_attn.forward_fused(qbc, pos.cuda(), None, layer.norm1)
+    assert _rel(sasa, taps['after_sasa']) < 2e-5, 'SASA block rel-to-max %.3e' % _rel(sasa, taps['after_sasa'])
+    after = taps['after_sasa'].cuda()
+    heads = layer.sampling._heads(after.reshape(Q, D))
+    pts, sw = ops.sample_points(qbc, heads, heads[:, G * P * 3:], cfg['pc_range'], L, num_points_total=G * P, ld_off=heads.shape[1], ld_log=heads.shape[1])
+    want_pts = taps['points'][:, :, 0].reshape(1, Q, G * P, 3).contiguous()                  # frame 0 has time_diff 0: the un-warped points
+    assert _rel(pts, want_pts) < 1e-5 and _rel(sw.reshape(1, Q, G, P, L), taps['scale_weights'][:, :, :, 0]) < 2e-5
+    exact = ops.sampling4d_fused(gfeats, want_pts.cuda(), qbc, metas_gpu[0]['time_diff'], metas_gpu[0]['lidar2img'],
+                                 taps['scale_weights'][:, :, :, 0].contiguous().cuda(), cfg['image_h'], cfg['image_w'], num_frames=T,
+                                 layout=layer.sampling.feat_layout)
+    assert _rel(exact, taps['sampled']) < 1e-6, 'gather on the oracle\'s points: rel-to-max %.3e' % _rel(exact, taps['sampled'])
+    sampled = layer.sampling(qbc, after, gfeats, metas_gpu)
     _rows_within(sampled, taps['sampled'], 2e-5, fragile, 'sampled features')
-    mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), taps['after_sasa'].cuda(), layer.norm2)
-    assert _rel(mixed, taps['mixed']) < LAYER_BAR, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])       # (no view pick inside: no exception)
-    print('%s T=%d: %d of %d query rows are view-border cases' % (name, T, flips, cfg['num_query']))
+    mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), after, layer.norm2)
+    assert _rel(mixed, taps['mixed']) < 2e-5, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])
+    q4 = torch.empty(Q, D, device='cuda')
+    mx = taps['mixed'].cuda().reshape(Q, D).contiguous()
+    ops.dense_chain(mx, D, Q, [layer._ffn0.layer(relu=True), layer._ffn1.layer(residual=mx, res_pre_ln=True, y=q4)])
+    assert _rel(q4, ffn_want[0]) < 2e-5
+    print('%s T=%d: %d of %d query rows are view-border cases' % (name, T, flips, Q))
 
 
 def test_mix_presplit_m900_vs_oracle():

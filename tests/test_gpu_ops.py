@@ -32,7 +32,7 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit', 'dense_pack', 'legacy_rotation')
+    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit', 'dense_pack', 'legacy_rotation', 'sasa_kq')
     defaults = {k: _lib.get_option(k) for k in names}
 
     def setter(name, value):
@@ -639,6 +639,33 @@ def test_sasa_vs_oracle(Q, impl, option):
     _close(got_m, want_m.transpose(1, 2).reshape(B, Q, D), rtol=1e-4, atol=1e-5, what='sasa core with dn mask')
     got_m3 = ops.sasa_split(packed, qb.to(dev()), pc, H, D, dn_mask=mask.to(dev()))
     _close(got_m3, want_m.transpose(1, 2).reshape(B, Q, D), rtol=1e-4, atol=2e-5, what='sasa core (split / v3) with dn mask')
+
+
+@pytest.mark.parametrize('kq', [4, 8, 0])
+def test_sasa_query_range_and_key_splits(kq, option):
+    """sbev_sasa_split_range_fwd: a query shard [qa, qb) attends to all keys; with the same key-split count its rows are
+    BIT-IDENTICAL to the full launch (a query's result does not depend on its tile mates), with 8 key splits per CTA (the
+    small-grid variant, chosen automatically for a shard) they agree with the oracle to the same bar."""
+    option('sasa_kq', kq)
+    ops = _ops()
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    Q, D, H = 900, 256, 8
+    qb = R.init_query_bbox(900, seed=3)[None].contiguous()
+    qkv = hashrand((1, Q, 3 * D), 5, -1.5, 1.5)
+    tau = hashrand((1, Q, H), 6, 0, 2)
+    q, k, v = [t.reshape(1, Q, H, 32).transpose(1, 2) for t in qkv.chunk(3, -1)]
+    bias = -R.pairwise_centre_dist(qb, pc)[:, None] * tau.permute(0, 2, 1)[..., None]
+    want = (torch.softmax(q * (1 / np.sqrt(32)) @ k.transpose(-1, -2) + bias, -1) @ v).transpose(1, 2).reshape(1, Q, D)
+    packed = torch.cat([qkv, tau], -1).reshape(Q, 3 * D + H).contiguous().to(dev())
+    full = ops.sasa_split(packed, qb.to(dev()), pc, H, D)
+    _close(full, want, rtol=1e-4, atol=2e-5, what='sasa full launch, sasa_kq=%d' % kq)
+    for qa, qe in ((0, 113), (339, 452), (791, 900), (450, 900), (37, 38), (5, 5)):
+        out = torch.full((1, Q, D), 7.0, device=dev())
+        ops.sasa_split(packed, qb.to(dev()), pc, H, D, q_range=(qa, qe), out=out)
+        assert bool((out[:, :qa] == 7.0).all()) and bool((out[:, qe:] == 7.0).all())          # rows outside the shard untouched
+        _close(out[:, qa:qe], want[:, qa:qe], rtol=1e-4, atol=2e-5, what='sasa shard [%d,%d), sasa_kq=%d' % (qa, qe, kq))
+        if kq != 0:
+            assert torch.equal(out[:, qa:qe], full[:, qa:qe])
 
 
 # ------------------------------------------------------------------------- tcgen05 GEMM + mixing
