@@ -64,8 +64,10 @@ const char* sbev_last_error(void);
  *                    (models/utils.py:66-71: rotation_3d_in_axis turns the other way; toggled like the reference's global
  *                    VERSION.name, val.py:128-129) -- affects sbev_sample_points_fwd and sbev_dense_chain_points_fwd
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
- *                    2 = 8 lanes/point x 8 channels, two levels at a time (fewest instructions per point; default);
- *                    3 = 2 + the next level pair's lines are prefetched into L2 while the current pair's loads are in flight */
+ *                    2 = 8 lanes/point x 8 channels, two levels at a time; 3 = 2 + the next level pair's lines are prefetched
+ *                    into L2; 4 = 2 + level blocks in which no point of the warp has a live tap are skipped by a warp-uniform
+ *                    branch (~30 % of the taps on a real camera rig fall outside every view); 5 = 4 at 3 CTAs/SM;
+ *                    6 = 4 with ONE level (8 loads per lane) at a time, 64 registers, 4 CTAs/SM (default: 54.0 -> 44.5 us at r50-T8) */
 int         sbev_set_option(const char* name, int value);
 /* current value of an option (the environment / built-in default until sbev_set_option overrides it); -1 = unknown name */
 int         sbev_get_option(const char* name);
@@ -407,6 +409,10 @@ int sbev_conv2d_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int Cin,
  * backbone) + folded BN + ReLU -> NHWC bf16 [Nimg][Ho][Wo][64].  w fp32 [7][7][3][64]. */
 int sbev_stem_conv_fwd(const float* img, int Nimg, int H, int W, const float* w, const float* scale, const float* shift,
                        uint16_t* out, void* stream);
+
+/* Same with a ksize x ksize kernel, ksize = 7 (pad 3) or 3 (pad 1: VoVNet's stem_1, models/backbones/vovnet.py:289); w fp32 [ksize][ksize][3][64]. */
+int sbev_stem_conv_k_fwd(const float* img, int Nimg, int H, int W, const float* w, int ksize, const float* scale, const float* shift,
+                         uint16_t* out, void* stream);
 
 /* 3x3 stride-2 pad-1 max pool, NHWC bf16, C % 8 == 0 -> [Nimg][(H-1)/2+1][(W-1)/2+1][C]. */
 int sbev_maxpool3x3s2_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int C, uint16_t* out, void* stream);

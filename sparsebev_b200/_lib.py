@@ -75,6 +75,7 @@ SIGNATURES = {
     'sbev_conv2d_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
                              c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp],
     'sbev_stem_conv_fwd': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'sbev_stem_conv_k_fwd': [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_maxpool3x3s2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_subsample2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_cast_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp],

@@ -205,19 +205,22 @@ conv_igemm_kernel(const __grid_constant__ ConvParams prm, const __grid_constant_
 // Stem: 7x7 stride-2 pad-3 convolution of the 3-channel NCHW fp32 image + folded BN + ReLU -> NHWC bf16 [N][Ho][Wo][64].
 // One CTA = 8 x 16 output pixels x 64 channels; the input patch (21 x 37 x 3) and all weights ([147][64] fp32, 37 KB)
 // sit in shared memory; a thread owns one pixel and 32 channels (weights are warp-uniform LDS.128 broadcasts).
-constexpr int STEM_TH = 8, STEM_TW = 16, STEM_PH = STEM_TH * 2 + 5, STEM_PW = STEM_TW * 2 + 5;
+// KS = 7 (ResNet stem, pad 3) or 3 (VoVNet stem_1, models/backbones/vovnet.py:289, pad 1); stride 2.
+constexpr int STEM_TH = 8, STEM_TW = 16;
+template <int KS>
 __global__ void __launch_bounds__(256)
-stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ w /* [7][7][3][64] */, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int Nimg, int H, int W, int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /* [KS][KS][3][64] */, const float* __restrict__ scale,
+                 const float* __restrict__ shift, int Nimg, int H, int W, int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+    constexpr int STEM_PH = STEM_TH * 2 + KS - 2, STEM_PW = STEM_TW * 2 + KS - 2, TAPS = KS * KS * 3;
     extern __shared__ float stem_smem[];
-    float* ws = stem_smem;                       // [147][64]
-    float* xs = stem_smem + 147 * 64;            // [3][STEM_PH][STEM_PW]
+    float* ws = stem_smem;                       // [TAPS][64]
+    float* xs = stem_smem + TAPS * 64;           // [3][STEM_PH][STEM_PW]
     const int tiles_w = (Wo + STEM_TW - 1) / STEM_TW, tiles_h = (Ho + STEM_TH - 1) / STEM_TH;
     const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
     pdl_wait();
     pdl_trigger();
-    for (int i = threadIdx.x; i < 147 * 64 / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = ldg4(w + 4 * i);
-    const int h_in0 = th * STEM_TH * 2 - 3, w_in0 = tw * STEM_TW * 2 - 3;
+    for (int i = threadIdx.x; i < TAPS * 64 / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = ldg4(w + 4 * i);
+    const int h_in0 = th * STEM_TH * 2 - KS / 2, w_in0 = tw * STEM_TW * 2 - KS / 2;
     for (int i = threadIdx.x; i < 3 * STEM_PH * STEM_PW; i += 256) {
         const int c = i / (STEM_PH * STEM_PW), r = (i / STEM_PW) % STEM_PH, q = i % STEM_PW;
         const int hh = h_in0 + r, ww = w_in0 + q;
@@ -229,12 +232,12 @@ stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ w /
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (int kh = 0; kh < 7; ++kh)
-        for (int kw = 0; kw < 7; ++kw)
+    for (int kh = 0; kh < KS; ++kh)
+        for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float x = xs[(c * STEM_PH + pr * 2 + kh) * STEM_PW + pc * 2 + kw];
-                const float4* wp = reinterpret_cast<const float4*>(ws + ((kh * 7 + kw) * 3 + c) * 64 + half * 32);
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((kh * KS + kw) * 3 + c) * 64 + half * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 wv = wp[j];
@@ -408,18 +411,37 @@ extern "C" int sbev_conv2d_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, i
     return launch_conv<64, 8>(prm, maps, (cudaStream_t)stream);
 }
 
+extern "C" int sbev_stem_conv_k_fwd(const float* img, int Nimg, int H, int W, const float* w, int ksize, const float* scale, const float* shift,
+                                    uint16_t* out, void* stream);
+
 extern "C" int sbev_stem_conv_fwd(const float* img, int Nimg, int H, int W, const float* w, const float* scale, const float* shift,
                                   uint16_t* out, void* stream) {
     SBEV_REQUIRE(img && w && scale && shift && out, SBEV_ERR_INVALID, "sbev_stem_conv_fwd: null pointer");
     SBEV_REQUIRE(Nimg >= 0 && H > 0 && W > 0, SBEV_ERR_INVALID, "sbev_stem_conv_fwd: bad sizes");
     SBEV_REQUIRE(((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, SBEV_ERR_INVALID, "sbev_stem_conv_fwd: w / out must be 16-byte aligned");
     if (Nimg == 0) return SBEV_OK;
-    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-    const size_t smem = (size_t)(147 * 64 + 3 * STEM_PH * STEM_PW) * sizeof(float);
-    SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return sbev_stem_conv_k_fwd(img, Nimg, H, W, w, 7, scale, shift, out, stream);
+}
+
+extern "C" int sbev_stem_conv_k_fwd(const float* img, int Nimg, int H, int W, const float* w, int ksize, const float* scale, const float* shift,
+                                    uint16_t* out, void* stream) {
+    SBEV_REQUIRE(img && w && scale && shift && out, SBEV_ERR_INVALID, "sbev_stem_conv_k_fwd: null pointer");
+    SBEV_REQUIRE(ksize == 7 || ksize == 3, SBEV_ERR_UNSUPPORTED, "sbev_stem_conv_k_fwd: kernel size 3 or 7 (got %d)", ksize);
+    SBEV_REQUIRE(Nimg >= 0 && H > 0 && W > 0, SBEV_ERR_INVALID, "sbev_stem_conv_k_fwd: bad sizes");
+    SBEV_REQUIRE(((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, SBEV_ERR_INVALID, "sbev_stem_conv_k_fwd: operands must be 16-byte aligned");
+    if (Nimg == 0) return SBEV_OK;
+    const int pad = ksize / 2;
+    const int Ho = (H + 2 * pad - ksize) / 2 + 1, Wo = (W + 2 * pad - ksize) / 2 + 1;
+    const size_t smem = (size_t)(ksize * ksize * 3 * 64 + 3 * (STEM_TH * 2 + ksize - 2) * (STEM_TW * 2 + ksize - 2)) * sizeof(float);
     const int tiles = Nimg * ((Wo + STEM_TW - 1) / STEM_TW) * ((Ho + STEM_TH - 1) / STEM_TH);
-    launch_pdl(stem_conv7x7_kernel, dim3(tiles), dim3(256), smem, (cudaStream_t)stream, img, w, scale, shift, Nimg, H, W, Ho, Wo,
-               reinterpret_cast<__nv_bfloat16*>(out));
+    if (ksize == 7) {
+        SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(stem_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        launch_pdl(stem_conv_kernel<7>, dim3(tiles), dim3(256), smem, (cudaStream_t)stream, img, w, scale, shift, Nimg, H, W, Ho, Wo,
+                   reinterpret_cast<__nv_bfloat16*>(out));
+    } else {
+        launch_pdl(stem_conv_kernel<3>, dim3(tiles), dim3(256), smem, (cudaStream_t)stream, img, w, scale, shift, Nimg, H, W, Ho, Wo,
+                   reinterpret_cast<__nv_bfloat16*>(out));
+    }
     return check_launch("sbev_stem_conv_fwd");
 }
 

@@ -582,17 +582,19 @@ def conv2d_nhwc(x, w, shift, scale=None, stride=1, pad=0, residual=None, relu=Fa
 
 
 def stem_conv(img, w, scale, shift):
-    """img NCHW fp32 [N,3,H,W], w fp32 [7,7,3,64] -> relu(bn(conv7x7/2)) as NHWC bf16 [N,Ho,Wo,64]."""
+    """img NCHW fp32 [N,3,H,W], w fp32 [k,k,3,64] (k = 7: ResNet stem, k = 3: VoVNet stem_1) -> relu(bn(conv kxk / 2, pad k//2)) as
+    NHWC bf16 [N,Ho,Wo,64]."""
     lib = _lib.load()
     _chk(img, 'img'); _chk(w, 'weight'); _chk(scale, 'scale'); _chk(shift, 'shift')
-    if img.dim() != 4 or img.shape[1] != 3 or tuple(w.shape) != (7, 7, 3, 64):
-        raise RuntimeError('stem_conv: img must be [N,3,H,W] and weight [7,7,3,64]')
+    k = w.shape[0]
+    if img.dim() != 4 or img.shape[1] != 3 or tuple(w.shape) != (k, k, 3, 64) or k not in (3, 7):
+        raise RuntimeError('stem_conv: img must be [N,3,H,W] and weight [k,k,3,64], k = 3 or 7')
     N, _, H, W = img.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty(N, Ho, Wo, 64, device=img.device, dtype=torch.bfloat16)
     with torch.cuda.device(img.device):
-        _lib.check(lib.sbev_stem_conv_fwd(img.data_ptr(), N, H, W, w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                          out.data_ptr(), _stream()), 'sbev_stem_conv_fwd')
+        _lib.check(lib.sbev_stem_conv_k_fwd(img.data_ptr(), N, H, W, w.data_ptr(), k, scale.data_ptr(), shift.data_ptr(),
+                                            out.data_ptr(), _stream()), 'sbev_stem_conv_k_fwd')
     return out
 
 
