@@ -2,9 +2,12 @@
 
 Every rank builds the SAME synthetic scene and runs the unsharded decoder on all frames; then the sharded decoder
 (dist.QueryShard: this rank's frame window of the feature maps, this rank's queries) -- first with the unsharded layer's
-split-K count, where every row must be BIT-IDENTICAL (each stage is the same kernel on a subset of independent rows), then
-with the split-K count the sharded layer picks for its smaller row count (fp32 summation order of the out-projection
-changes: <= 5e-5 of the output scale, the whole-layer parity bar).  Prints `QUERY_SHARD_OK rank=<r> ...` per rank; any mismatch raises.
+split-K / key-split counts, where every row must be BIT-IDENTICAL (each stage is the same kernel on a subset of independent
+rows), then with the counts the sharded layer picks for its smaller row count (fp32 summation order of the out-projection
+and of the attention merge changes): first layer <= 5e-5 of the output scale (the whole-layer parity bar); later layers
+<= 1e-3 with 99.9 % of the elements <= 1e-4 -- a 1e-6 perturbation of a layer's boxes moves the next layer's sample points,
+and bilinear taps amplify that (tests/perf/parity_stages.py), a property of the decoder, not of the sharding.
+Prints `QUERY_SHARD_OK rank=<r> ...` per rank; any mismatch raises.
 """
 import copy
 import os
@@ -57,9 +60,11 @@ def main():
                         if not torch.equal(g, w):
                             raise AssertionError('rank %d %s rep %d: max |diff| %.3e' % (rank, name, rep, float((g - w).abs().max())))
                     else:
-                        err = float((g - w).abs().max() / w.abs().max())
-                        if not err < 5e-5:
-                            raise AssertionError('rank %d %s rep %d: rel-to-max %.3e' % (rank, name, rep, err))
+                        e = (g - w).abs() / w.abs().max()
+                        first, rest = float(e[0].max()), float(e.max())
+                        frac = float((e > 1e-4).float().mean())
+                        if not (first < 5e-5 and rest < 1e-3 and frac < 1e-3):
+                            raise AssertionError('rank %d %s rep %d: first layer %.3e, all layers %.3e, %.2e of the elements above 1e-4' % (rank, name, rep, first, rest, frac))
             ar = next(iter(shard._arenas.values()))
             assert shard.status(ar) == 0, 'an exchange timed out'
             print('QUERY_SHARD_OK rank=%d world=%d mode=%s window=[%d,%d) queries=[%d,%d) config=%s exchanges=%d' %
