@@ -417,6 +417,18 @@ int sbev_stem_conv_k_fwd(const float* img, int Nimg, int H, int W, const float* 
 /* 3x3 stride-2 pad-1 max pool, NHWC bf16, C % 8 == 0 -> [Nimg][(H-1)/2+1][(W-1)/2+1][C]. */
 int sbev_maxpool3x3s2_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int C, uint16_t* out, void* stream);
 
+/* 3x3 stride-2 max pool with explicit padding (0 | 1) and torch's ceil_mode: VoVNet's OSA stages open with
+ * nn.MaxPool2d(kernel_size=3, stride=2, ceil_mode=True) (models/backbones/vovnet.py:228).  out [Nimg][Ho][Wo][C], Ho / Wo by
+ * torch.nn.MaxPool2d's rule (window positions beyond the input are ignored). */
+int sbev_maxpool3x3s2_ex_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int C, int pad, int ceil_mode, uint16_t* out, void* stream);
+
+/* Effective squeeze-excitation of a VoVNet OSA block (models/backbones/vovnet.py:157-178,213-218), NHWC bf16:
+ *   out = x * hsigmoid(fc(mean_{h,w} x)) (+ identity),   hsigmoid(v) = relu6(v + 3) / 6,   fc = 1x1 conv [C,C] + bias (fp32).
+ * Three launches (deterministic two-stage mean, gate mat-vec, scale); workspace = sbev_ese_workspace_floats(...) fp32, caller-owned. */
+long long sbev_ese_workspace_floats(int Nimg, int H, int W, int C);
+int sbev_ese_nhwc_fwd(const uint16_t* x, int Nimg, int H, int W, int C, const float* fc_weight, const float* fc_bias,
+                      const uint16_t* identity, float* workspace, uint16_t* out, void* stream);
+
 /* out[n,ho,wo,:] = x[n,2ho,2wo,:], fp32 NHWC, C % 4 == 0 (mmdet FPN extra level: F.max_pool2d(x, 1, stride=2)). */
 int sbev_subsample2_nhwc_fwd(const float* x, int Nimg, int H, int W, int C, float* out, void* stream);
 

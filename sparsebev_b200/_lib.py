@@ -77,6 +77,8 @@ SIGNATURES = {
     'sbev_stem_conv_fwd': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     'sbev_stem_conv_k_fwd': [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     'sbev_maxpool3x3s2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_maxpool3x3s2_ex_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'sbev_ese_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     'sbev_subsample2_nhwc_fwd': [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_cast_bf16': [c_vp, ctypes.c_int64, c_vp, c_vp],
 }
@@ -85,7 +87,7 @@ _lib = None
 
 
 def exported_symbols():
-    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option', 'sbev_msmv_bwd_det_workspace'])
+    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option', 'sbev_msmv_bwd_det_workspace', 'sbev_ese_workspace_floats'])
 
 
 def load():
@@ -107,6 +109,8 @@ def load():
     lib.sbev_get_option.restype = c_int
     lib.sbev_msmv_bwd_det_workspace.argtypes = [c_i32p, c_int, c_int, c_int, c_int, c_int]
     lib.sbev_msmv_bwd_det_workspace.restype = ctypes.c_longlong
+    lib.sbev_ese_workspace_floats.argtypes = [c_int, c_int, c_int, c_int]
+    lib.sbev_ese_workspace_floats.restype = ctypes.c_longlong
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -39,10 +39,17 @@ def weight_khwc(weight):
 
 
 class _FusedConv:
-    """Device-side cache of one conv (+ BN) in the kernel's layout; rebuilt when a parameter changes."""
+    """Device-side cache of one conv (+ BN) in the kernel's layout; rebuilt when a parameter changes.
 
-    def __init__(self, conv, bn=None):
+    in_index (optional, list of length Cin_padded): the kernel's input tensor carries Cin_padded >= conv.in_channels channels;
+    entry j names the conv input channel that padded channel j feeds (-1: a zero-padding channel, gets zero weights).
+    cout_pad (optional): emit cout_pad >= conv.out_channels channels, the extra ones identically zero (zero weights, zero shift).
+    Both exist for VoVNet's 160- / 224-channel OSA layers: the tcgen05 conv kernel wants Cin % 64 == 0, so those tensors are
+    carried as 192 / 256 channels with zeros in the tail."""
+
+    def __init__(self, conv, bn=None, in_index=None, cout_pad=None):
         self.conv, self.bn, self._key, self._val = conv, bn, None, None
+        self.in_index, self.cout_pad = in_index, cout_pad
 
     def get(self):
         ps = [self.conv.weight, self.conv.bias] + ([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var] if self.bn is not None else [])
@@ -56,25 +63,39 @@ class _FusedConv:
             else:
                 scale = None
                 shift = (conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=conv.weight.device)).contiguous()
-            w = ops.cast_bf16(weight_khwc(conv.weight))
+            wk = weight_khwc(conv.weight)                                       # [Cout, KH, KW, Cin]
+            if self.in_index is not None:
+                idx = torch.as_tensor(self.in_index, device=wk.device, dtype=torch.long)
+                wp = torch.zeros(wk.shape[0], wk.shape[1], wk.shape[2], idx.numel(), device=wk.device, dtype=wk.dtype)
+                wp[..., idx >= 0] = wk[..., idx[idx >= 0]]
+                wk = wp
+            if self.cout_pad is not None and self.cout_pad > wk.shape[0]:
+                extra = self.cout_pad - wk.shape[0]
+                wk = torch.cat([wk, torch.zeros(extra, *wk.shape[1:], device=wk.device, dtype=wk.dtype)], 0)
+                shift = torch.cat([shift, torch.zeros(extra, device=shift.device)]).contiguous()
+                if scale is not None:
+                    scale = torch.cat([scale, torch.ones(extra, device=scale.device)]).contiguous()
+            w = ops.cast_bf16(wk.contiguous())
             self._key, self._val = key, (w, scale, shift)
         return self._val
 
     def __call__(self, x, relu=False, residual=None, out_f32=False):
         conv = self.conv
-        _check_conv(conv)
+        _check_conv(conv, cin=len(self.in_index) if self.in_index is not None else None, cout=self.cout_pad)
         w, scale, shift = self.get()
         return ops.conv2d_nhwc(x, w, shift, scale, stride=conv.stride[0], pad=conv.padding[0], residual=residual, relu=relu, out_f32=out_f32)
 
 
-def _check_conv(conv):
+def _check_conv(conv, cin=None, cout=None):
+    cin = conv.in_channels if cin is None else cin
+    cout = conv.out_channels if cout is None else cout
     if conv.groups != 1 or conv.dilation != (1, 1) or conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] \
             or conv.kernel_size[0] != conv.kernel_size[1] or conv.stride[0] not in (1, 2) or conv.padding_mode != 'zeros':
         raise NotImplementedError('sparsebev_b200 conv kernel: groups=1, dilation=1, square kernel, stride 1|2, zero padding only '
                                   '(got %r); there is no cuDNN fallback' % (conv,))
-    if conv.in_channels % 64 or conv.out_channels % 32:
+    if cin % 64 or cout % 32:
         raise NotImplementedError('sparsebev_b200 conv kernel: in_channels %% 64 == 0 and out_channels %% 32 == 0 required (got %d -> %d)'
-                                  % (conv.in_channels, conv.out_channels))
+                                  % (cin, cout))
 
 
 def to_nhwc_bf16(x):
@@ -317,8 +338,153 @@ def extract_img_feat(backbone, neck, img):
     """img [B, T*N, 3, H, W] -> list of [B, T*N, C, H', W'] fp32 whose memory is channels-last, i.e. exactly what
     SparseBEVTransformerDecoder.prepare_feats consumes without a copy (reference: models/sparsebev.py:46-59,124-131)."""
     B, TN = img.shape[:2]
-    levels = neck.forward_nhwc(backbone.forward_nhwc(img.reshape(B * TN, *img.shape[2:])))
+    stages = backbone.forward_nhwc(img.reshape(B * TN, *img.shape[2:]))
+    if isinstance(stages, dict):                    # VoVNet returns a dict (models/sparsebev.py:52-53: list(x.values()))
+        stages = list(stages.values())
+    levels = neck.forward_nhwc(stages)
     return [f.view(B, TN, *f.shape[1:]).permute(0, 1, 4, 2, 3) for f in levels]
+
+
+# ------------------------------------------------------------------------------------------------
+# VoVNet (V-99-eSE and the other non-depthwise specs): /root/reference/models/backbones/vovnet.py:12-90 (specs), :157-178 (eSE),
+# :181-239 (OSA module / stage), :243-359 (network).  Same module tree and state-dict keys (`stem.stem_1/conv.weight`,
+# `stage3.OSA3_2.layers.4.OSA3_2_4/norm.running_var`, `stage5.OSA5_3.ese.fc.bias`, ...); inference only.
+_VOV_SPECS = {
+    'V-19-slim-eSE': dict(stem=[64, 64, 128], stage_conv_ch=[64, 80, 96, 112], stage_out_ch=[112, 256, 384, 512], layer_per_block=3, block_per_stage=[1, 1, 1, 1]),
+    'V-19-eSE': dict(stem=[64, 64, 128], stage_conv_ch=[128, 160, 192, 224], stage_out_ch=[256, 512, 768, 1024], layer_per_block=3, block_per_stage=[1, 1, 1, 1]),
+    'V-39-eSE': dict(stem=[64, 64, 128], stage_conv_ch=[128, 160, 192, 224], stage_out_ch=[256, 512, 768, 1024], layer_per_block=5, block_per_stage=[1, 1, 2, 2]),
+    'V-57-eSE': dict(stem=[64, 64, 128], stage_conv_ch=[128, 160, 192, 224], stage_out_ch=[256, 512, 768, 1024], layer_per_block=5, block_per_stage=[1, 1, 4, 3]),
+    'V-99-eSE': dict(stem=[64, 64, 128], stage_conv_ch=[128, 160, 192, 224], stage_out_ch=[256, 512, 768, 1024], layer_per_block=5, block_per_stage=[1, 3, 9, 3]),
+}
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class eSEModule(nn.Module):
+    """vovnet.py:166-178 (parameters: fc = 1x1 conv with bias)."""
+
+    def __init__(self, channel, reduction=4):
+        super().__init__()
+        self.fc = nn.Conv2d(channel, channel, kernel_size=1, padding=0)
+
+    def forward_nhwc(self, x, identity=None):
+        C = self.fc.out_channels
+        return ops.ese_nhwc(x, self.fc.weight.detach().float().reshape(C, C).contiguous(), self.fc.bias.detach().float().contiguous(), identity)
+
+
+class _OSA_module(nn.Module):
+    """One-shot-aggregation block (vovnet.py:181-225): layer_per_block 3x3 convs in sequence, all intermediate outputs (and the
+    input) concatenated, 1x1 conv, eSE, optional identity.  Channel counts that are not multiples of 64 (160, 224) travel
+    zero-padded to the next multiple; the consumers' weights are laid out for the padded tensors (_FusedConv.in_index)."""
+
+    def __init__(self, in_ch, stage_ch, concat_ch, layer_per_block, module_name, SE=False, identity=False, depthwise=False, with_cp=False):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError('sparsebev_b200 VoVNet: depthwise (dw) specs are not implemented')
+        self.identity = identity
+        self.layers = nn.ModuleList()
+        sp = _pad64(stage_ch)
+        self._fused = []
+        cin, cin_carried = in_ch, _pad64(in_ch)
+        for i in range(layer_per_block):
+            seq = nn.Sequential(OrderedDict(conv3x3(cin, stage_ch, module_name, i)))
+            self.layers.append(seq)
+            index = list(range(cin)) + [-1] * (cin_carried - cin)
+            self._fused.append(_FusedConv(seq[0], seq[1], in_index=index if cin_carried != cin else None, cout_pad=sp if sp != stage_ch else None))
+            cin, cin_carried = stage_ch, sp
+        self.concat = nn.Sequential(OrderedDict(conv1x1(in_ch + layer_per_block * stage_ch, concat_ch, module_name, 'concat')))
+        index = list(range(in_ch)) + [-1] * (_pad64(in_ch) - in_ch)
+        for i in range(layer_per_block):
+            index += list(range(in_ch + i * stage_ch, in_ch + (i + 1) * stage_ch)) + [-1] * (sp - stage_ch)
+        plain = index == list(range(len(index)))
+        self._fused_concat = _FusedConv(self.concat[0], self.concat[1], in_index=None if plain else index)
+        self.ese = eSEModule(concat_ch)
+
+    def forward_nhwc(self, x):
+        outs, h = [x], x
+        for f in self._fused:
+            h = f(h, relu=True)
+            outs.append(h)
+        xt = self._fused_concat(torch.cat(outs, dim=-1), relu=True)            # (the concatenation is a plain NHWC copy)
+        return self.ese.forward_nhwc(xt, x if self.identity else None)
+
+
+class _OSA_stage(nn.Sequential):
+    """vovnet.py:228-262: MaxPool2d(3, 2, ceil_mode=True) (all stages but stage2) + block_per_stage OSA modules."""
+
+    def __init__(self, in_ch, stage_ch, concat_ch, block_per_stage, layer_per_block, stage_num, SE=False, depthwise=False, with_cp=False):
+        super().__init__()
+        if stage_num != 2:
+            self.add_module('Pooling', nn.MaxPool2d(kernel_size=3, stride=2, ceil_mode=True))
+        name = 'OSA%d_1' % stage_num
+        self.add_module(name, _OSA_module(in_ch, stage_ch, concat_ch, layer_per_block, name, SE, depthwise=depthwise))
+        for i in range(block_per_stage - 1):
+            name = 'OSA%d_%d' % (stage_num, i + 2)
+            self.add_module(name, _OSA_module(concat_ch, stage_ch, concat_ch, layer_per_block, name, SE, identity=True, depthwise=depthwise))
+
+    def forward_nhwc(self, x):
+        for m in self.children():
+            x = ops.maxpool3x3s2_ex_nhwc(x, pad=0, ceil_mode=True) if isinstance(m, nn.MaxPool2d) else m.forward_nhwc(x)
+        return x
+
+
+class VoVNet(nn.Module):
+    """The reference's img_backbone for BASELINE config 5 (configs/vov99_dd3d_1600x640_trainval_future.py:14-22:
+    spec_name='V-99-eSE', out_features=['stage2', ..., 'stage5']), same constructor arguments and state-dict keys as
+    /root/reference/models/backbones/vovnet.py:265-359."""
+
+    def __init__(self, spec_name, input_ch=3, out_features=None, frozen_stages=-1, norm_eval=True, with_cp=False, pretrained=None, init_cfg=None):
+        super().__init__()
+        if spec_name not in _VOV_SPECS:
+            raise NotImplementedError('sparsebev_b200 VoVNet: spec %r (the depthwise specs are not implemented)' % (spec_name,))
+        if input_ch != 3:
+            raise NotImplementedError('sparsebev_b200 VoVNet: 3 input channels')
+        spec = _VOV_SPECS[spec_name]
+        stem_ch, stage_ch, concat_ch = spec['stem'], spec['stage_conv_ch'], spec['stage_out_ch']
+        self._out_features = list(out_features) if out_features is not None else ['stage2', 'stage3', 'stage4', 'stage5']
+        stem = conv3x3(input_ch, stem_ch[0], 'stem', '1', 2) + conv3x3(stem_ch[0], stem_ch[1], 'stem', '2', 1) + conv3x3(stem_ch[1], stem_ch[2], 'stem', '3', 2)
+        self.add_module('stem', nn.Sequential(OrderedDict(stem)))
+        if stem_ch[0] != 64:
+            raise NotImplementedError('sparsebev_b200 VoVNet: the 3-channel stem kernel emits 64 channels')
+        self._stem2, self._stem3 = _FusedConv(self.stem[3], self.stem[4]), _FusedConv(self.stem[6], self.stem[7])
+        in_ch = [stem_ch[2]] + concat_ch[:-1]
+        self.stage_names = []
+        for i in range(4):
+            name = 'stage%d' % (i + 2)
+            self.stage_names.append(name)
+            self.add_module(name, _OSA_stage(in_ch[i], stage_ch[i], concat_ch[i], spec['block_per_stage'][i], spec['layer_per_block'], i + 2, True, False))
+        self._stem_key, self._stem_val = None, None
+
+    def _stem1(self):
+        conv, bn = self.stem[0], self.stem[1]
+        ps = [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._stem_key:
+            scale, shift = fold_bn(bn)
+            self._stem_key, self._stem_val = key, (conv.weight.detach().float().permute(2, 3, 1, 0).contiguous(), scale, shift)   # [3,3,3,64]
+        return self._stem_val
+
+    @torch.no_grad()
+    def forward_nhwc(self, img):
+        """img NCHW fp32 [N,3,H,W] -> dict name -> NHWC bf16 (the reference returns a dict too, vovnet.py:327-337)."""
+        if self.training:
+            raise RuntimeError('sparsebev_b200 VoVNet: inference only (call .eval())')
+        w, scale, shift = self._stem1()
+        x = ops.stem_conv(img.float().contiguous(), w, scale, shift)
+        x = self._stem3(self._stem2(x, relu=True), relu=True)
+        outs = {}
+        if 'stem' in self._out_features:
+            outs['stem'] = x
+        for name in self.stage_names:
+            x = getattr(self, name).forward_nhwc(x)
+            if name in self._out_features:
+                outs[name] = x
+        return outs
+
+    def forward(self, img):
+        return {k: to_nchw_f32(v) for k, v in self.forward_nhwc(img).items()}
 
 
 def enable(force=False):
@@ -328,8 +494,10 @@ def enable(force=False):
     architecture-changing kwargs they do not implement (see _reject_unsupported)."""
     from mmdet.models.builder import BACKBONES, NECKS
     BACKBONES.register_module(name='ResNetB200', module=ResNet, force=True)
+    BACKBONES.register_module(name='VoVNetB200', module=VoVNet, force=True)
     NECKS.register_module(name='FPNB200', module=FPN, force=True)
     if force:
+        BACKBONES.register_module(module=VoVNet, force=True)
         BACKBONES.register_module(module=ResNet, force=True)
         NECKS.register_module(module=FPN, force=True)
 

@@ -608,6 +608,44 @@ def maxpool3x3s2_nhwc(x):
     return out
 
 
+def maxpool3x3s2_ex_nhwc(x, pad=0, ceil_mode=True):
+    """3x3 stride-2 max pool, NHWC bf16, torch.nn.MaxPool2d(3, 2, padding=pad, ceil_mode=ceil_mode) semantics."""
+    lib = _lib.load()
+    _chk(x, 'x', torch.bfloat16)
+    N, H, W, C = x.shape
+
+    def osz(s):
+        num = s + 2 * pad - 3
+        o = ((num + 1) // 2 if ceil_mode else num // 2) + 1
+        return o - 1 if (ceil_mode and (o - 1) * 2 >= s + pad) else o
+    out = torch.empty(N, osz(H), osz(W), C, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_maxpool3x3s2_ex_nhwc_fwd(x.data_ptr(), N, H, W, C, int(pad), int(bool(ceil_mode)), out.data_ptr(), _stream()),
+                   'sbev_maxpool3x3s2_ex_nhwc_fwd')
+    return out
+
+
+def ese_nhwc(x, fc_weight, fc_bias, identity=None):
+    """Effective squeeze-excitation (+ optional OSA identity): x NHWC bf16 [N,H,W,C], fc_weight fp32 [C,C], fc_bias fp32 [C]
+    -> x * hsigmoid(fc(mean_hw x)) (+ identity), NHWC bf16."""
+    lib = _lib.load()
+    _chk(x, 'x', torch.bfloat16); _chk(fc_weight, 'fc_weight'); _chk(fc_bias, 'fc_bias')
+    N, H, W, C = x.shape
+    if tuple(fc_weight.shape) != (C, C) or tuple(fc_bias.shape) != (C,):
+        raise RuntimeError('ese_nhwc: fc_weight must be [C,C] and fc_bias [C]')
+    if identity is not None:
+        _chk(identity, 'identity', torch.bfloat16)
+        if identity.shape != x.shape:
+            raise RuntimeError('ese_nhwc: identity must have the shape of x')
+    ws = torch.empty(lib.sbev_ese_workspace_floats(N, H, W, C), device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sbev_ese_nhwc_fwd(x.data_ptr(), N, H, W, C, fc_weight.data_ptr(), fc_bias.data_ptr(), _p(identity), ws.data_ptr(),
+                                         out.data_ptr(), _stream()), 'sbev_ese_nhwc_fwd')
+    _lib.launch_count += 2           # three kernels of ours per call
+    return out
+
+
 def subsample2_nhwc(x):
     lib = _lib.load()
     _chk(x, 'x')

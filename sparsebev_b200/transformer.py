@@ -447,7 +447,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self._graphs.clear()
 
     @torch.no_grad()
-    def _forward_graphed(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+    def _forward_graphed(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas, impl=None):
         """`use_cuda_graph`: the layer's launches (two streams, programmatic dependent launches included) are captured
         once per input signature and replayed.  The signature is everything the capture bakes in: shapes, the ADDRESSES
         of the feature maps (a steady-state inference loop gets the same blocks back from the caching allocator every
@@ -456,7 +456,8 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         time_diff, lidar2img (and the mask) are copied into the graph's static inputs -- host (pinned) or device sources
         alike -- and the three results are returned as copies of the static outputs."""
         meta = img_metas[0]
-        key = (tuple(query_bbox.shape), tuple(query_feat.shape), tuple((f.data_ptr(), tuple(f.shape)) for f in mlvl_feats),
+        impl = impl if impl is not None else self._forward_impl
+        key = (impl.__name__, tuple(query_bbox.shape), tuple(query_feat.shape), tuple((f.data_ptr(), tuple(f.shape)) for f in mlvl_feats),
                self.sampling.feat_layout, None if attn_mask is None else tuple(attn_mask.shape),
                tuple(meta['img_shape'][0]), tuple(meta['time_diff'].shape), tuple(meta['lidar2img'].shape),
                hash(tuple((p.data_ptr(), p._version) for p in self.parameters())), _lib.options_epoch, self.overlap,
@@ -474,7 +475,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
             smeta[0]['time_diff'], smeta[0]['lidar2img'] = static['td'], static['l2i']
             # (no reference to the feature tensors is kept: holding them would stop the allocator from handing the same
             # blocks to the next frame, and a graph whose addresses are never passed again is simply never replayed)
-            run = lambda: self._forward_impl(static['qb'], static['qf'], mlvl_feats, static['mask'], smeta)      # noqa: E731
+            run = lambda: impl(static['qb'], static['qf'], mlvl_feats, static['mask'], smeta)      # noqa: E731
             warm = torch.cuda.Stream(device=dev)           # one eager pass off the capture: weight caches, function attributes
             warm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(warm):
@@ -637,6 +638,9 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
                 raise RuntimeError('DUMP export needs the unsharded decoder layer')
             return self._forward_impl(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
         if self.query_shard is not None and self.query_shard.world > 1:
+            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+                # (every rank captures at the same call: the exchanges inside the graph are plain kernels of ours)
+                return self._forward_graphed(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas, impl=self._forward_qshard)
             return self._forward_qshard(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
         if (self.use_cuda_graph and (self.frame_shard is None or self.frame_shard.world == 1)
                 and not torch.cuda.is_current_stream_capturing()):

@@ -116,3 +116,22 @@ def test_sampling_shims_refuse_to_drop_gradients():
         sampling.sampling_4d(pts.detach(), feats, torch.zeros(1, 2, 4, 1, 4, 1), torch.zeros(1, 6, 4, 4), 8, 8)
     with pytest.raises(RuntimeError, match='forward-only'):
         sampling.make_sample_points(torch.zeros(1, 2, 10), torch.zeros(1, 2, 16, 3, requires_grad=True), [-1, -1, -1, 1, 1, 1])
+
+
+def test_vovnet_mirror_has_the_reference_state_dict(golden_dir):
+    """Key names and shapes of the VoVNet mirror equal those of the REAL reference class (tests/golden/vovnet.npz, written by
+    oracle/gen_golden_vovnet.py from /root/reference/models/backbones/vovnet.py): reference checkpoints load with strict=True."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, 'vovnet.npz'))
+    net = BB.VoVNet('V-99-eSE', out_features=['stage2', 'stage3', 'stage4', 'stage5'], norm_eval=True, frozen_stages=1, with_cp=True)
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g['keys']]
+    assert [str(list(v.shape)) for v in sd.values()] == [str(s) for s in g['shapes']]
+    assert sum(p.numel() for p in net.parameters()) == 69523520
+    # padded-channel bookkeeping of a 160-channel OSA block: 256 + 5 x 160 concat inputs carried as 256 + 5 x 192
+    osa = net.stage3.OSA3_1
+    assert osa._fused[1].in_index == list(range(160)) + [-1] * 32 and osa._fused[1].cout_pad == 192
+    idx = osa._fused_concat.in_index
+    assert len(idx) == 256 + 5 * 192 and [i for i in idx if i >= 0] == list(range(256 + 5 * 160))
+    assert net.stage4.OSA4_1._fused_concat.in_index is None                 # 192-channel stages need no padding

@@ -113,18 +113,19 @@ def _init_backbone(model, seed):
                 m.running_var.copy_(torch.rand(m.bias.shape, generator=g) * 0.5 + 0.75)
 
 
-@pytest.mark.parametrize('num_outs', [4, 5])
-def test_resnet50_fpn_vs_oracle_and_zero_copy_into_decoder_layout(num_outs):
+@pytest.mark.parametrize('depth,num_outs', [(50, 4), (50, 5), (101, 5)])
+def test_resnet_fpn_vs_oracle_and_zero_copy_into_decoder_layout(depth, num_outs):
+    """(50, 4): configs/r50_nuimg_704x256.py:31-45; (101, 5): BASELINE config 4, configs/r101_nuimg_1408x512.py:14-25."""
     import sparsebev_b200 as sb
     from sparsebev_b200 import backbone as BB
-    net = BB.ResNet(depth=50)
+    net = BB.ResNet(depth=depth, with_cp=True)
     neck = BB.FPN([256, 512, 1024, 2048], 256, num_outs)
     _init_backbone(net, 1); _init_backbone(neck, 2)
     net.eval(); neck.eval()
     B, TN, H, W = 1, 6, 64, 96
     img = torch.randn(B, TN, 3, H, W, generator=torch.Generator().manual_seed(5))
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    c = RB.resnet_forward(img.reshape(B * TN, 3, H, W), sd, 50, emulate_bf16=True)
+    c = RB.resnet_forward(img.reshape(B * TN, 3, H, W), sd, depth, emulate_bf16=True)
     want = RB.fpn_forward(c, {k: v.detach().clone() for k, v in neck.state_dict().items()}, num_outs, emulate_bf16=True)
     net.to(dev()); neck.to(dev())
     feats = BB.extract_img_feat(net, neck, img.to(dev()))
@@ -134,7 +135,7 @@ def test_resnet50_fpn_vs_oracle_and_zero_copy_into_decoder_layout(num_outs):
         assert f.shape == (B, TN, 256) + tuple(w_.shape[-2:]) and f.dtype == torch.float32
         assert f.permute(0, 1, 3, 4, 2).is_contiguous()                     # channels-last memory: the gather's zero-copy layout
         err = float((f.reshape(B * TN, 256, *w_.shape[-2:]).cpu() - w_).abs().max() / w_.abs().max())
-        assert err < 2e-2, 'FPN level %d: rel-to-max error %.3e' % (lvl, err)
+        assert err < (2e-2 if depth == 50 else 3e-2), 'FPN level %d: rel-to-max error %.3e' % (lvl, err)
     # the decoder consumes these tensors without a copy
     dec = sb.SparseBEVTransformer(256, num_frames=1, num_points=4, num_layers=1, num_levels=num_outs, pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]).decoder
     lst = list(feats)
@@ -166,3 +167,46 @@ def test_conv2d_wrapper_and_vovnet_style_sequence_drop_in():
     assert float((got_seq.cpu() - want_seq).abs().max() / want_seq.abs().max()) < 1e-2
     with pytest.raises(NotImplementedError):
         BB.Conv2d(64, 64, 3, groups=64).to(dev())(x.to(dev()))             # depthwise: no kernel, and no silent cuDNN fallback
+
+
+def test_maxpool_ceil_mode_and_ese_vs_torch():
+    """VoVNet's non-conv pieces: MaxPool2d(3, 2, ceil_mode=True) incl. odd sizes (window overhang), and the eSE block."""
+    import torch.nn.functional as F
+    from sparsebev_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (H, W, pad, ceil) in ((25, 41, 0, True), (12, 20, 0, True), (6, 10, 0, True), (24, 40, 1, False), (5, 5, 0, True)):
+        x = torch.randn(2, 64, H, W, generator=g).cuda()
+        xb = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        want = F.max_pool2d(xb.float().permute(0, 3, 1, 2), 3, 2, padding=pad, ceil_mode=ceil)
+        got = ops.maxpool3x3s2_ex_nhwc(xb, pad=pad, ceil_mode=ceil)
+        assert got.shape == (2, want.shape[2], want.shape[3], 64)
+        assert torch.equal(got.float().permute(0, 3, 1, 2), want)
+    C = 256
+    x = torch.randn(3, 13, 21, C, generator=g).cuda().to(torch.bfloat16)
+    idt = torch.randn(3, 13, 21, C, generator=g).cuda().to(torch.bfloat16)
+    w, b = (torch.randn(C, C, generator=g) * 0.2).cuda(), torch.randn(C, generator=g).cuda()
+    gate = F.relu6(x.float().mean((1, 2)) @ w.t() + b + 3.0) / 6.0
+    for identity in (None, idt):
+        want = x.float() * gate[:, None, None, :] + (0 if identity is None else identity.float())
+        got = ops.ese_nhwc(x, w, b, identity)
+        assert torch.allclose(got.float(), want, rtol=1e-2, atol=1e-2)          # bf16 output rounding
+
+
+def test_vovnet99_vs_real_reference_golden(golden_dir):
+    """BASELINE config 5's image backbone: the V-99-eSE mirror on our kernels (bf16 operands, fp32 accumulate) against the
+    stage outputs of the REAL reference class run in fp32 on the CPU (tests/golden/vovnet.npz), same seeded weights."""
+    import os
+    import numpy as np
+    from oracle.gen_golden_vovnet import seeded_init, test_image
+    from sparsebev_b200 import backbone as BB
+    g = np.load(os.path.join(golden_dir, 'vovnet.npz'))
+    feats = ['stage2', 'stage3', 'stage4', 'stage5']
+    net = seeded_init(BB.VoVNet('V-99-eSE', out_features=feats), seed=3).cuda().eval()
+    out = net.forward_nhwc(test_image().cuda())
+    for k in feats:
+        want = torch.from_numpy(g[k])
+        got = out[k].float().permute(0, 3, 1, 2).cpu()
+        assert got.shape == want.shape
+        rel = float((got - want).abs().max() / want.abs().max())
+        rms = float((got - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+        assert rel < 6e-2 and rms < 2e-2, '%s: rel-to-max %.3e, relative rms %.3e (bf16 activations through up to 99 convs)' % (k, rel, rms)
