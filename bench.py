@@ -745,6 +745,21 @@ def main():
 
     clk = b.clocks.stop() if rank == 0 else None
 
+    # partitioning A of SURVEY 8(e) (the north star's wording: "NCCL all-gather of per-camera features over NVLink"): what it would cost
+    # to replicate the pyramid instead of keeping frames local -- timed next to the headline, NOT part of it
+    if mode == 'queries' and not emulating:
+        try:
+            from sparsebev_b200 import dist as D
+            local = [f.permute(0, 1, 4, 2, 3) for f in b.feats] if layer.sampling.feat_layout == 'nhwc' else None
+            if local is not None:
+                ag_ms = b.max_over_ranks(event_ms(lambda: D.all_gather_features(local), iters=5, warm=2))
+                extra['feature_allgather'] = {'ms': ag_ms, 'bytes_received_per_gpu': b.feat_bytes * (world - 1),
+                                              'gbs_per_gpu': b.feat_bytes * (world - 1) / (ag_ms * 1e-3) / 1e9, 'per_layer_ms_over_%d_layers' % NUM_DEC_LAYERS: ag_ms / NUM_DEC_LAYERS,
+                                              'note': 'dist.all_gather_features: one NCCL all-gather per FPN level, every rank ends with the whole %d-frame pyramid; '
+                                                      'once per forward (6 layers).  The frame-local partition of the headline never moves the pyramid.' % T}
+        except Exception as exc:                          # pragma: no cover
+            extra['feature_allgather'] = {'error': repr(exc)[:300]}
+
     # second key at N > 1: the reference's own strategy (independent replicas, one scene per GPU), same build
     if mode == 'queries':
         try:

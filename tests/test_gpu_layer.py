@@ -245,7 +245,7 @@ def test_full_size_layer_vs_oracle(name, T):
     assert _rel(exact, taps['sampled']) < 1e-6, 'gather on the oracle\'s points: rel-to-max %.3e' % _rel(exact, taps['sampled'])
     sampled = layer.sampling(qbc, after, gfeats, metas_gpu)
     _rows_within(sampled, taps['sampled'], 5e-5, fragile, 'sampled features')
-    mixed = layer.mixing.forward_fused(taps['sampled'].cuda(), after, layer.norm2)
+    mixed = layer.mixing.forward_fused(taps['sampled'].contiguous().cuda(), after.contiguous(), layer.norm2)
     assert _rel(mixed, taps['mixed']) < 2e-5, 'mixing block rel-to-max %.3e' % _rel(mixed, taps['mixed'])
     q4 = torch.empty(Q, D, device='cuda')
     mx = taps['mixed'].cuda().reshape(Q, D).contiguous()
