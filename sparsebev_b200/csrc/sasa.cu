@@ -432,9 +432,10 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
             for (int c = 0; c < 4; ++c)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a * S3_ARR * 2 + c * 16), "l"(src + c * 8), "r"(nbytes) : "memory");
         }
-        if (mt == 0) {          // the key's normalised centre (x, y) = first 8 bytes of its box, asynchronously like K / V; decoded when consumed
-            const uint32_t kdst = (uint32_t)__cvta_generic_to_shared(buf + 4 * S3_ARR * 2) + lane * 8;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(kdst), "l"(query_bbox + (rowbase + (ok ? key : 0)) * 10), "r"(ok ? 8u : 0u) : "memory");
+        if (mt == 0) {
+            float* kc = reinterpret_cast<float*>(buf + 4 * S3_ARR * 2);
+            kc[lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
+            kc[S3_KT + lane] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + key) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -457,18 +458,9 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
         const __nv_bfloat16* Kl = Kh + S3_ARR;
         const __nv_bfloat16* Vh = Kl + S3_ARR;
         const __nv_bfloat16* Vl = Vh + S3_ARR;
-        const float2* kraw = reinterpret_cast<const float2*>(buf + 4 * S3_ARR * 2);
+        const float* kcx = reinterpret_cast<const float*>(buf + 4 * S3_ARR * 2);
+        const float* kcy = kcx + S3_KT;
         const int k0 = tile * S3_KT;
-        // this thread's 8 keys of the tile (columns 8n + 2*t4 + e): decode_bbox centre, separate multiply and add as in torch
-        float kcx[4][2], kcy[4][2];
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float2 c = kraw[8 * n + 2 * t4 + e];
-                kcx[n][e] = __fadd_rn(__fmul_rn(c.x, __fsub_rn(x_hi, x_lo)), x_lo);
-                kcy[n][e] = __fadd_rn(__fmul_rn(c.y, __fsub_rn(y_hi, y_lo)), y_lo);
-            }
 
         float sacc[4][4];
 #pragma unroll
@@ -492,7 +484,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int k = 8 * n + 2 * t4 + e;
-                    const float dx = rcx[r] - kcx[n][e], dy = rcy[r] - kcy[n][e];
+                    const float dx = rcx[r] - kcx[k], dy = rcy[r] - kcy[k];
                     float v = sacc[n][2 * r + e] * scale + (-sa_sqrt(dx * dx + dy * dy)) * rtau[r];
                     if (HAS_MASK && gq < qb && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
                     if (k0 + k >= Q) v = -INFINITY;
