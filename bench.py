@@ -353,7 +353,10 @@ class Bench:
         S, a = self.S, self.args
         if self.mode in ('queries', 'frames'):                       # ONE scene; this rank's frame window only
             t0, t1 = self.shard.window
-            return [f[:, t0 * 6:t1 * 6].contiguous() for f in S.make_feats(a.config, self.T, batch=1, seed=100, memory_format=self.fmt)]
+            full = S.make_feats(a.config, self.T, batch=1, seed=100, memory_format=self.fmt)
+            if self.fmt == 'nhwc':               # keep the channels-last memory of the window (a plain .contiguous() would re-lay it out as NCHW)
+                return [f.permute(0, 1, 3, 4, 2)[:, t0 * 6:t1 * 6].contiguous().permute(0, 1, 4, 2, 3) for f in full]
+            return [f[:, t0 * 6:t1 * 6].contiguous() for f in full]
         return S.make_feats(a.config, self.T, batch=1, seed=100 + (self.rank if self.mode == 'scenes' else 0), memory_format=self.fmt)
 
     def setup_sharding(self):
@@ -751,7 +754,9 @@ def main():
         try:
             from sparsebev_b200 import dist as D
             local = [f.permute(0, 1, 4, 2, 3) for f in b.feats] if layer.sampling.feat_layout == 'nhwc' else None
-            if local is not None:
+            if local is None:
+                extra['feature_allgather'] = {'skipped': 'needs the channels-last layout (got %r)' % (layer.sampling.feat_layout,)}
+            else:
                 ag_ms = b.max_over_ranks(event_ms(lambda: D.all_gather_features(local), iters=5, warm=2))
                 extra['feature_allgather'] = {'ms': ag_ms, 'bytes_received_per_gpu': b.feat_bytes * (world - 1),
                                               'gbs_per_gpu': b.feat_bytes * (world - 1) / (ag_ms * 1e-3) / 1e9, 'per_layer_ms_over_%d_layers' % NUM_DEC_LAYERS: ag_ms / NUM_DEC_LAYERS,
