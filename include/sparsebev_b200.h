@@ -63,6 +63,9 @@ const char* sbev_last_error(void);
  *   "legacy_rotation" 0 = v1.0.0 box convention (default); 1 = the sample-point rotation of checkpoints whose `version` is 'v0.17.1'
  *                    (models/utils.py:66-71: rotation_3d_in_axis turns the other way; toggled like the reference's global
  *                    VERSION.name, val.py:128-129) -- affects sbev_sample_points_fwd and sbev_dense_chain_points_fwd
+ *   "dense_ws"       which chains the host mirror (ops.dense_chain / dense_chain_reduce) sends to the weights-stationary cluster kernel
+ *                    (sbev_dense_chain_ws_*): 0 = none, 1 = every chain it can express (default), 2 = only chains of <= 256 rows
+ *   "dense_ws_rt"    rows per tile of that kernel: 0 = automatic (default), 16, 32
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time; 3 = 2 + the next level pair's lines are prefetched
  *                    into L2; 4 = 2 + level blocks in which no point of the warp has a live tap are skipped by a warp-uniform
@@ -298,6 +301,31 @@ int sbev_dense_chain_reduce_fwd(const float* partial, int nsplit, const float* b
                                 int M, int n_layers, const sbev_dense_layer* layers,
                                 const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
                                 void* stream);
+
+/* WEIGHTS-STATIONARY form of the two chain entry points above (same layers, same epilogues, same results to fp32 round-off;
+ * replaces the same reference lines): a cluster of 8 CTAs owns a block of rows and splits every layer's OUTPUT FEATURES 8 ways, each
+ * CTA keeping its slice of ALL layers' weights resident in shared memory (one bulk copy, issued under the previous kernel's tail),
+ * layer outputs exchanged through distributed shared memory.  No CTA streams a whole chain's weights, so the time scales with the
+ * row count instead of being pinned at 9-20 us by per-SM ingest (csrc/dense_ws.cu).
+ *   blob: the chain's weights pre-sliced per CTA rank c = 0..7, rank stride blob_stride_bytes (>= sbev_dense_chain_ws_blob_bytes,
+ *   multiple of 128, 128-byte aligned).  Rank c, layer i (layers back to back): [Kpad_i / 64][hi | lo][SW_i rows][64 k] bf16 with
+ *   SW_i = ceil(N_i / 8) rounded up to 8, row j = output feature c * SW_i + j (zero rows beyond N_i), every 128-byte row stored with its
+ *   16-byte chunks XOR-swizzled by (j & 7).  Only K, Kpad, N, bias, ln_w, ln_b, residual, flags, y, ldy, y_hi, y_lo of the layers are used.
+ * Limits: Kpad <= 512; a layer that feeds another one or ends in LayerNorm needs N <= 512, N % 4 == 0 and 16-byte aligned operands;
+ * the blob plus one row tile must fit 226 KB of shared memory (SBEV_ERR_UNSUPPORTED otherwise -- callers then use the streaming chain);
+ * the reduce prologue handles K0 == 256.  Option "dense_ws_rt": rows per tile (0 = automatic, 16, 32).
+ */
+long long sbev_dense_chain_ws_blob_bytes(int n_layers, const sbev_dense_layer* layers);
+int sbev_dense_chain_ws_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
+                            const uint16_t* blob, long long blob_stride_bytes,
+                            const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                            void* stream);
+int sbev_dense_chain_ws_reduce_fwd(const float* partial, int nsplit, const float* bias, const float* residual,
+                                   const float* ln_w, const float* ln_b, float* x_out,
+                                   int M, int n_layers, const sbev_dense_layer* layers,
+                                   const uint16_t* blob, long long blob_stride_bytes,
+                                   const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,
+                                   void* stream);
 
 /* Sampling head epilogue: box decode + offset scaling + yaw rotation + softmax over levels.
  * Replaces make_sample_points (models/sparsebev_sampling.py:8-24), decode_bbox (models/bbox/utils.py:63-77),

@@ -37,6 +37,9 @@ SIGNATURES = {
     'sbev_dense_chain_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_dense_chain_points_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'sbev_dense_chain_reduce_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
+    'sbev_dense_chain_ws_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, ctypes.c_longlong, c_vp, c_vp, c_int, c_int, c_vp],
+    'sbev_dense_chain_ws_reduce_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, ctypes.c_longlong,
+                                       c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_msmv_fwd': [c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     'sbev_msmv_bwd': [c_vp, c_vpp, c_i32p, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                       c_vpp, c_vp, c_vp, c_vp],
@@ -87,7 +90,8 @@ _lib = None
 
 
 def exported_symbols():
-    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option', 'sbev_msmv_bwd_det_workspace', 'sbev_ese_workspace_floats'])
+    return sorted(list(SIGNATURES) + ['sbev_abi_version', 'sbev_last_error', 'sbev_get_option', 'sbev_msmv_bwd_det_workspace', 'sbev_ese_workspace_floats',
+                                             'sbev_dense_chain_ws_blob_bytes'])
 
 
 def load():
@@ -111,6 +115,8 @@ def load():
     lib.sbev_msmv_bwd_det_workspace.restype = ctypes.c_longlong
     lib.sbev_ese_workspace_floats.argtypes = [c_int, c_int, c_int, c_int]
     lib.sbev_ese_workspace_floats.restype = ctypes.c_longlong
+    lib.sbev_dense_chain_ws_blob_bytes.argtypes = [c_int, ctypes.POINTER(DenseLayer)]
+    lib.sbev_dense_chain_ws_blob_bytes.restype = ctypes.c_longlong
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(CSRC, 'libsparsebev_b200.so')
-SOURCES = ['common.cu', 'msmv.cu', 'dense.cu', 'sasa.cu', 'mix.cu', 'gemm_tcgen05.cu', 'conv_tcgen05.cu', 'peer.cu', 'pool.cu']
+SOURCES = ['common.cu', 'msmv.cu', 'dense.cu', 'dense_ws.cu', 'sasa.cu', 'mix.cu', 'gemm_tcgen05.cu', 'conv_tcgen05.cu', 'peer.cu', 'pool.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -3,6 +3,7 @@
 PyTorch here is plumbing only: allocation, stream handle, dtype/contiguity checks.  Every function
 launches hand-written sm_100a kernels through libsparsebev_b200.so; nothing falls back to eager torch.
 """
+import collections
 import ctypes
 
 import torch
@@ -260,25 +261,120 @@ def pack_weight_tiles(w_hi, w_lo):
     return torch.stack([one(w_hi), one(w_lo)], dim=2).contiguous()                       # [nb, kc, 2, 128, 8, 8]
 
 
+class _ChainEntry(tuple):
+    """(sbev_dense_layer struct, tensors to keep alive) + the bf16 (hi, lo) weights the entry was built from."""
+    w_hi = w_lo = None
+
+
 def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None,
                 w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None, w_pack=None):
     """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path; w_pack
     (pack_weight_tiles) its bulk-copy weight stream."""
     flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
     keep = [t for t in (wt, bias, residual, y, w_hi, w_lo, y_hi, y_lo, w_pack) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
-    return _lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
-                           _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
-                           (ldy if ldy is not None else N) if (y is not None or y_hi is not None) else 0, _p(w_hi), _p(w_lo), kpad,
-                           _p(y_hi), _p(y_lo), _p(w_pack)), keep
+    e = _ChainEntry((_lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
+                                     _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
+                                     (ldy if ldy is not None else N) if (y is not None or y_hi is not None) else 0, _p(w_hi), _p(w_lo), kpad,
+                                     _p(y_hi), _p(y_lo), _p(w_pack)), keep))
+    e.w_hi, e.w_lo = w_hi, w_lo
+    return e
+
+
+WS_CLUSTER = 8                       # CTAs per cluster of the weights-stationary chain kernel (csrc/dense_ws.cu)
+WS_SMEM_CAP = 226 * 1024
+
+
+def ws_slice_width(N):
+    """Output features per CTA of a layer in the weights-stationary chain: ceil(N / 8) rounded up to the MMA's 8-feature tile."""
+    return ((N + WS_CLUSTER - 1) // WS_CLUSTER + 7) // 8 * 8
+
+
+def pack_ws_blob(weights):
+    """[(w_hi, w_lo)] (bf16 [N_i][Kpad_i], Kpad % 64 == 0) of a chain -> (blob uint8 [8][stride], stride): the per-CTA weight slices
+    of sbev_dense_chain_ws_fwd -- rank c, layers back to back, each [Kpad/64][hi|lo][SW rows][64 k] with row j = feature c * SW + j
+    (zero beyond N) and the 16-byte chunks of every 128-byte row XOR-swizzled by (j & 7)."""
+    dev = weights[0][0].device
+    parts = []
+    for w_hi, w_lo in weights:
+        N, Kp = w_hi.shape
+        SW, kc = ws_slice_width(N), Kp // 64
+        j = torch.arange(SW, device=dev)
+        src_chunk = torch.arange(8, device=dev)[None, :] ^ (j[:, None] & 7)            # stored position p of row j holds chunk p ^ (j & 7)
+
+        def one(w):
+            wp = torch.zeros(WS_CLUSTER * SW, Kp, device=dev, dtype=w.dtype)
+            wp[:N] = w
+            t = wp.view(WS_CLUSTER, SW, kc, 8, 8).permute(0, 2, 1, 3, 4)                # [c, kc, row, chunk, elem]
+            return t[:, :, j[:, None], src_chunk, :]                                    # [c, kc, row, position, elem]
+        both = torch.stack([one(w_hi), one(w_lo)], dim=2).contiguous()                  # [c, kc, 2, SW, 8, 8]
+        parts.append(both.view(WS_CLUSTER, -1).view(torch.uint8))
+    blob = torch.cat(parts, dim=1)
+    stride = (blob.shape[1] + 127) // 128 * 128
+    out = torch.zeros(WS_CLUSTER, stride, device=dev, dtype=torch.uint8)
+    out[:, :blob.shape[1]] = blob
+    return out, stride
+
+
+_ws_blobs = collections.OrderedDict()        # (id(w_hi), ...) -> (blob, stride, [w_hi, ...] kept alive so the ids stay unique)
+
+
+def _ws_blob(layers):
+    key = tuple(id(l.w_hi) for l in layers)
+    hit = _ws_blobs.get(key)
+    if hit is None:
+        blob, stride = pack_ws_blob([(l.w_hi, l.w_lo) for l in layers])
+        hit = (blob, stride, [l.w_hi for l in layers])
+        _ws_blobs[key] = hit
+        while len(_ws_blobs) > 64:
+            _ws_blobs.popitem(last=False)
+    else:
+        _ws_blobs.move_to_end(key)
+    return hit[0], hit[1]
+
+
+def ws_eligible(M, layers, reduce_k0=None):
+    """Can the weights-stationary cluster kernel run this chain (the limits listed at sbev_dense_chain_ws_fwd), and does option
+    "dense_ws" (1 = every such chain, 2 = only chains of <= 256 rows) send it there?"""
+    mode = _lib.get_option('dense_ws')
+    if mode == 0 or (mode == 2 and M > 256) or M == 0 or not (1 <= len(layers) <= 6):
+        return False
+    if any(getattr(l, 'w_hi', None) is None or not l.w_hi.is_cuda for l in layers):
+        return False
+    if reduce_k0 is not None and reduce_k0 != 256:
+        return False
+    blob_bytes, kmax, nex = 0, 64, (252 if reduce_k0 is not None else 4)
+    for i, l in enumerate(layers):
+        d = l[0]
+        last = i + 1 == len(layers)
+        exchange = not (last and not d.ln_w)
+        if d.Kpad > 512 or d.Kpad % 64:
+            return False
+        if exchange:
+            if d.N > 512 or d.N % 4 or (d.flags & DENSE_REFINE) or ((d.y or d.y_hi) and d.ldy % 4):
+                return False
+            if any((p or 0) % 16 for p in (d.ln_w, d.ln_b, d.residual, d.y)) or any((p or 0) % 8 for p in (d.y_hi, d.y_lo)):
+                return False
+            nex = max(nex, d.N)
+        blob_bytes += (d.Kpad // 64) * 2 * ws_slice_width(d.N) * 128
+        kmax = max(kmax, d.Kpad)
+    smem16 = (blob_bytes + 1023) // 1024 * 1024 + 2 * 16 * (kmax + 8) * 2 + 16 * (nex + 4) * 4 + 1024
+    return smem16 <= WS_SMEM_CAP
 
 
 def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):
-    """Run 1..6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers in ONE kernel (sbev_dense_chain_fwd).
-    `layers` = list of chain_layer(...) results; outputs are the `y` tensors given to them."""
+    """Run 1..6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers in ONE kernel: the weights-stationary cluster kernel
+    (sbev_dense_chain_ws_fwd) when it can express the chain and option "dense_ws" selects it, else the row-group kernel that
+    streams the weights (sbev_dense_chain_fwd).  `layers` = list of chain_layer(...) results; outputs are the `y` tensors given to them."""
     lib = _lib.load()
     _chk(x, 'x')
     arr = (_lib.DenseLayer * len(layers))(*[l[0] for l in layers])
     with torch.cuda.device(x.device):
+        if ws_eligible(M, layers):
+            blob, stride = _ws_blob(layers)
+            _lib.check(lib.sbev_dense_chain_ws_fwd(x.data_ptr(), ldx, M, len(layers), arr, blob.data_ptr(), stride,
+                                                   _p(refine_proposal), _p(refine_time_diff), refine_Q, refine_T, _stream()),
+                       'sbev_dense_chain_ws_fwd')
+            return
         _lib.check(lib.sbev_dense_chain_fwd(x.data_ptr(), ldx, M, len(layers), arr, _p(refine_proposal), _p(refine_time_diff),
                                             refine_Q, refine_T, _stream()), 'sbev_dense_chain_fwd')
 
@@ -309,6 +405,13 @@ def dense_chain_reduce(partial, bias, residual, ln_w, ln_b, x_out, layers, refin
     _chk(x_out, 'x_out')
     arr = (_lib.DenseLayer * len(layers))(*[l[0] for l in layers])
     with torch.cuda.device(partial.device):
+        if ws_eligible(M, layers, reduce_k0=K0) and all(t is None or t.data_ptr() % 16 == 0 for t in (partial, bias, residual, ln_w, ln_b, x_out)):
+            blob, stride = _ws_blob(layers)
+            _lib.check(lib.sbev_dense_chain_ws_reduce_fwd(partial.data_ptr(), S, _p(bias), _p(residual), _p(ln_w), _p(ln_b), x_out.data_ptr(),
+                                                          M, len(layers), arr, blob.data_ptr(), stride,
+                                                          _p(refine_proposal), _p(refine_time_diff), refine_Q, refine_T, _stream()),
+                       'sbev_dense_chain_ws_reduce_fwd')
+            return
         _lib.check(lib.sbev_dense_chain_reduce_fwd(partial.data_ptr(), S, _p(bias), _p(residual), _p(ln_w), _p(ln_b), x_out.data_ptr(),
                                                    M, len(layers), arr, _p(refine_proposal), _p(refine_time_diff), refine_Q, refine_T,
                                                    _stream()), 'sbev_dense_chain_reduce_fwd')
