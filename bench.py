@@ -62,6 +62,8 @@ def parse():
     ap.add_argument('--emulate-world', type=int, default=0, metavar='N', help='development: ONE GPU plays rank --emulate-rank of an N-GPU `--shard queries` run '
                     '(no peers; rank-local kernel sequence only, for ncu) -- the line is marked "emulated" and is not a benchmark result')
     ap.add_argument('--emulate-rank', type=int, default=0)
+    ap.add_argument('--timeline', default=None, metavar='FILE', help='development: after the headline, record the kernel timeline of 3 more steps with '
+                    'torch.profiler (CUPTI: true start / end of every kernel incl. the concurrent branches) and write the last step\'s kernels to FILE')
     return ap.parse_args()
 
 
@@ -426,6 +428,30 @@ class Bench:
         self.clocks = clocks
         return self.ms_per_step
 
+    def timeline(self, path, steps=3):
+        """Kernel timeline of `steps` more steps (development aid, never part of a reported number): torch.profiler's CUDA activity
+        records = CUPTI start / duration of every kernel, graph replays included; the LAST step's kernels are written to `path`."""
+        from torch.profiler import profile, ProfilerActivity
+        run_step = self.graph.replay if self.graph is not None else self.step
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(steps):
+                run_step()
+                torch.cuda.synchronize()
+        ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
+        ev.sort(key=lambda e: e.time_range.start)
+        if not ev:
+            json.dump({'error': 'no CUDA activity records'}, open(path, 'w'))
+            return
+        # split into steps at the largest gaps (the host synchronises between steps)
+        gaps = sorted(range(1, len(ev)), key=lambda i: ev[i].time_range.start - ev[i - 1].time_range.end, reverse=True)[:steps - 1]
+        first = max(gaps) if gaps else 0
+        last = ev[first:]
+        t0 = last[0].time_range.start
+        rows = [{'name': e.name[:70], 'start_us': round(e.time_range.start - t0, 2), 'dur_us': round(e.time_range.end - e.time_range.start, 2),
+                 'stream': getattr(e, 'device_resource_id', None)} for e in last]
+        json.dump({'step_us': round(last[-1].time_range.end - t0, 2), 'kernels': rows}, open(path, 'w'), indent=1)
+
     # ---- e2e: the reference-facing call with HOST buffers
     def e2e(self):
         """One SparseBEVTransformer.forward(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas) per step -- the call
@@ -704,6 +730,11 @@ def main():
     b = Bench(args, S, cfg)
     rank, world, mode, layer = b.rank, b.world, b.mode, b.layer
     ms_per_step = b.headline()
+    if args.timeline and rank == 0:
+        try:
+            b.timeline(args.timeline)
+        except Exception as exc:                          # pragma: no cover
+            json.dump({'error': repr(exc)[:500]}, open(args.timeline, 'w'))
     scenes = world if mode == 'scenes' else 1
     value = scenes * 1e3 / ms_per_step
     T, Q = b.T, b.Q

@@ -41,6 +41,8 @@ const char* sbev_last_error(void);
  *                    (sbev_gemm_bf16_tn_split, K = 256) stays on single CTAs (pairs measured slower there);
  *                    2 = CTA pairs for both; 3 = single CTAs for both; 1 = single CTAs + A-resident schedule for
  *                    small-K / many-N GEMMs (measured slower)
+ *                    5 = as 0, but the bf16-pair-output GEMM runs as CTA pairs with a THREE-stage operand ring (64 KB stages, single
+ *                    epilogue staging) instead of single CTAs with two 96 KB stages
  *   "mix_impl"       0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "sasa_impl"      0 = mma.sync bf16x3 (default), 1 = fp32 FFMA
  *   "dense_impl"     0 = mma.sync bf16x3 chain with TMA-streamed weights (default), 1 = fp32 FFMA chain
@@ -65,7 +67,7 @@ const char* sbev_last_error(void);
  *                    VERSION.name, val.py:128-129) -- affects sbev_sample_points_fwd and sbev_dense_chain_points_fwd
  *   "dense_ws"       which chains the host mirror (ops.dense_chain / dense_chain_reduce) sends to the weights-stationary cluster kernel
  *                    (sbev_dense_chain_ws_*): 0 = none, 1 = every chain it can express (default), 2 = only chains of <= 256 rows
- *   "dense_ws_rt"    rows per tile of that kernel: 0 = automatic (default), 16, 32
+ *   "dense_ws_groups" independent 16-row groups per CTA of that kernel: 0 = automatic (two when their buffers fit; default), 1, 2
  *   "gather_variant" 0 = 16 lanes/point, all levels in flight; 1 = 16 lanes/point, two levels at a time, 3 CTAs/SM;
  *                    2 = 8 lanes/point x 8 channels, two levels at a time; 3 = 2 + the next level pair's lines are prefetched
  *                    into L2; 4 = 2 + level blocks in which no point of the warp has a live tap are skipped by a warp-uniform
@@ -240,6 +242,9 @@ int sbev_peer_exchange(const sbev_peer_segment* segs, int nseg, int n_peers, int
 #define SBEV_DENSE_RELU        1
 #define SBEV_DENSE_RES_PRE_LN  2
 #define SBEV_DENSE_REFINE      4   /* chain only: box refinement epilogue, see sbev_dense_chain_fwd */
+#define SBEV_DENSE_WIDE_CTA    8   /* chain only, a HINT on the FIRST layer: 16 rows per CTA instead of 8 (half as many CTAs stream the
+                                      weights) -- for two chains that run side by side on two streams (cls || reg) so that both fit on the
+                                      SMs at once; honoured by the streaming tensor-core chain when every K, N <= 256, ignored otherwise */
 int sbev_dense_fwd(const float* x, int ldx, const float* Wt, int ldw, const float* bias,
                    const float* ln_w, const float* ln_b, const float* residual,
                    int M, int K, int N, int flags, float* y, void* stream);
@@ -305,17 +310,21 @@ int sbev_dense_chain_reduce_fwd(const float* partial, int nsplit, const float* b
 /* WEIGHTS-STATIONARY form of the two chain entry points above (same layers, same epilogues, same results to fp32 round-off;
  * replaces the same reference lines): a cluster of 8 CTAs owns a block of rows and splits every layer's OUTPUT FEATURES 8 ways, each
  * CTA keeping its slice of ALL layers' weights resident in shared memory (one bulk copy, issued under the previous kernel's tail),
- * layer outputs exchanged through distributed shared memory.  No CTA streams a whole chain's weights, so the time scales with the
+ * layer outputs exchanged through distributed shared memory (bulk shared->peer copies counted on the receiver's mbarrier).  No CTA streams a whole chain's weights, so the time scales with the
  * row count instead of being pinned at 9-20 us by per-SM ingest (csrc/dense_ws.cu).
  *   blob: the chain's weights pre-sliced per CTA rank c = 0..7, rank stride blob_stride_bytes (>= sbev_dense_chain_ws_blob_bytes,
  *   multiple of 128, 128-byte aligned).  Rank c, layer i (layers back to back): [Kpad_i / 64][hi | lo][SW_i rows][64 k] bf16 with
  *   SW_i = ceil(N_i / 8) rounded up to 8, row j = output feature c * SW_i + j (zero rows beyond N_i), every 128-byte row stored with its
  *   16-byte chunks XOR-swizzled by (j & 7).  Only K, Kpad, N, bias, ln_w, ln_b, residual, flags, y, ldy, y_hi, y_lo of the layers are used.
  * Limits: Kpad <= 512; a layer that feeds another one or ends in LayerNorm needs N <= 512, N % 4 == 0 and 16-byte aligned operands;
- * the blob plus one row tile must fit 226 KB of shared memory (SBEV_ERR_UNSUPPORTED otherwise -- callers then use the streaming chain);
- * the reduce prologue handles K0 == 256.  Option "dense_ws_rt": rows per tile (0 = automatic, 16, 32).
+ * the blob plus one 16-row group's buffers must fit 226 KB of shared memory (SBEV_ERR_UNSUPPORTED otherwise -- callers then use the streaming chain);
+ * the reduce prologue handles K0 == 256 and needs a last layer that ends in LayerNorm.
  */
 long long sbev_dense_chain_ws_blob_bytes(int n_layers, const sbev_dense_layer* layers);
+/* Diagnostics: while `stamps` (device memory, 64 x 8 bytes per CTA of the largest launch, zero-filled by the caller) is set, thread 0 of
+ * every CTA records clock64() at the kernel's phase boundaries (entry, barriers up, predecessor done, cluster up, rows staged, weights
+ * landed, then per layer: MMAs done / slice sent / slices received / rows finished, ..., work done, exit).  NULL switches it off. */
+int sbev_dense_chain_ws_debug(unsigned long long* stamps);
 int sbev_dense_chain_ws_fwd(const float* x, int ldx, int M, int n_layers, const sbev_dense_layer* layers,
                             const uint16_t* blob, long long blob_stride_bytes,
                             const float* refine_proposal, const float* refine_time_diff, int refine_Q, int refine_T,

@@ -37,6 +37,7 @@ SIGNATURES = {
     'sbev_dense_chain_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_dense_chain_points_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_f32p, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'sbev_dense_chain_reduce_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, c_vp, c_int, c_int, c_vp],
+    'sbev_dense_chain_ws_debug': [c_vp],
     'sbev_dense_chain_ws_fwd': [c_vp, c_int, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, ctypes.c_longlong, c_vp, c_vp, c_int, c_int, c_vp],
     'sbev_dense_chain_ws_reduce_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(DenseLayer), c_vp, ctypes.c_longlong,
                                        c_vp, c_vp, c_int, c_int, c_vp],

@@ -416,20 +416,23 @@ __device__ __forceinline__ void mc_mma(float (&d)[4], const uint32_t (&a)[4], co
 // SAME weight tiles: CTA r fetches rows [r*128/CL, (r+1)*128/CL) of each tile and TMA-multicasts them into the
 // shared memory of all CL CTAs, so every weight byte leaves L2 once per cluster instead of once per CTA.  A stage is
 // refilled only after the consumers of ALL CL CTAs released it (each consumer warp arrives on every CTA's barrier).
-template <int CL>
+// R = rows per CTA (8, or 16 = two n8 MMA tiles per warp: half as many CTAs stream the weights -- for chains that run side by side
+// with another chain on a second stream, cls || reg, so that both fit on the 148 SMs at once); XLD / YLD = row strides of the
+// activation operand / the layer output (the 16-row form is instantiated for K, N <= 256 only: its buffers must fit shared memory).
+template <int CL, int R = DENSE_ROWS, int XLD = MC_XLD, int YLD = MC_YLD>
 __global__ void __launch_bounds__(288, 1)
 dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_constant__ ChainMaps maps) {
     extern __shared__ uint8_t mc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* wring = smem;                                                             // [STAGES][hi tile | lo tile]
-    __nv_bfloat16* xbuf = reinterpret_cast<__nv_bfloat16*>(smem + MC_STAGES * 2 * MC_TILE_BYTES);   // [2 ping-pong][hi,lo][8][MC_XLD]
-    float* ys = reinterpret_cast<float*>(xbuf + 2 * 2 * DENSE_ROWS * MC_XLD);          // [8][MC_YLD]
-    float* vecs = ys + DENSE_ROWS * MC_YLD;                                            // [3][CHAIN_VEC_LD]  bias | ln_w | ln_b of the layer
+    __nv_bfloat16* xbuf = reinterpret_cast<__nv_bfloat16*>(smem + MC_STAGES * 2 * MC_TILE_BYTES);   // [2 ping-pong][hi,lo][R][XLD]
+    float* ys = reinterpret_cast<float*>(xbuf + 2 * 2 * R * XLD);                      // [R][YLD]
+    float* vecs = ys + R * YLD;                                            // [3][CHAIN_VEC_LD]  bias | ln_w | ln_b of the layer
     float* resb = vecs + 3 * CHAIN_VEC_LD;                                             // [8][MC_RES_LD]     residual rows of the layer
     __shared__ uint64_t full_bar[MC_STAGES], empty_bar[MC_STAGES];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * DENSE_ROWS;
+    const int row0 = blockIdx.x * R;
     if (tid == 0) {
         for (int s = 0; s < MC_STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(&full_bar[s])), "r"(1));
@@ -444,9 +447,10 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     if (prm.in_partial != nullptr) {
         // input stage: warp w reduces the split-K partials of row row0 + w (K0 = 128 or 256 columns: 1 or 2 float4 per lane),
         // adds bias + residual, LayerNorms (two-pass, like torch), stores the fp32 row and stages it as bf16 (hi, lo)
-        if (warp < DENSE_ROWS) {
+        if (warp < 8)
+        for (int rr = warp; rr < R; rr += 8) {
             const int K0 = prm.layer[0].K, per = K0 >> 7;
-            const int row = row0 + warp;
+            const int row = row0 + rr;
             const bool live = row < prm.M;
             const long long zs = (long long)prm.M * K0;
             float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -491,8 +495,8 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         acc[i].z = (acc[i].z - mean) * rstd * g.z + b.z; acc[i].w = (acc[i].w - mean) * rstd * g.w + b.w;
                     }
             }
-            __nv_bfloat16* xh = xbuf + warp * MC_XLD;
-            __nv_bfloat16* xl = xh + DENSE_ROWS * MC_XLD;
+            __nv_bfloat16* xh = xbuf + rr * XLD;
+            __nv_bfloat16* xl = xh + R * XLD;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
                 if (i < per) {
@@ -511,27 +515,27 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     {
         const int K0 = prm.layer[0].K, K0p = (K0 + 63) & ~63;
         __nv_bfloat16* xh = xbuf;
-        __nv_bfloat16* xl = xbuf + DENSE_ROWS * MC_XLD;
+        __nv_bfloat16* xl = xbuf + R * XLD;
         if ((K0 & 63) == 0 && (prm.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.x) & 15) == 0) {
             const int k4 = K0 >> 2;
-            for (int i = tid; i < DENSE_ROWS * k4; i += 288) {
+            for (int i = tid; i < R * k4; i += 288) {
                 const int r = i / k4, k = (i - r * k4) * 4;
                 const float4 v = (row0 + r < prm.M) ? ldg4(prm.x + (long long)(row0 + r) * prm.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                 uint32_t h0, l0, h1, l1;
                 mc_split2(v.x, v.y, h0, l0); mc_split2(v.z, v.w, h1, l1);
-                *reinterpret_cast<uint2*>(xh + r * MC_XLD + k) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(xl + r * MC_XLD + k) = make_uint2(l0, l1);
+                *reinterpret_cast<uint2*>(xh + r * XLD + k) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(xl + r * XLD + k) = make_uint2(l0, l1);
             }
         } else
-        for (int i = tid; i < DENSE_ROWS * (K0p / 2); i += 288) {
+        for (int i = tid; i < R * (K0p / 2); i += 288) {
             const int r = i / (K0p / 2), k = (i - r * (K0p / 2)) * 2;
             const bool ok = row0 + r < prm.M;
             const float a = (ok && k < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k) : 0.f;
             const float b = (ok && k + 1 < K0) ? __ldg(prm.x + (long long)(row0 + r) * prm.ldx + k + 1) : 0.f;
             uint32_t h, l;
             mc_split2(a, b, h, l);
-            *reinterpret_cast<uint32_t*>(xh + r * MC_XLD + k) = h;
-            *reinterpret_cast<uint32_t*>(xl + r * MC_XLD + k) = l;
+            *reinterpret_cast<uint32_t*>(xh + r * XLD + k) = h;
+            *reinterpret_cast<uint32_t*>(xl + r * XLD + k) = l;
         }
     }
     __syncthreads();
@@ -584,8 +588,8 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
     for (int li = 0; li < prm.n_layers; ++li) {
         const ChainLayer& L = prm.layer[li];
         const int kchunks = (L.K + 63) >> 6, nblocks = (L.N + 127) >> 7;
-        const __nv_bfloat16* xh = xbuf + ping * 2 * DENSE_ROWS * MC_XLD;
-        const __nv_bfloat16* xl = xh + DENSE_ROWS * MC_XLD;
+        const __nv_bfloat16* xh = xbuf + ping * 2 * R * XLD;
+        const __nv_bfloat16* xl = xh + R * XLD;
         // epilogue operands of this layer -> shared memory, asynchronously (LDGSTS), while the GEMM below runs
         const bool res_staged = L.residual != nullptr && L.N <= MC_RES_LD;
         {
@@ -602,7 +606,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                     if (L.ln_w) { cp16(vecs + CHAIN_VEC_LD + 4 * g, L.ln_w + 4 * g); cp16(vecs + 2 * CHAIN_VEC_LD + 4 * g, L.ln_b + 4 * g); }
                 }
                 if (res_staged)
-                    for (int i = tid; i < DENSE_ROWS * n4; i += 256) {
+                    for (int i = tid; i < R * n4; i += 256) {
                         const int r = i / n4, g = i - r * n4;
                         if (row0 + r < prm.M) cp16(resb + r * MC_RES_LD + 4 * g, L.residual + (long long)(row0 + r) * L.N + 4 * g);
                     }
@@ -612,7 +616,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                 if (L.ln_w) { cp4(vecs + CHAIN_VEC_LD + n, L.ln_w + n); cp4(vecs + 2 * CHAIN_VEC_LD + n, L.ln_b + n); }
             }
             if (res_staged)
-                for (int i = tid; i < DENSE_ROWS * L.N; i += 256) {
+                for (int i = tid; i < R * L.N; i += 256) {
                     const int r = i / L.N, n = i - r * L.N;
                     if (row0 + r < prm.M) cp4(resb + r * MC_RES_LD + n, L.residual + (long long)(row0 + r) * L.N + n);
                 }
@@ -620,14 +624,17 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         {
-            const uint32_t xh_addr = dsmem_u32(xh + lm_r * MC_XLD + 8 * (lm_id & 1));
-            const uint32_t xl_addr = dsmem_u32(xl + lm_r * MC_XLD + 8 * (lm_id & 1));
+            constexpr int NT = R / 8;                                     // n8 row tiles per warp
+            const uint32_t xh_addr = dsmem_u32(xh + lm_r * XLD + 8 * (lm_id & 1));
+            const uint32_t xl_addr = dsmem_u32(xl + lm_r * XLD + 8 * (lm_id & 1));
             for (int nb = 0; nb < nblocks; ++nb) {
-                // four independent accumulator chains (main / cross terms x k-step parity): one chain would serialise every
+                // six independent accumulator chains per row tile (main / cross terms x k-step parity): one chain would serialise every
                 // MMA of the tile behind the ~30-cycle MMA latency, this warp has no other tile to interleave with
-                float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
-                float accC[4] = {0.f, 0.f, 0.f, 0.f}, accD[4] = {0.f, 0.f, 0.f, 0.f};
-                float accE[4] = {0.f, 0.f, 0.f, 0.f}, accF[4] = {0.f, 0.f, 0.f, 0.f};      // six chains: no MMA of a k-step waits for another
+                float acc6[NT][6][4];
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) { acc6[t][c][0] = acc6[t][c][1] = acc6[t][c][2] = acc6[t][c][3] = 0.f; }
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const int stage = it % MC_STAGES;
                     chain_mbar_wait(&full_bar[stage], (it / MC_STAGES) & 1);
@@ -635,15 +642,18 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                     const uint32_t wl = wh + MC_TILE_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        uint32_t ah[4], al[4], bh[2], bl[2];
+                        uint32_t ah[4], al[4];
                         const uint32_t sw = (uint32_t)(((2 * ks + a_chunk) ^ (a_row & 7)) << 4);      // TMA 128-byte swizzle
                         mc_ldsm_x4(ah, wh + sw);
                         mc_ldsm_x4(al, wl + sw);
                         const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
-                        mc_ldsm_x2(bh, xh_addr + xo);
-                        mc_ldsm_x2(bl, xl_addr + xo);
-                        if (ks & 1) { mc_mma(accB, ah, bh); mc_mma(accD, al, bh); mc_mma(accF, ah, bl); }
-                        else        { mc_mma(accA, ah, bh); mc_mma(accC, al, bh); mc_mma(accE, ah, bl); }
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            uint32_t bh[2], bl[2];
+                            mc_ldsm_x2(bh, xh_addr + xo + (uint32_t)(t * 8 * XLD * 2));
+                            mc_ldsm_x2(bl, xl_addr + xo + (uint32_t)(t * 8 * XLD * 2));
+                            mc_mma(acc6[t][ks & 1], ah, bh); mc_mma(acc6[t][2 + (ks & 1)], al, bh); mc_mma(acc6[t][4 + (ks & 1)], ah, bl);
+                        }
                     }
                     __syncwarp();
                     if (CL == 1) {
@@ -654,36 +664,41 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
                     }
                 }
-                float acc[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = ((accC[i] + accD[i]) + (accE[i] + accF[i])) + (accA[i] + accB[i]);
-                // D fragment: (feature 16w+g8 [+8], row 2t4 [+1])
+                // D fragment: (feature 16w+g8 [+8], row 8t + 2t4 [+1])
                 const int n = nb * 128 + 16 * warp + g8;
-                if (n < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n] = acc[0]; ys[(2 * t4 + 1) * MC_YLD + n] = acc[1]; }
-                if (n + 8 < MC_YLD - 4) { ys[(2 * t4) * MC_YLD + n + 8] = acc[2]; ys[(2 * t4 + 1) * MC_YLD + n + 8] = acc[3]; }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    float acc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] = ((acc6[t][2][i] + acc6[t][3][i]) + (acc6[t][4][i] + acc6[t][5][i])) + (acc6[t][0][i] + acc6[t][1][i]);
+                    float* y0 = ys + (8 * t + 2 * t4) * YLD;
+                    if (n < YLD - 4) { y0[n] = acc[0]; y0[YLD + n] = acc[1]; }
+                    if (n + 8 < YLD - 4) { y0[n + 8] = acc[2]; y0[YLD + n + 8] = acc[3]; }
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int rr = warp; rr < R; rr += 8) {
         if (L.flags & CHAIN_FLAG_VEC4) {
             const bool more = li + 1 < prm.n_layers;
-            __nv_bfloat16* nh = more ? xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD : nullptr;
-            chain_row_epilogue_v4(prm, L, row0 + warp, ys + warp * MC_YLD, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr,
-                                  nh, more ? nh + DENSE_ROWS * MC_XLD : nullptr, more ? ((prm.layer[li + 1].K + 63) & ~63) : 0);
+            __nv_bfloat16* nh = more ? xbuf + (ping ^ 1) * 2 * R * XLD + rr * XLD : nullptr;
+            chain_row_epilogue_v4(prm, L, row0 + rr, ys + rr * YLD, lane, vecs, res_staged ? resb + rr * MC_RES_LD : nullptr,
+                                  nh, more ? nh + R * XLD : nullptr, more ? ((prm.layer[li + 1].K + 63) & ~63) : 0);
         } else {
-            float* yr = ys + warp * MC_YLD;
-            chain_row_epilogue(prm, L, row0 + warp, yr, lane, vecs, res_staged ? resb + warp * MC_RES_LD : nullptr);
+            float* yr = ys + rr * YLD;
+            chain_row_epilogue(prm, L, row0 + rr, yr, lane, vecs, res_staged ? resb + rr * MC_RES_LD : nullptr);
             __syncwarp();
-            if ((L.flags & CHAIN_FLAG_POINTS) && row0 + warp < prm.M) {           // lane gp: sample point gp of this query
-                const long long row = row0 + warp;
+            if ((L.flags & CHAIN_FLAG_POINTS) && row0 + rr < prm.M) {           // lane gp: sample point gp of this query
+                const long long row = row0 + rr;
                 for (int gp = lane; gp < prm.sp_GP; gp += 32)
                     sample_point_one(prm.sp_bbox + row * 10, yr + prm.sp_off_col + gp * 3, yr + prm.sp_log_col + gp * prm.sp_L, prm.sp_L,
                                      prm.sp_r[0], prm.sp_r[1], prm.sp_r[2], prm.sp_r[3], prm.sp_r[4], prm.sp_r[5],
                                      prm.sp_points + (row * prm.sp_GP + gp) * 3, prm.sp_scale_w + (row * prm.sp_GP + gp) * prm.sp_L, prm.sp_ssign);
             }
             if (li + 1 < prm.n_layers) {          // next layer's activation operand: bf16 (hi, lo), zero beyond N up to its padded K
-                __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * DENSE_ROWS * MC_XLD + warp * MC_XLD;
-                __nv_bfloat16* nl = nh + DENSE_ROWS * MC_XLD;
+                __nv_bfloat16* nh = xbuf + (ping ^ 1) * 2 * R * XLD + rr * XLD;
+                __nv_bfloat16* nl = nh + R * XLD;
                 const int Kn = (prm.layer[li + 1].K + 63) & ~63;
                 for (int k = 2 * lane; k < Kn; k += 64) {
                     const float a = (k < L.N) ? yr[k] : 0.f, b = (k + 1 < L.N) ? yr[k + 1] : 0.f;
@@ -693,6 +708,7 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                     *reinterpret_cast<uint32_t*>(nl + k) = l;
                 }
             }
+        }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         ping ^= 1;
@@ -1298,7 +1314,7 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
         c.Wt = l.Wt; c.bias = l.bias; c.ln_w = l.ln_w; c.ln_b = l.ln_b; c.residual = l.residual; c.y = l.y;
         c.y_hi = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_hi)); c.y_lo = reinterpret_cast<__nv_bfloat16*>(const_cast<uint16_t*>(l.y_lo));
         SBEV_REQUIRE((l.y_hi == nullptr) == (l.y_lo == nullptr), SBEV_ERR_INVALID, "sbev_dense_chain_fwd: y_hi and y_lo go together");
-        c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags & 0xff; c.ldy = l.ldy;
+        c.ldw = l.ldw; c.K = l.K; c.N = l.N; c.flags = l.flags & 0xff & ~SBEV_DENSE_WIDE_CTA; c.ldy = l.ldy;
         c.wpack = get_option(OPT_DENSE_PACK) ? reinterpret_cast<const uint8_t*>(l.W_pack) : nullptr;
         SBEV_REQUIRE((reinterpret_cast<uintptr_t>(l.W_pack) & 127) == 0, SBEV_ERR_INVALID, "sbev_dense_chain_fwd: layer %d: W_pack not 128-byte aligned", i);
         {
@@ -1407,6 +1423,18 @@ static int dense_chain_impl(const float* x, int ldx, const ChainInputReduce* in,
             cudaFuncSetAttribute(dense_chain_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
             cudaFuncSetAttribute(dense_chain_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
             cudaFuncSetAttribute(dense_chain_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+        // 16 rows per CTA (caller's hint on the first layer: the chain runs side by side with another one): narrow chains only
+        bool wide_cta = (layers[0].flags & SBEV_DENSE_WIDE_CTA) && cl == 1 && in == nullptr && !fuse_points && M > DENSE_ROWS;
+        for (int i = 0; i < n_layers; ++i)
+            if (layers[i].K > 256 || layers[i].N > 256) wide_cta = false;
+        if (wide_cta) {
+            constexpr int R16 = 16, XLD16 = 256 + 8, YLD16 = 256 + 4;
+            const size_t smem16 = (size_t)MC_STAGES * 2 * MC_TILE_BYTES + (size_t)2 * 2 * R16 * XLD16 * 2 + (size_t)R16 * YLD16 * 4 +
+                                  (size_t)(3 * CHAIN_VEC_LD + R16 * MC_RES_LD) * 4 + 1024;
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(dense_chain_mma_kernel<1, R16, XLD16, YLD16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            launch_pdl(dense_chain_mma_kernel<1, R16, XLD16, YLD16>, dim3((M + R16 - 1) / R16), dim3(288), smem16, (cudaStream_t)stream, prm, maps);
+            return check_launch("sbev_dense_chain_fwd(mma, 16 rows)");
+        }
         if (cl > 1) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((groups + cl - 1) / cl * cl);

@@ -342,7 +342,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
             const bool add_bias = (bias != nullptr) && (z == 0);
             // staging per epilogue warp: 2 x 4 KB (fp32: alternating boxes; bf16 split: one hi / lo pair), or -- CTA-pair bf16
             // split, whose smaller operand stages leave the room -- two hi / lo pairs so a store drains while the next box is built
-            constexpr int STG_PER_WARP = (OUT_SPLIT && PAIR) ? 4 : 2;
+            constexpr int STG_PER_WARP = (OUT_SPLIT && PAIR && STAGES <= 2) ? 4 : 2;      // (the 3-stage pair form spends that room on the ring)
             uint8_t* stg_warp = stg_base + (warp - 2) * STG_PER_WARP * 4096;
             uint8_t* my_stg = stg_warp;
             if constexpr (OUT_SPLIT) {
@@ -371,7 +371,7 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                         }
                     }
                     // the stores that last read this hi / lo buffer pair must have drained it
-                    if (PAIR) {
+                    if (STG_PER_WARP == 4) {
                         my_stg = stg_warp + (c & 1) * 8192;          // BN / 64 is even: the alternation carries over from tile to tile
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     } else {
@@ -663,9 +663,12 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     const void* ptrs[6] = {A_hi, A_lo, B_hi, B_lo, C_hi, C_lo};
     for (int i = 0; i < 6; ++i) SBEV_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: operands must be 16-byte aligned");
     SBEV_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, SBEV_ERR_INVALID, "sbev_gemm_bf16_tn_split: bias must be 16-byte aligned");
-    // CTA pairs only when forced: with K = 256 (four k-blocks per unit) the extra cross-SM hop per pipeline stage costs more
-    // than the saved operand traffic (measured 59.7 us vs 55.3 us for the parameter-generation GEMM)
-    const bool pair = get_option(OPT_GEMM_IMPL) == 2;
+    // CTA pairs only when forced.  gemm_impl 2: two 64 KB stages + double-buffered staging -- with K = 256 (four k-blocks per unit) the
+    // extra cross-SM hop per pipeline stage costs more than the saved operand traffic (measured 59.7 us vs 55.3 us for the
+    // parameter-generation GEMM); gemm_impl 5: THREE 64 KB stages + single staging (the single-CTA form has room for only two 96 KB
+    // stages, so every k-block's load is exposed behind the MMA that frees its stage)
+    const bool pair3 = get_option(OPT_GEMM_IMPL) == 5;
+    const bool pair = get_option(OPT_GEMM_IMPL) == 2 || pair3;
     GemmMapsV2 mp;
     int rc = make_bf16_map(&mp.a_hi, A_hi, M, K, GEMM_BM);   if (rc) return rc;
     rc = make_bf16_map(&mp.a_lo, A_lo, M, K, GEMM_BM);       if (rc) return rc;
@@ -679,6 +682,14 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     if (pair && num_sms >= 2) {
         const int num_units = ((m_tiles + 1) / 2) * n_tiles;
         const int clusters = num_units < num_sms / 2 ? num_units : num_sms / 2;
+        if (pair3) {
+            constexpr size_t smem3 = (size_t)3 * 2 * (GEMM_BM * GEMM_BK * 2 + 128 * GEMM_BK * 2) + 4 * 2 * 4096 + 1024;
+            SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, true, true>,
+                                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            launch_pair(gemm_bf16_tn_persistent_kernel<256, 3, true, 0, true, true>, clusters, smem3, (cudaStream_t)stream,
+                        mp, K / GEMM_BK, 1, m_tiles, n_tiles, num_units, bias, (float*)nullptr, M, N);
+            return check_launch("sbev_gemm_bf16_tn_split(pair, 3 stages)");
+        }
         SBEV_PER_DEVICE_ONCE(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>,
                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_PAIR_SPLIT_SMEM));
         launch_pair(gemm_bf16_tn_persistent_kernel<256, 2, true, 0, true, true>, clusters, GEMM_PAIR_SPLIT_SMEM, (cudaStream_t)stream,

@@ -15,6 +15,7 @@ OUT_POINTS = 128    # reference: out_points hard-coded, sparsebev_transformer.py
 DENSE_RELU = 1
 DENSE_RES_PRE_LN = 2
 DENSE_REFINE = 4
+DENSE_WIDE_CTA = 8
 
 
 def _stream():
@@ -267,10 +268,10 @@ class _ChainEntry(tuple):
 
 
 def chain_layer(wt, ldw, K, N, bias=None, ln=None, residual=None, relu=False, res_pre_ln=False, refine=False, y=None, ldy=None,
-                w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None, w_pack=None):
+                w_hi=None, w_lo=None, kpad=0, y_hi=None, y_lo=None, w_pack=None, wide_cta=False):
     """One entry of a dense chain (see dense_chain).  w_hi / w_lo (bf16 [N][kpad]) enable the tensor-core path; w_pack
     (pack_weight_tiles) its bulk-copy weight stream."""
-    flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0)
+    flags = (DENSE_RELU if relu else 0) | (DENSE_RES_PRE_LN if res_pre_ln else 0) | (DENSE_REFINE if refine else 0) | (DENSE_WIDE_CTA if wide_cta else 0)
     keep = [t for t in (wt, bias, residual, y, w_hi, w_lo, y_hi, y_lo, w_pack) if t is not None] + ([ln.weight, ln.bias] if ln is not None else [])
     e = _ChainEntry((_lib.DenseLayer(_p(wt), ldw, K, N, _p(bias), _p(ln.weight) if ln is not None else None,
                                      _p(ln.bias) if ln is not None else None, _p(residual), flags, _p(y),
@@ -342,7 +343,9 @@ def ws_eligible(M, layers, reduce_k0=None):
         return False
     if reduce_k0 is not None and reduce_k0 != 256:
         return False
-    blob_bytes, kmax, nex = 0, 64, (252 if reduce_k0 is not None else 4)
+    if reduce_k0 is not None and not layers[-1][0].ln_w:
+        return False
+    blob_bytes, kmax, swx = 0, 64, (8 if reduce_k0 is not None else 0)
     for i, l in enumerate(layers):
         d = l[0]
         last = i + 1 == len(layers)
@@ -354,11 +357,11 @@ def ws_eligible(M, layers, reduce_k0=None):
                 return False
             if any((p or 0) % 16 for p in (d.ln_w, d.ln_b, d.residual, d.y)) or any((p or 0) % 8 for p in (d.y_hi, d.y_lo)):
                 return False
-            nex = max(nex, d.N)
+            swx = max(swx, ws_slice_width(d.N))
         blob_bytes += (d.Kpad // 64) * 2 * ws_slice_width(d.N) * 128
         kmax = max(kmax, d.Kpad)
-    smem16 = (blob_bytes + 1023) // 1024 * 1024 + 2 * 16 * (kmax + 8) * 2 + 16 * (nex + 4) * 4 + 1024
-    return smem16 <= WS_SMEM_CAP
+    group_bytes = (2 * 16 * (kmax + 8) * 2 + (8 * 16 * swx + 2 * 16 * swx) * 4 + 127) // 128 * 128
+    return (blob_bytes + 1023) // 1024 * 1024 + group_bytes + 1024 <= WS_SMEM_CAP
 
 
 def dense_chain(x, ldx, M, layers, refine_proposal=None, refine_time_diff=None, refine_Q=0, refine_T=0):

@@ -19,6 +19,7 @@ is the eval path (dropout = identity, no activation checkpointing); training the
 modules is out of scope (the op-level autograd Functions in `wrapper.py` do have a backward).
 """
 import collections
+import os
 
 import numpy as np
 import torch
@@ -85,12 +86,12 @@ class _Dense:
         self.in_features = linear.in_features
         self.out_features = sum(l.out_features for l in self.linears)
 
-    def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None, y_hi=None, y_lo=None):
+    def layer(self, relu=False, residual=None, res_pre_ln=False, refine=False, y=None, ldy=None, y_hi=None, y_lo=None, wide_cta=False):
         wt, ldw, bias = self.cache.get_with_bias([l.weight for l in self.linears], [l.bias for l in self.linears])
         c = self.cache
         return ops.chain_layer(wt, ldw, self.in_features, self.out_features, bias=bias, ln=self.ln, residual=residual,
                                relu=relu, res_pre_ln=res_pre_ln, refine=refine, y=y, ldy=ldy, w_hi=c.w_hi, w_lo=c.w_lo, kpad=c.kpad,
-                               y_hi=y_hi, y_lo=y_lo, w_pack=c.w_pack)
+                               y_hi=y_hi, y_lo=y_lo, w_pack=c.w_pack, wide_cta=wide_cta)
 
     def __call__(self, x, relu=False, residual=None, res_pre_ln=False, k=None):
         M = x.shape[0]
@@ -382,6 +383,10 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self.frame_shard = None      # dist.FrameShard: this rank holds / samples only its window of the T frames
         self.query_shard = None      # dist.QueryShard: ONE scene across ranks -- frames local, every query-side stage sharded over queries
         self.qshard_split_k = None   # split-K slices of the out-projection in query-sharded mode (None: chosen from the local row count)
+        # cls || reg as 16-row CTAs (SBEV_DENSE_WIDE_CTA: 57 + 57 CTAs, both chains resident at once) when they run on two streams.
+        # OFF: measured on the B200 a 16-row CTA takes 34 us per chain against 15 us for 8 rows (the chain is bound by each warp's
+        # instruction stream, which doubles), so the pair finishes later (317 vs 311 us per step); SBEV_WIDE_CTA_HEADS=1 turns it on
+        self.wide_cta_heads = os.environ.get('SBEV_WIDE_CTA_HEADS', '0') == '1'
         self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
         self._graphs, self._graph_pool = collections.OrderedDict(), None
@@ -699,8 +704,11 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         def ffn(chain):
             ops.dense_chain_reduce(red['partial'], red['bias'], red['residual'], red['ln_w'], red['ln_b'], q3, chain)
         td = img_metas[0]['time_diff']
-        cls_chain = [l.layer(relu=True) for l in self._cls[:-1]] + [self._cls[-1].layer(y=cls_score)]
-        reg_chain = [l.layer(relu=True) for l in self._reg[:-1]] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
+        # cls || reg run side by side on two streams; with 8-row CTAs (113 + 113 on 148 SMs, one per SM) the second chain mostly runs in
+        # the first one's wake (kernel timeline: 17 + 30 us); the 16-row form that would make both resident is slower still (see __init__)
+        wide = side is not None and self.wide_cta_heads
+        cls_chain = [l.layer(relu=True, wide_cta=wide and i == 0) for i, l in enumerate(self._cls[:-1])] + [self._cls[-1].layer(y=cls_score)]
+        reg_chain = [l.layer(relu=True, wide_cta=wide and i == 0) for i, l in enumerate(self._reg[:-1])] + [self._reg[-1].layer(refine=True, y=bbox_pred)]
         ffn_chain = [self._ffn0.layer(relu=True), self._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
         if side is not None:
             ffn(ffn_chain)

@@ -1,6 +1,5 @@
-"""Device times of the decoder layer's five dense chains, streaming kernel (dense_ws 0) vs the weights-stationary cluster kernel
-(dense_ws 1; one or two row groups per CTA), at the row counts of the 1/2/4/8-GPU query shards, and of the whole layer (CUDA graph)
-with either.  Launch queue pre-filled, CUDA events.  Writes gpurun_out/ws_sweep.json.  Development tool."""
+"""Phase timeline of the weights-stationary chain kernel (sbev_dense_chain_ws_debug: clock64 stamps of thread 0 of every CTA) for
+the decoder layer's chains at a given row count.  usage: ws_timeline.py [M ...]   Development tool."""
 import json
 import os
 import sys
@@ -63,36 +62,34 @@ def main():
     q2, heads = new(Q, D), new(Q, smp._heads.out_features)
     pbuf = mixing.alloc_params(Q, dev)
     td = meta['time_diff']
-    modes = [('stream', 0, 0), ('ws', 1, 0), ('ws1g', 1, 1)]
-    for M in (900, 450, 225, 113):
+    lib = _lib.load()
+    _lib.set_option('dense_ws', 1)
+    stamps = torch.zeros(256 * 64, dtype=torch.int64, device=dev)
+    for M in [int(a) for a in sys.argv[1:] if a.isdigit()] or [113, 900]:
         part = torch.randn(18, M, D, device=dev) * 0.1
-        q3, q4, cls, box = new(M, D), torch.randn(M, D, device=dev), new(M, 10), new(M, 10)
-        q3.normal_()
+        q3, q4, cls, box = torch.randn(M, D, device=dev), torch.randn(M, D, device=dev), new(M, 10), new(M, 10)
         ffn_chain = [layer._ffn0.layer(relu=True), layer._ffn1.layer(residual=q3, res_pre_ln=True, y=q4)]
         cls_chain = [l.layer(relu=True) for l in layer._cls[:-1]] + [layer._cls[-1].layer(y=cls)]
-        reg_chain = [l.layer(relu=True) for l in layer._reg[:-1]] + [layer._reg[-1].layer(refine=True, y=box)]
         fns = {
             'A_posenc_inproj': lambda: ops.dense_chain(qb2, 10, M, [layer._pe0.layer(relu=True), layer._pe1.layer(relu=True, residual=x0, y=q1_all), attn.in_layer(qkvt, hi, lo)]),
-            'B_outproj_heads': lambda: ops.dense_chain(o, D, M, [attn.out_layer(q1_all, layer.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), smp.heads_layer(heads)]),
             'C_reduce18+ffn': lambda: ops.dense_chain_reduce(part, mixing.out_proj.bias, q2[:M], layer.norm2.weight, layer.norm2.bias, q3, ffn_chain),
-            'C_ffn': lambda: ops.dense_chain(q3, D, M, ffn_chain),
             'D_cls': lambda: ops.dense_chain(q4, D, M, cls_chain),
-            'E_reg': lambda: ops.dense_chain(q4, D, M, reg_chain, refine_proposal=qb2, refine_time_diff=td, refine_Q=M, refine_T=T),
         }
         for cname, fn in fns.items():
-            for mname, ws, rt in modes:
-                _lib.set_option('dense_ws', ws)
-                _lib.set_option('dense_ws_groups', rt)
-                rec('%s M%d %s' % (cname, M, mname), fn)
-    _lib.set_option('dense_ws_groups', 0)
-    # whole layer as one CUDA graph
-    layer.use_cuda_graph = True
-    for ws in (0, 1, 2):
-        _lib.set_option('dense_ws', ws)
-        layer.reset_graphs()
-        rec('layer graph dense_ws=%d' % ws, lambda: layer(qb, qf, feats, None, metas), iters=50, warm=5)
-    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'ws_sweep.json'), 'w'), indent=1)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            stamps.zero_()
+            lib.sbev_dense_chain_ws_debug(stamps.data_ptr())
+            fn()
+            torch.cuda.synchronize()
+            lib.sbev_dense_chain_ws_debug(None)
+            st = stamps.view(256, 64).cpu()
+            print('==', cname, 'M', M)
+            for cta in (0, 1, 7, 8, 15 * 8):
+                row = [int(v) for v in st[cta] if int(v) != 0]
+                if len(row) > 1:
+                    print('cta %3d  total %6d cyc  deltas %s' % (cta, row[-1] - row[0], ' '.join(str(b - a) for a, b in zip(row[:-1], row[1:]))))
 
 
 if __name__ == '__main__':

@@ -1,7 +1,7 @@
 """Weights-stationary dense chain (sbev_dense_chain_ws_fwd / _ws_reduce_fwd, csrc/dense_ws.cu) against an fp64 torch
 restatement of the reference's Linear / LayerNorm / ReLU / residual chains (/root/reference/models/sparsebev_transformer.py:113-183)
 and against the streaming chain kernel, for the five chain shapes of the decoder layer, at the row counts of the 1 / 2 / 4 / 8-GPU
-query shards and at ragged ones, with both row-tile sizes.  The blob layout itself is checked on CPU (test_ws_blob_layout)."""
+query shards and at ragged ones, with one and two row groups per CTA.  The blob layout itself is checked on CPU (test_ws_blob_layout)."""
 import copy
 
 import pytest
@@ -138,15 +138,15 @@ def _build(name, M, seed=0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('rt', [0, 16, 32])
+@pytest.mark.parametrize('groups', [0, 1])
 @pytest.mark.parametrize('M', [1, 15, 113, 225, 450, 900, 1601])
 @pytest.mark.parametrize('name', CHAINS)
-def test_ws_chain_vs_fp64(name, M, rt, option):
-    if rt != 0 and M not in (113, 900):
-        pytest.skip('forced row tiles only at the bench row counts')
+def test_ws_chain_vs_fp64(name, M, groups, option):
+    if groups != 0 and M not in (450, 900):
+        pytest.skip('a forced single row group only where two would be used')
     ops = _ops()
     option('dense_ws', 1)
-    option('dense_ws_rt', rt)
+    option('dense_ws_groups', groups)
     x, ldx, specs, wanted, refine = _build(name, M)
     want = _ref(x[:, :specs[0][0].in_features], specs)
     ys = [torch.full((M, s[0].out_features), float('nan'), device=dev()) if i in wanted else None for i, s in enumerate(specs)]
@@ -183,13 +183,13 @@ def test_ws_chain_vs_fp64(name, M, rt, option):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('rt', [16, 32])
+@pytest.mark.parametrize('groups', [0, 1])
 @pytest.mark.parametrize('M,nsplit,ln', [(900, 18, True), (113, 128, True), (113, 18, True), (37, 5, False), (1601, 18, True)])
-def test_ws_chain_reduce_vs_fp64(M, nsplit, ln, rt, option):
+def test_ws_chain_reduce_vs_fp64(M, nsplit, ln, groups, option):
     """sbev_dense_chain_ws_reduce_fwd: input rows = LN(sum_z partial + bias + residual), the FFN behind it."""
     ops = _ops()
     option('dense_ws', 1)
-    option('dense_ws_rt', rt)
+    option('dense_ws_groups', groups)
     torch.manual_seed(5)
     K0 = 256
     part, bias, res = torch.randn(nsplit, M, K0), torch.randn(K0), torch.randn(M, K0)
@@ -209,7 +209,7 @@ def test_ws_chain_reduce_vs_fp64(M, nsplit, ln, rt, option):
     assert ops.ws_eligible(M, ent, reduce_k0=K0)
     ops.dense_chain_reduce(part.to(dev()), bias.to(dev()), res.to(dev()), None if nd is None else nd.weight, None if nd is None else nd.bias, x_out, ent)
     torch.cuda.synchronize()
-    _close(x_out, x_in, 'reduce prologue rows', rtol=1e-5, atol=2e-5 * max(1.0, float(x_in.abs().max())))
+    _close(x_out, x_in, 'reduce prologue rows', rtol=1e-5, atol=2e-5 * max(1.0, float(x_in.detach().abs().max())))
     _close(y, want[1], 'ffn behind the reduce prologue')
 
 
@@ -229,3 +229,32 @@ def test_ws_not_eligible_falls_to_streaming(option):
     assert not ops.ws_eligible(M, ent)
     ops.dense_chain(x.to(dev()), ldx, M, ent)
     _close(ys[4], want[4], 'ffn + cls on the streaming kernel')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('M', [9, 113, 900, 905])
+@pytest.mark.parametrize('name', ['cls', 'reg', 'outproj_heads'])
+def test_wide_cta_chain_is_bit_identical(name, M, option):
+    """SBEV_DENSE_WIDE_CTA (16 rows per CTA of the streaming chain, the form cls || reg use when they run side by side): every row goes
+    through the same arithmetic as in the 8-row form -> bit-identical outputs; and both match the fp64 restatement."""
+    ops = _ops()
+    option('dense_ws', 0)
+    x, ldx, specs, wanted, refine = _build(name, M)
+    want = _ref(x, specs)
+    kw, extra8, extra16 = {}, {}, {0: dict(wide_cta=True)}
+    if refine is not None:
+        extra8[2] = dict(refine=True)
+        extra16[2] = dict(refine=True)
+        kw = dict(refine_proposal=refine['qb'].to(dev()), refine_time_diff=refine['td'].to(dev()), refine_Q=M, refine_T=3)
+        wb = R.refine_bbox(refine['qb'][None], want[2][None].float())
+        want[2] = torch.cat([wb[..., :8], wb[..., 8:] / 0.5], -1)[0]
+    outs = []
+    for extra in (extra8, extra16):
+        ys = [torch.full((M, s[0].out_features), float('nan'), device=dev()) if i in wanted else None for i, s in enumerate(specs)]
+        ent, keep = _entries(ops, specs, ys, extra)
+        ops.dense_chain(x.to(dev()), ldx, M, ent, **kw)
+        torch.cuda.synchronize()
+        outs.append(ys)
+    for i in wanted:
+        _close(outs[1][i], want[i], '%s M=%d layer %d (16-row CTAs)' % (name, M, i))
+        assert torch.equal(outs[0][i], outs[1][i]), '%s M=%d layer %d: 16-row CTAs differ from 8-row CTAs' % (name, M, i)

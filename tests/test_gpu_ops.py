@@ -32,7 +32,8 @@ def _ops():
 def option():
     """Select a kernel variant for one test, restore the defaults afterwards."""
     from sparsebev_b200 import _lib
-    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit', 'dense_pack', 'legacy_rotation', 'sasa_kq')
+    names = ('gemm_impl', 'mix_impl', 'sasa_impl', 'gather_variant', 'dense_impl', 'dense_cluster', 'dense_nsplit', 'dense_pack', 'legacy_rotation', 'sasa_kq',
+             'dense_ws', 'dense_ws_groups')
     defaults = {k: _lib.get_option(k) for k in names}
 
     def setter(name, value):
@@ -762,10 +763,10 @@ def test_reduce_ln_vs_torch(nsplit, M, N, ln):
     _close(got, want, rtol=1e-4, atol=1e-5, what='reduce_ln')
 
 
-@pytest.mark.parametrize('impl', [0, 2, 4])
+@pytest.mark.parametrize('impl', [0, 2, 4, 5])
 def test_gemm_split_output_and_tma_fed_mix(impl, option):
     """GEMM with bf16 (hi, lo) output + the TMA-fed mix kernel == the fp32-parameter path (impl 2: CTA-pair GEMM, 0: single CTAs,
-    4: A-resident single CTAs with 128-wide N tiles; M = 300 gives
+    4: A-resident single CTAs with 128-wide N tiles, 5: CTA pairs with a three-stage ring; M = 300 gives
     an odd number of 128-row tiles, so the last pair's second CTA is entirely out of range)."""
     option('gemm_impl', impl)
     ops = _ops()
