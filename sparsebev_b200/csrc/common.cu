@@ -16,10 +16,10 @@ void set_error(const char* fmt, ...) {
 
 // Implementation selectors (A/B testing of kernel variants).  Defaults come from the environment
 // (SBEV_GEMM_IMPL, SBEV_MIX_IMPL, SBEV_SASA_IMPL, SBEV_GATHER_VARIANT), sbev_set_option overrides.
-static const char* kOptNames[OPT_COUNT] = {"gemm_impl", "mix_impl", "sasa_impl", "gather_variant", "dense_impl", "dense_cluster", "pdl", "dense_nsplit", "dense_vec4", "dense_fuse_points", "mix_order", "legacy_rotation", "dense_pack", "sasa_kq", "dense_ws", "dense_ws_groups"};
-static const char* kOptEnv[OPT_COUNT] = {"SBEV_GEMM_IMPL", "SBEV_MIX_IMPL", "SBEV_SASA_IMPL", "SBEV_GATHER_VARIANT", "SBEV_DENSE_IMPL", "SBEV_DENSE_CLUSTER", "SBEV_PDL", "SBEV_DENSE_NSPLIT", "SBEV_DENSE_VEC4", "SBEV_DENSE_FUSE_POINTS", "SBEV_MIX_ORDER", "SBEV_LEGACY_ROTATION", "SBEV_DENSE_PACK", "SBEV_SASA_KQ", "SBEV_DENSE_WS", "SBEV_DENSE_WS_GROUPS"};
-static const int kOptDefault[OPT_COUNT] = {0, 0, 0, 6, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0};
-static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+static const char* kOptNames[OPT_COUNT] = {"gemm_impl", "mix_impl", "sasa_impl", "gather_variant", "dense_impl", "dense_cluster", "pdl", "dense_nsplit", "dense_vec4", "dense_fuse_points", "mix_order", "legacy_rotation", "dense_pack", "sasa_kq", "dense_ws", "dense_ws_groups", "gemm_l2_hints", "gather_l2_hint"};
+static const char* kOptEnv[OPT_COUNT] = {"SBEV_GEMM_IMPL", "SBEV_MIX_IMPL", "SBEV_SASA_IMPL", "SBEV_GATHER_VARIANT", "SBEV_DENSE_IMPL", "SBEV_DENSE_CLUSTER", "SBEV_PDL", "SBEV_DENSE_NSPLIT", "SBEV_DENSE_VEC4", "SBEV_DENSE_FUSE_POINTS", "SBEV_MIX_ORDER", "SBEV_LEGACY_ROTATION", "SBEV_DENSE_PACK", "SBEV_SASA_KQ", "SBEV_DENSE_WS", "SBEV_DENSE_WS_GROUPS", "SBEV_GEMM_L2_HINTS", "SBEV_GATHER_L2_HINT"};
+static const int kOptDefault[OPT_COUNT] = {0, 0, 0, 6, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 
 int get_option(int id) {
     if (g_opt[id] < 0) {

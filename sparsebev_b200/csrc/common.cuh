@@ -9,7 +9,7 @@
 namespace sbev {
 
 void set_error(const char* fmt, ...);
-enum { OPT_GEMM_IMPL = 0, OPT_MIX_IMPL = 1, OPT_SASA_IMPL = 2, OPT_GATHER_VARIANT = 3, OPT_DENSE_IMPL = 4, OPT_DENSE_CLUSTER = 5, OPT_PDL = 6, OPT_DENSE_NSPLIT = 7, OPT_DENSE_VEC4 = 8, OPT_DENSE_FUSE_POINTS = 9, OPT_MIX_ORDER = 10, OPT_LEGACY_ROTATION = 11, OPT_DENSE_PACK = 12, OPT_SASA_KQ = 13, OPT_DENSE_WS = 14, OPT_DENSE_WS_GROUPS = 15, OPT_COUNT = 16 };
+enum { OPT_GEMM_IMPL = 0, OPT_MIX_IMPL = 1, OPT_SASA_IMPL = 2, OPT_GATHER_VARIANT = 3, OPT_DENSE_IMPL = 4, OPT_DENSE_CLUSTER = 5, OPT_PDL = 6, OPT_DENSE_NSPLIT = 7, OPT_DENSE_VEC4 = 8, OPT_DENSE_FUSE_POINTS = 9, OPT_MIX_ORDER = 10, OPT_LEGACY_ROTATION = 11, OPT_DENSE_PACK = 12, OPT_SASA_KQ = 13, OPT_DENSE_WS = 14, OPT_DENSE_WS_GROUPS = 15, OPT_GEMM_L2_HINTS = 16, OPT_GATHER_L2_HINT = 17, OPT_COUNT = 18 };
 // 2-D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], 128 B swizzle, zero OOB fill (gemm_tcgen05.cu)
 int make_bf16_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows);
 int make_bf16_map_ex(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows, int box_cols, int swizzle_bytes);

@@ -160,7 +160,28 @@ struct GemmMapsV2 {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap c;          // fp32 [split_k][M][N], box {32 cols, 32 rows, 1}, 128-byte swizzle (epilogue TMA stores)
     CUtensorMap c_hi, c_lo; // OUT_SPLIT: bf16 [M][N] each, box {64 cols, 32 rows}, 128-byte swizzle
+    int hints = 0;          // L2 cache hints (option "gemm_l2_hints"): 1 = OUT_SPLIT stores evict_first, 2 = B (weight) tile loads evict_last
 };
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 
 // ARES (A-resident, for small K): the CTA is pinned to ONE M-tile, loads that tile's whole A operand (all k-blocks, hi and
 // lo) into shared memory once and then only streams B through the ring while it walks its N-tiles -- a third less
@@ -267,10 +288,12 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                     } else {
                         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                         tma_load_2d(st, &maps.a_hi, &full_bar[stage], kc, m0);
-                        tma_load_2d(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0);
+                        if (maps.hints & 2) tma_load_2d_hint(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0, l2_policy_evict_last());
+                        else tma_load_2d(st + A_BYTES, &maps.b_hi, &full_bar[stage], kc, n0);
                         if (X3) {
                             tma_load_2d(st + A_BYTES + B_BYTES, &maps.a_lo, &full_bar[stage], kc, m0);
-                            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0);
+                            if (maps.hints & 2) tma_load_2d_hint(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0, l2_policy_evict_last());
+                            else tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo, &full_bar[stage], kc, n0);
                         }
                     }
                 }
@@ -348,17 +371,20 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
             if constexpr (OUT_SPLIT) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
+                    // the chunk's 64 bias values first: their L2 round trip overlaps the TMEM load below (profile: the first FADD on a
+                    // bias value was 22 % of this kernel's stall samples when the loads sat inside the conversion loop)
+                    float4 bq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bq[j] = add_bias ? ldg4(bias + n0 + c * 64 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float v[64];
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64), v);
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 64 + 32), v + 32);
                     // bias + bf16 (hi, lo) split into registers FIRST: the TMA stores of the previous chunk drain the staging
-                    // buffers meanwhile (profile: the wait right after the TMEM load was 21 % of this kernel's stall samples,
-                    // the 64 scalar bias loads per chunk another 23 %)
+                    // buffers meanwhile (profile: the wait right after the TMEM load was 21 % of this kernel's stall samples)
                     uint32_t hw[8][4], lw[8][4];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {                      // 8 chunks of 8 bf16 (16 B) per 128-byte row
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (add_bias) { b0 = ldg4(bias + n0 + c * 64 + 8 * j); b1 = ldg4(bias + n0 + c * 64 + 8 * j + 4); }
+                        const float4 b0 = bq[2 * j], b1 = bq[2 * j + 1];
                         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -387,10 +413,16 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ GemmMapsV2 maps, int tota
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
+                        if (maps.hints & 1) {        // the parameter tensor is written once and read once, much later: do not let it evict hotter lines
+                            const uint64_t pol = l2_policy_evict_first();
+                            tma_store_2d_hint(&maps.c_hi, smem_u32(my_stg), n0 + c * 64, m0 + quarter * 32, pol);
+                            tma_store_2d_hint(&maps.c_lo, smem_u32(my_stg + 4096), n0 + c * 64, m0 + quarter * 32, pol);
+                        } else {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&maps.c_hi), "r"(smem_u32(my_stg)), "r"(n0 + c * 64), "r"(m0 + quarter * 32) : "memory");
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&maps.c_lo), "r"(smem_u32(my_stg + 4096)), "r"(n0 + c * 64), "r"(m0 + quarter * 32) : "memory");
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -677,6 +709,7 @@ extern "C" int sbev_gemm_bf16_tn_split(const uint16_t* A_hi, const uint16_t* A_l
     rc = make_bf16_store_map(&mp.c_hi, C_hi, N, M);          if (rc) return rc;
     rc = make_bf16_store_map(&mp.c_lo, C_lo, N, M);          if (rc) return rc;
     mp.c = mp.c_hi;
+    mp.hints = get_option(OPT_GEMM_L2_HINTS);
     const int num_sms = device_num_sms();
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = N / 256;
     if (pair && num_sms >= 2) {

@@ -367,6 +367,11 @@ constexpr int S3_BUF_BYTES = 4 * S3_ARR * 2 + 2 * S3_KT * 4;   // Kh,Kl,Vh,Vl + 
 // a third of the instructions of the IEEE sqrtf / expf sequences that were ~25 % of this kernel's instruction stream.
 __device__ __forceinline__ float sa_sqrt(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sa_exp(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f)); return y; }
+// v3 keeps its logits in the log2 domain (scale and tau pre-multiplied by log2(e): one FFMA per logit instead of FMUL + FFMA + FMUL) and
+// uses the flush-to-zero forms: without .ftz ptxas wraps every MUFU in a denormal-range rescue (FSETP + 2 FMUL + FSEL per call -- the
+// profile showed 10 FMUL per logit); a softmax weight below 1e-38 or a centre distance below 1e-19 m is zero for every purpose here
+__device__ __forceinline__ float sa_sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sa_exp2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // KQ = key splits per CTA (4: 256 threads, two CTAs per SM -- the full-size layer; 8: 512 threads, half as many key tiles per
 // warp -- when only a shard of the queries attends and the grid is far below one wave, latency per warp is what counts)
@@ -385,7 +390,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
     const int g8 = lane >> 2, t4 = lane & 3;
     const int q0 = qa + blockIdx.x * 32 + 16 * mt;      // queries [qa, qb) of this launch; keys are always all Q
     const int h = blockIdx.y, b = blockIdx.z;
-    const float scale = 0.17677669529663687f;
+    const float scale2 = 0.17677669529663687f * 1.4426950408889634f;      // 1 / sqrt(32) * log2(e): logits live in the log2 domain
     unsigned char* mybuf = s3_smem + kq * 2 * S3_BUF_BYTES;
     const long long rowbase = (long long)b * Q;
     const int bar_id = 1 + kq;
@@ -413,7 +418,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
         const bool ok = gq < qb;
         rcx[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10), __fsub_rn(x_hi, x_lo)), x_lo) : 0.f;
         rcy[r] = ok ? __fadd_rn(__fmul_rn(__ldg(query_bbox + (rowbase + gq) * 10 + 1), __fsub_rn(y_hi, y_lo)), y_lo) : 0.f;
-        rtau[r] = ok ? __ldg(tau + (rowbase + gq) * ld_tau + h) : 0.f;
+        rtau[r] = ok ? -1.4426950408889634f * __ldg(tau + (rowbase + gq) * ld_tau + h) : 0.f;      // -tau * log2(e)
     }
 
     const int num_tiles = (Q + S3_KT - 1) / S3_KT;
@@ -475,6 +480,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
                 sa_mma3(sacc[n], qh[ks], ql[ks], bh, bl);
             }
         float alpha[2];
+        const bool ragged = k0 + S3_KT > Q;                       // (warp-uniform) only the last tile has keys beyond Q
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             float mx = -INFINITY;
@@ -485,9 +491,9 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
                 for (int e = 0; e < 2; ++e) {
                     const int k = 8 * n + 2 * t4 + e;
                     const float dx = rcx[r] - kcx[k], dy = rcy[r] - kcy[k];
-                    float v = sacc[n][2 * r + e] * scale + (-sa_sqrt(dx * dx + dy * dy)) * rtau[r];
+                    float v = fmaf(sa_sqrt_ftz(fmaf(dx, dx, dy * dy)), rtau[r], sacc[n][2 * r + e] * scale2);
                     if (HAS_MASK && gq < qb && k0 + k < Q && dn_mask[(long long)gq * Q + k0 + k]) v = -INFINITY;
-                    if (k0 + k >= Q) v = -INFINITY;
+                    if (ragged && k0 + k >= Q) v = -INFINITY;
                     sacc[n][2 * r + e] = v;
                     mx = fmaxf(mx, v);
                 }
@@ -495,13 +501,13 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             const float m_new = fmaxf(m_run[r], mx);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            alpha[r] = sa_exp(m_run[r] - m_use);
+            alpha[r] = sa_exp2_ftz(m_run[r] - m_use);
             float rs = 0.f;
 #pragma unroll
             for (int n = 0; n < 4; ++n)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float pv = sa_exp(sacc[n][2 * r + e] - m_use);
+                    const float pv = sa_exp2_ftz(sacc[n][2 * r + e] - m_use);
                     sacc[n][2 * r + e] = pv;
                     rs += pv;
                 }
@@ -556,7 +562,7 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
 #pragma unroll
         for (int w = 0; w < KQ; ++w) {
             const float* row = mo + ((m2 * KQ + w) * 16 + r) * MLD;
-            const float f = sa_exp(row[SA_HD] - muse);
+            const float f = sa_exp2_ftz(row[SA_HD] - muse);
             num += f * row[d];
             den += f * row[SA_HD + 1];
         }

@@ -382,7 +382,8 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         self.overlap = True          # run independent kernels of a layer on a second stream (parallel graph branches)
         self.frame_shard = None      # dist.FrameShard: this rank holds / samples only its window of the T frames
         self.query_shard = None      # dist.QueryShard: ONE scene across ranks -- frames local, every query-side stage sharded over queries
-        self.qshard_split_k = None   # split-K slices of the out-projection in query-sharded mode (None: chosen from the local row count)
+        # split-K slices of the out-projection in query-sharded mode (None: chosen from the local row count; SBEV_QSHARD_SPLIT_K: A/B runs)
+        self.qshard_split_k = int(os.environ['SBEV_QSHARD_SPLIT_K']) if os.environ.get('SBEV_QSHARD_SPLIT_K') else None
         # cls || reg as 16-row CTAs (SBEV_DENSE_WIDE_CTA: 57 + 57 CTAs, both chains resident at once) when they run on two streams.
         # OFF: measured on the B200 a 16-row CTA takes 34 us per chain against 15 us for 8 rows (the chain is bound by each warp's
         # instruction stream, which doubles), so the pair finishes later (317 vs 311 us per step); SBEV_WIDE_CTA_HEADS=1 turns it on
@@ -553,51 +554,49 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         o = new(Q, D)
         pbuf = mixing.alloc_params(max(Ml, 1), dev)
         q2, heads = new(max(Ml, 1), D), new(max(Ml, 1), smp._heads.out_features)
+        main = torch.cuda.current_stream()
+        side = self._side_stream(dev) if self.overlap else None
+        params = None
         if Ml > 0:
             ops.sasa_split(qkvt, query_bbox, attn.pc_range, H, D, dn_mask=attn_mask, split=(hi, lo), q_range=(q0, q1), out=o.view(1, Q, D))
             mark('attention core (own queries)')
             ops.dense_chain(o[sl], D, Ml, [attn.out_layer(q1_all[sl], self.norm1, q2, pbuf['q_hi'], pbuf['q_lo']), smp.heads_layer(heads)])
             mark('out_proj+norm1+heads')
+            # (4a) the parameter GEMM needs only q2: it forks off HERE, so it already runs while the sample points are computed and
+            # exchanged (two kernels + one NVLink round trip), not only next to the gather
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    params = mixing.generate_params(q2, pbuf, presplit=True)
             ld = heads.shape[1]
             ops.sample_points(query_bbox[:, sl], heads, heads[:, GP * 3:], smp.pc_range, L, num_points_total=GP, ld_off=ld, ld_log=ld,
                               out=(v['points'][sl], v['scale_w'][sl]))
             mark('sample_points')
         sh.exchange(ar, [('points', q0, q1), ('scale_w', q0, q1)])
         mark('exchange 1 (points)')
-        # (3) gather: own frames, all queries, rows stored to the owning rank  ||  (4a) parameter GEMM of the own queries
+        # (3) gather: own frames, all queries, rows stored to the owning rank
         image_h, image_w, _ = img_metas[0]['img_shape'][0]
         meta = img_metas[0]
-
-        def gather():
-            ops.sampling4d_fused(mlvl_feats, v['points'].view(1, Q, GP, 3), query_bbox, meta['time_diff'], meta['lidar2img'],
-                                 v['scale_w'].view(1, Q, G, P, L), image_h, image_w, num_frames=T, num_views=NUM_VIEWS,
-                                 layout=smp.feat_layout, frame_window=sh.window, owner_ptrs=sh.peer_ptrs(ar, 'sampled'), q_per_rank=qpr)
-            mark('gather (own frames, rows to owners)')
-            sh.exchange(ar, [])
-            mark('barrier')
-        main = torch.cuda.current_stream()
-        side = self._side_stream(dev) if self.overlap else None
-        params = None
-        if side is not None and Ml > 0:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                params = mixing.generate_params(q2, pbuf, presplit=True)
-            gather()
+        if Ml > 0 and side is None:
+            params = mixing.generate_params(q2, pbuf, presplit=True)
+        ops.sampling4d_fused(mlvl_feats, v['points'].view(1, Q, GP, 3), query_bbox, meta['time_diff'], meta['lidar2img'],
+                             v['scale_w'].view(1, Q, G, P, L), image_h, image_w, num_frames=T, num_views=NUM_VIEWS,
+                             layout=smp.feat_layout, frame_window=sh.window, owner_ptrs=sh.peer_ptrs(ar, 'sampled'), q_per_rank=qpr)
+        mark('gather (own frames, rows to owners)')
+        sh.exchange(ar, [])
+        mark('barrier')
+        if Ml > 0 and side is not None:
             main.wait_stream(side)
-        else:
-            if Ml > 0:
-                params = mixing.generate_params(q2, pbuf, presplit=True)
-            gather()
         # (4b) mixing, (5) FFN, cls / reg + refine: own queries, results into this rank's rows of the output buffers -> exchange 2
         if Ml > 0:
             # split-K of the out-projection by local row count (tests/perf/kernel_sweep.py on the B200: the GEMM wants ~148 CTAs
             # of work, the reduce in front of the FFN chain wants few partials): 18 / 36 slices reduced in the FFN chain's
-            # prologue as in the unsharded layer, 72 / 128 slices by the one-CTA-per-row reduce kernel
+            # prologue as in the unsharded layer, 72 / 96 slices by the one-CTA-per-row reduce kernel
             keep_split = mixing.split_k
             if self.qshard_split_k is not None:
                 mixing.split_k = self.qshard_split_k
             else:
-                mixing.split_k = 128 if Ml <= 128 else 72 if Ml <= 256 else 36 if Ml <= 512 else keep_split
+                mixing.split_k = 96 if Ml <= 128 else 72 if Ml <= 256 else 36 if Ml <= 512 else keep_split      # (in-place A/B on the B200: tools/shots/r2_emu8.sh)
             separate_reduce = mixing.split_k > 36
             try:
                 red = mixing.mix_and_project(params, v['sampled'][:Ml], q2, self.norm2, defer_reduce=True)
