@@ -640,21 +640,27 @@ dense_chain_mma_kernel(const __grid_constant__ ChainParams prm, const __grid_con
                     chain_mbar_wait(&full_bar[stage], (it / MC_STAGES) & 1);
                     const uint32_t wh = dsmem_u32(wring + stage * 2 * MC_TILE_BYTES) + a_row * 128;
                     const uint32_t wl = wh + MC_TILE_BYTES;
+                    // all fragment loads of the stage first, then its MMAs: the asm statements keep their order, so interleaving them per
+                    // k-step exposed one ldmatrix round trip (~30 cycles) in front of every group of three MMAs
+                    uint32_t ah[4][4], al[4][4], bh[4][NT][2], bl[4][NT][2];
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        uint32_t ah[4], al[4];
                         const uint32_t sw = (uint32_t)(((2 * ks + a_chunk) ^ (a_row & 7)) << 4);      // TMA 128-byte swizzle
-                        mc_ldsm_x4(ah, wh + sw);
-                        mc_ldsm_x4(al, wl + sw);
+                        mc_ldsm_x4(ah[ks], wh + sw);
+                        mc_ldsm_x4(al[ks], wl + sw);
                         const uint32_t xo = (uint32_t)((kc * 64 + ks * 16) * 2);
 #pragma unroll
                         for (int t = 0; t < NT; ++t) {
-                            uint32_t bh[2], bl[2];
-                            mc_ldsm_x2(bh, xh_addr + xo + (uint32_t)(t * 8 * XLD * 2));
-                            mc_ldsm_x2(bl, xl_addr + xo + (uint32_t)(t * 8 * XLD * 2));
-                            mc_mma(acc6[t][ks & 1], ah, bh); mc_mma(acc6[t][2 + (ks & 1)], al, bh); mc_mma(acc6[t][4 + (ks & 1)], ah, bl);
+                            mc_ldsm_x2(bh[ks][t], xh_addr + xo + (uint32_t)(t * 8 * XLD * 2));
+                            mc_ldsm_x2(bl[ks][t], xl_addr + xo + (uint32_t)(t * 8 * XLD * 2));
                         }
                     }
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            mc_mma(acc6[t][ks & 1], ah[ks], bh[ks][t]); mc_mma(acc6[t][2 + (ks & 1)], al[ks], bh[ks][t]); mc_mma(acc6[t][4 + (ks & 1)], ah[ks], bl[ks][t]);
+                        }
                     __syncwarp();
                     if (CL == 1) {
                         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsmem_u32(&empty_bar[stage])) : "memory");

@@ -587,13 +587,20 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
             const uint32_t off = (uint32_t)(row * 128 + ((warp ^ (row & 7)) << 4));   // 16-byte chunk `warp` = columns 8w..8w+7
             asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(bh[0]), "=r"(bh[1]) : "r"(mh + off));
             asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(bl[0]), "=r"(bl[1]) : "r"(ml + off));
+            // fragments of both row tiles first, then the three bf16x3 products with the two accumulators interleaved (the products of
+            // ONE accumulator depend on each other; same order per accumulator as mma3: lo.hi, hi.lo, hi.hi)
+            uint32_t ah[2][4], al[2][4];
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                uint32_t ah[4], al[4];
-                ldsm_x4(ah, xh + (16 * m + a_row) * MX_LD + k0 + a_col);
-                ldsm_x4(al, xl + (16 * m + a_row) * MX_LD + k0 + a_col);
-                mma3(acc1[m], ah, al, bh, bl);
+                ldsm_x4(ah[m], xh + (16 * m + a_row) * MX_LD + k0 + a_col);
+                ldsm_x4(al[m], xl + (16 * m + a_row) * MX_LD + k0 + a_col);
             }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) mma_bf16(acc1[m], al[m], bh);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) mma_bf16(acc1[m], ah[m], bl);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) mma_bf16(acc1[m], ah[m], bh);
         }
         {
             Stat st;
@@ -637,13 +644,18 @@ mix_tma_kernel(const __grid_constant__ MixMaps maps, const float* __restrict__ x
             const uint32_t off = (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));   // TMA 64-byte swizzle
             asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(sh + off));
             asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(sl + off));
+            uint32_t bh[8][2], bl[8][2];
 #pragma unroll
             for (int nn = 0; nn < 8; ++nn) {
-                uint32_t bh[2], bl[2];
-                ldsm_x2_trans(bh, hh + (k0 + (lane & 15)) * MX_LD + 8 * nn);
-                ldsm_x2_trans(bl, hl + (k0 + (lane & 15)) * MX_LD + 8 * nn);
-                mma3(acc2[nn], ah, al, bh, bl);
+                ldsm_x2_trans(bh[nn], hh + (k0 + (lane & 15)) * MX_LD + 8 * nn);
+                ldsm_x2_trans(bl[nn], hl + (k0 + (lane & 15)) * MX_LD + 8 * nn);
             }
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) mma_bf16(acc2[nn], al, bh[nn]);
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) mma_bf16(acc2[nn], ah, bl[nn]);
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) mma_bf16(acc2[nn], ah, bh[nn]);
         }
         Stat st2;
         {

@@ -470,15 +470,28 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
         float sacc[4][4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+        {
+            // all K fragments of the tile first, then the MMAs with the four key blocks interleaved: the three bf16x3 products of one
+            // accumulator depend on each other (~35 cycles apiece), consecutive MMAs on DIFFERENT accumulators pipeline.  Every
+            // accumulator still sees lo.hi, hi.lo, hi.hi per k-step in this order (bit-identical to sa_mma3)
+            uint32_t kbh[2][4][2], kbl[2][4][2];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+            for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                uint32_t bh[2], bl[2];
-                sa_ldsm_x2(bh, Kh + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
-                sa_ldsm_x2(bl, Kl + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
-                sa_mma3(sacc[n], qh[ks], ql[ks], bh, bl);
+                for (int n = 0; n < 4; ++n) {
+                    sa_ldsm_x2(kbh[ks][n], Kh + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                    sa_ldsm_x2(kbl[ks][n], Kl + (8 * n + b_row) * SM_LD + 16 * ks + b_col);
+                }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) sa_mma(sacc[n], ql[ks], kbh[ks][n]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) sa_mma(sacc[n], qh[ks], kbl[ks][n]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) sa_mma(sacc[n], qh[ks], kbh[ks][n]);
             }
+        }
         float alpha[2];
         const bool ragged = k0 + S3_KT > Q;                       // (warp-uniform) only the last tile has keys beyond Q
 #pragma unroll
@@ -523,13 +536,18 @@ sasa_v3_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __
             sa_split2(sacc[2 * j][2], sacc[2 * j][3], ph[1], pl[1]);
             sa_split2(sacc[2 * j + 1][0], sacc[2 * j + 1][1], ph[2], pl[2]);
             sa_split2(sacc[2 * j + 1][2], sacc[2 * j + 1][3], ph[3], pl[3]);
+            uint32_t vbh[4][2], vbl[4][2];
 #pragma unroll
             for (int nd = 0; nd < 4; ++nd) {
-                uint32_t bh[2], bl[2];
-                sa_ldsm_x2_trans(bh, Vh + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
-                sa_ldsm_x2_trans(bl, Vl + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
-                sa_mma3(oacc[nd], ph, pl, bh, bl);
+                sa_ldsm_x2_trans(vbh[nd], Vh + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
+                sa_ldsm_x2_trans(vbl[nd], Vl + (16 * j + (lane & 15)) * SM_LD + 8 * nd);
             }
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) sa_mma(oacc[nd], pl, vbh[nd]);
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) sa_mma(oacc[nd], ph, vbl[nd]);
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) sa_mma(oacc[nd], ph, vbh[nd]);
         }
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");          // both warps done with this slot before it is refilled
     }

@@ -388,6 +388,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         # OFF: measured on the B200 a 16-row CTA takes 34 us per chain against 15 us for 8 rows (the chain is bound by each warp's
         # instruction stream, which doubles), so the pair finishes later (317 vs 311 us per step); SBEV_WIDE_CTA_HEADS=1 turns it on
         self.wide_cta_heads = os.environ.get('SBEV_WIDE_CTA_HEADS', '0') == '1'
+        self.phase_order = int(os.environ.get('SBEV_PHASE_ORDER', '0'))   # A/B of the gather / parameter-GEMM order (see _forward_impl)
         self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
         self._graphs, self._graph_pool = collections.OrderedDict(), None
@@ -684,7 +685,17 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         # fork so the caching allocator never sees cross-stream frees.
         main = torch.cuda.current_stream()
         side = self._side_stream(dev) if self.overlap else None
-        if side is not None:
+        order = self.phase_order
+        if order == 1:                   # experiment: one stream, gather FIRST, so that the mix starts on the GEMM's heels (its last-written
+            sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas, points)          # parameter groups are still in L2)
+            params = self.mixing.generate_params(q2, pbuf, presplit=True)
+        elif order == 2 and side is not None:      # experiment: two streams, the GEMM launched BEHIND the sample-points kernel's start
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas, points)
+            params = self.mixing.generate_params(q2, pbuf, presplit=True)
+            main.wait_stream(side)
+        elif side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 params = self.mixing.generate_params(q2, pbuf, presplit=True)
