@@ -87,9 +87,11 @@ __device__ __forceinline__ void chain_mbar_wait(uint64_t* bar, uint32_t parity) 
 // sv / sres (optional): shared-memory copies of the layer's bias | ln_w | ln_b (3 x CHAIN_VEC_LD floats) and of this row's
 // residual, prefetched with cp.async while the layer's GEMM ran -- the epilogue then waits on no global load.
 constexpr int CHAIN_VEC_LD = 1024;
-__device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane,
-                                                   const float* sv = nullptr, const float* sres = nullptr) {
-    constexpr int U = 8;                               // columns per lane per batch: their global operands are loaded together
+// U = columns per lane per batch (their global operands are loaded together): the unrolled batch is U instructions long whatever N
+// is, so narrow rows (the 10-wide cls / reg outputs) take the U = 1 instance -- see chain_row_epilogue below.
+template <int U>
+__device__ __forceinline__ void chain_row_epilogue_u(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane,
+                                                     const float* sv, const float* sres) {
     const int N = L.N;
     const bool live = row < prm.M;
     const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
@@ -162,6 +164,12 @@ __device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const
     }
 }
 
+__device__ __forceinline__ void chain_row_epilogue(const ChainParams& prm, const ChainLayer& L, int row, float* yr, int lane,
+                                                   const float* sv = nullptr, const float* sres = nullptr) {
+    if (L.N <= 32) chain_row_epilogue_u<1>(prm, L, row, yr, lane, sv, sres);      // (warp-uniform)
+    else chain_row_epilogue_u<8>(prm, L, row, yr, lane, sv, sres);
+}
+
 __device__ __forceinline__ void mc_split2(float a, float b, uint32_t& hi, uint32_t& lo);
 // Vectorised form of chain_row_epilogue for the tensor-core chains (profile: the scalar epilogue was ~45 % of the chain
 // kernels' warp-stall samples -- the kernels are bound by the length of each warp's instruction stream, not by weight
@@ -169,18 +177,23 @@ __device__ __forceinline__ void mc_split2(float a, float b, uint32_t& hi, uint32
 // between the three passes, every global / shared access is 16 bytes (8 for the bf16 outputs), and the next layer's
 // bf16 (hi, lo) operand row (nh / nl, zero padded up to Kn) is produced in the same pass.  Requires N % 4 == 0,
 // N <= 1024, ldy % 4 == 0, 16-byte aligned operands and no refine epilogue (host sets CHAIN_FLAG_VEC4 when that holds).
+// PER = 16-byte column groups per lane the three passes are unrolled for (N <= 128 PER): the loops used to be unrolled for the
+// maximum (8 groups, N = 1024) with the dead groups predicated off -- 462 issued instructions per warp and layer at N = 256, where
+// two groups are live (ncu source view of the cls chain: the epilogue was 36 % of all executed instructions and 45 % of the stall
+// samples).  The dispatcher below picks 2 / 4 / 8.
 constexpr int CHAIN_FLAG_VEC4 = 1 << 8;
-__device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, const ChainLayer& L, int row, const float* yr, int lane,
-                                                      const float* sv, const float* sres, __nv_bfloat16* nh, __nv_bfloat16* nl, int Kn) {
+template <int PER>
+__device__ __forceinline__ void chain_row_epilogue_v4_p(const ChainParams& prm, const ChainLayer& L, int row, const float* yr, int lane,
+                                                        const float* sv, const float* sres, __nv_bfloat16* nh, __nv_bfloat16* nl, int Kn) {
     const int N = L.N, ng = N >> 2;
     const bool live = row < prm.M;
     const bool pre_res = (L.flags & SBEV_DENSE_RES_PRE_LN) && L.residual != nullptr;
     const bool has_res = live && L.residual != nullptr;
     const float* res_row = L.residual ? L.residual + (long long)row * N : nullptr;
-    float4 v[8];
+    float4 v[PER];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int g = lane + 32 * i;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g < ng) {
@@ -203,7 +216,7 @@ __device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, co
         mean = warp_sum(s) / (float)N;
         float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < PER; ++i)
             if (lane + 32 * i < ng) {
                 const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
                 ss += (a * a + b * b) + (c * c + d * d);
@@ -212,7 +225,7 @@ __device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, co
     }
     const long long yoff = (long long)row * L.ldy;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int g = lane + 32 * i;
         if (g < ng) {
             float4 o = v[i];
@@ -247,6 +260,13 @@ __device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, co
             *reinterpret_cast<uint2*>(nh + k) = make_uint2(0u, 0u);
             *reinterpret_cast<uint2*>(nl + k) = make_uint2(0u, 0u);
         }
+}
+__device__ __forceinline__ void chain_row_epilogue_v4(const ChainParams& prm, const ChainLayer& L, int row, const float* yr, int lane,
+                                                      const float* sv, const float* sres, __nv_bfloat16* nh, __nv_bfloat16* nl, int Kn) {
+    const int per = ((L.N >> 2) + 31) >> 5;                   // (warp-uniform)
+    if (per <= 2) chain_row_epilogue_v4_p<2>(prm, L, row, yr, lane, sv, sres, nh, nl, Kn);
+    else if (per <= 4) chain_row_epilogue_v4_p<4>(prm, L, row, yr, lane, sv, sres, nh, nl, Kn);
+    else chain_row_epilogue_v4_p<8>(prm, L, row, yr, lane, sv, sres, nh, nl, Kn);
 }
 
 // A chain of up to 6 Linear(+bias)(+residual)(+LayerNorm)(+ReLU) layers (fp32 FFMA version; exact fp32).  One CTA owns 8 full rows from the
