@@ -388,7 +388,11 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         # OFF: measured on the B200 a 16-row CTA takes 34 us per chain against 15 us for 8 rows (the chain is bound by each warp's
         # instruction stream, which doubles), so the pair finishes later (317 vs 311 us per step); SBEV_WIDE_CTA_HEADS=1 turns it on
         self.wide_cta_heads = os.environ.get('SBEV_WIDE_CTA_HEADS', '0') == '1'
-        self.phase_order = int(os.environ.get('SBEV_PHASE_ORDER', '0'))   # A/B of the gather / parameter-GEMM order (see _forward_impl)
+        # order of the gather and the parameter GEMM (see _forward_impl): 0 = side by side on two streams, 1 = one stream, gather first,
+        # 2 = two streams, GEMM launched second; -1 (default) = 1 for the 8-frame configuration, 0 otherwise.  Measured on the B200 at
+        # r50-T8 (tools/shots/r2_order.sh): the two kernels do not overlap -- each runs near the L2 throughput cap -- and the step is
+        # 0.3049 ms with order 1 against 0.3077 ms with order 0; with one frame the gather is 7 us and hides under the GEMM
+        self.phase_order = int(os.environ.get('SBEV_PHASE_ORDER', '-1'))
         self.use_cuda_graph = False  # replay the layer's launches as ONE CUDA graph (captured on first use per input signature)
         self._streams = {}
         self._graphs, self._graph_pool = collections.OrderedDict(), None
@@ -685,7 +689,7 @@ class SparseBEVTransformerDecoderLayer(BaseModule):
         # fork so the caching allocator never sees cross-stream frees.
         main = torch.cuda.current_stream()
         side = self._side_stream(dev) if self.overlap else None
-        order = self.phase_order
+        order = self.phase_order if self.phase_order >= 0 else (1 if self.sampling.num_frames >= 8 else 0)
         if order == 1:                   # experiment: one stream, gather FIRST, so that the mix starts on the GEMM's heels (its last-written
             sampled = self._sample(query_bbox, heads, mlvl_feats, img_metas, points)          # parameter groups are still in L2)
             params = self.mixing.generate_params(q2, pbuf, presplit=True)
