@@ -57,6 +57,27 @@ def test_ws_blob_layout():
     assert off * 2 <= stride
 
 
+def test_ws_blob_bytes_match_the_c_side():
+    """The host mirror's slice width / blob size arithmetic (ops.ws_slice_width, ops.pack_ws_blob) equals the library's
+    (sbev_dense_chain_ws_blob_bytes: host code, callable without a GPU) for the decoder layer's five chains."""
+    from sparsebev_b200 import _lib, ops
+    lib = _lib.load()
+    chains = {'posenc_inproj': [(3, 256), (256, 256), (256, 776)], 'outproj_heads': [(256, 256), (256, 112)], 'ffn': [(256, 512), (512, 256)],
+              'cls': [(256, 256), (256, 256), (256, 10)], 'ffn+cls': [(256, 512), (512, 256), (256, 256), (256, 256), (256, 10)]}
+    for name, dims in chains.items():
+        layers = (_lib.DenseLayer * len(dims))()
+        ws = []
+        for i, (k, n) in enumerate(dims):
+            kpad = (k + 63) // 64 * 64
+            layers[i].K, layers[i].N, layers[i].Kpad = k, n, kpad
+            ws.append((torch.zeros(n, kpad, dtype=torch.bfloat16), torch.zeros(n, kpad, dtype=torch.bfloat16)))
+        want = int(lib.sbev_dense_chain_ws_blob_bytes(len(dims), layers))
+        mine = sum((kpad // 64) * 2 * ops.ws_slice_width(n) * 128 for (k, n), (w, _) in zip(dims, ws) for kpad in [w.shape[1]])
+        blob, stride = ops.pack_ws_blob(ws)
+        assert want == mine and mine <= stride < mine + 128, (name, want, mine, stride)
+    assert int(lib.sbev_dense_chain_ws_blob_bytes(0, None)) == -1
+
+
 def _mk(seed, *dims):
     torch.manual_seed(seed)
     lin = [torch.nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])]
