@@ -576,6 +576,42 @@ class Bench:
                 'note': 'public API call of ONE layer (layer.use_cuda_graph: the layer replays its own captured graph; eager_ms_per_step = plain '
                         'launches); feature pyramid already on the device as in the reference pipeline'}
 
+    def forward_resident(self, steps=10):
+        """The reference's real flow at full depth: ONE SparseBEVTransformer.forward (all decoder layers) per step with the feature pyramid
+        already on the device, img_metas as host numpy, results left on the device -- as plain launches, with the per-layer graphs and
+        with the decoder-level graph (decoder.use_cuda_graph: one replay per forward)."""
+        import copy
+        layer, dec = self.layer, self.model.decoder
+        if self.mode != 'single' or layer.sampling.feat_layout != 'nhwc':
+            return None
+        feats5 = [f.permute(0, 1, 4, 2, 3) for f in self.feats]          # L x [B, T*N, C, H, W] views of the channels-last maps
+
+        def timed():
+            for _ in range(3):
+                self.model(self.qb, self.qf, list(feats5), None, copy.deepcopy(self.metas_host))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.model(self.qb, self.qf, list(feats5), None, copy.deepcopy(self.metas_host))
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) * 1e3 / steps
+        res = {'layers_per_forward': dec.num_layers, 'eager_ms_per_forward': timed()}
+        try:
+            layer.use_cuda_graph = True
+            res['layer_graphs_ms_per_forward'] = timed()
+        finally:
+            layer.use_cuda_graph = False
+            layer.reset_graphs()
+        try:
+            dec.use_cuda_graph = True
+            res['decoder_graph_ms_per_forward'] = timed()
+        finally:
+            dec.use_cuda_graph = False
+            layer.reset_graphs()
+        res['decoder_layer_samples_per_s'] = dec.num_layers * 1e3 / res['decoder_graph_ms_per_forward']
+        res['note'] = 'wall clock of the public forward call, feature pyramid resident, host img_metas converted inside; not the headline'
+        return res
+
     # ---- rooflines
     def rooflines(self):
         a, cfg, layer, ops, dev = self.args, self.cfg, self.layer, self.ops, self.dev
@@ -771,6 +807,12 @@ def main():
             extra['e2e_resident_features'] = b.e2e_resident()
         except Exception as exc:                          # pragma: no cover
             extra['e2e_resident_features'] = {'error': repr(exc)[:300]}
+        try:
+            fr = b.forward_resident()
+            if fr is not None:
+                extra['forward_resident_features'] = fr
+        except Exception as exc:                          # pragma: no cover
+            extra['forward_resident_features'] = {'error': repr(exc)[:300]}
 
     try:
         roof, roof_u, roof_t = b.rooflines()

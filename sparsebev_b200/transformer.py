@@ -746,6 +746,7 @@ class SparseBEVTransformerDecoder(BaseModule):
                  code_size=10, pc_range=[], init_cfg=None):
         super().__init__(init_cfg)
         self.num_layers, self.pc_range = num_layers, pc_range
+        self.use_cuda_graph = False      # capture all layers of a forward into ONE CUDA graph (unsharded inference; see forward)
         # params are shared across all decoder layers
         self.decoder_layer = SparseBEVTransformerDecoderLayer(
             embed_dims, num_frames, num_points, num_levels, num_classes, code_size, pc_range=pc_range)
@@ -785,10 +786,7 @@ class SparseBEVTransformerDecoder(BaseModule):
         self.decoder_layer.sampling.feat_layout = layouts.pop()
         return mlvl_feats
 
-    @torch.no_grad()
-    def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
-        self.prepare_metas(img_metas, query_bbox.shape[0], query_bbox.device)
-        self.prepare_feats(mlvl_feats)
+    def _layers(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
         cls_scores, bbox_preds = [], []
         for i in range(self.num_layers):
             DUMP.stage_count = i
@@ -797,6 +795,27 @@ class SparseBEVTransformerDecoder(BaseModule):
             cls_scores.append(cls_score)
             bbox_preds.append(bbox_pred)
         return torch.stack(cls_scores), torch.stack(bbox_preds)
+
+    def _layers_one_graph(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        # body of the decoder-level graph: plain launches of all layers (no per-layer graphs inside the capture or its warm-up pass)
+        layer = self.decoder_layer
+        keep, layer.use_cuda_graph = layer.use_cuda_graph, False
+        try:
+            return self._layers(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
+        finally:
+            layer.use_cuda_graph = keep
+
+    @torch.no_grad()
+    def forward(self, query_bbox, query_feat, mlvl_feats, attn_mask, img_metas):
+        self.prepare_metas(img_metas, query_bbox.shape[0], query_bbox.device)
+        self.prepare_feats(mlvl_feats)
+        layer = self.decoder_layer
+        sharded = (layer.query_shard is not None and layer.query_shard.world > 1) or (layer.frame_shard is not None and layer.frame_shard.world > 1)
+        if self.use_cuda_graph and not sharded and not DUMP.enabled and not torch.cuda.is_current_stream_capturing():
+            # ONE graph for the whole decoder (num_layers x 11 launches): the small inputs are copied in and the two stacked results
+            # copied out once per forward instead of once per layer (same signature cache as the per-layer graphs)
+            return layer._forward_graphed(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas, impl=self._layers_one_graph)
+        return self._layers(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)
 
 
 class SparseBEVTransformer(BaseModule):

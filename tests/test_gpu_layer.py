@@ -389,3 +389,27 @@ def test_layer_cuda_graph_mode_equals_eager():
     finally:
         layer.use_cuda_graph = False
         layer.reset_graphs()
+
+
+def test_decoder_cuda_graph_mode_equals_eager():
+    """`decoder.use_cuda_graph`: ALL layers of a forward captured into one CUDA graph (inputs copied in and the two stacked results
+    copied out once per forward) return exactly what the eager launches return, for changing queries, and the graph is captured once
+    while the (channels-last, consumed in place) feature maps keep their addresses."""
+    B, L = 1, 3
+    cfg, sd, model, feats, metas, qb, qf = _setup('tiny', 4, B, seed=23, num_layers=L, memory_format='nhwc')
+    layer = model.decoder.decoder_layer
+    gf = [f.cuda() for f in feats]
+    inputs = [(qb, qf), (qb.flip(1).contiguous(), 0.5 * qf)]
+    want = [[t.clone() for t in model(a.cuda(), b.cuda(), list(gf), None, copy.deepcopy(metas))] for a, b in inputs]
+    assert want[0][0].shape[0] == L and not torch.equal(want[0][0], want[1][0])
+    model.decoder.use_cuda_graph = True
+    try:
+        for i, (a, b) in enumerate(inputs * 2):
+            got = model(a.cuda(), b.cuda(), list(gf), None, copy.deepcopy(metas))
+            torch.cuda.synchronize()
+            assert torch.equal(got[0], want[i % 2][0]) and torch.equal(got[1], want[i % 2][1]), 'decoder graph replay %d differs from eager' % i
+        assert len(layer._graphs) == 1
+    finally:
+        model.decoder.use_cuda_graph = False
+        layer.reset_graphs()
+
