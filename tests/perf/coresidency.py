@@ -57,7 +57,12 @@ def main():
     new = lambda m, n, dt=torch.float32: torch.empty(m, n, device=dev, dtype=dt)      # noqa: E731
     qb2, x0 = qb.reshape(Q, 10), qf.reshape(Q, D)
     import ctypes
-    hog = ctypes.CDLL(os.path.join(ROOT, 'tests', 'perf', 'csrc', 'libhog.so'))
+    so = os.path.join(ROOT, 'tests', 'perf', 'csrc', 'libhog.so')
+    if not os.path.exists(so):                 # (built in-tree so that it travels with the gpurun snapshot; git-ignored)
+        import subprocess
+        subprocess.check_call([os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc'), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-shared',
+                               '-Xcompiler', '-fPIC', '-o', so, os.path.join(ROOT, 'tests', 'perf', 'csrc', 'hog.cu'), '-lcudart'])
+    hog = ctypes.CDLL(so)
     hog.hog_launch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]
     smp = layer.sampling
     heads = torch.randn(Q, smp._heads.out_features, device=dev) * 0.1
