@@ -126,3 +126,46 @@ def test_invalidate_caches_hooks():
     assert all(c.key is None for c in caches) and len(layer._graphs) == 0
     poison(); layer.invalidate_caches()
     assert all(c.key is None for c in caches)
+
+
+def test_decoder_level_graph_dispatch(monkeypatch):
+    """decoder.use_cuda_graph sends a forward through ONE graph (layer._forward_graphed with the all-layers body) -- except with the DUMP
+    export on or a sharded layer, which take the plain loop -- and the all-layers body runs with the per-layer graphs switched off."""
+    import sparsebev_b200 as sb
+    from sparsebev_b200.utils import DUMP
+    m = sb.SparseBEVTransformer(256, num_frames=2, num_points=4, num_layers=3, num_levels=2, pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0])
+    dec, layer = m.decoder, m.decoder.decoder_layer
+    monkeypatch.setattr(dec, 'prepare_metas', lambda *a, **k: None)
+    monkeypatch.setattr(dec, 'prepare_feats', lambda f: f)
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
+    calls = []
+
+    def fake_layer(qb, qf, feats, mask, metas):
+        calls.append(('layer', layer.use_cuda_graph))
+        return qf, torch.zeros(1, 4, 10), torch.zeros(1, 4, 10)
+    monkeypatch.setattr(layer, 'forward', fake_layer)
+
+    def fake_graphed(qb, qf, feats, mask, metas, impl=None):
+        calls.append(('graphed', impl.__name__))
+        return impl(qb, qf, feats, mask, metas)
+    monkeypatch.setattr(layer, '_forward_graphed', fake_graphed)
+    args = (torch.zeros(1, 4, 10), torch.zeros(1, 4, 256), [], None, [{}])
+    cls, box = dec(*args)
+    assert cls.shape == (3, 1, 4, 10) and [c[0] for c in calls] == ['layer'] * 3
+    calls.clear()
+    dec.use_cuda_graph, layer.use_cuda_graph = True, True
+    dec(*args)
+    assert calls[0] == ('graphed', '_layers_one_graph') and calls[1:] == [('layer', False)] * 3      # per-layer graphs off inside the capture
+    assert layer.use_cuda_graph is True                                                             # ... and restored afterwards
+    calls.clear()
+    monkeypatch.setattr(DUMP, 'enabled', True)
+    dec(*args)
+    assert [c[0] for c in calls] == ['layer'] * 3
+    monkeypatch.setattr(DUMP, 'enabled', False)
+    calls.clear()
+
+    class _Shard:
+        world = 2
+    layer.query_shard = _Shard()
+    dec(*args)
+    assert [c[0] for c in calls] == ['layer'] * 3
