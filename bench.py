@@ -62,6 +62,8 @@ def parse():
     ap.add_argument('--emulate-world', type=int, default=0, metavar='N', help='development: ONE GPU plays rank --emulate-rank of an N-GPU `--shard queries` run '
                     '(no peers; rank-local kernel sequence only, for ncu) -- the line is marked "emulated" and is not a benchmark result')
     ap.add_argument('--emulate-rank', type=int, default=0)
+    ap.add_argument('--pinned', default='default', choices=['default', 'wc'], help='e2e: host feature buffers from torch\'s pinned allocator (default) or '
+                    'write-combined pinned memory (cudaHostAllocWriteCombined: not snooped on its way over PCIe; the CPU only ever writes it)')
     ap.add_argument('--timeline', default=None, metavar='FILE', help='development: after the headline, record the kernel timeline of 3 more steps with '
                     'torch.profiler (CUPTI: true start / end of every kernel incl. the concurrent branches) and write the last step\'s kernels to FILE')
     return ap.parse_args()
@@ -177,6 +179,26 @@ def committed_dram_traffic(key):
         return None if e is None else float(e['bytes'])
     except Exception:
         return None
+
+
+def wc_pinned_copy(t):
+    """A copy of CPU tensor `t` in write-combined pinned host memory (cudaHostAlloc + cudaHostAllocWriteCombined through cuda-python);
+    returns (tensor view, pointer to pass to wc_free once the tensor is dropped)."""
+    import ctypes
+    from cuda.bindings import runtime as rt
+    n = t.numel() * t.element_size()
+    err, ptr = rt.cudaHostAlloc(n, rt.cudaHostAllocWriteCombined)
+    if int(err) != 0:
+        raise RuntimeError('cudaHostAlloc(%d bytes, write-combined) failed: %r' % (n, err))
+    buf = (ctypes.c_byte * n).from_address(int(ptr))
+    out = torch.frombuffer(buf, dtype=t.dtype).view(t.shape)
+    out.copy_(t)
+    return out, int(ptr)
+
+
+def wc_free(ptr):
+    from cuda.bindings import runtime as rt
+    rt.cudaFreeHost(ptr)
 
 
 def event_ms(fn, iters=20, warm=3, prefill_ms=0.0):
@@ -462,7 +484,21 @@ class Bench:
         6 decoder-layer samples per forward."""
         a, model, dev = self.args, self.model, self.dev
         import copy
-        pinned = [f.contiguous().cpu().pin_memory() for f in self.feats]
+        wc_ptrs = []
+        if a.pinned == 'wc':
+            try:
+                pinned = []
+                for f in self.feats:
+                    t, ptr = wc_pinned_copy(f.contiguous().cpu())
+                    pinned.append(t); wc_ptrs.append(ptr)
+            except Exception as exc:                      # pragma: no cover  (no cuda-python / allocation refused: torch's pinned allocator)
+                sys.stderr.write('write-combined pinned memory unavailable (%r): using torch pinned memory\n' % (exc,))
+                for ptr in wc_ptrs:
+                    wc_free(ptr)
+                wc_ptrs = []
+                pinned = [f.contiguous().cpu().pin_memory() for f in self.feats]
+        else:
+            pinned = [f.contiguous().cpu().pin_memory() for f in self.feats]
         dbuf = [[torch.empty_like(f) for f in self.feats] for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         ncls = 10
@@ -523,8 +559,11 @@ class Bench:
             self.layer.use_cuda_graph = False
             self.layer.reset_graphs()
         del pinned, dbuf
+        for ptr in wc_ptrs:
+            wc_free(ptr)
         scenes = self.world if self.mode == 'scenes' else 1
         return {'value': scenes * NUM_DEC_LAYERS * 1e3 / ms, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'host_buffers': 'write-combined pinned (cudaHostAllocWriteCombined)' if wc_ptrs else 'pinned (torch caching host allocator)',
                 'ms_per_step': ms, 'steps': steps, 'decoder_layer_samples_per_step': NUM_DEC_LAYERS, 'layer_cuda_graph': not a.no_graph,
                 'api': 'SparseBEVTransformer.forward(query_bbox, query_feat, mlvl_feats, attn_mask, img_metas)' if layout == 'nhwc'
                        else 'decoder loop of SparseBEVTransformer.forward on pre-regrouped maps (prepare_metas inside, regroup copy skipped)',
